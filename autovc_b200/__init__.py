@@ -1,0 +1,13 @@
+"""autovc_b200 — B200-native (sm_100a) drop-in for the AutoVC Generator training hot path.
+
+Public surface mirrors the reference's modules for this path:
+  autovc_b200.model_vc_mel.Generator     <- model_vc_mel.Generator
+  autovc_b200.model_vc_stft.GeneratorSTFT <- model_vc_stft.GeneratorSTFT
+  autovc_b200.make_spect.Spect / logmel   <- make_spect.Spect (spmel branch)
+  autovc_b200.solver                      <- the step maths of solver_encoder.Solver.train + data parallelism
+"""
+from ._lib import AvcError, LIB_PATH, launch_count, load  # noqa: F401
+from .model_vc_mel import Generator  # noqa: F401
+from .model_vc_stft import GeneratorSTFT  # noqa: F401
+
+__all__ = ["Generator", "GeneratorSTFT", "AvcError", "load", "launch_count", "LIB_PATH"]

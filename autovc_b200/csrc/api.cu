@@ -1,0 +1,100 @@
+// C-ABI front door: error plumbing and precision dispatch.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace avc {
+
+static thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// fp32 CUDA-core implementations (gemm_simt.cu, lstm_simt.cu)
+int gemm_nt_taps_simt(const float*, int, const float*, const float*, float*, int, int, int, int, int, int, int, double*, int, cudaStream_t);
+int gemm_tn_taps_simt(const float*, int, const float*, int, float*, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
+size_t gemm_tn_workspace_simt(int, int, int, int, int);
+int lstm_seq_fwd_simt(const float*, const float*, float*, int, float*, float*, int, int, int, int, cudaStream_t);
+int lstm_seq_bwd_simt(const float*, int, const float*, const float*, const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
+size_t lstm_bwd_workspace_simt(int, int, int);
+
+}  // namespace avc
+
+using namespace avc;
+
+extern "C" int avc_version(void) { return AVC_VERSION; }
+extern "C" const char* avc_last_error(void) { return g_err; }
+extern "C" unsigned long long avc_launch_count(void) { return g_launches.load(); }
+
+extern "C" int avc_gemm_nt_taps(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int nB, int T,
+                                int N, int K, int ntaps, int shift0, double* chan_stats, int accumulate, int prec, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  AVC_REQUIRE(A && W && C, "avc_gemm_nt_taps: null pointer");
+  AVC_REQUIRE(nB > 0 && T > 0 && N > 0 && K > 0 && ntaps > 0, "avc_gemm_nt_taps: bad shape B=%d T=%d N=%d K=%d taps=%d", nB, T, N, K, ntaps);
+  AVC_REQUIRE(lda >= K && ldc >= N, "avc_gemm_nt_taps: leading dimensions lda=%d < K=%d or ldc=%d < N=%d", lda, K, ldc, N);
+  (void)workspace; (void)workspace_bytes;
+  if (prec == AVC_PREC_FP32)
+    return gemm_nt_taps_simt(A, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate, as_stream(stream));
+  set_error("avc_gemm_nt_taps: precision %d not available in this build", prec);
+  return AVC_ERR_UNSUPPORTED;
+}
+
+extern "C" int avc_gemm_tn_taps(const float* dY, int ldy, const float* X, int ldx, float* dW, int nB, int T, int N, int K,
+                                int ntaps, int shift0, int out_mode, int accumulate, int prec, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  AVC_REQUIRE(dY && X && dW, "avc_gemm_tn_taps: null pointer");
+  AVC_REQUIRE(nB > 0 && T > 0 && N > 0 && K > 0 && ntaps > 0, "avc_gemm_tn_taps: bad shape");
+  AVC_REQUIRE(ldy >= N && ldx >= K, "avc_gemm_tn_taps: bad leading dimensions");
+  AVC_REQUIRE(out_mode == 0 || out_mode == 1 || (out_mode == 2 && ntaps == 1 && N % 4 == 0), "avc_gemm_tn_taps: bad out_mode");
+  if (prec == AVC_PREC_FP32)
+    return gemm_tn_taps_simt(dY, ldy, X, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, accumulate, workspace,
+                             workspace_bytes, as_stream(stream));
+  set_error("avc_gemm_tn_taps: precision %d not available in this build", prec);
+  return AVC_ERR_UNSUPPORTED;
+}
+
+extern "C" size_t avc_gemm_tn_workspace_bytes(int nB, int T, int N, int K, int ntaps, int prec) {
+  (void)prec;
+  return gemm_tn_workspace_simt(nB, T, N, K, ntaps);
+}
+
+extern "C" int avc_lstm_seq_fwd(const float* P, const float* Whh_p, float* h_seq, int ldh, float* gates, float* c_seq, int nB,
+                                int T, int H, int reverse, int prec, void* stream) {
+  AVC_REQUIRE(P && Whh_p && h_seq && gates && c_seq, "avc_lstm_seq_fwd: null pointer");
+  AVC_REQUIRE(nB > 0 && T > 0 && H > 0 && ldh >= H, "avc_lstm_seq_fwd: bad shape");
+  if (prec == AVC_PREC_FP32) return lstm_seq_fwd_simt(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, H, reverse, as_stream(stream));
+  set_error("avc_lstm_seq_fwd: precision %d not available in this build", prec);
+  return AVC_ERR_UNSUPPORTED;
+}
+
+extern "C" int avc_lstm_seq_bwd(const float* dH, int lddh, const float* Whh_p, const float* Whh_pT, const float* gates,
+                                const float* c_seq, float* dP, int nB, int T, int H, int reverse, int prec, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  AVC_REQUIRE(dH && Whh_p && Whh_pT && gates && c_seq && dP, "avc_lstm_seq_bwd: null pointer");
+  AVC_REQUIRE(nB > 0 && T > 0 && H > 0 && lddh >= H, "avc_lstm_seq_bwd: bad shape");
+  if (prec == AVC_PREC_FP32)
+    return lstm_seq_bwd_simt(dH, lddh, Whh_p, Whh_pT, gates, c_seq, dP, nB, T, H, reverse, workspace, workspace_bytes,
+                             as_stream(stream));
+  set_error("avc_lstm_seq_bwd: precision %d not available in this build", prec);
+  return AVC_ERR_UNSUPPORTED;
+}
+
+extern "C" size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H) { return lstm_bwd_workspace_simt(nB, T, H); }

@@ -1,0 +1,335 @@
+// Train/eval BatchNorm1d + activation (+ residual) forward/backward, channel reductions, losses.
+// Reference call sites: nn.BatchNorm1d model_vc_mel.py:57,:101,:139,:150,:160; F.relu :69,:115;
+// torch.tanh :165; residual :197; F.mse_loss / F.l1_loss solver_encoder.py:230,:233,:236.
+#include "common.cuh"
+
+namespace avc {
+
+// ---------------------------------------------------------------------------------------
+// column reductions over (M, C): block = 32 columns x 8 row-lanes; fp32 per-thread partials over a
+// bounded row chunk, fp64 across chunks (one atomic per column per block).
+// ---------------------------------------------------------------------------------------
+constexpr int CR_COLS = 32, CR_ROWS = 8;
+
+template <int MODE>  // 0: sum & sumsq of x;  1: BN backward sums of g and g*xhat
+__global__ void __launch_bounds__(CR_COLS* CR_ROWS)
+col_reduce_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ z, const float* __restrict__ y,
+                  const float* __restrict__ mean, const float* __restrict__ rstd, int M, int C, int rows_per_block,
+                  int act, double* __restrict__ out) {
+  __shared__ float sa[CR_ROWS][CR_COLS + 1], sb[CR_ROWS][CR_COLS + 1];
+  const int c = blockIdx.x * CR_COLS + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float a = 0.f, b = 0.f;
+  if (c < C) {
+    float mu = 0.f, rs = 0.f;
+    if (MODE == 1) {
+      mu = mean[c];
+      rs = rstd[c];
+    }
+    for (int r = r0 + threadIdx.y; r < r1; r += CR_ROWS) {
+      if (MODE == 0) {
+        const float v = x[(size_t)r * ldx + c];
+        a += v;
+        b = fmaf(v, v, b);
+      } else {
+        const size_t i = (size_t)r * C + c;
+        float g = x[i];  // dz
+        if (act == AVC_ACT_RELU) g = z[i] > 0.f ? g : 0.f;
+        else if (act == AVC_ACT_TANH) g *= (1.f - z[i] * z[i]);
+        const float xh = (y[i] - mu) * rs;
+        a += g;
+        b = fmaf(g, xh, b);
+      }
+    }
+  }
+  sa[threadIdx.y][threadIdx.x] = a;
+  sb[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double da = 0.0, db = 0.0;
+#pragma unroll
+    for (int i = 0; i < CR_ROWS; ++i) {
+      da += (double)sa[i][threadIdx.x];
+      db += (double)sb[i][threadIdx.x];
+    }
+    atomicAdd(out + c, da);
+    atomicAdd(out + C + c, db);
+  }
+}
+
+static void col_reduce_grid(int M, int C, dim3& grid, int& rows_per_block) {
+  const int cb = ceil_div(C, CR_COLS);
+  int rb = ceil_div(8 * num_sms(), cb);
+  rows_per_block = ceil_div(M, rb);
+  if (rows_per_block < 64) rows_per_block = 64;
+  rb = ceil_div(M, rows_per_block);
+  grid = dim3(cb, rb);
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int M, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ rmean,
+                                   float* __restrict__ rvar) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = stats[c] / M;
+  double var = stats[C + c] / M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)mu;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (rmean) rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mu;
+  if (rvar) {
+    const double unbiased = M > 1 ? var * ((double)M / (double)(M - 1)) : var;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar, int C, float eps,
+                                     float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = rmean[c];
+  rstd[c] = 1.0f / sqrtf(rvar[c] + eps);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == AVC_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == AVC_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+// z = act(y*scale + shift) (+ residual); grid-stride over (M, C) with per-element channel lookup
+__global__ void bn_act_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean,
+                                  const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, const float* __restrict__ res, float* __restrict__ z,
+                                  size_t total, int C, int act) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const float sc = rstd[c] * gamma[c];
+    float v = (y[i] - mean[c]) * sc + beta[c];
+    v = apply_act(v, act);
+    if (res) v += res[i];
+    z[i] = v;
+  }
+}
+
+__global__ void bn_act_fwd_vec4_kernel(const float4* __restrict__ y, const float* __restrict__ mean,
+                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float4* __restrict__ res,
+                                       float4* __restrict__ z, size_t total4, int C, int act) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i * 4) % C);
+    const float4 v = y[i];
+    float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sc = rstd[c + j] * gamma[c + j];
+      o[j] = apply_act((o[j] - mean[c + j]) * sc + beta[c + j], act);
+    }
+    if (res) {
+      const float4 r = res[i];
+      o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+    }
+    z[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ z,
+                                        const float* __restrict__ y, const float* __restrict__ mean,
+                                        const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                        const double* __restrict__ sums, float* __restrict__ dy, size_t total, int M,
+                                        int C, int act) {
+  const float invM = 1.0f / (float)M;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    float g = dz[i];
+    if (act == AVC_ACT_RELU) g = z[i] > 0.f ? g : 0.f;
+    else if (act == AVC_ACT_TANH) g *= (1.f - z[i] * z[i]);
+    const float rs = rstd[c];
+    const float xh = (y[i] - mean[c]) * rs;
+    const float sg = (float)sums[c] * invM, sgx = (float)sums[C + c] * invM;
+    dy[i] = gamma[c] * rs * (g - sg - xh * sgx);
+  }
+}
+
+__global__ void bn_param_grad_kernel(const double* __restrict__ sums, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int C, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float dg = (float)sums[C + c], db = (float)sums[c];
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + dg : dg;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + db : db;
+}
+
+__global__ void colsum_finalize_kernel(const double* __restrict__ sums, float* __restrict__ out, float* __restrict__ out2,
+                                       int C, int out_mode, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  int o = c;
+  if (out_mode == 2) {
+    const int H = C >> 2;
+    o = (c & 3) * H + (c >> 2);
+  }
+  const float v = (float)sums[c];
+  out[o] = accumulate ? out[o] + v : v;
+  if (out2) out2[o] = accumulate ? out2[o] + v : v;
+}
+
+// ---------------------------------------------------------------------------------------
+// losses
+// ---------------------------------------------------------------------------------------
+template <bool L1>
+__global__ void loss_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
+                                double* __restrict__ acc) {
+  float s = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float d = a[i] - b[i];
+    s += L1 ? fabsf(d) : d * d;
+  }
+  s = warp_sum(s);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += (double)ws[i];
+    atomicAdd(acc, t);
+  }
+}
+__global__ void loss_finalize_kernel(const double* __restrict__ acc, size_t n, float* __restrict__ out) {
+  out[0] = (float)(acc[0] / (double)n);
+}
+__global__ void loss_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n,
+                                const float* __restrict__ gout, int is_l1, float* __restrict__ da,
+                                float* __restrict__ db, int accumulate) {
+  const float scale = gout[0] / (float)n;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float d = a[i] - b[i];
+    const float g = is_l1 ? (d > 0.f ? scale : (d < 0.f ? -scale : 0.f)) : 2.f * d * scale;
+    if (da) da[i] = accumulate ? da[i] + g : g;
+    if (db) db[i] = accumulate ? db[i] - g : -g;
+  }
+}
+
+static int ew_blocks(size_t total) {
+  return (int)std::min<size_t>(ceil_div(total, (size_t)256), (size_t)num_sms() * 16);
+}
+
+}  // namespace avc
+
+using namespace avc;
+
+extern "C" int avc_channel_stats(const float* x, int ldx, int M, int C, double* stats, void* stream) {
+  AVC_REQUIRE(x && stats && M > 0 && C > 0 && ldx >= C, "avc_channel_stats: bad arguments");
+  dim3 grid;
+  int rpb;
+  col_reduce_grid(M, C, grid, rpb);
+  col_reduce_kernel<0><<<grid, dim3(CR_COLS, CR_ROWS), 0, as_stream(stream)>>>(x, ldx, nullptr, nullptr, nullptr, nullptr,
+                                                                              M, C, rpb, 0, stats);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_bn_finalize(const double* stats, int M, int C, float eps, float momentum, float* mean, float* rstd,
+                               float* running_mean, float* running_var, void* stream) {
+  AVC_REQUIRE(stats && mean && rstd && M > 0 && C > 0, "avc_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(stats, M, C, eps, momentum, mean, rstd,
+                                                                       running_mean, running_var);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean,
+                                 float* rstd, void* stream) {
+  AVC_REQUIRE(running_mean && running_var && mean && rstd && C > 0, "avc_bn_eval_stats: bad arguments");
+  bn_eval_stats_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(running_mean, running_var, C, eps, mean, rstd);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_bn_act_fwd(const float* y, const float* mean, const float* rstd, const float* gamma,
+                              const float* beta, const float* residual, float* z, int M, int C, int act, void* stream) {
+  AVC_REQUIRE(y && mean && rstd && gamma && beta && z && M > 0 && C > 0, "avc_bn_act_fwd: bad arguments");
+  const size_t total = (size_t)M * C;
+  const bool vec = (C % 4 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)z % 16 == 0) &&
+                   (!residual || (uintptr_t)residual % 16 == 0);
+  if (vec)
+    bn_act_fwd_vec4_kernel<<<ew_blocks(total / 4), 256, 0, as_stream(stream)>>>(
+        (const float4*)y, mean, rstd, gamma, beta, (const float4*)residual, (float4*)z, total / 4, C, act);
+  else
+    bn_act_fwd_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(y, mean, rstd, gamma, beta, residual, z, total, C, act);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_bn_act_bwd_reduce(const float* dz, const float* z, const float* y, const float* mean,
+                                     const float* rstd, double* sums, int M, int C, int act, void* stream) {
+  AVC_REQUIRE(dz && z && y && mean && rstd && sums && M > 0 && C > 0, "avc_bn_act_bwd_reduce: bad arguments");
+  dim3 grid;
+  int rpb;
+  col_reduce_grid(M, C, grid, rpb);
+  col_reduce_kernel<1><<<grid, dim3(CR_COLS, CR_ROWS), 0, as_stream(stream)>>>(dz, C, z, y, mean, rstd, M, C, rpb, act, sums);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_bn_act_bwd_apply(const float* dz, const float* z, const float* y, const float* mean,
+                                    const float* rstd, const float* gamma, const double* sums, float* dy, float* dgamma,
+                                    float* dbeta, int M, int C, int act, int accumulate, void* stream) {
+  AVC_REQUIRE(dz && z && y && mean && rstd && gamma && sums && dy && M > 0 && C > 0, "avc_bn_act_bwd_apply: bad arguments");
+  const size_t total = (size_t)M * C;
+  bn_act_bwd_apply_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(dz, z, y, mean, rstd, gamma, sums, dy, total, M, C, act);
+  AVC_LAUNCHED();
+  if (dgamma || dbeta) {
+    bn_param_grad_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(sums, dgamma, dbeta, C, accumulate);
+    AVC_LAUNCHED();
+  }
+  return AVC_OK;
+}
+
+extern "C" int avc_colsum(const float* x, int ldx, int M, int C, float* out, float* out2, int out_mode, int accumulate,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  AVC_REQUIRE(x && out && M > 0 && C > 0 && ldx >= C, "avc_colsum: bad arguments");
+  AVC_REQUIRE(out_mode == 0 || (out_mode == 2 && C % 4 == 0), "avc_colsum: bad out_mode");
+  if (!workspace || workspace_bytes < 2 * sizeof(double) * (size_t)C) {
+    set_error("avc_colsum: workspace too small");
+    return AVC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  AVC_CUDA(cudaMemsetAsync(workspace, 0, 2 * sizeof(double) * (size_t)C, st));
+  dim3 grid;
+  int rpb;
+  col_reduce_grid(M, C, grid, rpb);
+  col_reduce_kernel<0><<<grid, dim3(CR_COLS, CR_ROWS), 0, st>>>(x, ldx, nullptr, nullptr, nullptr, nullptr, M, C, rpb, 0,
+                                                               (double*)workspace);
+  AVC_LAUNCHED();
+  colsum_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const double*)workspace, out, out2, C, out_mode, accumulate);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_mse_loss_fwd(const float* a, const float* b, size_t n, double* scratch, float* out, void* stream) {
+  AVC_REQUIRE(a && b && scratch && out && n > 0, "avc_mse_loss_fwd: bad arguments");
+  loss_fwd_kernel<false><<<ew_blocks(n), 256, 0, as_stream(stream)>>>(a, b, n, scratch);
+  AVC_LAUNCHED();
+  loss_finalize_kernel<<<1, 1, 0, as_stream(stream)>>>(scratch, n, out);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_l1_loss_fwd(const float* a, const float* b, size_t n, double* scratch, float* out, void* stream) {
+  AVC_REQUIRE(a && b && scratch && out && n > 0, "avc_l1_loss_fwd: bad arguments");
+  loss_fwd_kernel<true><<<ew_blocks(n), 256, 0, as_stream(stream)>>>(a, b, n, scratch);
+  AVC_LAUNCHED();
+  loss_finalize_kernel<<<1, 1, 0, as_stream(stream)>>>(scratch, n, out);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_loss_bwd(const float* a, const float* b, size_t n, const float* gout, int is_l1, float* da, float* db,
+                            int accumulate, void* stream) {
+  AVC_REQUIRE(a && b && gout && (da || db) && n > 0, "avc_loss_bwd: bad arguments");
+  loss_bwd_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(a, b, n, gout, is_l1, da, db, accumulate);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}

@@ -1,0 +1,233 @@
+// make_spect front-end on the GPU: make_spect.py:72-83 (spmel branch) + butter_highpass :30-34 + pySTFT :36-48.
+//
+//   stage 1  filtfilt (fp64, scipy semantics: odd extension by padlen=18, lfilter_zi initial state,
+//            direct-form-II-transposed forward pass then the same filter run backwards)          :74
+//   stage 2  wav' = 0.96*y + (dither - 0.5)*1e-6, stored fp32                                      :76
+//   stage 3  per frame: reflect-pad(512) framing, periodic Hann, 1024-point FFT (two real frames
+//            per complex transform), |.|, mel projection (only the non-zero band of each filter),
+//            20*log10(max(1e-5,.)) - 16, (x+100)/100 clipped to [0,1]                              :78-83
+// HBM-bound by design: every stage streams its input once; the FFT, window, mel and log work stay in
+// shared memory / registers.
+#include "common.cuh"
+
+namespace avc {
+
+constexpr int FE_NFFT = 1024, FE_HOP = 256, FE_BINS = 513, FE_MELS = 80, FE_PADLEN = 18, FE_REFLECT = 512;
+constexpr int FE_FRAMES_PER_CTA = 8;   // 4 complex FFTs per CTA
+constexpr int FE_THREADS = 256;
+
+struct FeTables {           // lives at the head of the workspace
+  float2 tw[FE_NFFT / 2];   // exp(-2*pi*i*k/1024)
+  float win[FE_NFFT];       // periodic Hann
+  int2 band[FE_MELS];       // [first, last+1) non-zero FFT bin of each mel filter
+};
+
+__global__ void fe_tables_kernel(const float* __restrict__ mel_basis, FeTables* __restrict__ tb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < FE_NFFT / 2) {
+    double s, c;
+    sincospi(-2.0 * (double)i / (double)FE_NFFT, &s, &c);
+    tb->tw[i] = make_float2((float)c, (float)s);
+  }
+  if (i < FE_NFFT) tb->win[i] = (float)(0.5 - 0.5 * cospi(2.0 * (double)i / (double)FE_NFFT));
+  if (i < FE_MELS) {
+    int lo = FE_BINS, hi = 0;
+    for (int k = 0; k < FE_BINS; ++k)
+      if (mel_basis[k * FE_MELS + i] != 0.f) {
+        lo = min(lo, k);
+        hi = max(hi, k + 1);
+      }
+    if (hi == 0) lo = 0;
+    tb->band[i] = make_int2(lo, hi);
+  }
+}
+
+// --- stage 1+2: one thread per utterance, fp64 recurrences -------------------------------------------
+struct Df2t {
+  double b[6], a[6], z[5];
+  __device__ __forceinline__ double step(double x) {
+    const double y = fma(b[0], x, z[0]);
+    z[0] = fma(-a[1], y, fma(b[1], x, z[1]));
+    z[1] = fma(-a[2], y, fma(b[2], x, z[2]));
+    z[2] = fma(-a[3], y, fma(b[3], x, z[3]));
+    z[3] = fma(-a[4], y, fma(b[4], x, z[4]));
+    z[4] = fma(-a[5], y, b[5] * x);
+    return y;
+  }
+};
+
+// odd extension of x (length n) by FE_PADLEN at both ends; index i in [0, n + 2*padlen)
+__device__ __forceinline__ double odd_ext(const float* __restrict__ x, int n, int i) {
+  if (i < FE_PADLEN) return 2.0 * (double)x[0] - (double)x[FE_PADLEN - i];
+  if (i < FE_PADLEN + n) return (double)x[i - FE_PADLEN];
+  return 2.0 * (double)x[n - 1] - (double)x[n - 2 - (i - FE_PADLEN - n)];
+}
+
+__global__ void fe_filtfilt_kernel(const float* __restrict__ wav, const float* __restrict__ dither,
+                                   const int* __restrict__ lengths, int n_utt, int max_len,
+                                   const double* __restrict__ filt, const double* __restrict__ zi,
+                                   double* __restrict__ fwd_buf, float* __restrict__ out) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_utt) return;
+  const int n = lengths[u];
+  const float* x = wav + (size_t)u * max_len;
+  const float* dz = dither + (size_t)u * max_len;
+  float* o = out + (size_t)u * max_len;
+  double* y1 = fwd_buf + (size_t)u * (max_len + 2 * FE_PADLEN);
+  if (n <= FE_PADLEN) {   // scipy raises for such inputs; emit silence deterministically
+    for (int i = 0; i < n; ++i) o[i] = (float)(((double)dz[i] - 0.5) * 1e-6);
+    return;
+  }
+  Df2t f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    f.b[i] = filt[i];
+    f.a[i] = filt[6 + i];
+  }
+  const int ne = n + 2 * FE_PADLEN;
+  const double x0 = odd_ext(x, n, 0);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) f.z[i] = zi[i] * x0;
+  for (int i = 0; i < ne; ++i) y1[i] = f.step(odd_ext(x, n, i));
+  const double y0 = y1[ne - 1];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) f.z[i] = zi[i] * y0;
+  for (int i = ne - 1; i >= 0; --i) {
+    const double y = f.step(y1[i]);
+    const int j = i - FE_PADLEN;
+    if (j >= 0 && j < n) o[j] = (float)(y * 0.96 + ((double)dz[j] - 0.5) * 1e-6);
+  }
+}
+
+// --- stage 3: framing + FFT + mel + log ---------------------------------------------------------------
+__device__ __forceinline__ int bitrev10(int v) { return (int)(__brev((unsigned)v) >> 22); }
+
+__global__ void __launch_bounds__(FE_THREADS)
+fe_stft_mel_kernel(const float* __restrict__ sig, const int* __restrict__ lengths, int max_len,
+                   const float* __restrict__ mel_basis, const FeTables* __restrict__ tb, float* __restrict__ out,
+                   int max_frames) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NPAIR = FE_FRAMES_PER_CTA / 2;
+  constexpr int CHUNK = (FE_FRAMES_PER_CTA - 1) * FE_HOP + FE_NFFT;
+  float2* z = reinterpret_cast<float2*>(smem_raw);                 // [NPAIR][1024]
+  float2* tw = z + NPAIR * FE_NFFT;                                // [512]
+  float* win = reinterpret_cast<float*>(tw + FE_NFFT / 2);         // [1024]
+  float* chunk = win + FE_NFFT;                                    // [CHUNK]
+  float* mag = chunk + CHUNK;                                      // [FRAMES][513 (+pad)]
+  constexpr int MAGLD = FE_BINS + 3;
+
+  const int u = blockIdx.y;
+  const int f0 = blockIdx.x * FE_FRAMES_PER_CTA;
+  const int n = lengths[u];
+  const int n_frames = n > FE_PADLEN ? 1 + n / FE_HOP : 0;
+  const int tid = threadIdx.x;
+  float* o = out + ((size_t)u * max_frames + f0) * FE_MELS;
+  if (f0 >= n_frames) {   // zero padding frames (conversion.py:40-44 pad_seq)
+    for (int i = tid; i < FE_FRAMES_PER_CTA * FE_MELS; i += FE_THREADS)
+      if (f0 + i / FE_MELS < max_frames) o[i] = 0.f;
+    return;
+  }
+  for (int i = tid; i < FE_NFFT / 2; i += FE_THREADS) tw[i] = tb->tw[i];
+  for (int i = tid; i < FE_NFFT; i += FE_THREADS) win[i] = tb->win[i];
+  // reflect-padded samples [f0*hop, f0*hop + CHUNK) of the padded signal (np.pad mode='reflect')
+  const float* x = sig + (size_t)u * max_len;
+  for (int i = tid; i < CHUNK; i += FE_THREADS) {
+    int j = f0 * FE_HOP + i - FE_REFLECT;
+    if (j < 0) j = -j;
+    if (j >= n) j = 2 * (n - 1) - j;
+    chunk[i] = (j >= 0 && j < n) ? x[j] : 0.f;
+  }
+  __syncthreads();
+  // windowed frames -> bit-reversed complex buffers (frame 2p real, frame 2p+1 imaginary)
+  for (int i = tid; i < NPAIR * FE_NFFT; i += FE_THREADS) {
+    const int p = i >> 10, k = i & 1023;
+    const float w = win[k];
+    z[p * FE_NFFT + bitrev10(k)] = make_float2(w * chunk[(2 * p) * FE_HOP + k], w * chunk[(2 * p + 1) * FE_HOP + k]);
+  }
+  __syncthreads();
+  // radix-2 DIT, 10 stages, NPAIR*512 butterflies per stage
+#pragma unroll 1
+  for (int s = 0; s < 10; ++s) {
+    const int half = 1 << s;
+    for (int i = tid; i < NPAIR * (FE_NFFT / 2); i += FE_THREADS) {
+      const int p = i >> 9, j = i & 511;
+      const int pos = j & (half - 1);
+      const int i0 = ((j >> s) << (s + 1)) + pos;
+      const float2 w = tw[pos << (9 - s)];
+      float2* zz = z + p * FE_NFFT;
+      const float2 a = zz[i0], b = zz[i0 + half];
+      const float2 t = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
+      zz[i0] = make_float2(a.x + t.x, a.y + t.y);
+      zz[i0 + half] = make_float2(a.x - t.x, a.y - t.y);
+    }
+    __syncthreads();
+  }
+  // split the two real spectra and take magnitudes
+  for (int i = tid; i < NPAIR * FE_BINS; i += FE_THREADS) {
+    const int p = i / FE_BINS, k = i - p * FE_BINS;
+    const float2 a = z[p * FE_NFFT + k];
+    const float2 b = z[p * FE_NFFT + ((FE_NFFT - k) & (FE_NFFT - 1))];
+    const float ar = 0.5f * (a.x + b.x), ai = 0.5f * (a.y - b.y);      // frame 2p
+    const float br = 0.5f * (a.y + b.y), bi = 0.5f * (b.x - a.x);      // frame 2p+1
+    mag[(2 * p) * MAGLD + k] = sqrtf(ar * ar + ai * ai);
+    mag[(2 * p + 1) * MAGLD + k] = sqrtf(br * br + bi * bi);
+  }
+  __syncthreads();
+  for (int i = tid; i < FE_FRAMES_PER_CTA * FE_MELS; i += FE_THREADS) {
+    const int fr = i / FE_MELS, m = i - fr * FE_MELS;
+    if (f0 + fr >= max_frames) continue;
+    float v = 0.f;
+    if (f0 + fr < n_frames) {
+      const int2 bd = tb->band[m];
+      float acc = 0.f;
+      for (int k = bd.x; k < bd.y; ++k) acc = fmaf(mag[fr * MAGLD + k], __ldg(mel_basis + k * FE_MELS + m), acc);
+      const float db = 20.f * log10f(fmaxf(1e-5f, acc)) - 16.f;
+      v = fminf(fmaxf((db + 100.f) / 100.f, 0.f), 1.f);
+    }
+    o[i] = v;
+  }
+}
+
+static size_t fe_tables_bytes() { return (sizeof(FeTables) + 255) / 256 * 256; }
+
+}  // namespace avc
+
+using namespace avc;
+
+extern "C" size_t avc_logmel_workspace_bytes(int n_utt, int max_len) {
+  if (n_utt <= 0 || max_len <= 0) return 0;
+  const size_t fwd = (size_t)n_utt * (max_len + 2 * FE_PADLEN) * sizeof(double);
+  const size_t sig = ((size_t)n_utt * max_len * sizeof(float) + 255) / 256 * 256;
+  return fe_tables_bytes() + sig + fwd;
+}
+
+extern "C" int avc_logmel_frontend(const float* wav, const float* dither, const int* lengths, int n_utt, int max_len,
+                                   const float* mel_basis, const double* filt, const double* zi, float* out,
+                                   int max_frames, void* workspace, size_t workspace_bytes, void* stream) {
+  AVC_REQUIRE(wav && dither && lengths && mel_basis && filt && zi && out, "avc_logmel_frontend: null pointer");
+  AVC_REQUIRE(n_utt > 0 && max_len > 0 && max_frames > 0, "avc_logmel_frontend: bad shape");
+  AVC_REQUIRE(max_frames >= 1 + max_len / FE_HOP, "avc_logmel_frontend: max_frames %d < 1 + max_len/256 = %d", max_frames,
+              1 + max_len / FE_HOP);
+  if (!workspace || workspace_bytes < avc_logmel_workspace_bytes(n_utt, max_len)) {
+    set_error("avc_logmel_frontend: workspace too small");
+    return AVC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  unsigned char* ws = (unsigned char*)workspace;
+  FeTables* tb = (FeTables*)ws;
+  float* sig = (float*)(ws + fe_tables_bytes());
+  double* fwd = (double*)(ws + fe_tables_bytes() + ((size_t)n_utt * max_len * sizeof(float) + 255) / 256 * 256);
+  fe_tables_kernel<<<ceil_div(FE_NFFT, 256), 256, 0, st>>>(mel_basis, tb);
+  AVC_LAUNCHED();
+  fe_filtfilt_kernel<<<ceil_div(n_utt, 32), 32, 0, st>>>(wav, dither, lengths, n_utt, max_len, filt, zi, fwd, sig);
+  AVC_LAUNCHED();
+  constexpr int NPAIR = FE_FRAMES_PER_CTA / 2;
+  constexpr int CHUNK = (FE_FRAMES_PER_CTA - 1) * FE_HOP + FE_NFFT;
+  const size_t smem = NPAIR * FE_NFFT * sizeof(float2) + (FE_NFFT / 2) * sizeof(float2) + FE_NFFT * sizeof(float) +
+                      CHUNK * sizeof(float) + FE_FRAMES_PER_CTA * (FE_BINS + 3) * sizeof(float);
+  AVC_CUDA(cudaFuncSetAttribute(fe_stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(max_frames, FE_FRAMES_PER_CTA), n_utt);
+  fe_stft_mel_kernel<<<grid, FE_THREADS, smem, st>>>(sig, lengths, max_len, mel_basis, tb, out, max_frames);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}

@@ -1,0 +1,297 @@
+// fp32 CUDA-core implementations of the GEMM-with-taps family + weight packers.
+#include "simt_gemm.cuh"
+
+namespace avc {
+
+// ---------------------------------------------------------------------------------------
+// NT + taps (conv fwd/dgrad, input projections, linear)
+// ---------------------------------------------------------------------------------------
+template <bool STATS, bool ACCUM>
+__global__ void __launch_bounds__(SG_THREADS)
+gemm_nt_taps_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W,
+                         const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int T, int N,
+                         int K, int ntaps, int shift0, double* __restrict__ stats) {
+  __shared__ SimtSmem s;
+  const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+  const TapRows rows{T, shift0};
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  auto loadA = [&](int m, int tap, int k) -> float {
+    if (m >= M || k >= K) return 0.f;
+    const int r = rows(m, tap);
+    return r >= 0 ? __ldg(A + (size_t)r * lda + k) : 0.f;
+  };
+  auto loadB = [&](int n, int tap, int k) -> float {
+    return (n < N && k < K) ? __ldg(W + ((size_t)tap * N + n) * K + k) : 0.f;
+  };
+  simt_mainloop_nt(s, acc, m0, n0, K, ntaps, loadA, loadB);
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float bj[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int n = n0 + acc_col(tx, j);
+    bj[j] = (bias != nullptr && n < N) ? bias[n] : 0.f;
+  }
+  float csum[8], csq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) csum[j] = csq[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + acc_row(ty, i);
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + acc_col(tx, j);
+      if (n < N) {
+        float v = acc[i][j] + bj[j];
+        if (ACCUM) v += C[(size_t)m * ldc + n];
+        C[(size_t)m * ldc + n] = v;
+        if (STATS) {
+          csum[j] += v;
+          csq[j] = fmaf(v, v, csq[j]);
+        }
+      }
+    }
+  }
+  if (STATS) {
+    // reduce the 16 row-groups (ty) of each column through shared memory, then one fp64 atomic per column
+    float* red = &s.a[0][0];  // 2 * 16 * 128 floats = 16 KB <= sizeof(SimtSmem)
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      red[ty * 128 + acc_col(tx, j)] = csum[j];
+      red[2048 + ty * 128 + acc_col(tx, j)] = csq[j];
+    }
+    __syncthreads();
+    if (tid < 128) {
+      const int n = n0 + tid;
+      if (n < N) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          a += (double)red[r * 128 + tid];
+          b += (double)red[2048 + r * 128 + tid];
+        }
+        atomicAdd(stats + n, a);
+        atomicAdd(stats + N + n, b);
+      }
+    }
+  }
+}
+
+int gemm_nt_taps_simt(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int nB, int T,
+                      int N, int K, int ntaps, int shift0, double* stats, int accumulate, cudaStream_t st) {
+  const int M = nB * T;
+  dim3 grid(ceil_div(N, SG_BN), ceil_div(M, SG_BM));
+  if (stats && accumulate) {
+    set_error("avc_gemm_nt_taps: chan_stats and accumulate are mutually exclusive");
+    return AVC_ERR_UNSUPPORTED;
+  }
+  if (stats)
+    gemm_nt_taps_simt_kernel<true, false><<<grid, SG_THREADS, 0, st>>>(A, lda, W, bias, C, ldc, M, T, N, K, ntaps, shift0, stats);
+  else if (accumulate)
+    gemm_nt_taps_simt_kernel<false, true><<<grid, SG_THREADS, 0, st>>>(A, lda, W, bias, C, ldc, M, T, N, K, ntaps, shift0, nullptr);
+  else
+    gemm_nt_taps_simt_kernel<false, false><<<grid, SG_THREADS, 0, st>>>(A, lda, W, bias, C, ldc, M, T, N, K, ntaps, shift0, nullptr);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// TN + taps (weight gradients) : split over rows, partials to workspace, then a mapped reduce
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SG_THREADS)
+gemm_tn_taps_simt_kernel(const float* __restrict__ dY, int ldy, const float* __restrict__ X, int ldx,
+                         float* __restrict__ part, int M, int T, int N, int K, int ntaps, int shift0, int splits,
+                         int rows_per_split) {
+  __shared__ SimtSmem s;
+  const int n0 = blockIdx.x * SG_BN, k0 = blockIdx.y * SG_BN;
+  const int tap = blockIdx.z % ntaps, split = blockIdx.z / ntaps;
+  const int r0 = split * rows_per_split;
+  const int r1 = min(M, r0 + rows_per_split);
+  const TapRows rows{T, shift0};
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  auto loadA = [&](int r, int n) -> float { return n < N ? __ldg(dY + (size_t)r * ldy + n) : 0.f; };
+  auto loadB = [&](int r, int tp, int k) -> float {
+    if (k >= K) return 0.f;
+    const int src = rows(r, tp);
+    return src >= 0 ? __ldg(X + (size_t)src * ldx + k) : 0.f;
+  };
+  simt_mainloop_tn(s, acc, n0, k0, r0, r1, tap, loadA, loadB);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  float* out = part + ((size_t)split * ntaps + tap) * N * K;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int n = n0 + acc_row(ty, i);
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + acc_col(tx, j);
+      if (k < K) out[(size_t)n * K + k] = acc[i][j];
+    }
+  }
+}
+
+// out index map shared with the tensor-core path
+__device__ __forceinline__ size_t wgrad_out_index(int tap, int n, int k, int N, int K, int ntaps, int out_mode) {
+  if (out_mode == 1) return ((size_t)n * K + k) * ntaps + tap;                 // PyTorch Conv1d (N, K, taps)
+  if (out_mode == 2) {                                                          // LSTM: packed row u*4+g -> g*H+u
+    const int H = N >> 2, u = n >> 2, g = n & 3;
+    return (size_t)(g * H + u) * K + k;
+  }
+  return ((size_t)tap * N + n) * K + k;
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dW, int N, int K, int ntaps,
+                                    int splits, int out_mode, int accumulate) {
+  const size_t total = (size_t)ntaps * N * K;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += part[(size_t)s * total + i];
+    const int k = (int)(i % K);
+    const int n = (int)((i / K) % N);
+    const int tap = (int)(i / ((size_t)K * N));
+    const size_t o = wgrad_out_index(tap, n, k, N, K, ntaps, out_mode);
+    dW[o] = accumulate ? dW[o] + v : v;
+  }
+}
+
+static int tn_splits(int M, int N, int K, int ntaps) {
+  const int tiles = ceil_div(N, SG_BN) * ceil_div(K, SG_BN) * ntaps;
+  int splits = ceil_div(3 * num_sms(), tiles);
+  const int max_splits = ceil_div(M, 512);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
+size_t gemm_tn_workspace_simt(int nB, int T, int N, int K, int ntaps) {
+  return (size_t)tn_splits(nB * T, N, K, ntaps) * ntaps * N * K * sizeof(float);
+}
+
+int launch_wgrad_reduce(const float* part, float* dW, int N, int K, int ntaps, int splits, int out_mode, int accumulate,
+                        cudaStream_t st) {
+  const size_t total = (size_t)ntaps * N * K;
+  int blocks = (int)std::min<size_t>(ceil_div(total, (size_t)256), (size_t)num_sms() * 8);
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(part, dW, N, K, ntaps, splits, out_mode, accumulate);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+int gemm_tn_taps_simt(const float* dY, int ldy, const float* X, int ldx, float* dW, int nB, int T, int N, int K,
+                      int ntaps, int shift0, int out_mode, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int M = nB * T;
+  const int splits = tn_splits(M, N, K, ntaps);
+  const size_t need = (size_t)splits * ntaps * N * K * sizeof(float);
+  if (ws == nullptr || ws_bytes < need) {
+    set_error("avc_gemm_tn_taps: workspace %zu < %zu", ws_bytes, need);
+    return AVC_ERR_WORKSPACE;
+  }
+  int rps = ceil_div(M, splits);
+  rps = ceil_div(rps, SG_BK) * SG_BK;
+  dim3 grid(ceil_div(N, SG_BN), ceil_div(K, SG_BN), ntaps * splits);
+  gemm_tn_taps_simt_kernel<<<grid, SG_THREADS, 0, st>>>(dY, ldy, X, ldx, (float*)ws, M, T, N, K, ntaps, shift0, splits, rps);
+  AVC_LAUNCHED();
+  return launch_wgrad_reduce((const float*)ws, dW, N, K, ntaps, splits, out_mode, accumulate, st);
+}
+
+// ---------------------------------------------------------------------------------------
+// weight packers
+// ---------------------------------------------------------------------------------------
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wd,
+                                        int Cout, int Cin, int ntaps) {
+  const size_t total = (size_t)Cout * Cin * ntaps;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % ntaps);
+    const int ci = (int)((i / ntaps) % Cin);
+    const int co = (int)(i / ((size_t)ntaps * Cin));
+    const float v = w[i];
+    if (wf) wf[((size_t)tap * Cout + co) * Cin + ci] = v;
+    // dgrad: dX[t, ci] = sum_tap' sum_co dY[t + tap' - 2, co] * w[co, ci, 4 - tap']
+    if (wd) wd[((size_t)(ntaps - 1 - tap) * Cin + ci) * Cout + co] = v;
+  }
+}
+
+__global__ void pack_lstm_weight_kernel(const float* __restrict__ w, float* __restrict__ p, float* __restrict__ pT,
+                                        int H, int I) {
+  const size_t total = (size_t)4 * H * I;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % I);
+    const int row = (int)(i / I);  // g*H + u
+    const int g = row / H, u = row - g * H;
+    const int pr = u * 4 + g;
+    const float v = w[i];
+    if (p) p[(size_t)pr * I + k] = v;
+    if (pT) pT[(size_t)k * 4 * H + pr] = v;
+  }
+}
+
+__global__ void pack_lstm_bias_kernel(const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                      float* __restrict__ out, int H) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 4 * H) {
+    const int g = i / H, u = i - g * H;
+    out[u * 4 + g] = b_ih[i] + b_hh[i];
+  }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < C) out[(size_t)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+}  // namespace avc
+
+using namespace avc;
+
+extern "C" int avc_pack_conv_weight(const float* w, float* w_fwd, float* w_dgrad, int Cout, int Cin, int ntaps,
+                                    void* stream) {
+  AVC_REQUIRE(w && (w_fwd || w_dgrad) && Cout > 0 && Cin > 0 && ntaps > 0, "avc_pack_conv_weight: bad arguments");
+  const size_t total = (size_t)Cout * Cin * ntaps;
+  int blocks = (int)std::min<size_t>(ceil_div(total, (size_t)256), (size_t)num_sms() * 8);
+  pack_conv_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, w_fwd, w_dgrad, Cout, Cin, ntaps);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_pack_lstm_weight(const float* w, float* out_p, float* out_pT, int H, int I, void* stream) {
+  AVC_REQUIRE(w && (out_p || out_pT) && H > 0 && I > 0, "avc_pack_lstm_weight: bad arguments");
+  const size_t total = (size_t)4 * H * I;
+  int blocks = (int)std::min<size_t>(ceil_div(total, (size_t)256), (size_t)num_sms() * 8);
+  pack_lstm_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, out_p, out_pT, H, I);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_pack_lstm_bias(const float* b_ih, const float* b_hh, float* out, int H, void* stream) {
+  AVC_REQUIRE(b_ih && b_hh && out && H > 0, "avc_pack_lstm_bias: bad arguments");
+  pack_lstm_bias_kernel<<<ceil_div(4 * H, 256), 256, 0, as_stream(stream)>>>(b_ih, b_hh, out, H);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_transpose(const float* in, float* out, int R, int C, void* stream) {
+  AVC_REQUIRE(in && out && R > 0 && C > 0, "avc_transpose: bad arguments");
+  dim3 grid(ceil_div(C, 32), ceil_div(R, 32));
+  transpose_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(in, out, R, C);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}

@@ -1,0 +1,207 @@
+"""Drop-in ``Generator`` for the reference's ``model_vc_mel.Generator`` (model_vc_mel.py:172-203).
+
+Same constructor ``Generator(dim_neck, dim_emb, dim_pre, freq)``, same ``forward(x, c_org, c_trg)``
+contract and return values, same sub-module names (``encoder``, ``decoder``, ``postnet``), same
+parameter/buffer names, shapes, registration order and initialisers — so ``torch.manual_seed(s)``
+followed by construction gives the reference's init bit for bit, ``state_dict()`` /
+``load_state_dict()`` / the optimizer-state indexing of a reference checkpoint carry over, and the
+reference ``Solver`` loop (solver_encoder.py:182-421) runs unchanged on top of it.
+
+What differs is who does the arithmetic: the torch.nn layers below are used only as *parameter
+containers*; every forward/backward computation goes through ``autovc_b200.ops`` into the CUDA
+kernels of libautovc_b200.so.  Activations stay channels-last (B, T, C) from end to end, so none of
+the reference's transposes (model_vc_mel.py:64,:70,:112,:116,:196-197) exist here.  There is no
+CPU path: parameters and inputs must live on a CUDA device.
+
+Extra (non-reference) constructor keywords: ``n_bins`` (80; 513 builds the model_vc_stft layer
+shapes) and ``precision`` ("fp32" | "bf16", also settable later through ``set_precision``).
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import ACT_CODES, PREC_BF16, PREC_FP32
+
+_PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+
+
+def _default_precision() -> str:
+    return os.environ.get("AUTOVC_B200_PRECISION", "fp32")
+
+
+class LinearNorm(nn.Module):
+    """Parameter container mirroring model_vc_mel.py:7-17 (``linear_layer`` + Xavier init)."""
+
+    def __init__(self, in_dim, out_dim, bias=True, w_init_gain="linear"):
+        super().__init__()
+        self.linear_layer = nn.Linear(in_dim, out_dim, bias=bias)
+        nn.init.xavier_uniform_(self.linear_layer.weight, gain=nn.init.calculate_gain(w_init_gain))
+        self.prec = PREC_FP32
+
+    def forward(self, x):
+        return ops.Linear.apply(x, self.linear_layer.weight, self.linear_layer.bias, self.prec)
+
+
+class ConvNorm(nn.Module):
+    """Parameter container mirroring model_vc_mel.py:20-38 (``conv`` + Xavier init).  Only the
+    kernel_size=5 / stride 1 / 'same' padding / dilation 1 case the Generator uses is supported."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=5, stride=1, padding=None, dilation=1, bias=True,
+                 w_init_gain="linear"):
+        super().__init__()
+        if padding is None:
+            padding = dilation * (kernel_size - 1) // 2
+        if kernel_size % 2 != 1 or stride != 1 or dilation != 1 or padding != (kernel_size - 1) // 2 or not bias:
+            raise ValueError("autovc_b200.ConvNorm supports odd kernel, stride 1, dilation 1, 'same' padding, bias=True")
+        self.conv = nn.Conv1d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding,
+                              dilation=dilation, bias=bias)
+        nn.init.xavier_uniform_(self.conv.weight, gain=nn.init.calculate_gain(w_init_gain))
+
+    def forward(self, signal):
+        raise RuntimeError("ConvNorm is fused with its BatchNorm and activation; call the owning block")
+
+
+def _conv_bn_act(block: nn.Sequential, x, act: str, residual=None, prec=PREC_FP32):
+    """act(BN(conv(x))) (+ residual) on channels-last x; bumps num_batches_tracked like nn.BatchNorm1d."""
+    conv, bn = block[0].conv, block[1]
+    training = bn.training
+    z = ops.ConvBnAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
+                            ACT_CODES[act], training, prec)
+    if training:
+        bn.num_batches_tracked += 1
+    return z
+
+
+def _lstm(x, lstm: nn.LSTM, prec):
+    """Run an nn.LSTM's parameters through the LstmLayer kernels, layer by layer."""
+    for l in range(lstm.num_layers):
+        ws = []
+        for suffix in (("", "_reverse") if lstm.bidirectional else ("",)):
+            ws += [getattr(lstm, f"{n}_l{l}{suffix}") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+        x = ops.LstmLayer.apply(x, prec, *ws)
+    return x
+
+
+class Encoder(nn.Module):
+    """model_vc_mel.py:41-81."""
+
+    def __init__(self, dim_neck, dim_emb, freq, n_bins=80):
+        super().__init__()
+        self.dim_neck = dim_neck
+        self.freq = freq
+        self.prec = PREC_FP32
+        convolutions = []
+        for i in range(3):
+            convolutions.append(nn.Sequential(
+                ConvNorm(n_bins + dim_emb if i == 0 else 512, 512, kernel_size=5, stride=1, padding=2, dilation=1,
+                         w_init_gain="relu"),
+                nn.BatchNorm1d(512)))
+        self.convolutions = nn.ModuleList(convolutions)
+        self.lstm = nn.LSTM(512, dim_neck, 2, batch_first=True, bidirectional=True)
+
+    def codes(self, x, c_org):
+        """(B,T,n_bins) | (B,1,T,n_bins), (B,dim_emb) -> codes (B, T/freq, 2*dim_neck)."""
+        if x.dim() == 4:
+            x = x.squeeze(1)
+        h = ops.ConcatEmb.apply(x, c_org)
+        for block in self.convolutions:
+            h = _conv_bn_act(block, h, "relu", prec=self.prec)
+        h = _lstm(h, self.lstm, self.prec)
+        return ops.Codes.apply(h, self.dim_neck, self.freq)
+
+    def forward(self, x, c_org):
+        return list(self.codes(x, c_org).unbind(1))       # the reference returns a list (model_vc_mel.py:77-81)
+
+
+class Decoder(nn.Module):
+    """model_vc_mel.py:84-122."""
+
+    def __init__(self, dim_neck, dim_emb, dim_pre, n_bins=80):
+        super().__init__()
+        self.prec = PREC_FP32
+        self.lstm1 = nn.LSTM(dim_neck * 2 + dim_emb, dim_pre, 1, batch_first=True)
+        convolutions = []
+        for i in range(3):
+            convolutions.append(nn.Sequential(
+                ConvNorm(dim_pre, dim_pre, kernel_size=5, stride=1, padding=2, dilation=1, w_init_gain="relu"),
+                nn.BatchNorm1d(dim_pre)))
+        self.convolutions = nn.ModuleList(convolutions)
+        self.lstm2 = nn.LSTM(dim_pre, 1024, 2, batch_first=True)
+        self.linear_projection = LinearNorm(1024, n_bins)
+
+    def forward(self, x):
+        h = _lstm(x, self.lstm1, self.prec)
+        for block in self.convolutions:
+            h = _conv_bn_act(block, h, "relu", prec=self.prec)
+        h = _lstm(h, self.lstm2, self.prec)
+        lin = self.linear_projection.linear_layer
+        return ops.Linear.apply(h, lin.weight, lin.bias, self.prec)
+
+
+class Postnet(nn.Module):
+    """model_vc_mel.py:125-169 — five conv(k5)+BN layers, tanh on the first four."""
+
+    def __init__(self, n_bins=80):
+        super().__init__()
+        self.prec = PREC_FP32
+        self.convolutions = nn.ModuleList()
+        self.convolutions.append(nn.Sequential(
+            ConvNorm(n_bins, 512, kernel_size=5, stride=1, padding=2, dilation=1, w_init_gain="tanh"),
+            nn.BatchNorm1d(512)))
+        for _ in range(1, 5 - 1):
+            self.convolutions.append(nn.Sequential(
+                ConvNorm(512, 512, kernel_size=5, stride=1, padding=2, dilation=1, w_init_gain="tanh"),
+                nn.BatchNorm1d(512)))
+        self.convolutions.append(nn.Sequential(
+            ConvNorm(512, n_bins, kernel_size=5, stride=1, padding=2, dilation=1, w_init_gain="linear"),
+            nn.BatchNorm1d(n_bins)))
+
+    def channels_last(self, x, residual=None):
+        """x (B,T,n_bins) -> postnet(x) (+ residual), channels-last."""
+        n = len(self.convolutions)
+        for i in range(n - 1):
+            x = _conv_bn_act(self.convolutions[i], x, "tanh", prec=self.prec)
+        return _conv_bn_act(self.convolutions[-1], x, "none", residual=residual, prec=self.prec)
+
+    def forward(self, x):
+        # reference layout: channel-first (B, n_bins, T) in and out (model_vc_mel.py:163-169, :196)
+        return self.channels_last(x.transpose(1, 2).contiguous()).transpose(1, 2)
+
+
+class Generator(nn.Module):
+    """Generator network (model_vc_mel.py:172-203)."""
+
+    def __init__(self, dim_neck, dim_emb, dim_pre, freq, n_bins: int = 80, precision: Optional[str] = None):
+        super().__init__()
+        self.encoder = Encoder(dim_neck, dim_emb, freq, n_bins=n_bins)
+        self.decoder = Decoder(dim_neck, dim_emb, dim_pre, n_bins=n_bins)
+        self.postnet = Postnet(n_bins=n_bins)
+        self.set_precision(precision or _default_precision())
+
+    def set_precision(self, precision: str):
+        if precision not in _PREC:
+            raise ValueError(f"precision must be one of {sorted(_PREC)}")
+        self.precision = precision
+        for m in (self.encoder, self.decoder, self.postnet, self.decoder.linear_projection):
+            m.prec = _PREC[precision]
+        return self
+
+    def forward(self, x, c_org, c_trg):
+        if c_trg is None:                                            # model_vc_mel.py:183-184
+            codes = self.encoder.codes(x, c_org)
+            return codes.reshape(codes.size(0), -1)
+        if x.dim() != 3:
+            raise ValueError("full forward takes x of shape (B, T, n_bins)")
+        ops._GLOBAL_CACHE.begin_step()
+        T = x.size(1)
+        codes = self.encoder.codes(x, c_org)
+        dec_in = ops.UpsampleConcat.apply(codes, c_trg, T)          # :186-192
+        x_identic = self.decoder(dec_in)                             # :194
+        x_identic_psnt = self.postnet.channels_last(x_identic, residual=x_identic)   # :196-197
+        code_real = codes.reshape(codes.size(0), -1)                 # :201
+        return x_identic.unsqueeze(1), x_identic_psnt.unsqueeze(1), code_real

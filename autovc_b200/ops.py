@@ -1,0 +1,426 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (include/autovc_b200.h).
+
+PyTorch is plumbing here: it owns device memory (caching allocator), the current stream and
+the autograd graph.  All arithmetic on the path happens in libautovc_b200.so.  Activations
+are channels-last (B, T, C) float32 contiguous.  No CPU fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ACT_CODES, ACT_NONE, PREC_BF16, PREC_FP32, call, query
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+_NULL = ctypes.c_void_p(0)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return _NULL if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.AvcError("autovc_b200 ops need CUDA tensors (there is no CPU fallback)")
+        if t.dtype != torch.float32:
+            raise _lib.AvcError(f"autovc_b200 ops take float32 tensors, got {t.dtype}")
+        if not t.is_contiguous():
+            raise _lib.AvcError("autovc_b200 ops need contiguous tensors")
+
+
+def _ws(nbytes: int, device) -> Optional[torch.Tensor]:
+    if nbytes <= 0:
+        return None
+    return torch.empty((nbytes + 15) // 16 * 2, dtype=torch.float64, device=device)
+
+
+# --------------------------------------------------------------------------------------
+# thin kernel launchers
+# --------------------------------------------------------------------------------------
+def gemm_nt_taps(A, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, stats=None, accumulate=False, prec=PREC_FP32):
+    call("avc_gemm_nt_taps", _p(A), lda, _p(W), _p(bias), _p(C), ldc, nB, T, N, K, ntaps, shift0, _p(stats),
+         int(accumulate), prec, _NULL, 0, _stream())
+
+
+def gemm_tn_taps(dY, ldy, X, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, accumulate=False, prec=PREC_FP32):
+    nbytes = query("avc_gemm_tn_workspace_bytes", nB, T, N, K, ntaps, prec)
+    ws = _ws(nbytes, dY.device)
+    call("avc_gemm_tn_taps", _p(dY), ldy, _p(X), ldx, _p(dW), nB, T, N, K, ntaps, shift0, out_mode, int(accumulate),
+         prec, _p(ws), nbytes, _stream())
+
+
+def colsum(x, ldx, M, C, out, out2=None, out_mode=0, accumulate=False):
+    ws = torch.empty(2 * C, dtype=torch.float64, device=x.device)
+    call("avc_colsum", _p(x), ldx, M, C, _p(out), _p(out2), out_mode, int(accumulate), _p(ws), ws.numel() * 8, _stream())
+
+
+class PackCache:
+    """Packed copies of the weights so the two encoder passes of one step pack once.
+
+    An entry is valid while the parameter object is alive, its in-place version counter (bumped by
+    the optimizer) and its storage address are unchanged.  ``begin_step()`` drops everything; the
+    Generator calls it at the start of each full forward, which also covers writers that bypass
+    the version counter (``param.data.copy_`` in solver_encoder.py:168-177)."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, kind, param: torch.Tensor, builder):
+        k = (kind, id(param))
+        hit = self._d.get(k)
+        if hit is not None and hit[0]() is param and hit[1] == param._version and hit[2] == param.data_ptr():
+            return hit[3]
+        val = builder()
+        self._d[k] = (weakref.ref(param), param._version, param.data_ptr(), val)
+        return val
+
+    def begin_step(self):
+        self._d.clear()
+
+
+_GLOBAL_CACHE = PackCache()
+
+
+def pack_conv(weight: torch.Tensor, cache: PackCache = _GLOBAL_CACHE):
+    """(Cout, Cin, 5) -> fwd [5][Cout][Cin], dgrad [5][Cin][Cout] (taps flipped)."""
+    def build():
+        Cout, Cin, k = weight.shape
+        w = weight.detach()
+        wf = torch.empty(k, Cout, Cin, device=w.device, dtype=torch.float32)
+        wd = torch.empty(k, Cin, Cout, device=w.device, dtype=torch.float32)
+        call("avc_pack_conv_weight", _p(w), _p(wf), _p(wd), Cout, Cin, k, _stream())
+        return wf, wd
+    return cache.get("conv", weight, build)
+
+
+def pack_lstm_w(weight: torch.Tensor, cache: PackCache = _GLOBAL_CACHE):
+    """(4H, I) -> interleaved (4H, I) and its transpose (I, 4H)."""
+    def build():
+        G, I = weight.shape
+        w = weight.detach()
+        p = torch.empty(G, I, device=w.device, dtype=torch.float32)
+        pT = torch.empty(I, G, device=w.device, dtype=torch.float32)
+        call("avc_pack_lstm_weight", _p(w), _p(p), _p(pT), G // 4, I, _stream())
+        return p, pT
+    return cache.get("lstm_w", weight, build)
+
+
+def pack_lstm_b(b_ih: torch.Tensor, b_hh: torch.Tensor, cache: PackCache = _GLOBAL_CACHE):
+    def build():
+        out = torch.empty_like(b_ih)
+        call("avc_pack_lstm_bias", _p(b_ih.detach()), _p(b_hh.detach()), _p(out), b_ih.numel() // 4, _stream())
+        return out
+    # both versions matter: key on b_ih, fold b_hh's version into the key
+    return cache.get(("lstm_b", id(b_hh), b_hh.data_ptr(), b_hh._version), b_ih, build)
+
+
+def transpose2d(w: torch.Tensor, cache: PackCache = _GLOBAL_CACHE):
+    def build():
+        R, C = w.shape
+        out = torch.empty(C, R, device=w.device, dtype=torch.float32)
+        call("avc_transpose", _p(w.detach()), _p(out), R, C, _stream())
+        return out
+    return cache.get("T", w, build)
+
+
+# --------------------------------------------------------------------------------------
+# Conv1d(k=5,p=2) + BatchNorm1d + activation (+ residual)      model_vc_mel.py:28-31,:57,:69,:115,:165-167,:197
+# --------------------------------------------------------------------------------------
+class ConvBnAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, residual, act: int, training: bool,
+                prec: int):
+        x = x.contiguous()
+        _check(x, weight, bias, gamma, beta, running_mean, running_var, residual)
+        if residual is not None and act != ACT_NONE:
+            raise _lib.AvcError("residual is only supported with act='none'")
+        B, T, Cin = x.shape
+        Cout, Cin_w, k = weight.shape
+        if Cin_w != Cin:
+            raise _lib.AvcError(f"conv: input has {Cin} channels, weight expects {Cin_w}")
+        M = B * T
+        wf, wd = pack_conv(weight)
+        y = torch.empty(B, T, Cout, device=x.device, dtype=torch.float32)
+        mean = torch.empty(Cout, device=x.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        if training:
+            stats = torch.zeros(2 * Cout, device=x.device, dtype=torch.float64)
+            gemm_nt_taps(x, Cin, wf, bias, y, Cout, B, T, Cout, Cin, k, -(k // 2), stats=stats, prec=prec)
+            call("avc_bn_finalize", _p(stats), M, Cout, BN_EPS, BN_MOMENTUM, _p(mean), _p(rstd), _p(running_mean),
+                 _p(running_var), _stream())
+        else:
+            gemm_nt_taps(x, Cin, wf, bias, y, Cout, B, T, Cout, Cin, k, -(k // 2), prec=prec)
+            call("avc_bn_eval_stats", _p(running_mean), _p(running_var), Cout, BN_EPS, _p(mean), _p(rstd), _stream())
+        z = torch.empty_like(y)
+        call("avc_bn_act_fwd", _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(z), M, Cout, act, _stream())
+        ctx.save_for_backward(x, weight, gamma, y, z, mean, rstd)
+        ctx.act, ctx.training, ctx.prec, ctx.has_res = act, training, prec, residual is not None
+        ctx.wd = wd
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, weight, gamma, y, z, mean, rstd = ctx.saved_tensors
+        if not ctx.training:
+            raise _lib.AvcError("backward through eval-mode BatchNorm is not on the supported path")
+        dz = dz.contiguous()
+        B, T, Cin = x.shape
+        Cout, _, k = weight.shape
+        M = B * T
+        prec = ctx.prec
+        sums = torch.zeros(2 * Cout, device=x.device, dtype=torch.float64)
+        call("avc_bn_act_bwd_reduce", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(sums), M, Cout, ctx.act, _stream())
+        dy = torch.empty_like(y)
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        call("avc_bn_act_bwd_apply", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(gamma), _p(sums), _p(dy), _p(dgamma),
+             _p(dbeta), M, Cout, ctx.act, 0, _stream())
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            gemm_nt_taps(dy, Cout, ctx.wd, None, dx, Cin, B, T, Cin, Cout, k, -(k // 2), prec=prec)
+        dw = torch.empty_like(weight)
+        gemm_tn_taps(dy, Cout, x, Cin, dw, B, T, Cout, Cin, k, -(k // 2), out_mode=1, prec=prec)
+        # d(conv bias) is identically zero under train-mode BatchNorm (sum_m dy[m, c] = 0); the reference
+        # produces 1e-8-level rounding noise there.
+        db = torch.zeros(Cout, device=x.device, dtype=torch.float32)
+        dres = dz if ctx.has_res else None
+        return dx, dw, db, dgamma, dbeta, None, None, dres, None, None, None
+
+
+# --------------------------------------------------------------------------------------
+# one nn.LSTM layer (1 or 2 directions)                        model_vc_mel.py:61/:73, :90/:111, :104/:118
+# --------------------------------------------------------------------------------------
+class LstmLayer(torch.autograd.Function):
+    """x (B,T,I) -> (B,T,D*H).  weights = [w_ih, w_hh, b_ih, b_hh] per direction (forward first)."""
+
+    @staticmethod
+    def forward(ctx, x, prec: int, *weights):
+        x = x.contiguous()
+        _check(x, *weights)
+        D = len(weights) // 4
+        B, T, I = x.shape
+        H = weights[1].shape[1]
+        G = 4 * H
+        out = torch.empty(B, T, D * H, device=x.device, dtype=torch.float32)
+        saved = []
+        packs = []
+        for d in range(D):
+            w_ih, w_hh, b_ih, b_hh = weights[4 * d:4 * d + 4]
+            wi_p, wi_pT = pack_lstm_w(w_ih)
+            wh_p, wh_pT = pack_lstm_w(w_hh)
+            b_p = pack_lstm_b(b_ih, b_hh)
+            packs += [wi_pT, wh_p, wh_pT]
+            Pre = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
+            gemm_nt_taps(x, I, wi_p, b_p, Pre, G, B, T, G, I, 1, 0, prec=prec)
+            gates = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
+            c_seq = torch.empty(B, T, H, device=x.device, dtype=torch.float32)
+            h_view = out.view(-1)[d * H:]
+            call("avc_lstm_seq_fwd", _p(Pre), _p(wh_p), _p(h_view), D * H, _p(gates), _p(c_seq), B, T, H, int(d == 1), prec,
+                 _stream())
+            saved += [gates, c_seq]
+        ctx.save_for_backward(x, out, *weights, *saved)
+        ctx.D, ctx.prec, ctx.packs = D, prec, packs
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        D, prec = ctx.D, ctx.prec
+        t = ctx.saved_tensors
+        x, out = t[0], t[1]
+        weights = t[2:2 + 4 * D]
+        saved = t[2 + 4 * D:]
+        dout = dout.contiguous()
+        B, T, I = x.shape
+        H = weights[1].shape[1]
+        G = 4 * H
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty_like(x) if need_dx else None
+        grads: List[Optional[torch.Tensor]] = []
+        for d in range(D):
+            w_ih, w_hh, b_ih, b_hh = weights[4 * d:4 * d + 4]
+            gates, c_seq = saved[2 * d:2 * d + 2]
+            wi_pT, wh_p, wh_pT = ctx.packs[3 * d:3 * d + 3]
+            dP = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
+            nbytes = query("avc_lstm_bwd_workspace_bytes", B, T, H)
+            ws = _ws(nbytes, x.device)
+            rev = int(d == 1)
+            call("avc_lstm_seq_bwd", _p(dout.view(-1)[d * H:]), D * H, _p(wh_p), _p(wh_pT), _p(gates), _p(c_seq), _p(dP),
+                 B, T, H, rev, prec, _p(ws), nbytes, _stream())
+            dw_ih = torch.empty_like(w_ih)
+            gemm_tn_taps(dP, G, x, I, dw_ih, B, T, G, I, 1, 0, out_mode=2, prec=prec)
+            dw_hh = torch.empty_like(w_hh)
+            # dW_hh = sum_t dG_t^T h_{t-1}: the h operand is the output sequence shifted one step back
+            # along the walk direction (zero at the first step)
+            gemm_tn_taps(dP, G, out.view(-1)[d * H:], D * H, dw_hh, B, T, G, H, 1, (+1 if rev else -1), out_mode=2, prec=prec)
+            db_ih = torch.empty_like(b_ih)
+            db_hh = torch.empty_like(b_hh)
+            colsum(dP, G, B * T, G, db_ih, db_hh, out_mode=2)
+            if need_dx:
+                gemm_nt_taps(dP, G, wi_pT, None, dx, I, B, T, I, G, 1, 0, accumulate=(d > 0), prec=prec)
+            grads += [dw_ih, dw_hh, db_ih, db_hh]
+        return (dx, None, *grads)
+
+
+# --------------------------------------------------------------------------------------
+# Linear(1024 -> n_bins)                                        model_vc_mel.py:10,:120
+# --------------------------------------------------------------------------------------
+class Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, prec: int):
+        x = x.contiguous()
+        _check(x, weight, bias)
+        B, T, K = x.shape
+        N = weight.shape[0]
+        y = torch.empty(B, T, N, device=x.device, dtype=torch.float32)
+        gemm_nt_taps(x, K, weight.detach(), bias, y, N, B, T, N, K, 1, 0, prec=prec)
+        ctx.save_for_backward(x, weight)
+        ctx.prec = prec
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        B, T, K = x.shape
+        N = weight.shape[0]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wT = transpose2d(weight, PackCache())         # (K, N): [N'=K][K'=N]; tiny, not cached
+            dx = torch.empty_like(x)
+            gemm_nt_taps(dy, N, wT, None, dx, K, B, T, K, N, 1, 0, prec=ctx.prec)
+        dw = torch.empty_like(weight)
+        gemm_tn_taps(dy, N, x, K, dw, B, T, N, K, 1, 0, out_mode=0, prec=ctx.prec)
+        db = torch.empty(N, device=x.device, dtype=torch.float32)
+        colsum(dy, N, B * T, N, db)
+        return dx, dw, db, None
+
+
+# --------------------------------------------------------------------------------------
+# glue                                                          model_vc_mel.py:64-66, :74-79, :186-192
+# --------------------------------------------------------------------------------------
+class ConcatEmb(torch.autograd.Function):
+    """[x (B,T,Cx) | e (B,E) broadcast over T] -> (B,T,Cx+E)."""
+
+    @staticmethod
+    def forward(ctx, x, e):
+        x = x.contiguous()
+        e = e.contiguous()
+        _check(x, e)
+        B, T, Cx = x.shape
+        E = e.shape[1]
+        out = torch.empty(B, T, Cx + E, device=x.device, dtype=torch.float32)
+        call("avc_concat_bcast", _p(x), Cx, _p(e), _p(out), B, T, Cx, E, _stream())
+        ctx.shape = (B, T, Cx, E)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, T, Cx, E = ctx.shape
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dout = dout.contiguous()
+            dx = torch.empty(B, T, Cx, device=dout.device, dtype=torch.float32)
+            call("avc_copy2d", _p(dout), Cx + E, _p(dx), Cx, B * T, Cx, _stream())
+        if ctx.needs_input_grad[1]:
+            raise _lib.AvcError("gradient w.r.t. the speaker embedding is not on the supported path")
+        return dx, None
+
+
+class Codes(torch.autograd.Function):
+    """enc (B,T,2n) -> codes (B,T/f,2n): forward half sampled at the end of each group, backward half
+    at its start (model_vc_mel.py:77-79)."""
+
+    @staticmethod
+    def forward(ctx, enc, n: int, f: int):
+        enc = enc.contiguous()
+        _check(enc)
+        B, T, n2 = enc.shape
+        if T % f != 0:
+            raise _lib.AvcError(f"T={T} must be a multiple of freq={f}")
+        codes = torch.empty(B, T // f, n2, device=enc.device, dtype=torch.float32)
+        call("avc_codes_fwd", _p(enc), _p(codes), B, T, n, f, _stream())
+        ctx.meta = (B, T, n, f)
+        return codes
+
+    @staticmethod
+    def backward(ctx, dcodes):
+        B, T, n, f = ctx.meta
+        dcodes = dcodes.contiguous()
+        denc = torch.zeros(B, T, 2 * n, device=dcodes.device, dtype=torch.float32)
+        call("avc_codes_bwd", _p(dcodes), _p(denc), B, T, n, f, _stream())
+        return denc, None, None
+
+
+class UpsampleConcat(torch.autograd.Function):
+    """codes (B,J,2n), c_trg (B,E) -> (B,T,2n+E) (model_vc_mel.py:186-192)."""
+
+    @staticmethod
+    def forward(ctx, codes, c_trg, T: int):
+        codes = codes.contiguous()
+        c_trg = c_trg.contiguous()
+        _check(codes, c_trg)
+        B, J, n2 = codes.shape
+        E = c_trg.shape[1]
+        f = T // J
+        out = torch.empty(B, T, n2 + E, device=codes.device, dtype=torch.float32)
+        call("avc_upsample_concat_fwd", _p(codes), _p(c_trg), _p(out), B, T, n2, f, E, _stream())
+        ctx.meta = (B, T, J, n2, E, f)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, T, J, n2, E, f = ctx.meta
+        dout = dout.contiguous()
+        dcodes = torch.empty(B, J, n2, device=dout.device, dtype=torch.float32)
+        call("avc_upsample_concat_bwd", _p(dout), n2 + E, _p(dcodes), B, T, n2, f, 0, _stream())
+        return dcodes, None, None
+
+
+# --------------------------------------------------------------------------------------
+# losses                                                        solver_encoder.py:230,:233,:236
+# --------------------------------------------------------------------------------------
+class _Loss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, is_l1: bool):
+        a = a.contiguous()
+        b = b.contiguous()
+        _check(a, b)
+        if a.numel() != b.numel():
+            raise _lib.AvcError("loss operands differ in size")
+        scratch = torch.zeros(1, device=a.device, dtype=torch.float64)
+        out = torch.empty((), device=a.device, dtype=torch.float32)
+        call("avc_l1_loss_fwd" if is_l1 else "avc_mse_loss_fwd", _p(a), _p(b), a.numel(), _p(scratch), _p(out), _stream())
+        ctx.save_for_backward(a, b)
+        ctx.is_l1 = is_l1
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b = ctx.saved_tensors
+        gout = gout.contiguous().float()
+        da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        if da is not None or db is not None:
+            call("avc_loss_bwd", _p(a), _p(b), a.numel(), _p(gout), int(ctx.is_l1), _p(da), _p(db), 0, _stream())
+        return da, db, None
+
+
+def mse_loss(a, b):
+    return _Loss.apply(a, b, False)
+
+
+def l1_loss(a, b):
+    return _Loss.apply(a, b, True)

@@ -1,0 +1,159 @@
+"""Host side of the training step: the step maths of the reference ``Solver.train`` loop
+(solver_encoder.py:227-243 losses, :293-300 zero_grad/backward/Adam) and the data-parallel
+gradient exchange the B200 build adds.
+
+The reference ``Solver`` class itself runs unchanged on ``autovc_b200.Generator`` (its loop only
+calls ``self.G(...)``, ``F.mse_loss``/``F.l1_loss``, ``backward`` and the optimizer).  This module
+offers the same step as a function — with the three losses going through the fused CUDA loss
+kernels instead of ATen — plus ``GradBucketReducer`` for one-process-per-GPU data parallelism:
+gradients are all-reduced in ~25 MB buckets in reverse registration order (postnet -> decoder ->
+encoder) as soon as each bucket's gradients are final, on a side stream, overlapped with the rest
+of backward.  BatchNorm statistics stay rank-local (DDP semantics, ``broadcast_buffers=False``).
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def generator_losses(G, x_real, emb_org, lambda_cd: float = 1.0):
+    """solver_encoder.py:228-243 with the fused loss kernels."""
+    x_identic, x_identic_psnt, code_real = G(x_real, emb_org, emb_org)          # :228
+    g_loss_id = ops.mse_loss(x_real, x_identic.squeeze(1))                      # :230
+    g_loss_id_psnt = ops.mse_loss(x_real, x_identic_psnt.squeeze(1))            # :233
+    code_reconst = G(x_identic_psnt, emb_org, None)                             # :235
+    g_loss_cd = ops.l1_loss(code_real, code_reconst)                            # :236
+    g_loss = g_loss_id + g_loss_id_psnt + lambda_cd * g_loss_cd                 # :243
+    return g_loss, (g_loss_id, g_loss_id_psnt, g_loss_cd), (x_identic, x_identic_psnt, code_real, code_reconst)
+
+
+def train_step(G, optimizer, x_real, emb_org, lambda_cd: float = 1.0, reducer: "Optional[GradBucketReducer]" = None,
+               return_outputs: bool = False, sync_losses: bool = True):
+    """One training iteration (solver_encoder.py:228-300).  Returns the three loss terms the
+    reference logs with ``.item()`` (:315-317) — as floats when ``sync_losses`` (one device sync,
+    like the reference), else as device tensors."""
+    g_loss, (l_id, l_id_psnt, l_cd), outs = generator_losses(G, x_real, emb_org, lambda_cd)
+    optimizer.zero_grad()                                                       # :293
+    if reducer is not None:
+        reducer.begin_backward()
+    g_loss.backward()                                                           # :294
+    if reducer is not None:
+        reducer.finish()
+    result: Dict[str, object] = {}
+    if return_outputs:
+        result["grads"] = {n: p.grad.detach().clone() for n, p in G.named_parameters()}
+        for k, v in zip(("x_identic", "x_identic_psnt", "code_real", "code_reconst"), outs):
+            result[k] = v.detach()
+    optimizer.step()                                                            # :300
+    if sync_losses:
+        vals = torch.stack([g_loss.detach(), l_id.detach(), l_id_psnt.detach(), l_cd.detach()]).tolist()
+    else:
+        vals = [g_loss.detach(), l_id.detach(), l_id_psnt.detach(), l_cd.detach()]
+    result.update({"g_loss": vals[0], "L_id": vals[1], "L_id_psnt": vals[2], "L_cd": vals[3]})
+    return result
+
+
+class GradBucketReducer:
+    """Bucketed, backward-overlapped gradient all-reduce (mean) over a process group.
+
+    * parameters are bucketed in REVERSE registration order so buckets fill in the order backward
+      produces gradients; encoder gradients (sum of the two passes of a step) finalise last;
+    * each parameter's post-accumulate-grad hook copies its gradient into the bucket's flat
+      buffer and re-points ``param.grad`` at that slice; when a bucket is complete its all-reduce
+      is issued asynchronously on ``comm_stream`` (CUDA) so it overlaps the remaining backward;
+    * ``finish()`` waits for all buckets (and divides by world size when the backend has no AVG).
+    Works with NCCL on GPUs and with gloo on CPU tensors (used by the world_size-2 CPU tests).
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None, bucket_mb: float = 25.0):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.backend = dist.get_backend(process_group) if dist.is_initialized() else "none"
+        cap = int(bucket_mb * 1024 * 1024)
+        self.buckets: List[dict] = []
+        cur, cur_bytes = [], 0
+        for p in reversed(self.params):
+            nbytes = p.numel() * p.element_size()
+            if cur and cur_bytes + nbytes > cap:
+                self._close_bucket(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nbytes
+        if cur:
+            self._close_bucket(cur)
+        self._where = {}
+        for bi, b in enumerate(self.buckets):
+            off = 0
+            for p in b["params"]:
+                self._where[p] = (bi, off)
+                off += p.numel()
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        dev = self.params[0].device
+        self.comm_stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+        self._pending: List = []
+        self.launch_order: List[int] = []
+
+    def _close_bucket(self, plist):
+        n = sum(p.numel() for p in plist)
+        flat = torch.zeros(n, dtype=plist[0].dtype, device=plist[0].device)
+        self.buckets.append({"params": list(plist), "flat": flat, "ready": 0})
+
+    def begin_backward(self):
+        for b in self.buckets:
+            b["ready"] = 0
+        self._pending.clear()
+        self.launch_order.clear()
+
+    def _on_grad(self, p):
+        bi, off = self._where[p]
+        b = self.buckets[bi]
+        view = b["flat"][off:off + p.numel()].view_as(p)
+        view.copy_(p.grad)
+        p.grad = view
+        b["ready"] += 1
+        if b["ready"] == len(b["params"]):
+            self._launch(bi)
+
+    def _launch(self, bi):
+        b = self.buckets[bi]
+        self.launch_order.append(bi)
+        if self.world == 1:
+            return
+        op = dist.ReduceOp.AVG if self.backend == "nccl" else dist.ReduceOp.SUM
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                work = dist.all_reduce(b["flat"], op=op, group=self.group, async_op=True)
+        else:
+            work = dist.all_reduce(b["flat"], op=op, group=self.group, async_op=True)
+        self._pending.append((work, bi))
+
+    def finish(self):
+        missing = [bi for bi, b in enumerate(self.buckets) if b["ready"] != len(b["params"])]
+        if missing:
+            raise RuntimeError(f"GradBucketReducer: buckets {missing} never filled (a parameter received no gradient)")
+        for work, bi in self._pending:
+            work.wait()
+            if self.backend != "nccl":
+                self.buckets[bi]["flat"].div_(self.world)
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        self._pending.clear()
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):
+    """Make every rank start from rank ``src``'s parameters and buffers (done once)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)

@@ -1,0 +1,199 @@
+/* autovc_b200 — C-ABI of the B200-native AutoVC hot path (libautovc_b200.so).
+ *
+ * Drop-in boundary for ONE path of sebakeaaen/autovc: the model_vc_mel.Generator
+ * forward/backward training step driven by solver_encoder.py and the make_spect.py log-mel
+ * front-end.  The reference has no native layer (it calls torch.nn -> cuDNN/cuBLAS/oneDNN),
+ * so each entry point below names the reference call site (file:line, relative to the
+ * upstream tree) whose library call it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain C linkage, raw device pointers + sizes, no C++/torch types, no exceptions.
+ *   - every function returns 0 on success, non-zero on failure; avc_last_error() returns a
+ *     thread-local message.  Shape/alignment violations are errors, never silent fallbacks.
+ *   - the library never allocates, frees or retains device memory: the caller (PyTorch's
+ *     caching allocator) owns every buffer, including workspaces whose sizes the
+ *     avc_*_workspace_bytes queries report.
+ *   - all launches are asynchronous on `stream` (a cudaStream_t passed as void*); nothing
+ *     synchronises.  Re-entrant; callable from the autograd worker thread.
+ *   - activations are channels-last: (B, T, C) row-major, row m = b*T + t, channel stride 1,
+ *     row stride `ld*` in elements (so column slices of wider buffers can be addressed).
+ *   - `prec`: AVC_PREC_FP32 = CUDA-core FFMA, fp32 operands and accumulation (parity mode,
+ *     <=1e-4 of the reference's fp32 path); AVC_PREC_BF16 = tcgen05/TMEM tensor-core path,
+ *     bf16 operands, fp32 accumulation and fp32 statistics/state.
+ */
+#ifndef AUTOVC_B200_H_
+#define AUTOVC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define AVC_VERSION 100
+
+enum { AVC_PREC_FP32 = 0, AVC_PREC_BF16 = 1 };
+enum { AVC_ACT_NONE = 0, AVC_ACT_RELU = 1, AVC_ACT_TANH = 2 };
+enum {
+  AVC_OK = 0,
+  AVC_ERR_INVALID = 1,      /* bad shape / alignment / null pointer */
+  AVC_ERR_CUDA = 2,         /* a CUDA runtime/driver call failed    */
+  AVC_ERR_UNSUPPORTED = 3,  /* combination not implemented          */
+  AVC_ERR_WORKSPACE = 4     /* workspace too small                  */
+};
+
+int avc_version(void);
+const char* avc_last_error(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+unsigned long long avc_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * GEMM family with time-shifted operand rows ("taps").  One kernel family implements
+ *   Conv1d(k=5,p=2) forward        model_vc_mel.py:28-31 (ConvNorm.conv), called :69,:115,:165,:167
+ *   Conv1d data gradient           autograd of the above (solver_encoder.py:294)
+ *   LSTM input projections         x W_ih^T of nn.LSTM, model_vc_mel.py:73,:111,:118
+ *   Linear(1024 -> n_bins)         model_vc_mel.py:10,:120
+ * as  C[m, n] = bias[n] + sum_{tap<ntaps} sum_{k<K} A[row(m, tap), k] * W[tap][n][k],
+ * where m = b*T + t and row(m, tap) = b*T + (t + shift0 + tap), rows outside [0,T) of the
+ * same utterance reading as zero (= the convolution's zero padding).
+ *   A: (nB*T, K) row stride lda.  W: packed [ntaps][N][K] (see avc_pack_conv_weight).
+ *   C: (nB*T, N) row stride ldc.  bias may be NULL.
+ * If chan_stats != NULL (double[2*N]: sum, sum of squares; caller zero-fills) the per-channel
+ * batch statistics of C that train-mode BatchNorm1d needs (model_vc_mel.py:57) are accumulated.
+ * accumulate != 0: C += result (sums the two directions' input gradients of the BiLSTM).
+ */
+int avc_gemm_nt_taps(const float* A, int lda, const float* W, const float* bias, float* C, int ldc,
+                     int nB, int T, int N, int K, int ntaps, int shift0, double* chan_stats, int accumulate,
+                     int prec, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Weight gradients (conv wgrad, LSTM dW_ih / dW_hh, Linear dW), reduction over rows:
+ *   dW[tap][n][k] = sum_m dY[m, n] * X[row(m, tap), k]
+ * dY: (nB*T, N) ld ldy; X: (nB*T, K) ld ldx.  Deterministic split-M reduction through
+ * `workspace`.  The result is written through an output map:
+ *   out_mode 0: packed [ntaps][N][K];
+ *   out_mode 1: PyTorch Conv1d layout (N, K, ntaps);
+ *   out_mode 2: LSTM rows un-permuted: packed row r = u*4+g goes to row g*H+u (N = 4H), ntaps=1.
+ * `accumulate` != 0 adds into dW instead of overwriting (second encoder pass). */
+int avc_gemm_tn_taps(const float* dY, int ldy, const float* X, int ldx, float* dW,
+                     int nB, int T, int N, int K, int ntaps, int shift0, int out_mode, int accumulate,
+                     int prec, void* workspace, size_t workspace_bytes, void* stream);
+size_t avc_gemm_tn_workspace_bytes(int nB, int T, int N, int K, int ntaps, int prec);
+
+/* Weight repacking (once per optimizer step; weights are tiny next to activations).
+ *   avc_pack_conv_weight: PyTorch (Cout, Cin, 5) ->  fwd  [tap][Cout][Cin]
+ *                                                    dgrad [tap][Cin][Cout] with taps flipped
+ *   avc_pack_lstm_weight: (4H, I) gate-blocked rows i,f,g,o -> gate-interleaved rows u*4+g:
+ *                         out_p (4H, I) and its transpose out_pT (I, 4H); either may be NULL.
+ *   avc_pack_lstm_bias:   b_ih + b_hh, interleaved.
+ *   avc_transpose:        (R, C) -> (C, R).                                                   */
+int avc_pack_conv_weight(const float* w, float* w_fwd, float* w_dgrad, int Cout, int Cin, int ntaps, void* stream);
+int avc_pack_lstm_weight(const float* w, float* out_p, float* out_pT, int H, int I, void* stream);
+int avc_pack_lstm_bias(const float* b_ih, const float* b_hh, float* out, int H, void* stream);
+int avc_transpose(const float* in, float* out, int R, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * BatchNorm1d (train mode) + activation, model_vc_mel.py:57,:69,:115,:165-167 and the
+ * residual add :197.
+ */
+/* Per-channel sum / sum-of-squares of x (M, C) ld ldx, accumulated into stats (double[2*C]). */
+int avc_channel_stats(const float* x, int ldx, int M, int C, double* stats, void* stream);
+/* stats -> mean, rstd (saved for backward), and the running-stat update of nn.BatchNorm1d
+ * (momentum, unbiased variance).  running_* may be NULL (no update). */
+int avc_bn_finalize(const double* stats, int M, int C, float eps, float momentum,
+                    float* mean, float* rstd, float* running_mean, float* running_var, void* stream);
+/* eval mode: mean/rstd from the running statistics. */
+int avc_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps,
+                      float* mean, float* rstd, void* stream);
+/* z = act((y - mean) * rstd * gamma + beta) (+ residual).  y,z,(residual): (M, C). */
+int avc_bn_act_fwd(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                   const float* residual, float* z, int M, int C, int act, void* stream);
+/* backward, two passes: (1) g = dz * act'(z); sums[0:C] += sum g, sums[C:2C] += sum g*xhat
+ * (double[2*C], caller zero-fills); (2) dy = gamma*rstd*(g - sum_g/M - xhat*sum_gx/M),
+ * dgamma = sum_gx, dbeta = sum_g (overwritten unless accumulate). */
+int avc_bn_act_bwd_reduce(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
+                          double* sums, int M, int C, int act, void* stream);
+int avc_bn_act_bwd_apply(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
+                         const float* gamma, const double* sums, float* dy, float* dgamma, float* dbeta,
+                         int M, int C, int act, int accumulate, void* stream);
+/* column sums of x (M, C) -> out (C), used for Linear / LSTM bias gradients.
+ * out_mode 0: out[c]; 2: LSTM un-permute (c = u*4+g -> g*H+u), written to BOTH out and out2
+ * when out2 != NULL (b_ih and b_hh receive the same gradient). */
+int avc_colsum(const float* x, int ldx, int M, int C, float* out, float* out2, int out_mode, int accumulate,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * LSTM recurrences, nn.LSTM at model_vc_mel.py:61/:73 (encoder BiLSTM), :90/:111 (lstm1),
+ * :104/:118 (lstm2).  P = x W_ih^T + b_ih + b_hh is computed by avc_gemm_nt_taps with the
+ * interleaved packing, so P, gates and dP use column index u*4+g (g: 0=i,1=f,2=g,3=o).
+ *   P      (nB, T, 4H)  pre-activations from the input projection
+ *   Whh_p  (4H, H)      interleaved rows (forward);  Whh_pT (H, 4H) its transpose (backward)
+ *   h_seq  (nB, T, H) with row stride ldh (so fwd/bwd directions can share one (B,T,2H) buffer)
+ *   gates  (nB, T, 4H)  activated gates saved for backward;  c_seq (nB, T, H) cell states
+ * reverse != 0 walks t = T-1 .. 0 (the *_reverse direction).  h0 = c0 = 0.
+ * scratch: fwd needs 2*nB*H floats (h ping-pong is taken from h_seq itself; c from c_seq; no
+ * scratch for small H); bwd needs avc_lstm_bwd_workspace_bytes.
+ */
+int avc_lstm_seq_fwd(const float* P, const float* Whh_p, float* h_seq, int ldh, float* gates, float* c_seq,
+                     int nB, int T, int H, int reverse, int prec, void* stream);
+/* BPTT: dH (nB,T,H) ld lddh = gradient w.r.t. h_seq from above -> dP (nB,T,4H). */
+int avc_lstm_seq_bwd(const float* dH, int lddh, const float* Whh_p, const float* Whh_pT, const float* gates, const float* c_seq,
+                     float* dP, int nB, int T, int H, int reverse, int prec,
+                     void* workspace, size_t workspace_bytes, void* stream);
+size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H);
+
+/* ---------------------------------------------------------------------------------------
+ * Glue that the reference does with squeeze/transpose/expand/cat/slicing.
+ */
+/* model_vc_mel.py:64-66: out (B,T,Cx+E) = [x (B,T,Cx) ld ldx | e (B,E) broadcast over T]. */
+int avc_concat_bcast(const float* x, int ldx, const float* e, float* out, int nB, int T, int Cx, int E, void* stream);
+/* model_vc_mel.py:74-79,:201: codes (B, T/f, 2n) from enc (B,T,2n):
+ *   codes[b,j,:n] = enc[b, j*f+f-1, :n];  codes[b,j,n:] = enc[b, j*f, n:]. */
+int avc_codes_fwd(const float* enc, float* codes, int nB, int T, int n, int f, void* stream);
+/* scatter-add of dcodes back into denc (B,T,2n), which the caller zero-fills. */
+int avc_codes_bwd(const float* dcodes, float* denc, int nB, int T, int n, int f, void* stream);
+/* model_vc_mel.py:186-192: out (B,T,2n+E) = [codes[b, t/f, :] | c_trg[b,:]]. */
+int avc_upsample_concat_fwd(const float* codes, const float* c_trg, float* out, int nB, int T, int n2, int f, int E, void* stream);
+/* dcodes[b,j,:] (+)= sum_{t in group j} dout[b,t,:n2]   (dout ld = lddo). */
+int avc_upsample_concat_bwd(const float* dout, int lddo, float* dcodes, int nB, int T, int n2, int f, int accumulate, void* stream);
+/* strided 2-D copy dst(M, C) ld lddst <- src(M, C) ld ldsrc (slice of the concat gradient). */
+int avc_copy2d(const float* src, int ldsrc, float* dst, int lddst, int M, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Losses, solver_encoder.py:230,:233 (F.mse_loss) and :236 (F.l1_loss), reduction='mean'.
+ * out[0] = mean((a-b)^2) or mean(|a-b|).  scratch: double[1], caller zero-fills.
+ * bwd: da = scale * 2(a-b)/n  or  scale * sign(a-b)/n  with scale read from *gout (device);
+ * db = -da when db != NULL.  `accumulate` adds into da/db. */
+int avc_mse_loss_fwd(const float* a, const float* b, size_t n, double* scratch, float* out, void* stream);
+int avc_l1_loss_fwd(const float* a, const float* b, size_t n, double* scratch, float* out, void* stream);
+int avc_loss_bwd(const float* a, const float* b, size_t n, const float* gout, int is_l1,
+                 float* da, float* db, int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * make_spect front-end, make_spect.py:72-83 (spmel branch) + :30-48:
+ *   y = filtfilt(butter(5, 30 Hz HP), wav) [fp64, scipy odd-extension padlen 18, lfilter_zi]
+ *   wav' = 0.96*y + (dither - 0.5)*1e-6
+ *   D = |rfft(hann_periodic * frames(reflect_pad(wav', 512), 1024, hop 256))|
+ *   S = clip((20*log10(max(1e-5, D @ mel_basis)) - 16 + 100)/100, 0, 1)
+ * wav, dither: (n_utt, max_len) float32 rows (dither = the uniform [0,1) draws of
+ * make_spect.py:76, supplied by the host so the stream matches); lengths[i] <= max_len;
+ * out: (n_utt, max_frames, 80) float32, frames beyond 1 + lengths[i]/256 are zero-filled
+ * (= conversion.py:40-44 pad_seq).  mel_basis: (513, 80) float32 (librosa.filters.mel^T).
+ * filt: double[12] = Butterworth b[0..5], a[0..5]; zi: double[5] = scipy lfilter_zi(b, a).
+ * workspace: avc_logmel_workspace_bytes(n_utt, max_len).
+ */
+int avc_logmel_frontend(const float* wav, const float* dither, const int* lengths, int n_utt, int max_len,
+                        const float* mel_basis, const double* filt, const double* zi,
+                        float* out, int max_frames, void* workspace, size_t workspace_bytes, void* stream);
+size_t avc_logmel_workspace_bytes(int n_utt, int max_len);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUTOVC_B200_H_ */
