@@ -26,7 +26,9 @@ def _build(name):
         G = autovc_b200.Generator(dim_neck, 256, 512, freq)
     else:
         G = autovc_b200.GeneratorSTFT(dim_neck, 256, 512, freq).model
-    np.testing.assert_array_equal(np.stack([digest(p) for p in G.parameters()]), g["param_digest0"])
+    got = np.stack([digest(p) for p in G.parameters()])
+    np.testing.assert_array_equal(got[:, 3:], g["param_digest0"][:, 3:])          # sampled values: bit-exact init
+    np.testing.assert_allclose(got[:, :3], g["param_digest0"][:, :3], rtol=1e-12)  # reductions: summation order only
     return g, G.cuda(), (dim_neck, freq, B, T, n_bins, iseed)
 
 

@@ -57,3 +57,15 @@ def test_frontend_matches_all_71_reference_goldens():
             worst = max(worst, float(np.abs(S - np.load(npy)).max()))
             n += 1
     assert n == 71 and worst < 2e-6, (n, worst)
+
+
+def test_product_mel_basis_equals_oracle_filterbank():
+    """Host-side constant of the product (autovc_b200.make_spect.mel_basis) vs the oracle's
+    restatement of librosa.filters.mel."""
+    from autovc_b200.make_spect import Spect, mel_basis
+    np.testing.assert_allclose(mel_basis(), fref.mel_filterbank().T, rtol=3e-7, atol=0)   # 1 float32 ulp
+    assert int((mel_basis() != 0).sum()) == 941
+    b, a = Spect().butter_highpass()
+    rb, ra = fref.butter_highpass()
+    np.testing.assert_array_equal(b, rb)
+    np.testing.assert_array_equal(a, ra)

@@ -17,7 +17,8 @@ def test_seeded_init_matches_reference(name):
     params, _ = gref.split_state_dict(sd)
     assert list(params.keys()) == g["param_names"].tolist()
     got = np.stack([digest(p) for p in params.values()])
-    np.testing.assert_array_equal(got, g["param_digest0"])
+    np.testing.assert_array_equal(got[:, 3:], g["param_digest0"][:, 3:])          # sampled values: bit-exact init
+    np.testing.assert_allclose(got[:, :3], g["param_digest0"][:, :3], rtol=1e-12)  # reductions: summation order only
 
 
 @pytest.mark.parametrize("name", ["train_16_16_b2_t128", "train_32_32_b3_t64", "train_stft_16_16_b2_t32"])
