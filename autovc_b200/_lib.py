@@ -77,10 +77,35 @@ def load():
     return lib
 
 
+_timing = None   # None, or a list of (name, args, start_event, end_event) while bench.py profiles
+
+
+def enable_timing(on: bool):
+    """Bracket every C-ABI call with CUDA events on the launching stream (bench.py roofline leg)."""
+    global _timing
+    _timing = [] if on else None
+
+
+def collect_timing():
+    """[(name, args, milliseconds)] for the calls since enable_timing(True); caller synchronises first."""
+    out = [(n, a, s.elapsed_time(e)) for n, a, s, e in (_timing or [])]
+    if _timing is not None:
+        _timing.clear()
+    return out
+
+
 def call(name: str, *args):
     """Call an int-returning entry point; raise AvcError(avc_last_error()) on failure."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if _timing is not None:
+        import torch
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = getattr(lib, name)(*args)
+        e.record()
+        _timing.append((name, [a if isinstance(a, int) else None for a in args], s, e))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise AvcError(f"{name} failed (code {rc}): {lib.avc_last_error().decode()}")
 

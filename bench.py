@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py — AutoVC Generator training throughput (utterance-crops/sec) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1]): Generator(dim_neck=16, dim_emb=256, dim_pre=512, freq=16),
+synthetic 80-bin mel crops, batch 256 per GPU, len_crop 128; one step = solver_encoder.py:228-300
+(two Generator calls, three losses, zero_grad, backward, Adam.step, gradient all-reduce when N>1).
+Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for the definition of every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+# forward MACs per frame of the module definitions; train FLOPs = 3 * 2 * MAC
+MAC_PER_FRAME = {(16, 80): 31_784_960, (32, 80): 32_030_720, (16, 513): 36_662_272, (32, 513): 36_908_032}
+
+
+def synth_batch(B, T, n_bins, dim_emb, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, T, n_bins, generator=g)
+    e = F.normalize(torch.randn(B, dim_emb, generator=g), dim=-1) * 0.8
+    return x, e
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_sustained": d.get("bf16_tflops_sustained"), "bf16_burst": d.get("bf16_tflops"),
+                "hbm": d.get("hbm_gbs"), "source": "MEASURED_PEAKS.json"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's PyTorch CPU path
+# ----------------------------------------------------------------------------------------
+def cpu_reference_throughput(dim_neck, freq, T, sample_B, steps, warmup, threads=None):
+    from oracle import generator_ref as gref
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    G = gref.build_reference_like_module(dim_neck, 256, 512, freq).train()
+    opt = torch.optim.Adam(G.parameters(), 1e-4)
+    x, e = synth_batch(sample_B, T, 80, 256, 1234)
+    for _ in range(warmup):
+        gref.module_train_step(G, opt, x, e)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        gref.module_train_step(G, opt, x, e)
+    dt = (time.perf_counter() - t0) / steps
+    return sample_B / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_B = args.cpu_sample_batch
+    val, dt, threads = cpu_reference_throughput(args.dim_neck, args.freq, args.len_crop, sample_B, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "AutoVC train utterance-crops/sec", "value": val, "unit": "crops/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": workload_config(args, note=f"CPU: each step is a {sample_B}-crop sample of the 256-crop batch"),
+        "cpu_baseline": {"value": val, "unit": "crops/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample_B} crops x {args.len_crop} frames per step, {args.warmup} warm-up + {args.steps} timed steps, "
+                                   f"torch {torch.__version__} CPU (oneDNN) through the oracle port of model_vc_mel.py + solver_encoder.py:228-300"},
+        "e2e": {"value": val, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, note=None):
+    c = {"workload": f"AutoVC mel Generator train step (solver_encoder.py:228-300), dim_neck={args.dim_neck} dim_emb=256 dim_pre=512 "
+                     f"freq={args.freq}, synthetic 80-bin mel, batch {args.batch} per GPU, len_crop {args.len_crop}",
+         "global_batch": args.batch * args.gpus, "len_crop": args.len_crop, "precision": args.precision,
+         "parallelism": f"dp{args.gpus}",
+         "l2": "per-step working set (>5 GB of activations) far exceeds the 126 MB L2; no explicit flush"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ----------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------
+def kernel_flops(name, a):
+    """Algorithmic FLOPs of one C-ABI call from its scalar arguments (see include/autovc_b200.h)."""
+    if name == "avc_gemm_nt_taps":
+        nB, T, N, K, taps = a[6], a[7], a[8], a[9], a[10]
+        return 2.0 * nB * T * N * K * taps
+    if name == "avc_gemm_tn_taps":
+        nB, T, N, K, taps = a[5], a[6], a[7], a[8], a[9]
+        return 2.0 * nB * T * N * K * taps
+    if name == "avc_lstm_seq_fwd":
+        nB, T, H = a[6], a[7], a[8]
+        return 2.0 * nB * T * 4 * H * H
+    if name == "avc_lstm_seq_bwd":
+        nB, T, H = a[7], a[8], a[9]
+        return 2.0 * nB * T * 4 * H * H
+    return 0.0
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import autovc_b200
+    from autovc_b200 import _lib, solver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    G = autovc_b200.Generator(args.dim_neck, 256, 512, args.freq, precision=args.precision).to(dev).train()
+    opt = torch.optim.Adam(G.parameters(), 1e-4)
+    reducer = None
+    if world > 1:
+        solver.broadcast_parameters(G)
+        reducer = solver.GradBucketReducer(G.parameters(), bucket_mb=25.0)
+    B, T = args.batch, args.len_crop
+    x_host, e_host = synth_batch(B, T, 80, 256, 1234 + rank)
+    x_pin, e_pin = x_host.pin_memory(), e_host.pin_memory()
+    x_dev, e_dev = x_host.to(dev), e_host.to(dev)
+
+    def step_resident():
+        return solver.train_step(G, opt, x_dev, e_dev, reducer=reducer, sync_losses=False)
+
+    def step_e2e():
+        xd = x_pin.to(dev, non_blocking=True)
+        ed = e_pin.to(dev, non_blocking=True)
+        return solver.train_step(G, opt, xd, ed, reducer=reducer, sync_losses=True)      # D2H of the losses, like :315-317
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n0 = autovc_b200.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = (autovc_b200.launch_count() - n0) // args.steps
+    clocks = sampler.stop() if sampler else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # per-kernel-family device time over instrumented steps (CUDA events on the launching stream)
+    prof_steps = max(1, min(3, args.steps))
+    _lib.enable_timing(True)
+    for _ in range(prof_steps):
+        step_resident()
+    torch.cuda.synchronize()
+    records = _lib.collect_timing()
+    _lib.enable_timing(False)
+    fam = {}
+    for name, scalars, ms_k in records:
+        f = fam.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
+        f["ms"] += ms_k
+        f["n"] += 1
+        f["flops"] += kernel_flops(name, scalars)
+    tot_ms = sum(f["ms"] for f in fam.values()) or 1.0
+    top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    peaks = measured_peaks()
+    step_flops = 6.0 * MAC_PER_FRAME[(args.dim_neck, 80)] * B * T
+    top_name, top_f = top
+    achieved = top_f["flops"] / (top_f["ms"] * 1e-3) / 1e12 if top_f["ms"] > 0 else 0.0
+    roofline = {
+        "bound": "tensor", "kernel": top_name, "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+        "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+        "launches_per_step": top_f["n"] / prof_steps, "avg_launch_ms": top_f["ms"] / max(1, top_f["n"]),
+        "share_of_step_kernel_time": top_f["ms"] / tot_ms,
+        "step": {"flops": step_flops, "achieved_tflops": step_flops / (ms * 1e-3) / 1e12,
+                 "frac": step_flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"]},
+        "families": {k: {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["n"] / prof_steps,
+                         "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None}
+                     for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:8]},
+    }
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            val, dt, threads = cpu_reference_throughput(args.dim_neck, args.freq, T, args.cpu_sample_batch, 2, 1)
+            cpu = {"value": val, "unit": "crops/s", "cores": threads, "kind": "port",
+                   "sample": f"{args.cpu_sample_batch} crops x {T} frames per step (a slice of the {B}-crop batch), 1 warm-up + 2 timed steps, "
+                             f"oracle port of the reference's PyTorch CPU path"}
+        line = {
+            "metric": "AutoVC train utterance-crops/sec", "value": B * world / (ms * 1e-3), "unit": "crops/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": workload_config(args),
+            "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "crops/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": (x_pin.numel() + e_pin.numel()) * 4, "d2h_bytes_per_step": 16},
+            "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("AUTOVC_B200_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=256, help="crops per GPU")
+    ap.add_argument("--len-crop", dest="len_crop", type=int, default=128)
+    ap.add_argument("--dim-neck", dest="dim_neck", type=int, default=16)
+    ap.add_argument("--freq", type=int, default=16)
+    ap.add_argument("--cpu-sample-batch", dest="cpu_sample_batch", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
