@@ -24,6 +24,7 @@ SIGNATURES = {
     "avc_last_error": (ctypes.c_char_p, []),
     "avc_launch_count": (c_ulonglong, []),
     "avc_gemm_nt_taps": (c_int, [P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, P, c_size_t, P]),
+    "avc_gemm_nt_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "avc_gemm_tn_taps": (c_int, [P, c_int, P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
     "avc_gemm_tn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "avc_pack_conv_weight": (c_int, [P, P, P, c_int, c_int, c_int, P]),

@@ -35,6 +35,11 @@ size_t gemm_tn_workspace_simt(int, int, int, int, int);
 int lstm_seq_fwd_simt(const float*, const float*, float*, int, float*, float*, int, int, int, int, cudaStream_t);
 int lstm_seq_bwd_simt(const float*, int, const float*, const float*, const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
 size_t lstm_bwd_workspace_simt(int, int, int);
+// tensor-core implementations (tc_gemm.cu)
+int gemm_nt_taps_tc(const float*, int, const float*, const float*, float*, int, int, int, int, int, int, int, double*, int, void*, size_t, cudaStream_t);
+int gemm_tn_taps_tc(const float*, int, const float*, int, float*, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
+size_t gemm_nt_workspace_tc(int, int, int, int, int);
+size_t gemm_tn_workspace_tc(int, int, int, int, int);
 
 }  // namespace avc
 
@@ -50,9 +55,11 @@ extern "C" int avc_gemm_nt_taps(const float* A, int lda, const float* W, const f
   AVC_REQUIRE(A && W && C, "avc_gemm_nt_taps: null pointer");
   AVC_REQUIRE(nB > 0 && T > 0 && N > 0 && K > 0 && ntaps > 0, "avc_gemm_nt_taps: bad shape B=%d T=%d N=%d K=%d taps=%d", nB, T, N, K, ntaps);
   AVC_REQUIRE(lda >= K && ldc >= N, "avc_gemm_nt_taps: leading dimensions lda=%d < K=%d or ldc=%d < N=%d", lda, K, ldc, N);
-  (void)workspace; (void)workspace_bytes;
   if (prec == AVC_PREC_FP32)
     return gemm_nt_taps_simt(A, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate, as_stream(stream));
+  if (prec == AVC_PREC_BF16)
+    return gemm_nt_taps_tc(A, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate, workspace,
+                           workspace_bytes, as_stream(stream));
   set_error("avc_gemm_nt_taps: precision %d not available in this build", prec);
   return AVC_ERR_UNSUPPORTED;
 }
@@ -67,20 +74,28 @@ extern "C" int avc_gemm_tn_taps(const float* dY, int ldy, const float* X, int ld
   if (prec == AVC_PREC_FP32)
     return gemm_tn_taps_simt(dY, ldy, X, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, accumulate, workspace,
                              workspace_bytes, as_stream(stream));
+  if (prec == AVC_PREC_BF16)
+    return gemm_tn_taps_tc(dY, ldy, X, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, accumulate, workspace,
+                           workspace_bytes, as_stream(stream));
   set_error("avc_gemm_tn_taps: precision %d not available in this build", prec);
   return AVC_ERR_UNSUPPORTED;
 }
 
 extern "C" size_t avc_gemm_tn_workspace_bytes(int nB, int T, int N, int K, int ntaps, int prec) {
-  (void)prec;
+  if (prec == AVC_PREC_BF16) return gemm_tn_workspace_tc(nB, T, N, K, ntaps);
   return gemm_tn_workspace_simt(nB, T, N, K, ntaps);
+}
+
+extern "C" size_t avc_gemm_nt_workspace_bytes(int nB, int T, int N, int K, int ntaps, int prec) {
+  if (prec == AVC_PREC_BF16) return gemm_nt_workspace_tc(nB, T, N, K, ntaps);
+  return 0;
 }
 
 extern "C" int avc_lstm_seq_fwd(const float* P, const float* Whh_p, float* h_seq, int ldh, float* gates, float* c_seq, int nB,
                                 int T, int H, int reverse, int prec, void* stream) {
   AVC_REQUIRE(P && Whh_p && h_seq && gates && c_seq, "avc_lstm_seq_fwd: null pointer");
   AVC_REQUIRE(nB > 0 && T > 0 && H > 0 && ldh >= H, "avc_lstm_seq_fwd: bad shape");
-  if (prec == AVC_PREC_FP32) return lstm_seq_fwd_simt(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, H, reverse, as_stream(stream));
+  if (prec == AVC_PREC_FP32 || prec == AVC_PREC_BF16) return lstm_seq_fwd_simt(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, H, reverse, as_stream(stream));
   set_error("avc_lstm_seq_fwd: precision %d not available in this build", prec);
   return AVC_ERR_UNSUPPORTED;
 }
@@ -90,7 +105,7 @@ extern "C" int avc_lstm_seq_bwd(const float* dH, int lddh, const float* Whh_p, c
                                 size_t workspace_bytes, void* stream) {
   AVC_REQUIRE(dH && Whh_p && Whh_pT && gates && c_seq && dP, "avc_lstm_seq_bwd: null pointer");
   AVC_REQUIRE(nB > 0 && T > 0 && H > 0 && lddh >= H, "avc_lstm_seq_bwd: bad shape");
-  if (prec == AVC_PREC_FP32)
+  if (prec == AVC_PREC_FP32 || prec == AVC_PREC_BF16)
     return lstm_seq_bwd_simt(dH, lddh, Whh_p, Whh_pT, gates, c_seq, dP, nB, T, H, reverse, workspace, workspace_bytes,
                              as_stream(stream));
   set_error("avc_lstm_seq_bwd: precision %d not available in this build", prec);

@@ -50,8 +50,10 @@ def _ws(nbytes: int, device) -> Optional[torch.Tensor]:
 # thin kernel launchers
 # --------------------------------------------------------------------------------------
 def gemm_nt_taps(A, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, stats=None, accumulate=False, prec=PREC_FP32):
+    nbytes = query("avc_gemm_nt_workspace_bytes", nB, T, N, K, ntaps, prec) if prec != PREC_FP32 else 0
+    ws = _ws(nbytes, A.device)
     call("avc_gemm_nt_taps", _p(A), lda, _p(W), _p(bias), _p(C), ldc, nB, T, N, K, ntaps, shift0, _p(stats),
-         int(accumulate), prec, _NULL, 0, _stream())
+         int(accumulate), prec, _p(ws), nbytes, _stream())
 
 
 def gemm_tn_taps(dY, ldy, X, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, accumulate=False, prec=PREC_FP32):

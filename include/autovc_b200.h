@@ -69,6 +69,8 @@ unsigned long long avc_launch_count(void);
 int avc_gemm_nt_taps(const float* A, int lda, const float* W, const float* bias, float* C, int ldc,
                      int nB, int T, int N, int K, int ntaps, int shift0, double* chan_stats, int accumulate,
                      int prec, void* workspace, size_t workspace_bytes, void* stream);
+/* bytes of workspace avc_gemm_nt_taps needs (0 for AVC_PREC_FP32; bf16 staging copies otherwise) */
+size_t avc_gemm_nt_workspace_bytes(int nB, int T, int N, int K, int ntaps, int prec);
 
 /* Weight gradients (conv wgrad, LSTM dW_ih / dW_hh, Linear dW), reduction over rows:
  *   dW[tap][n][k] = sum_m dY[m, n] * X[row(m, tap), k]

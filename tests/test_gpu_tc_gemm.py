@@ -1,0 +1,87 @@
+"""tcgen05/TMA GEMM-with-taps (AVC_PREC_BF16) against an fp64 product of the bf16-rounded operands:
+the only difference allowed is fp32 accumulation order."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from autovc_b200 import ops
+    from autovc_b200._lib import PREC_BF16, PREC_FP32
+
+DEV = "cuda"
+
+
+def _rand(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g).to(DEV)
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).double()
+
+
+def _ref_nt(A, W, bias, nB, T, ntaps, shift0):
+    """A (nB*T, K), W (ntaps, N, K) -> (nB*T, N) in fp64 from bf16-rounded operands."""
+    K = A.shape[1]
+    A3 = _bf(A).view(nB, T, K)
+    out = torch.zeros(nB, T, W.shape[1], dtype=torch.double, device=DEV)
+    for tap in range(ntaps):
+        s = shift0 + tap
+        lo, hi = max(0, -s), min(T, T - s)
+        if hi > lo:
+            out[:, lo:hi] += A3[:, lo + s:hi + s] @ _bf(W[tap]).t()
+    if bias is not None:
+        out += bias.double()
+    return out.view(nB * T, -1)
+
+
+@pytest.mark.parametrize("nB,T,N,K,ntaps", [(2, 128, 512, 336, 5), (3, 128, 128, 64, 1), (2, 48, 130, 769, 5),
+                                            (4, 256, 80, 1024, 1), (1, 20, 64, 512, 1), (5, 64, 2048, 288, 1)])
+def test_nt_taps_bf16(nB, T, N, K, ntaps):
+    A = _rand(nB * T, K, seed=1)
+    W = _rand(ntaps, N, K, seed=2) * 0.05
+    bias = _rand(N, seed=3)
+    C = torch.empty(nB * T, N, device=DEV)
+    stats = torch.zeros(2 * N, dtype=torch.double, device=DEV)
+    shift0 = -(ntaps // 2)
+    ops.gemm_nt_taps(A, K, W, bias, C, N, nB, T, N, K, ntaps, shift0, stats=stats, prec=PREC_BF16)
+    ref = _ref_nt(A, W, bias, nB, T, ntaps, shift0)
+    scale = float(ref.abs().max())
+    assert float((C.double() - ref).abs().max()) < 2e-5 * scale * max(1.0, (K * ntaps / 256) ** 0.5)
+    torch.testing.assert_close(stats[:N], ref.sum(0), rtol=1e-4, atol=1e-3 * scale)
+    torch.testing.assert_close(stats[N:], (ref * ref).sum(0), rtol=1e-4, atol=1e-3 * scale * scale)
+    # accumulate mode, no bias
+    C2 = C.clone()
+    ops.gemm_nt_taps(A, K, W, None, C2, N, nB, T, N, K, ntaps, shift0, accumulate=True, prec=PREC_BF16)
+    ref2 = C.double() + _ref_nt(A, W, None, nB, T, ntaps, shift0)
+    assert float((C2.double() - ref2).abs().max()) < 4e-5 * scale * max(1.0, (K * ntaps / 256) ** 0.5)
+
+
+@pytest.mark.parametrize("nB,T,N,K,ntaps,shift0,mode", [(2, 128, 512, 336, 5, -2, 1), (3, 64, 64, 512, 1, 0, 2),
+                                                        (2, 48, 130, 769, 5, -2, 1), (4, 128, 4096, 1024, 1, -1, 2),
+                                                        (4, 128, 2048, 512, 1, 1, 2), (3, 100, 80, 1024, 1, 0, 0)])
+def test_tn_taps_bf16(nB, T, N, K, ntaps, shift0, mode):
+    dY = _rand(nB * T, N, seed=4)
+    X = _rand(nB * T, K, seed=5)
+    shape = {0: (ntaps, N, K), 1: (N, K, ntaps), 2: (N, K)}[mode]
+    dW = torch.empty(*shape, device=DEV)
+    ops.gemm_tn_taps(dY, N, X, K, dW, nB, T, N, K, ntaps, shift0, out_mode=mode, prec=PREC_BF16)
+    Y3, X3 = _bf(dY).view(nB, T, N), _bf(X).view(nB, T, K)
+    ref = torch.zeros(ntaps, N, K, dtype=torch.double, device=DEV)
+    for tap in range(ntaps):
+        s = shift0 + tap
+        lo, hi = max(0, -s), min(T, T - s)
+        if hi > lo:
+            ref[tap] = torch.einsum("btn,btk->nk", Y3[:, lo:hi], X3[:, lo + s:hi + s])
+    if mode == 1:
+        ref = ref.permute(1, 2, 0)
+    elif mode == 2:
+        H = N // 4
+        ref = ref[0].view(H, 4, K).permute(1, 0, 2).reshape(N, K)     # packed row u*4+g -> g*H+u
+    scale = float(ref.abs().max())
+    assert float((dW.double() - ref).abs().max()) < 3e-5 * scale * max(1.0, (nB * T / 256) ** 0.5)
+    # the fp32 path computes the same contraction from unrounded operands
+    dW32 = torch.empty_like(dW)
+    ops.gemm_tn_taps(dY, N, X, K, dW32, nB, T, N, K, ntaps, shift0, out_mode=mode, prec=PREC_FP32)
+    assert float((dW32 - dW).abs().max()) < 2e-2 * scale
