@@ -163,6 +163,7 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     make_train_golden("train_16_16_b2_t128", 16, 16, 2, 128)
     make_train_golden("train_32_32_b3_t64", 32, 32, 3, 64, steps=1)
+    make_train_golden("train_16_16_b16_t128", 16, 16, 16, 128, steps=1)   # bf16-mode gate (rel-L2) at a less noisy batch
     make_train_golden("train_stft_16_16_b2_t32", 16, 16, 2, 32, n_bins=513, stft=True, steps=1)
     make_eval_golden("eval_32_32_b2_t96", 32, 32, 2, 96)
     make_frontend_goldens()
