@@ -40,6 +40,11 @@ int gemm_nt_taps_tc(const float*, int, const float*, const float*, float*, int, 
 int gemm_tn_taps_tc(const float*, int, const float*, int, float*, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 size_t gemm_nt_workspace_tc(int, int, int, int, int);
 size_t gemm_tn_workspace_tc(int, int, int, int, int);
+// persistent tensor-core recurrences (lstm_tc.cu)
+bool lstm_tc_supported(int H);
+size_t lstm_tc_workspace(int nB, int T, int H, bool bwd);
+int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh, float* gates, float* c_seq, const float* dH,
+                int lddh, float* dP, int nB, int T, int H, int reverse, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace avc
 
@@ -92,12 +97,23 @@ extern "C" size_t avc_gemm_nt_workspace_bytes(int nB, int T, int N, int K, int n
 }
 
 extern "C" int avc_lstm_seq_fwd(const float* P, const float* Whh_p, float* h_seq, int ldh, float* gates, float* c_seq, int nB,
-                                int T, int H, int reverse, int prec, void* stream) {
+                                int T, int H, int reverse, int prec, void* workspace, size_t workspace_bytes, void* stream) {
   AVC_REQUIRE(P && Whh_p && h_seq && gates && c_seq, "avc_lstm_seq_fwd: null pointer");
   AVC_REQUIRE(nB > 0 && T > 0 && H > 0 && ldh >= H, "avc_lstm_seq_fwd: bad shape");
-  if (prec == AVC_PREC_FP32 || prec == AVC_PREC_BF16) return lstm_seq_fwd_simt(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, H, reverse, as_stream(stream));
-  set_error("avc_lstm_seq_fwd: precision %d not available in this build", prec);
+  if (prec == AVC_PREC_BF16 && lstm_tc_supported(H)) {
+    AVC_REQUIRE(ldh % 4 == 0, "avc_lstm_seq_fwd(bf16): ldh must be a multiple of 4");
+    return lstm_seq_tc(false, Whh_p, P, h_seq, ldh, gates, c_seq, nullptr, 0, nullptr, nB, T, H, reverse, workspace,
+                       workspace_bytes, as_stream(stream));
+  }
+  if (prec == AVC_PREC_FP32 || prec == AVC_PREC_BF16)
+    return lstm_seq_fwd_simt(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, H, reverse, as_stream(stream));
+  set_error("avc_lstm_seq_fwd: unknown precision %d", prec);
   return AVC_ERR_UNSUPPORTED;
+}
+
+extern "C" size_t avc_lstm_fwd_workspace_bytes(int nB, int T, int H, int prec) {
+  if (prec == AVC_PREC_BF16 && lstm_tc_supported(H)) return lstm_tc_workspace(nB, T, H, false);
+  return 0;
 }
 
 extern "C" int avc_lstm_seq_bwd(const float* dH, int lddh, const float* Whh_p, const float* Whh_pT, const float* gates,
@@ -105,11 +121,19 @@ extern "C" int avc_lstm_seq_bwd(const float* dH, int lddh, const float* Whh_p, c
                                 size_t workspace_bytes, void* stream) {
   AVC_REQUIRE(dH && Whh_p && Whh_pT && gates && c_seq && dP, "avc_lstm_seq_bwd: null pointer");
   AVC_REQUIRE(nB > 0 && T > 0 && H > 0 && lddh >= H, "avc_lstm_seq_bwd: bad shape");
+  if (prec == AVC_PREC_BF16 && lstm_tc_supported(H)) {
+    AVC_REQUIRE(lddh % 4 == 0, "avc_lstm_seq_bwd(bf16): lddh must be a multiple of 4");
+    return lstm_seq_tc(true, Whh_pT, nullptr, nullptr, 0, const_cast<float*>(gates), const_cast<float*>(c_seq), dH, lddh, dP,
+                       nB, T, H, reverse, workspace, workspace_bytes, as_stream(stream));
+  }
   if (prec == AVC_PREC_FP32 || prec == AVC_PREC_BF16)
     return lstm_seq_bwd_simt(dH, lddh, Whh_p, Whh_pT, gates, c_seq, dP, nB, T, H, reverse, workspace, workspace_bytes,
                              as_stream(stream));
-  set_error("avc_lstm_seq_bwd: precision %d not available in this build", prec);
+  set_error("avc_lstm_seq_bwd: unknown precision %d", prec);
   return AVC_ERR_UNSUPPORTED;
 }
 
-extern "C" size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H) { return lstm_bwd_workspace_simt(nB, T, H); }
+extern "C" size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H, int prec) {
+  if (prec == AVC_PREC_BF16 && lstm_tc_supported(H)) return lstm_tc_workspace(nB, T, H, true);
+  return lstm_bwd_workspace_simt(nB, T, H);
+}

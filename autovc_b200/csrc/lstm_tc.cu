@@ -1,0 +1,428 @@
+// Persistent tensor-core LSTM recurrences (AVC_PREC_BF16): one cooperative launch runs the whole
+// sequence of a layer-direction, forward or BPTT.
+//
+// nn.LSTM (model_vc_mel.py:90/:111 lstm1, :104/:118 lstm2): per step  gates = P_t + h_{t-1} W_hh^T.
+// Grid = (batch tiles of 128 utterances) x (column tiles); every CTA keeps ITS slice of W_hh
+// resident in shared memory for the whole sequence (bf16, K-major, 128B swizzle -- loaded once by
+// TMA), streams the step's activation tile (h_{t-1}, or dG_{t+1} for BPTT) through a TMA ring,
+// multiplies with tcgen05.mma into a TMEM accumulator, and finishes the step in the epilogue warps:
+// gate nonlinearities + cell update (cell state lives in registers for the whole sequence), or the
+// BPTT gate-gradient algebra.  The new h_t / dG_t slice is published in a bf16 exchange buffer and a
+// per-batch-tile release counter; consumers acquire it before their next TMA loads.  Only CTAs that
+// share a batch tile synchronise with each other.
+//
+//   forward : CTA owns BN gate columns (BN/4 hidden units, gate-interleaved), K = H
+//   backward: CTA owns 16 hidden units of dh, K = 4H (dh = dG_{t+1} W_hh)
+#include <cooperative_groups.h>
+
+#include "tc_common.cuh"
+
+namespace avc {
+
+constexpr int LT_THREADS = 192;
+constexpr int LT_STAGE = 128 * 64 * 2;   // one activation k-block: 128 utterances x 64 bf16
+
+struct LstmTcParams {
+  int nB, T, H, K, reverse;
+  int MT, NT, nBpad, stages;
+  const float* P;       // fwd: (nB,T,4H) pre-activations
+  float* h_seq;         // fwd: out (nB,T,H) ld ldh
+  int ldh;
+  float* gates;         // fwd: out / bwd: in  (nB,T,4H) activated gates
+  float* c_seq;         // fwd: out / bwd: in  (nB,T,H)
+  const float* dH;      // bwd: (nB,T,H) ld lddh
+  int lddh;
+  float* dP;            // bwd: out (nB,T,4H)
+  __nv_bfloat16* xbuf;  // exchange buffer [2][nBpad][K]
+  unsigned int* counters;  // [MT], zero-initialised
+};
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v);
+template <>
+__device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, float* v) {
+  float t[32];
+  tmem_ld32(taddr, t);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = t[i];
+}
+template <>
+__device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// BWD = false: BN = gate columns per CTA (64 or 32).  BWD = true: BN = hidden units per CTA (16).
+template <bool BWD, int BN>
+__global__ void __launch_bounds__(LT_THREADS, 1)
+lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const LstmTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const int kblocks = p.K / 64;
+  const uint32_t w_block = BN * 128;                       // bytes of one resident weight k-block
+  const uint32_t w_base = base;
+  const uint32_t ring = base + kblocks * w_block;          // multiples of 1024 (BN*128 with BN >= 16 and kblocks even)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + kblocks * w_block + p.stages * LT_STAGE);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
+  const uint32_t w_bar = bar0 + 8u * 16, tfull = bar0 + 8u * 17, tempty = bar0 + 8u * 18;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = blockIdx.x % p.NT, mt = blockIdx.x / p.NT;
+  const int T = p.T, H = p.H, G = 4 * p.H;
+  constexpr int TM_COLS = BN < 32 ? 32 : BN;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(w_bar, 1);
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  unsigned* counter = p.counters + mt;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, kblocks * w_block);
+      for (int kb = 0; kb < kblocks; ++kb) tma_load_3d(w_base + kb * w_block, &mapW, w_bar, kb * 64, nt * BN, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 1; s < T; ++s) {
+        const unsigned target = (unsigned)s * (unsigned)p.NT;     // every column tile has published step s-1
+        while (ld_acquire(counter) < target) __nanosleep(32);
+        fence_proxy_async();
+        const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), LT_STAGE);
+          tma_load_3d(ring + stage * LT_STAGE, &mapX, full_bar(stage), kb * 64, row0, 0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+      mbar_wait(w_bar, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < T; ++s) {
+        mbar_wait(tempty, (s & 1) ^ 1);
+        tc_fence_after();
+        if (s == 0) {
+          mbar_arrive(tfull);               // h_{-1} = 0 / no later step: nothing to multiply
+          continue;
+        }
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = ring + stage * LT_STAGE, sb = w_base + kb * w_block;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc,
+                     (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull);
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int b = mt * 128 + row;
+    const bool live = b < p.nB;
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (!BWD) {
+      constexpr int U = BN / 4;                 // hidden units owned per thread-row
+      const int n0 = nt * BN, u0 = nt * U;
+      float c[U];
+#pragma unroll
+      for (int i = 0; i < U; ++i) c[i] = 0.f;
+      for (int s = 0; s < T; ++s) {
+        const int t = p.reverse ? T - 1 - s : s;
+        const size_t rowi = (size_t)b * T + t;
+        float pre[BN];
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < BN; j += 4)
+            *reinterpret_cast<float4*>(&pre[j]) = __ldg(reinterpret_cast<const float4*>(p.P + rowi * G + n0 + j));
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN; ++j) pre[j] = 0.f;
+        }
+        mbar_wait(tfull, s & 1);
+        tc_fence_after();
+        if (s > 0) {
+          float d[BN];
+#pragma unroll
+          for (int cc = 0; cc < BN / 32; ++cc) tmem_ld_cols<32>(t_addr + cc * 32, d + cc * 32);
+#pragma unroll
+          for (int j = 0; j < BN; ++j) pre[j] += d[j];
+        }
+        tc_fence_before();
+        __nv_bfloat16 hb[U];
+        float hf[U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          const float gi = sigmoid_fast(pre[4 * i + 0]);
+          const float gf = sigmoid_fast(pre[4 * i + 1]);
+          const float gg = tanh_fast(pre[4 * i + 2]);
+          const float go = sigmoid_fast(pre[4 * i + 3]);
+          c[i] = fmaf(gf, c[i], gi * gg);
+          hf[i] = go * tanh_fast(c[i]);
+          hb[i] = __float2bfloat16_rn(hf[i]);
+          pre[4 * i + 0] = gi; pre[4 * i + 1] = gf; pre[4 * i + 2] = gg; pre[4 * i + 3] = go;
+        }
+        if (live) {
+          __nv_bfloat16* xb = p.xbuf + ((size_t)(s & 1) * p.nBpad + b) * p.K + u0;
+#pragma unroll
+          for (int i = 0; i < U; i += 4)
+            *reinterpret_cast<uint2*>(xb + i) = *reinterpret_cast<const uint2*>(&hb[i]);
+#pragma unroll
+          for (int j = 0; j < BN; j += 4)
+            *reinterpret_cast<float4*>(p.gates + rowi * G + n0 + j) = *reinterpret_cast<const float4*>(&pre[j]);
+#pragma unroll
+          for (int i = 0; i < U; i += 4) {
+            *reinterpret_cast<float4*>(p.c_seq + rowi * H + u0 + i) = *reinterpret_cast<const float4*>(&c[i]);
+            *reinterpret_cast<float4*>(p.h_seq + rowi * p.ldh + u0 + i) = *reinterpret_cast<const float4*>(&hf[i]);
+          }
+        }
+        // publish: every thread's stores -> proxy fence -> gpu-scope fence -> CTA barrier -> one release add
+        fence_proxy_async();
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) red_release_add(counter, 1u);
+        if (lane == 0) mbar_arrive(tempty);
+      }
+    } else {
+      constexpr int U = BN;                      // 16 hidden units
+      const int u0 = nt * U;
+      float dc_rec[U];
+#pragma unroll
+      for (int i = 0; i < U; ++i) dc_rec[i] = 0.f;
+      for (int s = 0; s < T; ++s) {
+        const int t = p.reverse ? s : T - 1 - s;                 // BPTT walks against the forward direction
+        const bool has_prev = s < T - 1;                         // a forward-earlier step exists
+        const int t_prev = p.reverse ? t + 1 : t - 1;
+        const size_t rowi = (size_t)b * T + t;
+        float dh[U], ct[U], cp[U], g4[4 * U];
+        if (live) {
+#pragma unroll
+          for (int i = 0; i < U; i += 4) {
+            *reinterpret_cast<float4*>(&dh[i]) = __ldg(reinterpret_cast<const float4*>(p.dH + rowi * p.lddh + u0 + i));
+            *reinterpret_cast<float4*>(&ct[i]) = __ldg(reinterpret_cast<const float4*>(p.c_seq + rowi * H + u0 + i));
+            if (has_prev)
+              *reinterpret_cast<float4*>(&cp[i]) =
+                  __ldg(reinterpret_cast<const float4*>(p.c_seq + ((size_t)b * T + t_prev) * H + u0 + i));
+            else
+              cp[i] = cp[i + 1] = cp[i + 2] = cp[i + 3] = 0.f;
+          }
+#pragma unroll
+          for (int j = 0; j < 4 * U; j += 4)
+            *reinterpret_cast<float4*>(&g4[j]) = __ldg(reinterpret_cast<const float4*>(p.gates + rowi * G + 4 * u0 + j));
+        } else {
+#pragma unroll
+          for (int i = 0; i < U; ++i) dh[i] = ct[i] = cp[i] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4 * U; ++j) g4[j] = 0.f;
+        }
+        mbar_wait(tfull, s & 1);
+        tc_fence_after();
+        if (s > 0) {
+          float d[U];
+          tmem_ld_cols<16>(t_addr, d);
+#pragma unroll
+          for (int i = 0; i < U; ++i) dh[i] += d[i];
+        }
+        tc_fence_before();
+        __nv_bfloat16 gb[4 * U];
+#pragma unroll
+        for (int i = 0; i < U; ++i) {
+          const float gi = g4[4 * i], gf = g4[4 * i + 1], gg = g4[4 * i + 2], go = g4[4 * i + 3];
+          const float tc = tanh_fast(ct[i]);
+          const float dc = fmaf(dh[i] * go, 1.f - tc * tc, dc_rec[i]);
+          const float di = dc * gg * gi * (1.f - gi);
+          const float df = dc * cp[i] * gf * (1.f - gf);
+          const float dg = dc * gi * (1.f - gg * gg);
+          const float dO = dh[i] * tc * go * (1.f - go);
+          dc_rec[i] = dc * gf;
+          g4[4 * i] = di; g4[4 * i + 1] = df; g4[4 * i + 2] = dg; g4[4 * i + 3] = dO;
+          gb[4 * i] = __float2bfloat16_rn(di); gb[4 * i + 1] = __float2bfloat16_rn(df);
+          gb[4 * i + 2] = __float2bfloat16_rn(dg); gb[4 * i + 3] = __float2bfloat16_rn(dO);
+        }
+        if (live) {
+          __nv_bfloat16* xb = p.xbuf + ((size_t)(s & 1) * p.nBpad + b) * p.K + 4 * u0;
+#pragma unroll
+          for (int j = 0; j < 4 * U; j += 8)
+            *reinterpret_cast<uint4*>(xb + j) = *reinterpret_cast<const uint4*>(&gb[j]);
+#pragma unroll
+          for (int j = 0; j < 4 * U; j += 4)
+            *reinterpret_cast<float4*>(p.dP + rowi * G + 4 * u0 + j) = *reinterpret_cast<const float4*>(&g4[j]);
+        }
+        fence_proxy_async();
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) red_release_add(counter, 1u);
+        if (lane == 0) mbar_arrive(tempty);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TM_COLS);
+  }
+}
+
+// fp32 -> bf16 copy of a weight matrix
+__global__ void cvt_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+bool lstm_tc_supported(int H) { return H >= 128 && H <= 1024 && H % 64 == 0; }
+
+static int fwd_bn(int H) { return H >= 1024 ? 64 : 32; }
+
+struct LtPlan {
+  int BN, NT, MTmax, K, stages;
+  size_t smem, w_bytes, off_w, off_x, off_cnt, total;
+  int chunk;   // utterances per launch
+};
+static LtPlan lt_plan(int nB, int H, bool bwd) {
+  LtPlan pl;
+  pl.K = bwd ? 4 * H : H;
+  pl.BN = bwd ? 16 : fwd_bn(H);
+  pl.NT = bwd ? H / 16 : 4 * H / pl.BN;
+  pl.MTmax = std::max(1, num_sms() / pl.NT);
+  pl.w_bytes = (size_t)pl.BN * pl.K * 2;
+  const size_t budget = 225 * 1024;
+  int stages = (int)((budget - 1024 - 256 - pl.w_bytes) / LT_STAGE);
+  pl.stages = std::min(8, std::max(2, stages));
+  pl.smem = 1024 + pl.w_bytes + (size_t)pl.stages * LT_STAGE + 256;
+  pl.chunk = std::min(nB, pl.MTmax * 128);
+  const int MT = ceil_div(pl.chunk, 128);
+  pl.off_w = 0;
+  pl.off_x = align256((size_t)4 * H * H * 2);
+  pl.off_cnt = pl.off_x + align256((size_t)2 * MT * 128 * pl.K * 2);
+  const int nchunks = ceil_div(nB, pl.chunk);
+  pl.total = pl.off_cnt + align256((size_t)nchunks * 64 * sizeof(unsigned));
+  return pl;
+}
+size_t lstm_tc_workspace(int nB, int T, int H, bool bwd) {
+  (void)T;
+  return lt_plan(nB, H, bwd).total;
+}
+
+template <bool BWD, int BN>
+static int lt_launch(const CUtensorMap& mW, const CUtensorMap& mX, const LstmTcParams& p, const LtPlan& pl, cudaStream_t st) {
+  auto kern = lstm_tc_kernel<BWD, BN>;
+  AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  void* args[] = {(void*)&mW, (void*)&mX, (void*)&p};
+  AVC_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(p.MT * p.NT), dim3(LT_THREADS), args, pl.smem, st));
+  g_launches.fetch_add(1);
+  return AVC_OK;
+}
+
+// W: fwd -> Whh_p (4H, H);  bwd -> Whh_pT (H, 4H)  (fp32, packed/interleaved)
+int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh, float* gates, float* c_seq,
+                const float* dH, int lddh, float* dP, int nB, int T, int H, int reverse, void* ws, size_t ws_bytes,
+                cudaStream_t st) {
+  const LtPlan pl = lt_plan(nB, H, bwd);
+  if (!ws || ws_bytes < pl.total) {
+    set_error("avc_lstm_seq_%s(bf16): workspace %zu < %zu", bwd ? "bwd" : "fwd", ws_bytes, pl.total);
+    return AVC_ERR_WORKSPACE;
+  }
+  if (pl.smem > 227 * 1024) {
+    set_error("avc_lstm_seq(bf16): H=%d needs %zu bytes of shared memory", H, pl.smem);
+    return AVC_ERR_UNSUPPORTED;
+  }
+  uint8_t* w8 = (uint8_t*)ws;
+  __nv_bfloat16* Wb = (__nv_bfloat16*)(w8 + pl.off_w);
+  __nv_bfloat16* xbuf = (__nv_bfloat16*)(w8 + pl.off_x);
+  unsigned* counters = (unsigned*)(w8 + pl.off_cnt);
+  const size_t wn = (size_t)4 * H * H;
+  cvt_bf16_kernel<<<(int)std::min<size_t>(ceil_div(wn, (size_t)256), (size_t)num_sms() * 8), 256, 0, st>>>(W, Wb, wn);
+  AVC_LAUNCHED();
+  const int nchunks = ceil_div(nB, pl.chunk);
+  AVC_CUDA(cudaMemsetAsync(counters, 0, (size_t)nchunks * 64 * sizeof(unsigned), st));
+  CUtensorMap mW, mX;
+  const int w_rows = bwd ? H : 4 * H;
+  int rc = make_map3(&mW, Wb, pl.K, w_rows, 1, pl.K, (uint64_t)w_rows * pl.K, 64, pl.BN);
+  if (rc) return rc;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int b0 = ch * pl.chunk;
+    const int nb = std::min(pl.chunk, nB - b0);
+    LstmTcParams p{};
+    p.nB = nb; p.T = T; p.H = H; p.K = pl.K; p.reverse = reverse;
+    p.MT = ceil_div(nb, 128); p.NT = pl.NT; p.nBpad = p.MT * 128; p.stages = pl.stages;
+    const size_t G = 4 * (size_t)H;
+    p.P = P ? P + (size_t)b0 * T * G : nullptr;
+    p.h_seq = h_seq ? h_seq + (size_t)b0 * T * ldh : nullptr;
+    p.ldh = ldh;
+    p.gates = gates + (size_t)b0 * T * G;
+    p.c_seq = c_seq + (size_t)b0 * T * H;
+    p.dH = dH ? dH + (size_t)b0 * T * lddh : nullptr;
+    p.lddh = lddh;
+    p.dP = dP ? dP + (size_t)b0 * T * G : nullptr;
+    p.xbuf = xbuf;
+    p.counters = counters + ch * 64;
+    rc = make_map3(&mX, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, 128);
+    if (rc) return rc;
+    if (bwd) rc = lt_launch<true, 16>(mW, mX, p, pl, st);
+    else if (pl.BN == 64) rc = lt_launch<false, 64>(mW, mX, p, pl, st);
+    else rc = lt_launch<false, 32>(mW, mX, p, pl, st);
+    if (rc) return rc;
+  }
+  return AVC_OK;
+}
+
+}  // namespace avc

@@ -230,8 +230,10 @@ class LstmLayer(torch.autograd.Function):
             gates = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
             c_seq = torch.empty(B, T, H, device=x.device, dtype=torch.float32)
             h_view = out.view(-1)[d * H:]
+            nbytes = query("avc_lstm_fwd_workspace_bytes", B, T, H, prec)
+            ws = _ws(nbytes, x.device)
             call("avc_lstm_seq_fwd", _p(Pre), _p(wh_p), _p(h_view), D * H, _p(gates), _p(c_seq), B, T, H, int(d == 1), prec,
-                 _stream())
+                 _p(ws), nbytes, _stream())
             saved += [gates, c_seq]
         ctx.save_for_backward(x, out, *weights, *saved)
         ctx.D, ctx.prec, ctx.packs = D, prec, packs
@@ -256,7 +258,7 @@ class LstmLayer(torch.autograd.Function):
             gates, c_seq = saved[2 * d:2 * d + 2]
             wi_pT, wh_p, wh_pT = ctx.packs[3 * d:3 * d + 3]
             dP = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
-            nbytes = query("avc_lstm_bwd_workspace_bytes", B, T, H)
+            nbytes = query("avc_lstm_bwd_workspace_bytes", B, T, H, prec)
             ws = _ws(nbytes, x.device)
             rev = int(d == 1)
             call("avc_lstm_seq_bwd", _p(dout.view(-1)[d * H:]), D * H, _p(wh_p), _p(wh_pT), _p(gates), _p(c_seq), _p(dP),

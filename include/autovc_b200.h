@@ -136,16 +136,21 @@ int avc_colsum(const float* x, int ldx, int M, int C, float* out, float* out2, i
  *   h_seq  (nB, T, H) with row stride ldh (so fwd/bwd directions can share one (B,T,2H) buffer)
  *   gates  (nB, T, 4H)  activated gates saved for backward;  c_seq (nB, T, H) cell states
  * reverse != 0 walks t = T-1 .. 0 (the *_reverse direction).  h0 = c0 = 0.
- * scratch: fwd needs 2*nB*H floats (h ping-pong is taken from h_seq itself; c from c_seq; no
- * scratch for small H); bwd needs avc_lstm_bwd_workspace_bytes.
+ * AVC_PREC_FP32: H <= 64 runs the whole sequence in one launch (W_hh in shared memory), larger H
+ * one launch per step.  AVC_PREC_BF16 with 128 <= H <= 1024, H % 64 == 0: ONE persistent cooperative
+ * launch per layer-direction -- W_hh slices resident in shared memory across the SMs, tcgen05 MMAs
+ * into TMEM, fused gate math, per-step release/acquire exchange of h_t (or dG_t) in bf16; cell state
+ * and all saved tensors stay fp32.  Workspace sizes come from the *_workspace_bytes queries.
  */
 int avc_lstm_seq_fwd(const float* P, const float* Whh_p, float* h_seq, int ldh, float* gates, float* c_seq,
-                     int nB, int T, int H, int reverse, int prec, void* stream);
+                     int nB, int T, int H, int reverse, int prec,
+                     void* workspace, size_t workspace_bytes, void* stream);
+size_t avc_lstm_fwd_workspace_bytes(int nB, int T, int H, int prec);
 /* BPTT: dH (nB,T,H) ld lddh = gradient w.r.t. h_seq from above -> dP (nB,T,4H). */
 int avc_lstm_seq_bwd(const float* dH, int lddh, const float* Whh_p, const float* Whh_pT, const float* gates, const float* c_seq,
                      float* dP, int nB, int T, int H, int reverse, int prec,
                      void* workspace, size_t workspace_bytes, void* stream);
-size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H);
+size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H, int prec);
 
 /* ---------------------------------------------------------------------------------------
  * Glue that the reference does with squeeze/transpose/expand/cat/slicing.
