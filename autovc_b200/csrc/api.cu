@@ -36,10 +36,10 @@ int lstm_seq_fwd_simt(const float*, const float*, float*, int, float*, float*, i
 int lstm_seq_bwd_simt(const float*, int, const float*, const float*, const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
 size_t lstm_bwd_workspace_simt(int, int, int);
 // tensor-core implementations (tc_gemm.cu)
-int gemm_nt_taps_tc(const float*, int, const float*, const float*, float*, int, int, int, int, int, int, int, double*, int, void*, size_t, cudaStream_t);
-int gemm_tn_taps_tc(const float*, int, const float*, int, float*, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
-size_t gemm_nt_workspace_tc(int, int, int, int, int);
-size_t gemm_tn_workspace_tc(int, int, int, int, int);
+int gemm_nt_taps_tc(const float*, int, const float*, const float*, float*, int, int, int, int, int, int, int, double*, int, int, void*, size_t, cudaStream_t);
+int gemm_tn_taps_tc(const float*, int, const float*, int, float*, int, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
+size_t gemm_nt_workspace_tc(int, int, int, int, int, int);
+size_t gemm_tn_workspace_tc(int, int, int, int, int, int);
 // persistent tensor-core recurrences (lstm_tc.cu)
 bool lstm_tc_supported(int H);
 size_t lstm_tc_workspace(int nB, int T, int H, bool bwd);
@@ -62,9 +62,9 @@ extern "C" int avc_gemm_nt_taps(const float* A, int lda, const float* W, const f
   AVC_REQUIRE(lda >= K && ldc >= N, "avc_gemm_nt_taps: leading dimensions lda=%d < K=%d or ldc=%d < N=%d", lda, K, ldc, N);
   if (prec == AVC_PREC_FP32)
     return gemm_nt_taps_simt(A, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate, as_stream(stream));
-  if (prec == AVC_PREC_BF16)
-    return gemm_nt_taps_tc(A, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate, workspace,
-                           workspace_bytes, as_stream(stream));
+  if (prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32)
+    return gemm_nt_taps_tc(A, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate,
+                           prec == AVC_PREC_BF16 ? 2 : 4, workspace, workspace_bytes, as_stream(stream));
   set_error("avc_gemm_nt_taps: precision %d not available in this build", prec);
   return AVC_ERR_UNSUPPORTED;
 }
@@ -79,20 +79,20 @@ extern "C" int avc_gemm_tn_taps(const float* dY, int ldy, const float* X, int ld
   if (prec == AVC_PREC_FP32)
     return gemm_tn_taps_simt(dY, ldy, X, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, accumulate, workspace,
                              workspace_bytes, as_stream(stream));
-  if (prec == AVC_PREC_BF16)
-    return gemm_tn_taps_tc(dY, ldy, X, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, accumulate, workspace,
-                           workspace_bytes, as_stream(stream));
+  if (prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32)
+    return gemm_tn_taps_tc(dY, ldy, X, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, accumulate,
+                           prec == AVC_PREC_BF16 ? 2 : 4, workspace, workspace_bytes, as_stream(stream));
   set_error("avc_gemm_tn_taps: precision %d not available in this build", prec);
   return AVC_ERR_UNSUPPORTED;
 }
 
 extern "C" size_t avc_gemm_tn_workspace_bytes(int nB, int T, int N, int K, int ntaps, int prec) {
-  if (prec == AVC_PREC_BF16) return gemm_tn_workspace_tc(nB, T, N, K, ntaps);
+  if (prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32) return gemm_tn_workspace_tc(nB, T, N, K, ntaps, prec == AVC_PREC_BF16 ? 2 : 4);
   return gemm_tn_workspace_simt(nB, T, N, K, ntaps);
 }
 
 extern "C" size_t avc_gemm_nt_workspace_bytes(int nB, int T, int N, int K, int ntaps, int prec) {
-  if (prec == AVC_PREC_BF16) return gemm_nt_workspace_tc(nB, T, N, K, ntaps);
+  if (prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32) return gemm_nt_workspace_tc(nB, T, N, K, ntaps, prec == AVC_PREC_BF16 ? 2 : 4);
   return 0;
 }
 
@@ -100,19 +100,19 @@ extern "C" int avc_lstm_seq_fwd(const float* P, const float* Whh_p, float* h_seq
                                 int T, int H, int reverse, int prec, void* workspace, size_t workspace_bytes, void* stream) {
   AVC_REQUIRE(P && Whh_p && h_seq && gates && c_seq, "avc_lstm_seq_fwd: null pointer");
   AVC_REQUIRE(nB > 0 && T > 0 && H > 0 && ldh >= H, "avc_lstm_seq_fwd: bad shape");
-  if (prec == AVC_PREC_BF16 && lstm_tc_supported(H)) {
+  if ((prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32) && lstm_tc_supported(H)) {
     AVC_REQUIRE(ldh % 4 == 0, "avc_lstm_seq_fwd(bf16): ldh must be a multiple of 4");
     return lstm_seq_tc(false, Whh_p, P, h_seq, ldh, gates, c_seq, nullptr, 0, nullptr, nB, T, H, reverse, workspace,
                        workspace_bytes, as_stream(stream));
   }
-  if (prec == AVC_PREC_FP32 || prec == AVC_PREC_BF16)
+  if (prec == AVC_PREC_FP32 || prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32)
     return lstm_seq_fwd_simt(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, H, reverse, as_stream(stream));
   set_error("avc_lstm_seq_fwd: unknown precision %d", prec);
   return AVC_ERR_UNSUPPORTED;
 }
 
 extern "C" size_t avc_lstm_fwd_workspace_bytes(int nB, int T, int H, int prec) {
-  if (prec == AVC_PREC_BF16 && lstm_tc_supported(H)) return lstm_tc_workspace(nB, T, H, false);
+  if ((prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32) && lstm_tc_supported(H)) return lstm_tc_workspace(nB, T, H, false);
   return 0;
 }
 
@@ -121,12 +121,12 @@ extern "C" int avc_lstm_seq_bwd(const float* dH, int lddh, const float* Whh_p, c
                                 size_t workspace_bytes, void* stream) {
   AVC_REQUIRE(dH && Whh_p && Whh_pT && gates && c_seq && dP, "avc_lstm_seq_bwd: null pointer");
   AVC_REQUIRE(nB > 0 && T > 0 && H > 0 && lddh >= H, "avc_lstm_seq_bwd: bad shape");
-  if (prec == AVC_PREC_BF16 && lstm_tc_supported(H)) {
+  if ((prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32) && lstm_tc_supported(H)) {
     AVC_REQUIRE(lddh % 4 == 0, "avc_lstm_seq_bwd(bf16): lddh must be a multiple of 4");
     return lstm_seq_tc(true, Whh_pT, nullptr, nullptr, 0, const_cast<float*>(gates), const_cast<float*>(c_seq), dH, lddh, dP,
                        nB, T, H, reverse, workspace, workspace_bytes, as_stream(stream));
   }
-  if (prec == AVC_PREC_FP32 || prec == AVC_PREC_BF16)
+  if (prec == AVC_PREC_FP32 || prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32)
     return lstm_seq_bwd_simt(dH, lddh, Whh_p, Whh_pT, gates, c_seq, dP, nB, T, H, reverse, workspace, workspace_bytes,
                              as_stream(stream));
   set_error("avc_lstm_seq_bwd: unknown precision %d", prec);
@@ -134,6 +134,6 @@ extern "C" int avc_lstm_seq_bwd(const float* dH, int lddh, const float* Whh_p, c
 }
 
 extern "C" size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H, int prec) {
-  if (prec == AVC_PREC_BF16 && lstm_tc_supported(H)) return lstm_tc_workspace(nB, T, H, true);
+  if ((prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32) && lstm_tc_supported(H)) return lstm_tc_workspace(nB, T, H, true);
   return lstm_bwd_workspace_simt(nB, T, H);
 }

@@ -55,6 +55,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <int EB>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  if (EB == 2) umma_f16(tmem_d, da, db, idesc, accumulate);
+  else umma_tf32(tmem_d, da, db, idesc, accumulate);
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -85,9 +97,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-// instruction descriptor for kind::f16: bf16 x bf16 -> f32 (cute::UMMA::InstrDescriptor bit layout)
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((uint32_t)a_mn_major << 15) |
+// instruction descriptor (cute::UMMA::InstrDescriptor bit layout): fmt 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32); D = f32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, int fmt = 1) {
+  return (1u << 4) /*D=f32*/ | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn_major << 15) |
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -113,17 +125,18 @@ static inline PFN_encodeTiled get_encode() {
 
 // 3-D bf16 tensor map over a row-major (d2, d1, d0) array: d0 contiguous, 128B swizzle, zero OOB fill
 static inline int make_map3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
-                     uint64_t stride2_elems, uint32_t box0, uint32_t box1) {
+                     uint64_t stride2_elems, uint32_t box0, uint32_t box1, int elem_bytes = 2) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
     return AVC_ERR_CUDA;
   }
   cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
+  cuuint64_t strides[2] = {stride1_elems * elem_bytes, stride2_elems * elem_bytes};
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, es,
+  // fp32 operands are fetched as TFLOAT32: the TMA unit rounds them to tf32 on the way into shared memory
+  CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

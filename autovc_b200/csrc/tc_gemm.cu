@@ -16,9 +16,18 @@
 
 namespace avc {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;
+constexpr int TC_BM = 128, TC_BN = 128;
 constexpr int TC_STAGES = 6;
-constexpr int TC_STAGE_A = TC_BM * TC_BK * 2, TC_STAGE_B = TC_BN * TC_BK * 2;   // 16 KB each
+constexpr int TC_STAGE_A = TC_BM * 128, TC_STAGE_B = TC_BN * 128;   // 128 rows x one 128-byte swizzle row = 16 KB each
+// EB = operand element bytes: 2 = bf16 (kind::f16), 4 = fp32 read as tf32 (kind::tf32).  One 128-byte row holds
+// 128/EB elements of K (NT) or of channels (TN); one MMA consumes 32 bytes of K = 32/EB elements.
+template <int EB> struct TcGeom {
+  static constexpr int ROW = 128 / EB;         // elements per swizzle row
+  static constexpr int KMMA = 32 / EB;         // K elements per tcgen05.mma
+  static constexpr int RS = 4 * KMMA;          // TN: frames per pipeline stage (4 MMAs)
+  static constexpr int NBOX = 128 / ROW;       // TN: 128-channel tile = NBOX TMA boxes of ROW channels
+  static constexpr int BOX_BYTES = RS * 128;   // TN: bytes of one box (RS frames x 128 B)
+};
 constexpr int TC_STAGE_BYTES = TC_STAGE_A + TC_STAGE_B;
 constexpr int TC_THREADS = 192;
 constexpr int TC_TMEM_COLS = 256;  // two 128-column fp32 accumulators
@@ -31,13 +40,13 @@ struct TcParams {
   int nB, T, ntaps, shift0;
   int N, K;            // logical (unpadded) sizes of the output's two dims (NT: C cols = N; TN: dW is N x K)
   // NT
-  int t_tiles, n_tiles, kblocks;   // tiles along T (128 frames), along N (128 cols), 64-wide k blocks per tap
+  int t_tiles, n_tiles, kblocks;   // tiles along T (128 frames), along N (128 cols), one-swizzle-row k blocks per tap
   const float* bias;
   float* C;
   int ldc, accumulate;
   double* stats;
   // TN
-  int k_tiles, splits, rblocks, rblocks_per_split, tb64;   // tb64 = ceil(T/64)
+  int k_tiles, splits, rblocks, rblocks_per_split, tbr;   // tbr = ceil(T / frames-per-stage)
   float* part;
 };
 
@@ -59,7 +68,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, int EB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -77,6 +86,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  using Gm = TcGeom<EB>;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -120,8 +130,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_wait(empty_bar(stage), phase ^ 1);
             mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
             const uint32_t sa = stage0 + stage * TC_STAGE_BYTES;
-            tma_load_3d(sa, &mapA, full_bar(stage), kb * TC_BK, t0 + p.shift0 + tap, b);
-            tma_load_3d(sa + TC_STAGE_A, &mapB, full_bar(stage), kb * TC_BK, n_tile * TC_BN, tap);
+            tma_load_3d(sa, &mapA, full_bar(stage), kb * Gm::ROW, t0 + p.shift0 + tap, b);
+            tma_load_3d(sa + TC_STAGE_A, &mapB, full_bar(stage), kb * Gm::ROW, n_tile * TC_BN, tap);
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
         } else {
@@ -133,14 +143,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const int rb0 = split * p.rblocks_per_split;
           const int rb1 = min(p.rblocks, rb0 + p.rblocks_per_split);
           for (int rb = rb0; rb < rb1; ++rb) {
-            const int b = rb / p.tb64, t0 = (rb % p.tb64) * 64;
+            const int b = rb / p.tbr, t0 = (rb % p.tbr) * Gm::RS;
             mbar_wait(empty_bar(stage), phase ^ 1);
             mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
             const uint32_t sa = stage0 + stage * TC_STAGE_BYTES;
-            tma_load_3d(sa, &mapA, full_bar(stage), n_tile * TC_BM, t0, b);
-            tma_load_3d(sa + TC_STAGE_A / 2, &mapA, full_bar(stage), n_tile * TC_BM + 64, t0, b);
-            tma_load_3d(sa + TC_STAGE_A, &mapB, full_bar(stage), k_tile * TC_BN, t0 + p.shift0 + tap, b);
-            tma_load_3d(sa + TC_STAGE_A + TC_STAGE_B / 2, &mapB, full_bar(stage), k_tile * TC_BN + 64, t0 + p.shift0 + tap, b);
+#pragma unroll
+            for (int h = 0; h < Gm::NBOX; ++h) {
+              tma_load_3d(sa + h * Gm::BOX_BYTES, &mapA, full_bar(stage), n_tile * TC_BM + h * Gm::ROW, t0, b);
+              tma_load_3d(sa + TC_STAGE_A + h * Gm::BOX_BYTES, &mapB, full_bar(stage), k_tile * TC_BN + h * Gm::ROW,
+                          t0 + p.shift0 + tap, b);
+            }
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -149,7 +161,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TC_BM, TC_BN, MODE == MODE_TN, MODE == MODE_TN);
+      constexpr uint32_t idesc = make_idesc(TC_BM, TC_BN, MODE == MODE_TN, MODE == MODE_TN, EB == 2 ? 1 : 2);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -169,19 +181,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tc_fence_after();
           const uint32_t sa = stage0 + stage * TC_STAGE_BYTES, sb = sa + TC_STAGE_A;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k) {
+          for (int k = 0; k < 4; ++k) {
             uint64_t da, db;
             if (MODE == MODE_NT) {
-              // K-major: 128-byte rows, 8-row groups 1024 B apart; a K=16 slice is 32 B further along the row
+              // K-major: 128-byte rows, 8-row groups 1024 B apart; one MMA's K slice is 32 B further along the row
               da = make_desc(sa + k * 32, 16, 1024);
               db = make_desc(sb + k * 32, 16, 1024);
             } else {
-              // MN-major: each frame is a 128-byte row of 64 channels; 8-frame groups 1024 B apart (SBO),
-              // the second 64-channel half of the tile 8192 B further (LBO); a K=16 slice = 16 frames = 2048 B
-              da = make_desc(sa + k * 2048, TC_STAGE_A / 2, 1024);
-              db = make_desc(sb + k * 2048, TC_STAGE_B / 2, 1024);
+              // MN-major: each frame is a 128-byte row of ROW channels; 8-frame groups 1024 B apart (SBO), the
+              // next ROW-channel box of the tile BOX_BYTES further (LBO); one MMA's K slice = KMMA frames
+              da = make_desc(sa + k * Gm::KMMA * 128, Gm::BOX_BYTES, 1024);
+              db = make_desc(sb + k * Gm::KMMA * 128, Gm::BOX_BYTES, 1024);
             }
-            umma_f16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma<EB>(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));                // frees the smem slot when these MMAs retire
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -338,6 +350,16 @@ __global__ void cvt_pad_w_bf16_kernel(const float* __restrict__ src, __nv_bfloat
   }
 }
 
+__global__ void cvt_pad_w_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int ntaps, int N, int K, int Np, int Kp) {
+  const size_t total = (size_t)ntaps * Np * Kp;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kp);
+    const int n = (int)((i / Kp) % Np);
+    const int tap = (int)(i / ((size_t)Kp * Np));
+    dst[i] = (n < N && k < K) ? src[((size_t)tap * N + n) * K + k] : 0.f;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -347,54 +369,105 @@ static int cvt_blocks(size_t total) { return (int)std::min<size_t>(ceil_div(tota
 static int ensure_smem_attr() {
   static bool done = false;
   if (!done) {
-    AVC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    AVC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    AVC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_NT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    AVC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_TN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    AVC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_NT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    AVC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_TN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     done = true;
   }
   return AVC_OK;
 }
 
-size_t gemm_nt_workspace_tc(int nB, int T, int N, int K, int ntaps) {
-  const int Kp = round_up(K, TC_BK), Np = round_up(N, TC_BN);
-  return align256((size_t)nB * T * Kp * 2) + align256((size_t)ntaps * Np * Kp * 2);
+// fp32 -> padded fp32 staging for the tf32 path when the caller's strides are not 16-byte multiples
+__global__ void cvt_pad_f32_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int Cp, size_t R, int C) {
+  const size_t total = R * (size_t)Cp;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / Cp;
+    const int c = (int)(i % Cp);
+    dst[i] = c < C ? src[r * lds + c] : 0.f;
+  }
+}
+
+static inline bool direct_ok(const void* p, int ld) { return ((uintptr_t)p & 15) == 0 && (ld & 3) == 0; }
+
+// ---- NT -------------------------------------------------------------------------------------------
+// eb = 2: both operands are staged as zero-padded bf16.  eb = 4: operands are read in place by TMA when
+// their row strides are 16-byte multiples (OOB zero fill covers K/N tails), otherwise staged as padded fp32.
+struct NtPlan {
+  int Kp, Np;
+  bool stageA, stageW;
+  size_t offA, offW, total;
+};
+static NtPlan nt_plan(const float* A, int lda, const float* W, int nB, int T, int N, int K, int ntaps, int eb) {
+  NtPlan pl;
+  const int row = 128 / eb;
+  pl.Kp = round_up(K, row);
+  pl.Np = round_up(N, TC_BN);
+  pl.stageA = eb == 2 || !direct_ok(A, lda);
+  pl.stageW = eb == 2 || !direct_ok(W, K);
+  pl.offA = 0;
+  pl.offW = pl.stageA ? align256((size_t)nB * T * pl.Kp * eb) : 0;
+  pl.total = pl.offW + (pl.stageW ? align256((size_t)ntaps * pl.Np * pl.Kp * eb) : 0);
+  return pl;
+}
+size_t gemm_nt_workspace_tc(int nB, int T, int N, int K, int ntaps, int eb) {
+  // worst case (pointers unknown): assume staging
+  const int row = 128 / eb;
+  const int Kp = round_up(K, row), Np = round_up(N, TC_BN);
+  return align256((size_t)nB * T * Kp * eb) + align256((size_t)ntaps * Np * Kp * eb);
 }
 
 int gemm_nt_taps_tc(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int nB, int T, int N,
-                    int K, int ntaps, int shift0, double* stats, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    int K, int ntaps, int shift0, double* stats, int accumulate, int eb, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
   if (stats && accumulate) {
     set_error("avc_gemm_nt_taps: chan_stats and accumulate are mutually exclusive");
     return AVC_ERR_UNSUPPORTED;
   }
-  if (!ws || ws_bytes < gemm_nt_workspace_tc(nB, T, N, K, ntaps)) {
-    set_error("avc_gemm_nt_taps(bf16): workspace %zu < %zu", ws_bytes, gemm_nt_workspace_tc(nB, T, N, K, ntaps));
+  const NtPlan pl = nt_plan(A, lda, W, nB, T, N, K, ntaps, eb);
+  if (pl.total > 0 && (!ws || ws_bytes < pl.total)) {
+    set_error("avc_gemm_nt_taps(tensor): workspace %zu < %zu", ws_bytes, pl.total);
     return AVC_ERR_WORKSPACE;
   }
   int rc = ensure_smem_attr();
   if (rc) return rc;
-  const int Kp = round_up(K, TC_BK), Np = round_up(N, TC_BN);
   const size_t M = (size_t)nB * T;
-  __nv_bfloat16* Ab = (__nv_bfloat16*)ws;
-  __nv_bfloat16* Wb = (__nv_bfloat16*)((uint8_t*)ws + align256(M * Kp * 2));
-  cvt_pad_bf16_kernel<<<cvt_blocks(M * (Kp / 2)), 256, 0, st>>>(A, lda, Ab, Kp, M, M, K);
-  AVC_LAUNCHED();
-  cvt_pad_w_bf16_kernel<<<cvt_blocks((size_t)ntaps * Np * Kp), 256, 0, st>>>(W, Wb, ntaps, N, K, Np, Kp);
-  AVC_LAUNCHED();
+  const int row = 128 / eb;
+  const void* Aop = A;
+  const void* Wop = W;
+  uint64_t a_ld = lda, a_k = K, w_k = K, w_n = N, w_ld = K;
+  if (pl.stageA) {
+    void* dst = (uint8_t*)ws + pl.offA;
+    if (eb == 2) cvt_pad_bf16_kernel<<<cvt_blocks(M * (pl.Kp / 2)), 256, 0, st>>>(A, lda, (__nv_bfloat16*)dst, pl.Kp, M, M, K);
+    else cvt_pad_f32_kernel<<<cvt_blocks(M * pl.Kp), 256, 0, st>>>(A, lda, (float*)dst, pl.Kp, M, K);
+    AVC_LAUNCHED();
+    Aop = dst; a_ld = pl.Kp; a_k = pl.Kp;
+  }
+  if (pl.stageW) {
+    void* dst = (uint8_t*)ws + pl.offW;
+    if (eb == 2) cvt_pad_w_bf16_kernel<<<cvt_blocks((size_t)ntaps * pl.Np * pl.Kp), 256, 0, st>>>(W, (__nv_bfloat16*)dst, ntaps, N, K, pl.Np, pl.Kp);
+    else cvt_pad_w_f32_kernel<<<cvt_blocks((size_t)ntaps * pl.Np * pl.Kp), 256, 0, st>>>(W, (float*)dst, ntaps, N, K, pl.Np, pl.Kp);
+    AVC_LAUNCHED();
+    Wop = dst; w_k = pl.Kp; w_n = pl.Np; w_ld = pl.Kp;
+  }
   CUtensorMap mA, mB;
-  rc = make_map3(&mA, Ab, Kp, T, nB, Kp, (uint64_t)T * Kp, TC_BK, TC_BM);
+  rc = make_map3(&mA, Aop, a_k, T, nB, a_ld, (uint64_t)T * a_ld, row, TC_BM, eb);
   if (rc) return rc;
-  rc = make_map3(&mB, Wb, Kp, Np, ntaps, Kp, (uint64_t)Np * Kp, TC_BK, TC_BN);
+  rc = make_map3(&mB, Wop, w_k, w_n, ntaps, w_ld, w_n * w_ld, row, TC_BN, eb);
   if (rc) return rc;
   TcParams p{};
   p.nB = nB; p.T = T; p.ntaps = ntaps; p.shift0 = shift0; p.N = N; p.K = K;
-  p.t_tiles = ceil_div(T, TC_BM); p.n_tiles = Np / TC_BN; p.kblocks = Kp / TC_BK;
+  p.t_tiles = ceil_div(T, TC_BM); p.n_tiles = pl.Np / TC_BN; p.kblocks = pl.Kp / row;
   p.bias = bias; p.C = C; p.ldc = ldc; p.accumulate = accumulate; p.stats = stats;
   const int tiles = nB * p.t_tiles * p.n_tiles;
   const int grid = std::min(tiles, num_sms());
-  tc_gemm_kernel<MODE_NT><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mA, mB, p);
+  if (eb == 2) tc_gemm_kernel<MODE_NT, 2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mA, mB, p);
+  else tc_gemm_kernel<MODE_NT, 4><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mA, mB, p);
   AVC_LAUNCHED();
   return AVC_OK;
 }
 
+// ---- TN -------------------------------------------------------------------------------------------
 static int tn_splits_tc(int rblocks, int tiles) {
   const int sms = num_sms();
   int best = 1;
@@ -412,58 +485,76 @@ static int tn_splits_tc(int rblocks, int tiles) {
 }
 
 struct TnPlan {
-  int Np, Kp, rblocks, tiles, splits, rps;
+  int Np, Kp, rs, rblocks, tiles, splits, rps;
   size_t off_y, off_x, off_part, total;
 };
-static TnPlan tn_plan(int nB, int T, int N, int K, int ntaps) {
+static TnPlan tn_plan(int nB, int T, int N, int K, int ntaps, int eb, bool stage_y, bool stage_x) {
   TnPlan pl;
   pl.Np = round_up(N, TC_BM);
   pl.Kp = round_up(K, TC_BN);
-  pl.rblocks = nB * ceil_div(T, 64);
+  pl.rs = eb == 2 ? 64 : 32;
+  pl.rblocks = nB * ceil_div(T, pl.rs);
   pl.tiles = ntaps * (pl.Np / TC_BM) * (pl.Kp / TC_BN);
   pl.splits = tn_splits_tc(pl.rblocks, pl.tiles);
   pl.rps = ceil_div(pl.rblocks, pl.splits);
   const size_t M = (size_t)nB * T;
   pl.off_y = 0;
-  pl.off_x = align256(M * pl.Np * 2);
-  pl.off_part = pl.off_x + align256(M * pl.Kp * 2);
+  pl.off_x = stage_y ? align256(M * pl.Np * eb) : 0;
+  pl.off_part = pl.off_x + (stage_x ? align256(M * pl.Kp * eb) : 0);
   pl.total = pl.off_part + align256((size_t)pl.splits * ntaps * N * K * 4);
   return pl;
 }
-size_t gemm_tn_workspace_tc(int nB, int T, int N, int K, int ntaps) { return tn_plan(nB, T, N, K, ntaps).total; }
+size_t gemm_tn_workspace_tc(int nB, int T, int N, int K, int ntaps, int eb) {
+  return tn_plan(nB, T, N, K, ntaps, eb, true, true).total;
+}
 
 int launch_wgrad_reduce(const float* part, float* dW, int N, int K, int ntaps, int splits, int out_mode, int accumulate,
                         cudaStream_t st);
 
 int gemm_tn_taps_tc(const float* dY, int ldy, const float* X, int ldx, float* dW, int nB, int T, int N, int K, int ntaps,
-                    int shift0, int out_mode, int accumulate, void* ws, size_t ws_bytes, cudaStream_t st) {
-  const TnPlan pl = tn_plan(nB, T, N, K, ntaps);
+                    int shift0, int out_mode, int accumulate, int eb, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const bool stage_y = eb == 2 || !direct_ok(dY, ldy);
+  const bool stage_x = eb == 2 || !direct_ok(X, ldx);
+  const TnPlan pl = tn_plan(nB, T, N, K, ntaps, eb, stage_y, stage_x);
   if (!ws || ws_bytes < pl.total) {
-    set_error("avc_gemm_tn_taps(bf16): workspace %zu < %zu", ws_bytes, pl.total);
+    set_error("avc_gemm_tn_taps(tensor): workspace %zu < %zu", ws_bytes, pl.total);
     return AVC_ERR_WORKSPACE;
   }
   int rc = ensure_smem_attr();
   if (rc) return rc;
   const size_t M = (size_t)nB * T;
-  __nv_bfloat16* Yb = (__nv_bfloat16*)((uint8_t*)ws + pl.off_y);
-  __nv_bfloat16* Xb = (__nv_bfloat16*)((uint8_t*)ws + pl.off_x);
+  const int row = 128 / eb;
   float* part = (float*)((uint8_t*)ws + pl.off_part);
-  cvt_pad_bf16_kernel<<<cvt_blocks(M * (pl.Np / 2)), 256, 0, st>>>(dY, ldy, Yb, pl.Np, M, M, N);
-  AVC_LAUNCHED();
-  cvt_pad_bf16_kernel<<<cvt_blocks(M * (pl.Kp / 2)), 256, 0, st>>>(X, ldx, Xb, pl.Kp, M, M, K);
-  AVC_LAUNCHED();
+  const void* Yop = dY;
+  const void* Xop = X;
+  uint64_t y_ld = ldy, y_c = N, x_ld = ldx, x_c = K;
+  if (stage_y) {
+    void* dst = (uint8_t*)ws + pl.off_y;
+    if (eb == 2) cvt_pad_bf16_kernel<<<cvt_blocks(M * (pl.Np / 2)), 256, 0, st>>>(dY, ldy, (__nv_bfloat16*)dst, pl.Np, M, M, N);
+    else cvt_pad_f32_kernel<<<cvt_blocks(M * pl.Np), 256, 0, st>>>(dY, ldy, (float*)dst, pl.Np, M, N);
+    AVC_LAUNCHED();
+    Yop = dst; y_ld = pl.Np; y_c = pl.Np;
+  }
+  if (stage_x) {
+    void* dst = (uint8_t*)ws + pl.off_x;
+    if (eb == 2) cvt_pad_bf16_kernel<<<cvt_blocks(M * (pl.Kp / 2)), 256, 0, st>>>(X, ldx, (__nv_bfloat16*)dst, pl.Kp, M, M, K);
+    else cvt_pad_f32_kernel<<<cvt_blocks(M * pl.Kp), 256, 0, st>>>(X, ldx, (float*)dst, pl.Kp, M, K);
+    AVC_LAUNCHED();
+    Xop = dst; x_ld = pl.Kp; x_c = pl.Kp;
+  }
   CUtensorMap mA, mB;
-  rc = make_map3(&mA, Yb, pl.Np, T, nB, pl.Np, (uint64_t)T * pl.Np, 64, 64);
+  rc = make_map3(&mA, Yop, y_c, T, nB, y_ld, (uint64_t)T * y_ld, row, pl.rs, eb);
   if (rc) return rc;
-  rc = make_map3(&mB, Xb, pl.Kp, T, nB, pl.Kp, (uint64_t)T * pl.Kp, 64, 64);
+  rc = make_map3(&mB, Xop, x_c, T, nB, x_ld, (uint64_t)T * x_ld, row, pl.rs, eb);
   if (rc) return rc;
   TcParams p{};
   p.nB = nB; p.T = T; p.ntaps = ntaps; p.shift0 = shift0; p.N = N; p.K = K;
   p.n_tiles = pl.Np / TC_BM; p.k_tiles = pl.Kp / TC_BN; p.splits = pl.splits; p.rblocks = pl.rblocks;
-  p.rblocks_per_split = pl.rps; p.tb64 = ceil_div(T, 64); p.part = part;
+  p.rblocks_per_split = pl.rps; p.tbr = ceil_div(T, pl.rs); p.part = part;
   const int items = pl.tiles * pl.splits;
   const int grid = std::min(items, num_sms());
-  tc_gemm_kernel<MODE_TN><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mA, mB, p);
+  if (eb == 2) tc_gemm_kernel<MODE_TN, 2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mA, mB, p);
+  else tc_gemm_kernel<MODE_TN, 4><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mA, mB, p);
   AVC_LAUNCHED();
   return launch_wgrad_reduce(part, dW, N, K, ntaps, pl.splits, out_mode, accumulate, st);
 }

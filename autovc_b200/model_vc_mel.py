@@ -27,7 +27,7 @@ import torch.nn as nn
 from . import ops
 from ._lib import ACT_CODES, PREC_BF16, PREC_FP32
 
-_PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+_PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": 2}
 
 
 def _default_precision() -> str:

@@ -18,8 +18,9 @@
  *   - activations are channels-last: (B, T, C) row-major, row m = b*T + t, channel stride 1,
  *     row stride `ld*` in elements (so column slices of wider buffers can be addressed).
  *   - `prec`: AVC_PREC_FP32 = CUDA-core FFMA, fp32 operands and accumulation (parity mode,
- *     <=1e-4 of the reference's fp32 path); AVC_PREC_BF16 = tcgen05/TMEM tensor-core path,
- *     bf16 operands, fp32 accumulation and fp32 statistics/state.
+ *     <=1e-4 of the reference's fp32 path); AVC_PREC_BF16 / AVC_PREC_TF32 = tcgen05/TMEM tensor-core
+ *     path with bf16 operands, or fp32 operands fetched by TMA as tf32 (no staging copies); fp32
+ *     accumulation, fp32 statistics and fp32 recurrent state in both.
  */
 #ifndef AUTOVC_B200_H_
 #define AUTOVC_B200_H_
@@ -36,7 +37,7 @@ extern "C" {
 
 #define AVC_VERSION 100
 
-enum { AVC_PREC_FP32 = 0, AVC_PREC_BF16 = 1 };
+enum { AVC_PREC_FP32 = 0, AVC_PREC_BF16 = 1, AVC_PREC_TF32 = 2 };
 enum { AVC_ACT_NONE = 0, AVC_ACT_RELU = 1, AVC_ACT_TANH = 2 };
 enum {
   AVC_OK = 0,

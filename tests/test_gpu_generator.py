@@ -136,17 +136,18 @@ def _rel_l2(a, b):
 
 
 @pytest.mark.parametrize("name", ["train_16_16_b16_t128", "train_16_16_b2_t128"])
-def test_bf16_mode_within_rel_l2_gate(name):
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_tensor_core_modes_within_rel_l2_gate(name, precision):
     """bf16 mode (tcgen05 bf16 operands, fp32 accumulate/statistics/state): <= 1e-2 relative L2 on the
     outputs versus the reference's fp32 path (BASELINE.json north_star); gradients are checked loosely."""
     g, G, (dim_neck, freq, B, T, n_bins, iseed) = _build(name)
-    G.set_precision("bf16")
+    G.set_precision(precision)
     x, e, _ = synth_inputs(B, T, n_bins, 256, iseed)
     opt = torch.optim.Adam(G.parameters(), 1e-4)
     out = solver.train_step(G.train(), opt, x.cuda(), e.cuda(), return_outputs=True)
     errs = {k: _rel_l2(out[k].cpu().numpy(), g["s0_" + k]) for k in ("x_identic", "x_identic_psnt", "code_real", "code_reconst")}
     lerr = {k: abs(out[k] - r) / abs(r) for k, r in zip(("g_loss", "L_id", "L_id_psnt", "L_cd"), g["s0_losses"])}
-    print("bf16 rel-L2:", errs, "loss rel err:", lerr)
+    print(precision, name, "rel-L2:", errs, "loss rel err:", lerr)
     tol = 1e-2 if B >= 16 else 3e-2       # B=2: 256 samples per BatchNorm channel, the noisiest case in the suite
     assert max(errs.values()) < tol, errs
     assert max(lerr.values()) < tol, lerr

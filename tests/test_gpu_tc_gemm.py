@@ -7,7 +7,7 @@ pytestmark = pytest.mark.gpu
 
 if torch.cuda.is_available():
     from autovc_b200 import ops
-    from autovc_b200._lib import PREC_BF16, PREC_FP32
+    from autovc_b200._lib import PREC_BF16, PREC_FP32, PREC_TF32
 
 DEV = "cuda"
 
@@ -17,20 +17,25 @@ def _rand(*shape, seed=0):
     return torch.randn(*shape, generator=g).to(DEV)
 
 
-def _bf(x):
-    return x.to(torch.bfloat16).double()
+def _bf(x, prec=1):
+    """Operand rounding of the tensor-core path: bf16 (RN), or tf32 (RN to 10 mantissa bits, done by the TMA unit)."""
+    if prec == 1:
+        return x.to(torch.bfloat16).double()
+    i = x.contiguous().view(torch.int32)
+    i = (i + 0x1000) & ~0x1FFF
+    return i.view(torch.float32).double()
 
 
-def _ref_nt(A, W, bias, nB, T, ntaps, shift0):
+def _ref_nt(A, W, bias, nB, T, ntaps, shift0, prec=1):
     """A (nB*T, K), W (ntaps, N, K) -> (nB*T, N) in fp64 from bf16-rounded operands."""
     K = A.shape[1]
-    A3 = _bf(A).view(nB, T, K)
+    A3 = _bf(A, prec).view(nB, T, K)
     out = torch.zeros(nB, T, W.shape[1], dtype=torch.double, device=DEV)
     for tap in range(ntaps):
         s = shift0 + tap
         lo, hi = max(0, -s), min(T, T - s)
         if hi > lo:
-            out[:, lo:hi] += A3[:, lo + s:hi + s] @ _bf(W[tap]).t()
+            out[:, lo:hi] += A3[:, lo + s:hi + s] @ _bf(W[tap], prec).t()
     if bias is not None:
         out += bias.double()
     return out.view(nB * T, -1)
@@ -38,36 +43,38 @@ def _ref_nt(A, W, bias, nB, T, ntaps, shift0):
 
 @pytest.mark.parametrize("nB,T,N,K,ntaps", [(2, 128, 512, 336, 5), (3, 128, 128, 64, 1), (2, 48, 130, 769, 5),
                                             (4, 256, 80, 1024, 1), (1, 20, 64, 512, 1), (5, 64, 2048, 288, 1)])
-def test_nt_taps_bf16(nB, T, N, K, ntaps):
+@pytest.mark.parametrize("prec", [1, 2])
+def test_nt_taps_tensor(nB, T, N, K, ntaps, prec):
     A = _rand(nB * T, K, seed=1)
     W = _rand(ntaps, N, K, seed=2) * 0.05
     bias = _rand(N, seed=3)
     C = torch.empty(nB * T, N, device=DEV)
     stats = torch.zeros(2 * N, dtype=torch.double, device=DEV)
     shift0 = -(ntaps // 2)
-    ops.gemm_nt_taps(A, K, W, bias, C, N, nB, T, N, K, ntaps, shift0, stats=stats, prec=PREC_BF16)
-    ref = _ref_nt(A, W, bias, nB, T, ntaps, shift0)
+    ops.gemm_nt_taps(A, K, W, bias, C, N, nB, T, N, K, ntaps, shift0, stats=stats, prec=prec)
+    ref = _ref_nt(A, W, bias, nB, T, ntaps, shift0, prec)
     scale = float(ref.abs().max())
     assert float((C.double() - ref).abs().max()) < 2e-5 * scale * max(1.0, (K * ntaps / 256) ** 0.5)
     torch.testing.assert_close(stats[:N], ref.sum(0), rtol=1e-4, atol=1e-3 * scale)
     torch.testing.assert_close(stats[N:], (ref * ref).sum(0), rtol=1e-4, atol=1e-3 * scale * scale)
     # accumulate mode, no bias
     C2 = C.clone()
-    ops.gemm_nt_taps(A, K, W, None, C2, N, nB, T, N, K, ntaps, shift0, accumulate=True, prec=PREC_BF16)
-    ref2 = C.double() + _ref_nt(A, W, None, nB, T, ntaps, shift0)
+    ops.gemm_nt_taps(A, K, W, None, C2, N, nB, T, N, K, ntaps, shift0, accumulate=True, prec=prec)
+    ref2 = C.double() + _ref_nt(A, W, None, nB, T, ntaps, shift0, prec)
     assert float((C2.double() - ref2).abs().max()) < 4e-5 * scale * max(1.0, (K * ntaps / 256) ** 0.5)
 
 
 @pytest.mark.parametrize("nB,T,N,K,ntaps,shift0,mode", [(2, 128, 512, 336, 5, -2, 1), (3, 64, 64, 512, 1, 0, 2),
                                                         (2, 48, 130, 769, 5, -2, 1), (4, 128, 4096, 1024, 1, -1, 2),
                                                         (4, 128, 2048, 512, 1, 1, 2), (3, 100, 80, 1024, 1, 0, 0)])
-def test_tn_taps_bf16(nB, T, N, K, ntaps, shift0, mode):
+@pytest.mark.parametrize("prec", [1, 2])
+def test_tn_taps_tensor(nB, T, N, K, ntaps, shift0, mode, prec):
     dY = _rand(nB * T, N, seed=4)
     X = _rand(nB * T, K, seed=5)
     shape = {0: (ntaps, N, K), 1: (N, K, ntaps), 2: (N, K)}[mode]
     dW = torch.empty(*shape, device=DEV)
-    ops.gemm_tn_taps(dY, N, X, K, dW, nB, T, N, K, ntaps, shift0, out_mode=mode, prec=PREC_BF16)
-    Y3, X3 = _bf(dY).view(nB, T, N), _bf(X).view(nB, T, K)
+    ops.gemm_tn_taps(dY, N, X, K, dW, nB, T, N, K, ntaps, shift0, out_mode=mode, prec=prec)
+    Y3, X3 = _bf(dY, prec).view(nB, T, N), _bf(X, prec).view(nB, T, K)
     ref = torch.zeros(ntaps, N, K, dtype=torch.double, device=DEV)
     for tap in range(ntaps):
         s = shift0 + tap
