@@ -87,13 +87,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 // shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address        bits [0,14)
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset  bits [16,30)
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;  // stride byte offset   bits [32,46)
   d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;                  // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B (MN-major 32-bit operands)
   return d;
 }
 
@@ -125,7 +125,7 @@ static inline PFN_encodeTiled get_encode() {
 
 // 3-D bf16 tensor map over a row-major (d2, d1, d0) array: d0 contiguous, 128B swizzle, zero OOB fill
 static inline int make_map3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
-                     uint64_t stride2_elems, uint32_t box0, uint32_t box1, int elem_bytes = 2) {
+                     uint64_t stride2_elems, uint32_t box0, uint32_t box1, int elem_bytes = 2, bool atom32 = false) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -137,7 +137,8 @@ static inline int make_map3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64
   cuuint32_t es[3] = {1, 1, 1};
   // fp32 operands are fetched as TFLOAT32: the TMA unit rounds them to tf32 on the way into shared memory
   CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (dims %llu,%llu,%llu box %u,%u)", (int)r,

@@ -190,8 +190,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             } else {
               // MN-major: each frame is a 128-byte row of ROW channels; 8-frame groups 1024 B apart (SBO), the
               // next ROW-channel box of the tile BOX_BYTES further (LBO); one MMA's K slice = KMMA frames
-              da = make_desc(sa + k * Gm::KMMA * 128, Gm::BOX_BYTES, 1024);
-              db = make_desc(sb + k * Gm::KMMA * 128, Gm::BOX_BYTES, 1024);
+              // (32-bit operands: the only MN-major layout is SWIZZLE_128B_BASE32B -- 32-byte swizzle atoms, 4-frame
+              //  groups 512 B apart -- which the TMA map produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+              da = make_desc(sa + k * Gm::KMMA * 128, Gm::BOX_BYTES, EB == 2 ? 1024 : 512, EB == 2 ? 2 : 1);
+              db = make_desc(sb + k * Gm::KMMA * 128, Gm::BOX_BYTES, EB == 2 ? 1024 : 512, EB == 2 ? 2 : 1);
             }
             umma<EB>(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
@@ -543,9 +545,9 @@ int gemm_tn_taps_tc(const float* dY, int ldy, const float* X, int ldx, float* dW
     Xop = dst; x_ld = pl.Kp; x_c = pl.Kp;
   }
   CUtensorMap mA, mB;
-  rc = make_map3(&mA, Yop, y_c, T, nB, y_ld, (uint64_t)T * y_ld, row, pl.rs, eb);
+  rc = make_map3(&mA, Yop, y_c, T, nB, y_ld, (uint64_t)T * y_ld, row, pl.rs, eb, eb == 4);
   if (rc) return rc;
-  rc = make_map3(&mB, Xop, x_c, T, nB, x_ld, (uint64_t)T * x_ld, row, pl.rs, eb);
+  rc = make_map3(&mB, Xop, x_c, T, nB, x_ld, (uint64_t)T * x_ld, row, pl.rs, eb, eb == 4);
   if (rc) return rc;
   TcParams p{};
   p.nB = nB; p.T = T; p.ntaps = ntaps; p.shift0 = shift0; p.N = N; p.K = K;
