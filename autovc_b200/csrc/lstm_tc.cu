@@ -129,7 +129,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       uint32_t phase = 0;
       for (int s = 1; s < T; ++s) {
         const unsigned target = (unsigned)s * (unsigned)p.NT;     // every column tile has published step s-1
-        while (ld_acquire(counter) < target) __nanosleep(32);
+        while (ld_acquire(counter) < target) {
+        }
         fence_proxy_async();
         const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
         for (int kb = 0; kb < kblocks; ++kb) {
@@ -216,11 +217,19 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           hb[i] = __float2bfloat16_rn(hf[i]);
           pre[4 * i + 0] = gi; pre[4 * i + 1] = gf; pre[4 * i + 2] = gg; pre[4 * i + 3] = go;
         }
+        // publish h_t first: bf16 slice -> proxy fence -> gpu-scope fence -> CTA barrier -> one release add.
+        // The (much larger) fp32 tensors saved for BPTT are stored after the release, off the critical path.
         if (live) {
           __nv_bfloat16* xb = p.xbuf + ((size_t)(s & 1) * p.nBpad + b) * p.K + u0;
 #pragma unroll
           for (int i = 0; i < U; i += 4)
             *reinterpret_cast<uint2*>(xb + i) = *reinterpret_cast<const uint2*>(&hb[i]);
+        }
+        fence_proxy_async();
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) red_release_add(counter, 1u);
+        if (live) {
 #pragma unroll
           for (int j = 0; j < BN; j += 4)
             *reinterpret_cast<float4*>(p.gates + rowi * G + n0 + j) = *reinterpret_cast<const float4*>(&pre[j]);
@@ -230,11 +239,6 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             *reinterpret_cast<float4*>(p.h_seq + rowi * p.ldh + u0 + i) = *reinterpret_cast<const float4*>(&hf[i]);
           }
         }
-        // publish: every thread's stores -> proxy fence -> gpu-scope fence -> CTA barrier -> one release add
-        fence_proxy_async();
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) red_release_add(counter, 1u);
         if (lane == 0) mbar_arrive(tempty);
       }
     } else {
@@ -298,14 +302,16 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 4 * U; j += 8)
             *reinterpret_cast<uint4*>(xb + j) = *reinterpret_cast<const uint4*>(&gb[j]);
-#pragma unroll
-          for (int j = 0; j < 4 * U; j += 4)
-            *reinterpret_cast<float4*>(p.dP + rowi * G + 4 * u0 + j) = *reinterpret_cast<const float4*>(&g4[j]);
         }
         fence_proxy_async();
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 64) red_release_add(counter, 1u);
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 4 * U; j += 4)
+            *reinterpret_cast<float4*>(p.dP + rowi * G + 4 * u0 + j) = *reinterpret_cast<const float4*>(&g4[j]);
+        }
         if (lane == 0) mbar_arrive(tempty);
       }
     }

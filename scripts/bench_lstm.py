@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Per-timestep latency of the persistent LSTM recurrence kernels (north_star: 'per-timestep latency
+for the recurrence').  Times avc_lstm_seq_fwd / avc_lstm_seq_bwd alone with CUDA events."""
+import ctypes
+import json
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from autovc_b200 import _lib
+from autovc_b200.ops import _p, _stream, _ws
+
+dev = "cuda"
+res = []
+for (B, T, H) in [(256, 128, 1024), (256, 128, 512), (128, 256, 1024)]:
+    G = 4 * H
+    prec = _lib.PREC_BF16
+    P = torch.randn(B, T, G, device=dev) * 0.5
+    W = torch.randn(G, H, device=dev) * (1.0 / H ** 0.5)
+    WT = W.t().contiguous()
+    h = torch.empty(B, T, H, device=dev); gates = torch.empty(B, T, G, device=dev); c = torch.empty(B, T, H, device=dev)
+    dH = torch.randn(B, T, H, device=dev) * 0.1
+    dP = torch.empty(B, T, G, device=dev)
+    nf = _lib.query("avc_lstm_fwd_workspace_bytes", B, T, H, prec); wf = _ws(nf, dev)
+    nb = _lib.query("avc_lstm_bwd_workspace_bytes", B, T, H, prec); wb = _ws(nb, dev)
+    def fwd():
+        _lib.call("avc_lstm_seq_fwd", _p(P), _p(W), _p(h), H, _p(gates), _p(c), B, T, H, 0, prec, _p(wf), nf, _stream())
+    def bwd():
+        _lib.call("avc_lstm_seq_bwd", _p(dH), H, _p(W), _p(WT), _p(gates), _p(c), _p(dP), B, T, H, 0, prec, _p(wb), nb, _stream())
+    for name, fn in (("fwd", fwd), ("bwd", bwd)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        flops = 2.0 * B * T * G * H
+        res.append({"kernel": f"lstm_seq_{name}", "B": B, "T": T, "H": H, "ms": ms, "us_per_step": ms * 1e3 / T,
+                    "tflops": flops / (ms * 1e-3) / 1e12})
+        print(json.dumps(res[-1]), flush=True)
