@@ -50,6 +50,19 @@ struct TcParams {
   float* part;
 };
 
+// TN work-item order: (k_tile, n_tile, tap) vary fastest and the row split slowest, so the CTAs that run
+// concurrently (consecutive item indices) sweep the SAME row range of dY / X with different output tiles and
+// re-use it from L2 instead of re-reading HBM (r01 ncu: 790 MB DRAM reads for 134 MB of operands before this).
+struct TnItem { int tap, n_tile, k_tile, split; };
+__device__ __forceinline__ TnItem tn_decode(int tile, int k_tiles, int n_tiles, int ntaps) {
+  TnItem it;
+  it.k_tile = tile % k_tiles; tile /= k_tiles;
+  it.n_tile = tile % n_tiles; tile /= n_tiles;
+  it.tap = tile % ntaps; tile /= ntaps;
+  it.split = tile;
+  return it;
+}
+
 // butterfly transpose-reduce: on return lane l holds sum over the warp's 32 lanes of v[l]
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 #pragma unroll
@@ -135,11 +148,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
         } else {
-          int r = tile;
-          const int split = r % p.splits; r /= p.splits;
-          const int k_tile = r % p.k_tiles; r /= p.k_tiles;
-          const int n_tile = r % p.n_tiles; r /= p.n_tiles;
-          const int tap = r;
+          const TnItem wi = tn_decode(tile, p.k_tiles, p.n_tiles, p.ntaps);
+          const int split = wi.split, k_tile = wi.k_tile, n_tile = wi.n_tile, tap = wi.tap;
           const int rb0 = split * p.rblocks_per_split;
           const int rb1 = min(p.rblocks, rb0 + p.rblocks_per_split);
           for (int rb = rb0; rb < rb1; ++rb) {
@@ -169,7 +179,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int iters = kiters;
         if (MODE == MODE_TN) {
-          const int split = tile % p.splits;
+          const int split = tn_decode(tile, p.k_tiles, p.n_tiles, p.ntaps).split;
           const int rb0 = split * p.rblocks_per_split;
           iters = max(0, min(p.rblocks, rb0 + p.rblocks_per_split) - rb0);
         }
@@ -213,7 +223,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       bool has_work = true;
       if (MODE == MODE_TN) {
-        const int split = tile % p.splits;
+        const int split = tn_decode(tile, p.k_tiles, p.n_tiles, p.ntaps).split;
         has_work = split * p.rblocks_per_split < p.rblocks;
       }
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -285,11 +295,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       } else {
-        int r = tile;
-        const int split = r % p.splits; r /= p.splits;
-        const int k_tile = r % p.k_tiles; r /= p.k_tiles;
-        const int n_tile = r % p.n_tiles; r /= p.n_tiles;
-        const int tap = r;
+        const TnItem wi = tn_decode(tile, p.k_tiles, p.n_tiles, p.ntaps);
+        const int split = wi.split, k_tile = wi.k_tile, n_tile = wi.n_tile, tap = wi.tap;
         const int n = n_tile * TC_BM + row;
         float* orow = p.part + (((size_t)split * p.ntaps + tap) * p.N + n) * p.K;
 #pragma unroll 1
