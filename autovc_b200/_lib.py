@@ -42,6 +42,7 @@ SIGNATURES = {
     "avc_lstm_fwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "avc_lstm_seq_bwd": (c_int, [P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
     "avc_lstm_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "avc_debug_set_trace": (None, [P]),
     "avc_concat_bcast": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, P]),
     "avc_codes_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "avc_codes_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),

@@ -42,6 +42,7 @@ size_t gemm_nt_workspace_tc(int, int, int, int, int, int);
 size_t gemm_tn_workspace_tc(int, int, int, int, int, int);
 // persistent tensor-core recurrences (lstm_tc.cu)
 bool lstm_tc_supported(int H);
+void lstm_tc_set_trace(unsigned long long* p);
 size_t lstm_tc_workspace(int nB, int T, int H, bool bwd);
 int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh, float* gates, float* c_seq, const float* dH,
                 int lddh, float* dP, int nB, int T, int H, int reverse, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -137,3 +138,5 @@ extern "C" size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H, int prec) {
   if ((prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32) && lstm_tc_supported(H)) return lstm_tc_workspace(nB, T, H, true);
   return lstm_bwd_workspace_simt(nB, T, H);
 }
+
+extern "C" void avc_debug_set_trace(unsigned long long* device_buffer) { lstm_tc_set_trace(device_buffer); }

@@ -35,6 +35,7 @@ struct LstmTcParams {
   float* dP;            // bwd: out (nB,T,4H)
   __nv_bfloat16* xbuf;  // exchange buffer [2][nBpad][K]
   unsigned int* counters;  // [MT], zero-initialised
+  unsigned long long* trace;  // optional per-step timestamps of CTA 0 (avc_debug_set_trace), else nullptr
 };
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -75,6 +76,17 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// trace slot layout per step: 0 barrier passed, 1 first TMA issued, 2 last TMA issued, 3 first k-block landed,
+// 4 last k-block landed, 5 all MMAs issued, 6 epilogue woke (tfull), 7 math done, 8 published
+#define LT_TRACE(slot)                                                         \
+  do {                                                                         \
+    if (p.trace != nullptr && blockIdx.x == 0) p.trace[(size_t)s * 16 + (slot)] = gtime(); \
+  } while (0)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // BWD = false: BN = gate columns per CTA (64 or 32).  BWD = true: BN = hidden units per CTA (16).
@@ -131,14 +143,17 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         const unsigned target = (unsigned)s * (unsigned)p.NT;     // every column tile has published step s-1
         while (ld_acquire(counter) < target) {
         }
+        LT_TRACE(0);
         fence_proxy_async();
         const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_expect_tx(full_bar(stage), LT_STAGE);
           tma_load_3d(ring + stage * LT_STAGE, &mapX, full_bar(stage), kb * 64, row0, 0);
+          if (kb == 0) LT_TRACE(1);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+        LT_TRACE(2);
       }
     }
   } else if (warp == 1) {
@@ -157,6 +172,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         }
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          if (kb == 0) LT_TRACE(3);
+          if (kb == kblocks - 1) LT_TRACE(4);
           tc_fence_after();
           const uint32_t sa = ring + stage * LT_STAGE, sb = w_base + kb * w_block;
 #pragma unroll
@@ -167,6 +184,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull);
+        LT_TRACE(5);
       }
     }
   } else {
@@ -195,6 +213,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           for (int j = 0; j < BN; ++j) pre[j] = 0.f;
         }
         mbar_wait(tfull, s & 1);
+        if (threadIdx.x == 64) LT_TRACE(6);
         tc_fence_after();
         if (s > 0) {
           float d[BN];
@@ -225,10 +244,14 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           for (int i = 0; i < U; i += 4)
             *reinterpret_cast<uint2*>(xb + i) = *reinterpret_cast<const uint2*>(&hb[i]);
         }
+        if (threadIdx.x == 64) LT_TRACE(7);
         fence_proxy_async();
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) red_release_add(counter, 1u);
+        if (threadIdx.x == 64) {
+          red_release_add(counter, 1u);
+          LT_TRACE(8);
+        }
         if (live) {
 #pragma unroll
           for (int j = 0; j < BN; j += 4)
@@ -274,6 +297,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           for (int j = 0; j < 4 * U; ++j) g4[j] = 0.f;
         }
         mbar_wait(tfull, s & 1);
+        if (threadIdx.x == 64) LT_TRACE(6);
         tc_fence_after();
         if (s > 0) {
           float d[U];
@@ -303,10 +327,14 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           for (int j = 0; j < 4 * U; j += 8)
             *reinterpret_cast<uint4*>(xb + j) = *reinterpret_cast<const uint4*>(&gb[j]);
         }
+        if (threadIdx.x == 64) LT_TRACE(7);
         fence_proxy_async();
         __threadfence();
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) red_release_add(counter, 1u);
+        if (threadIdx.x == 64) {
+          red_release_add(counter, 1u);
+          LT_TRACE(8);
+        }
         if (live) {
 #pragma unroll
           for (int j = 0; j < 4 * U; j += 4)
@@ -334,6 +362,9 @@ __global__ void cvt_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+static unsigned long long* g_trace = nullptr;
+void lstm_tc_set_trace(unsigned long long* p) { g_trace = p; }
+
 bool lstm_tc_supported(int H) { return H >= 128 && H <= 1024 && H % 64 == 0; }
 
 static int fwd_bn(int H) { return H >= 1024 ? 64 : 32; }
@@ -421,6 +452,7 @@ int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh,
     p.dP = dP ? dP + (size_t)b0 * T * G : nullptr;
     p.xbuf = xbuf;
     p.counters = counters + ch * 64;
+    p.trace = (ch == 0) ? g_trace : nullptr;
     rc = make_map3(&mX, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, 128);
     if (rc) return rc;
     if (bwd) rc = lt_launch<true, 16>(mW, mX, p, pl, st);

@@ -153,6 +153,10 @@ int avc_lstm_seq_bwd(const float* dH, int lddh, const float* Whh_p, const float*
                      void* workspace, size_t workspace_bytes, void* stream);
 size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H, int prec);
 
+/* Profiling hook: when set to a device buffer of >= 16*T uint64, CTA 0 of the next persistent recurrence
+ * launches records %globaltimer stamps per step (slot layout in lstm_tc.cu).  NULL disables it. */
+void avc_debug_set_trace(unsigned long long* device_buffer);
+
 /* ---------------------------------------------------------------------------------------
  * Glue that the reference does with squeeze/transpose/expand/cat/slicing.
  */

@@ -40,3 +40,35 @@ for (B, T, H) in [(256, 128, 1024), (256, 128, 512), (128, 256, 1024)]:
         res.append({"kernel": f"lstm_seq_{name}", "B": B, "T": T, "H": H, "ms": ms, "us_per_step": ms * 1e3 / T,
                     "tflops": flops / (ms * 1e-3) / 1e12})
         print(json.dumps(res[-1]), flush=True)
+
+# ---- per-step event trace of CTA 0 (one forward and one backward launch, H=1024) ----
+B, T, H = 256, 128, 1024
+G = 4 * H
+prec = _lib.PREC_BF16
+P = torch.randn(B, T, G, device=dev) * 0.5
+W = torch.randn(G, H, device=dev) * (1.0 / H ** 0.5)
+WT = W.t().contiguous()
+h = torch.empty(B, T, H, device=dev); gates = torch.empty(B, T, G, device=dev); c = torch.empty(B, T, H, device=dev)
+dH = torch.randn(B, T, H, device=dev) * 0.1
+dP = torch.empty(B, T, G, device=dev)
+nf = _lib.query("avc_lstm_fwd_workspace_bytes", B, T, H, prec); wf = _ws(nf, dev)
+nb = _lib.query("avc_lstm_bwd_workspace_bytes", B, T, H, prec); wb = _ws(nb, dev)
+names = ["barrier", "tma0", "tmaN", "land0", "landN", "mma_issued", "epi_wake", "math_done", "published"]
+for which in ("fwd", "bwd"):
+    trace = torch.zeros(16 * T, dtype=torch.int64, device=dev)
+    _lib.load().avc_debug_set_trace(ctypes.c_void_p(trace.data_ptr()))
+    if which == "fwd":
+        _lib.call("avc_lstm_seq_fwd", _p(P), _p(W), _p(h), H, _p(gates), _p(c), B, T, H, 0, prec, _p(wf), nf, _stream())
+    else:
+        _lib.call("avc_lstm_seq_bwd", _p(dH), H, _p(W), _p(WT), _p(gates), _p(c), _p(dP), B, T, H, 0, prec, _p(wb), nb, _stream())
+    torch.cuda.synchronize()
+    _lib.load().avc_debug_set_trace(ctypes.c_void_p(0))
+    tr = trace.cpu().view(T, 16)[:, :9].double()
+    # steps 20..100: offsets of each event relative to the previous step's 'published'
+    rows = []
+    for s in range(20, 100):
+        base = tr[s - 1, 8]
+        rows.append(((tr[s] - base) / 1e3).tolist())
+    import numpy as np
+    med = np.median(np.array(rows), axis=0)
+    print(which, "median us after previous publish:", {n: round(float(v), 2) for n, v in zip(names, med)}, flush=True)
