@@ -164,6 +164,6 @@ def test_tensor_core_modes_within_rel_l2_gate(name, precision):
         if ".conv.bias" in n:
             continue
         d = digest(out["grads"][n])
-        if abs(d[2] - ref[i][2]) > 0.08 * ref[i][2] + 1e-9:
+        if abs(d[2] - ref[i][2]) > (0.08 if precision == "tf32" else 0.25) * ref[i][2] + 1e-9:
             bad.append((n, d[2], ref[i][2]))
     assert not bad, bad

@@ -54,7 +54,7 @@ def test_nt_taps_tensor(nB, T, N, K, ntaps, prec):
     ops.gemm_nt_taps(A, K, W, bias, C, N, nB, T, N, K, ntaps, shift0, stats=stats, prec=prec)
     ref = _ref_nt(A, W, bias, nB, T, ntaps, shift0, prec)
     scale = float(ref.abs().max())
-    tol = (2e-5 if prec == 1 else 6e-5) * scale * max(1.0, (K * ntaps / 256) ** 0.5)   # tf32: emulated RN vs the TMA unit's rounding
+    tol = (2e-5 if prec == 1 else 2e-4) * scale * max(1.0, (K * ntaps / 256) ** 0.5)   # tf32: emulated RN vs the TMA unit's rounding
     assert float((C.double() - ref).abs().max()) < tol
     torch.testing.assert_close(stats[:N], ref.sum(0), rtol=1e-4, atol=1e-3 * scale)
     torch.testing.assert_close(stats[N:], (ref * ref).sum(0), rtol=1e-4, atol=1e-3 * scale * scale)
@@ -88,7 +88,7 @@ def test_tn_taps_tensor(nB, T, N, K, ntaps, shift0, mode, prec):
         H = N // 4
         ref = ref[0].view(H, 4, K).permute(1, 0, 2).reshape(N, K)     # packed row u*4+g -> g*H+u
     scale = float(ref.abs().max())
-    assert float((dW.double() - ref).abs().max()) < (3e-5 if prec == 1 else 9e-5) * scale * max(1.0, (nB * T / 256) ** 0.5)
+    assert float((dW.double() - ref).abs().max()) < (3e-5 if prec == 1 else 3e-4) * scale * max(1.0, (nB * T / 256) ** 0.5)
     # the fp32 path computes the same contraction from unrounded operands
     dW32 = torch.empty_like(dW)
     ops.gemm_tn_taps(dY, N, X, K, dW32, nB, T, N, K, ntaps, shift0, out_mode=mode, prec=PREC_FP32)
