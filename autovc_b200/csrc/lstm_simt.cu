@@ -24,6 +24,15 @@ __global__ void lstm_small_fwd_kernel(const float* __restrict__ P, const float* 
                                       float* __restrict__ c_seq, int nB, int T, int H, int reverse) {
   extern __shared__ float sm[];
   const int G = 4 * H;
+  if (reverse == 2) {   // both directions of a BiLSTM in one launch: blockIdx.y = direction, operands stacked [2]
+    const int d = blockIdx.y;
+    P += (size_t)d * nB * T * G;
+    Whh_p += (size_t)d * G * H;
+    gates += (size_t)d * nB * T * G;
+    c_seq += (size_t)d * nB * T * H;
+    h_seq += d * H;
+    reverse = d;
+  }
   float* Ws = sm;                       // [G][H+1]
   float* hs = sm + (size_t)G * (H + 1);  // [UPB][H]
   const int j = threadIdx.x;            // gate column u*4+g
@@ -71,6 +80,15 @@ __global__ void lstm_small_bwd_kernel(const float* __restrict__ dH, int lddh, co
                                       float* __restrict__ dP, int nB, int T, int H, int reverse) {
   extern __shared__ float sm[];
   const int G = 4 * H;
+  if (reverse == 2) {
+    const int d = blockIdx.y;
+    dH += d * H;
+    Whh_p += (size_t)d * G * H;
+    gates += (size_t)d * nB * T * G;
+    c_seq += (size_t)d * nB * T * H;
+    dP += (size_t)d * nB * T * G;
+    reverse = d;
+  }
   float* Ws = sm;                              // [G][H+1]   (row j = gate column, col = hidden unit)
   float* dgs = Ws + (size_t)G * (H + 1);       // [UPB][G]   dG of the step processed just before
   float* dhs = dgs + (size_t)blockDim.y * G;   // [UPB][H]
@@ -222,9 +240,13 @@ int lstm_seq_fwd_simt(const float* P, const float* Whh_p, float* h_seq, int ldh,
     const size_t smem = ((size_t)G * (H + 1) + (size_t)upb * H) * sizeof(float);
     if (smem > 48 * 1024)
       AVC_CUDA(cudaFuncSetAttribute(lstm_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lstm_small_fwd_kernel<<<ceil_div(nB, upb), dim3(G, upb), smem, st>>>(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, H, reverse);
+    lstm_small_fwd_kernel<<<dim3(ceil_div(nB, upb), reverse == 2 ? 2 : 1), dim3(G, upb), smem, st>>>(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, H, reverse);
     AVC_LAUNCHED();
     return AVC_OK;
+  }
+  if (reverse == 2) {
+    set_error("avc_lstm_seq_fwd: reverse=2 (both directions in one launch) needs H <= 64, H %% 8 == 0");
+    return AVC_ERR_UNSUPPORTED;
   }
   dim3 grid(ceil_div(G, SG_BN), ceil_div(nB, SG_BM));
   for (int step = 0; step < T; ++step) {
@@ -247,9 +269,13 @@ int lstm_seq_bwd_simt(const float* dH, int lddh, const float* Whh_p, const float
     const size_t smem = ((size_t)G * (H + 1) + (size_t)upb * G + (size_t)upb * H) * sizeof(float);
     if (smem > 48 * 1024)
       AVC_CUDA(cudaFuncSetAttribute(lstm_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lstm_small_bwd_kernel<<<ceil_div(nB, upb), dim3(G, upb), smem, st>>>(dH, lddh, Whh_p, gates, c_seq, dP, nB, T, H, reverse);
+    lstm_small_bwd_kernel<<<dim3(ceil_div(nB, upb), reverse == 2 ? 2 : 1), dim3(G, upb), smem, st>>>(dH, lddh, Whh_p, gates, c_seq, dP, nB, T, H, reverse);
     AVC_LAUNCHED();
     return AVC_OK;
+  }
+  if (reverse == 2) {
+    set_error("avc_lstm_seq_bwd: reverse=2 (both directions in one launch) needs H <= 64, H %% 8 == 0");
+    return AVC_ERR_UNSUPPORTED;
   }
   if (!ws || ws_bytes < lstm_bwd_workspace_simt(nB, T, H)) {
     set_error("avc_lstm_seq_bwd: workspace too small");

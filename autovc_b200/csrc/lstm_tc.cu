@@ -13,7 +13,7 @@
 //
 //   forward : CTA owns BN gate columns (BN/4 hidden units, gate-interleaved), K = H
 //   backward: CTA owns 16 hidden units of dh, K = 4H (dh = dG_{t+1} W_hh)
-#include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -90,7 +90,9 @@ __device__ __forceinline__ unsigned long long gtime() {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // BWD = false: BN = gate columns per CTA (64 or 32).  BWD = true: BN = hidden units per CTA (16).
-template <bool BWD, int BN>
+// CL = thread-block cluster size along the column tiles of one batch tile: the activation k-block (identical for
+// all of them) is fetched ONCE per cluster -- each CTA loads 128/CL of its rows and multicasts them to its peers.
+template <bool BWD, int BN, int CL>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const LstmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -118,7 +120,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);       // every CTA of the cluster must have consumed the slot
     }
     mbar_init(w_bar, 1);
     mbar_init(tfull, 1);
@@ -128,9 +130,13 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();        // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   unsigned* counter = p.counters + mt;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+  constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1);
+  constexpr int SLICE_ROWS = 128 / CL;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -149,7 +155,11 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_expect_tx(full_bar(stage), LT_STAGE);
-          tma_load_3d(ring + stage * LT_STAGE, &mapX, full_bar(stage), kb * 64, row0, 0);
+          if (CL == 1)
+            tma_load_3d(ring + stage * LT_STAGE, &mapX, full_bar(stage), kb * 64, row0, 0);
+          else
+            tma_load_3d_mc(ring + stage * LT_STAGE + crank * SLICE_ROWS * 128, &mapX, full_bar(stage), kb * 64,
+                           row0 + crank * SLICE_ROWS, 0, cmask);
           if (kb == 0) LT_TRACE(1);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -180,7 +190,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           for (int k = 0; k < 4; ++k)
             umma_f16(tmem_base, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc,
                      (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(stage));
+          if (CL == 1) umma_commit(empty_bar(stage));
+          else umma_commit_mc(empty_bar(stage), cmask);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(tfull);
@@ -245,10 +256,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             *reinterpret_cast<uint2*>(xb + i) = *reinterpret_cast<const uint2*>(&hb[i]);
         }
         if (threadIdx.x == 64) LT_TRACE(7);
-        fence_proxy_async();
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // all 128 rows' slices are written (CTA scope)
+        if (threadIdx.x == 64) {                             // one cumulative gpu-scope release for the CTA
+          fence_proxy_async();
+          __threadfence();
           red_release_add(counter, 1u);
           LT_TRACE(8);
         }
@@ -328,10 +339,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             *reinterpret_cast<uint4*>(xb + j) = *reinterpret_cast<const uint4*>(&gb[j]);
         }
         if (threadIdx.x == 64) LT_TRACE(7);
-        fence_proxy_async();
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 64) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // all 128 rows' slices are written (CTA scope)
+        if (threadIdx.x == 64) {                             // one cumulative gpu-scope release for the CTA
+          fence_proxy_async();
+          __threadfence();
           red_release_add(counter, 1u);
           LT_TRACE(8);
         }
@@ -347,6 +358,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();        // no CTA leaves while peers may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TM_COLS);
@@ -399,14 +411,51 @@ size_t lstm_tc_workspace(int nB, int T, int H, bool bwd) {
   return lt_plan(nB, H, bwd).total;
 }
 
-template <bool BWD, int BN>
+template <bool BWD, int BN, int CL>
 static int lt_launch(const CUtensorMap& mW, const CUtensorMap& mX, const LstmTcParams& p, const LtPlan& pl, cudaStream_t st) {
-  auto kern = lstm_tc_kernel<BWD, BN>;
+  auto kern = lstm_tc_kernel<BWD, BN, CL>;
   AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-  void* args[] = {(void*)&mW, (void*)&mX, (void*)&p};
-  AVC_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(p.MT * p.NT), dim3(LT_THREADS), args, pl.smem, st));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.MT * p.NT);
+  cfg.blockDim = dim3(LT_THREADS);
+  cfg.dynamicSmemBytes = pl.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  attrs[na].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: they spin on each other's counters
+  attrs[na].val.cooperative = 1;
+  ++na;
+  if (CL > 1) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = CL;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  AVC_CUDA(cudaLaunchKernelEx(&cfg, kern, mW, mX, p));
   g_launches.fetch_add(1);
   return AVC_OK;
+}
+
+template <bool BWD, int BN>
+static int lt_launch_cl(int cl, const CUtensorMap& mW, const CUtensorMap& mX, const LstmTcParams& p, const LtPlan& pl,
+                        cudaStream_t st) {
+  if (cl == 8) return lt_launch<BWD, BN, 8>(mW, mX, p, pl, st);
+  if (cl == 4) return lt_launch<BWD, BN, 4>(mW, mX, p, pl, st);
+  return lt_launch<BWD, BN, 1>(mW, mX, p, pl, st);
+}
+
+static int lt_cluster_size(int NT) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("AVC_LSTM_CLUSTER");
+    forced = e ? atoi(e) : 0;
+  }
+  int cl = forced > 0 ? forced : 8;
+  while (cl > 1 && NT % cl != 0) cl >>= 1;
+  return (cl == 8 || cl == 4) ? cl : 1;
 }
 
 // W: fwd -> Whh_p (4H, H);  bwd -> Whh_pT (H, 4H)  (fp32, packed/interleaved)
@@ -453,11 +502,12 @@ int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh,
     p.xbuf = xbuf;
     p.counters = counters + ch * 64;
     p.trace = (ch == 0) ? g_trace : nullptr;
-    rc = make_map3(&mX, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, 128);
+    const int cl = lt_cluster_size(p.NT);
+    rc = make_map3(&mX, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, 128 / cl);
     if (rc) return rc;
-    if (bwd) rc = lt_launch<true, 16>(mW, mX, p, pl, st);
-    else if (pl.BN == 64) rc = lt_launch<false, 64>(mW, mX, p, pl, st);
-    else rc = lt_launch<false, 32>(mW, mX, p, pl, st);
+    if (bwd) rc = lt_launch_cl<true, 16>(cl, mW, mX, p, pl, st);
+    else if (pl.BN == 64) rc = lt_launch_cl<false, 64>(cl, mW, mX, p, pl, st);
+    else rc = lt_launch_cl<false, 32>(cl, mW, mX, p, pl, st);
     if (rc) return rc;
   }
   return AVC_OK;

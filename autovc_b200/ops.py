@@ -219,7 +219,22 @@ class LstmLayer(torch.autograd.Function):
         out = torch.empty(B, T, D * H, device=x.device, dtype=torch.float32)
         saved = []
         packs = []
-        for d in range(D):
+        fused = D == 2 and H <= 64 and H % 8 == 0          # both directions of the encoder BiLSTM in one launch
+        if fused:
+            Pre = torch.empty(2, B, T, G, device=x.device, dtype=torch.float32)
+            gates = torch.empty(2, B, T, G, device=x.device, dtype=torch.float32)
+            c_seq = torch.empty(2, B, T, H, device=x.device, dtype=torch.float32)
+            wh2 = torch.empty(2, G, H, device=x.device, dtype=torch.float32)
+            for d in range(2):
+                w_ih, w_hh, b_ih, b_hh = weights[4 * d:4 * d + 4]
+                wi_p, wi_pT = pack_lstm_w(w_ih)
+                wh_p, wh_pT = pack_lstm_w(w_hh)
+                wh2[d].copy_(wh_p)
+                gemm_nt_taps(x, I, wi_p, pack_lstm_b(b_ih, b_hh), Pre[d], G, B, T, G, I, 1, 0, prec=prec)
+                packs += [wi_pT, wh_p, wh_pT]
+            call("avc_lstm_seq_fwd", _p(Pre), _p(wh2), _p(out), 2 * H, _p(gates), _p(c_seq), B, T, H, 2, prec, _NULL, 0, _stream())
+            saved = [gates, c_seq, wh2]
+        for d in range(0 if not fused else D, D):
             w_ih, w_hh, b_ih, b_hh = weights[4 * d:4 * d + 4]
             wi_p, wi_pT = pack_lstm_w(w_ih)
             wh_p, wh_pT = pack_lstm_w(w_hh)
@@ -236,7 +251,7 @@ class LstmLayer(torch.autograd.Function):
                  _p(ws), nbytes, _stream())
             saved += [gates, c_seq]
         ctx.save_for_backward(x, out, *weights, *saved)
-        ctx.D, ctx.prec, ctx.packs = D, prec, packs
+        ctx.D, ctx.prec, ctx.packs, ctx.fused = D, prec, packs, fused
         return out
 
     @staticmethod
@@ -253,16 +268,25 @@ class LstmLayer(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         dx = torch.empty_like(x) if need_dx else None
         grads: List[Optional[torch.Tensor]] = []
+        dP2 = None
+        if ctx.fused:
+            gates2, c2, wh2 = saved
+            dP2 = torch.empty(2, B, T, G, device=x.device, dtype=torch.float32)
+            call("avc_lstm_seq_bwd", _p(dout), 2 * H, _p(wh2), _p(wh2), _p(gates2), _p(c2), _p(dP2), B, T, H, 2, prec,
+                 _NULL, 0, _stream())
         for d in range(D):
             w_ih, w_hh, b_ih, b_hh = weights[4 * d:4 * d + 4]
-            gates, c_seq = saved[2 * d:2 * d + 2]
             wi_pT, wh_p, wh_pT = ctx.packs[3 * d:3 * d + 3]
-            dP = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
-            nbytes = query("avc_lstm_bwd_workspace_bytes", B, T, H, prec)
-            ws = _ws(nbytes, x.device)
             rev = int(d == 1)
-            call("avc_lstm_seq_bwd", _p(dout.view(-1)[d * H:]), D * H, _p(wh_p), _p(wh_pT), _p(gates), _p(c_seq), _p(dP),
-                 B, T, H, rev, prec, _p(ws), nbytes, _stream())
+            if ctx.fused:
+                dP = dP2[d]
+            else:
+                gates, c_seq = saved[2 * d:2 * d + 2]
+                dP = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
+                nbytes = query("avc_lstm_bwd_workspace_bytes", B, T, H, prec)
+                ws = _ws(nbytes, x.device)
+                call("avc_lstm_seq_bwd", _p(dout.view(-1)[d * H:]), D * H, _p(wh_p), _p(wh_pT), _p(gates), _p(c_seq), _p(dP),
+                     B, T, H, rev, prec, _p(ws), nbytes, _stream())
             dw_ih = torch.empty_like(w_ih)
             gemm_tn_taps(dP, G, x, I, dw_ih, B, T, G, I, 1, 0, out_mode=2, prec=prec)
             dw_hh = torch.empty_like(w_hh)

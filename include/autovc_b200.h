@@ -136,7 +136,9 @@ int avc_colsum(const float* x, int ldx, int M, int C, float* out, float* out2, i
  *   Whh_p  (4H, H)      interleaved rows (forward);  Whh_pT (H, 4H) its transpose (backward)
  *   h_seq  (nB, T, H) with row stride ldh (so fwd/bwd directions can share one (B,T,2H) buffer)
  *   gates  (nB, T, 4H)  activated gates saved for backward;  c_seq (nB, T, H) cell states
- * reverse != 0 walks t = T-1 .. 0 (the *_reverse direction).  h0 = c0 = 0.
+ * reverse = 1 walks t = T-1 .. 0 (the *_reverse direction).  h0 = c0 = 0.  reverse = 2 (H <= 64 only): both
+ * directions of a BiLSTM in ONE launch; P, Whh_p, gates, c_seq, dP are stacked [2][...] (forward first) and
+ * direction d reads/writes h_seq / dH at column offset d*H of a shared (nB,T,2H) buffer (ldh = lddh = 2H).
  * AVC_PREC_FP32: H <= 64 runs the whole sequence in one launch (W_hh in shared memory), larger H
  * one launch per step.  AVC_PREC_BF16 with 128 <= H <= 1024, H % 64 == 0: ONE persistent cooperative
  * launch per layer-direction -- W_hh slices resident in shared memory across the SMs, tcgen05 MMAs
