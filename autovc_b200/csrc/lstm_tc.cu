@@ -422,18 +422,28 @@ static int lt_launch(const CUtensorMap& mW, const CUtensorMap& mX, const LstmTcP
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
   int na = 0;
-  attrs[na].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: they spin on each other's counters
-  attrs[na].val.cooperative = 1;
-  ++na;
   if (CL > 1) {
     attrs[na].id = cudaLaunchAttributeClusterDimension;
     attrs[na].val.clusterDim.x = CL;
     attrs[na].val.clusterDim.y = 1;
     attrs[na].val.clusterDim.z = 1;
     ++na;
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
+    // all CTAs must be co-resident (they spin on each other's counters): check that the clusters fit at once
+    int max_clusters = 0;
+    AVC_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+    if (max_clusters * CL < p.MT * p.NT) {
+      set_error("lstm_tc: only %d clusters of %d CTAs can be co-resident, %d needed", max_clusters, CL, p.MT * p.NT / CL);
+      return AVC_ERR_UNSUPPORTED;
+    }
+  } else {
+    attrs[na].id = cudaLaunchAttributeCooperative;    // the runtime enforces co-residency
+    attrs[na].val.cooperative = 1;
+    ++na;
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
   }
-  cfg.attrs = attrs;
-  cfg.numAttrs = na;
   AVC_CUDA(cudaLaunchKernelEx(&cfg, kern, mW, mX, p));
   g_launches.fetch_add(1);
   return AVC_OK;
@@ -453,7 +463,7 @@ static int lt_cluster_size(int NT) {
     const char* e = getenv("AVC_LSTM_CLUSTER");
     forced = e ? atoi(e) : 0;
   }
-  int cl = forced > 0 ? forced : 8;
+  int cl = forced > 0 ? forced : 1;   // default: unicast (r01: multicast of 4 measured no faster)
   while (cl > 1 && NT % cl != 0) cl >>= 1;
   return (cl == 8 || cl == 4) ? cl : 1;
 }
@@ -502,12 +512,18 @@ int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh,
     p.xbuf = xbuf;
     p.counters = counters + ch * 64;
     p.trace = (ch == 0) ? g_trace : nullptr;
-    const int cl = lt_cluster_size(p.NT);
+    int cl = lt_cluster_size(p.NT);
     rc = make_map3(&mX, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, 128 / cl);
     if (rc) return rc;
-    if (bwd) rc = lt_launch_cl<true, 16>(cl, mW, mX, p, pl, st);
-    else if (pl.BN == 64) rc = lt_launch_cl<false, 64>(cl, mW, mX, p, pl, st);
-    else rc = lt_launch_cl<false, 32>(cl, mW, mX, p, pl, st);
+    for (;;) {
+      if (bwd) rc = lt_launch_cl<true, 16>(cl, mW, mX, p, pl, st);
+      else if (pl.BN == 64) rc = lt_launch_cl<false, 64>(cl, mW, mX, p, pl, st);
+      else rc = lt_launch_cl<false, 32>(cl, mW, mX, p, pl, st);
+      if (rc != AVC_ERR_UNSUPPORTED || cl == 1) break;
+      cl = cl == 8 ? 4 : 1;                             // clusters do not fit: retry with a smaller cluster
+      rc = make_map3(&mX, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, 128 / cl);
+      if (rc) return rc;
+    }
     if (rc) return rc;
   }
   return AVC_OK;

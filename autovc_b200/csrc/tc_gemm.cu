@@ -12,13 +12,24 @@
 // two TMEM accumulators (tmem_full/tmem_empty) so the epilogue of tile i overlaps the mainloop of i+1.
 // bf16 operands, fp32 accumulation in TMEM; BatchNorm channel sums are reduced in the epilogue in
 // fp32 per tile and accumulated in fp64.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace avc {
 
-constexpr int TC_BM = 128, TC_BN = 128;
-constexpr int TC_STAGES = 6;
-constexpr int TC_STAGE_A = TC_BM * 128, TC_STAGE_B = TC_BN * 128;   // 128 rows x one 128-byte swizzle row = 16 KB each
+constexpr int TC_BM = 128;
+constexpr int TC_STAGE_A = TC_BM * 128;   // 128 rows x one 128-byte swizzle row = 16 KB
+// BN = tile width (output columns per CTA tile): 128 or 256.  Shared-memory bandwidth (operand reads by the MMA
+// plus TMA fills) is what bounds a 128x128 tile (r01 ncu: tensor pipe 48%); 128x256 moves 25% fewer bytes per MAC.
+template <int BN> struct TcCfg {
+  static constexpr int STAGE_B = BN * 128;
+  static constexpr int STAGE_BYTES = TC_STAGE_A + STAGE_B;
+  static constexpr int STAGES = BN == 128 ? 6 : 4;
+  static constexpr int TMEM_COLS = 2 * BN;          // two fp32 accumulators
+  static constexpr int STAT_BYTES = 4 * 2 * BN * 4;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + STAT_BYTES + 256 /*barriers*/;
+};
 // EB = operand element bytes: 2 = bf16 (kind::f16), 4 = fp32 read as tf32 (kind::tf32).  One 128-byte row holds
 // 128/EB elements of K (NT) or of channels (TN); one MMA consumes 32 bytes of K = 32/EB elements.
 template <int EB> struct TcGeom {
@@ -28,10 +39,7 @@ template <int EB> struct TcGeom {
   static constexpr int NBOX = 128 / ROW;       // TN: 128-channel tile = NBOX TMA boxes of ROW channels
   static constexpr int BOX_BYTES = RS * 128;   // TN: bytes of one box (RS frames x 128 B)
 };
-constexpr int TC_STAGE_BYTES = TC_STAGE_A + TC_STAGE_B;
 constexpr int TC_THREADS = 192;
-constexpr int TC_TMEM_COLS = 256;  // two 128-column fp32 accumulators
-constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * TC_STAGE_BYTES + 4 * 2 * TC_BN * 4 /*stats*/ + 256 /*barriers*/;
 
 enum { MODE_NT = 0, MODE_TN = 1 };
 
@@ -81,16 +89,18 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-template <int MODE, int EB>
+template <int MODE, int EB, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  using Cf = TcCfg<BN>;
+  constexpr int TC_STAGES = Cf::STAGES, TC_STAGE_BYTES = Cf::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* gen = smem_raw + (base - raw);
   const uint32_t stage0 = base;
   float* stat_s = reinterpret_cast<float*>(gen + TC_STAGES * TC_STAGE_BYTES);           // [4 warps][2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + TC_STAGES * TC_STAGE_BYTES + 4 * 2 * TC_BN * 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + TC_STAGES * TC_STAGE_BYTES + Cf::STAT_BYTES);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
@@ -114,7 +124,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TC_TMEM_COLS);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), Cf::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -144,7 +154,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
             const uint32_t sa = stage0 + stage * TC_STAGE_BYTES;
             tma_load_3d(sa, &mapA, full_bar(stage), kb * Gm::ROW, t0 + p.shift0 + tap, b);
-            tma_load_3d(sa + TC_STAGE_A, &mapB, full_bar(stage), kb * Gm::ROW, n_tile * TC_BN, tap);
+            tma_load_3d(sa + TC_STAGE_A, &mapB, full_bar(stage), kb * Gm::ROW, n_tile * BN, tap);
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
         } else {
@@ -158,11 +168,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
             const uint32_t sa = stage0 + stage * TC_STAGE_BYTES;
 #pragma unroll
-            for (int h = 0; h < Gm::NBOX; ++h) {
+            for (int h = 0; h < Gm::NBOX; ++h)
               tma_load_3d(sa + h * Gm::BOX_BYTES, &mapA, full_bar(stage), n_tile * TC_BM + h * Gm::ROW, t0, b);
-              tma_load_3d(sa + TC_STAGE_A + h * Gm::BOX_BYTES, &mapB, full_bar(stage), k_tile * TC_BN + h * Gm::ROW,
+#pragma unroll
+            for (int h = 0; h < BN / Gm::ROW; ++h)
+              tma_load_3d(sa + TC_STAGE_A + h * Gm::BOX_BYTES, &mapB, full_bar(stage), k_tile * BN + h * Gm::ROW,
                           t0 + p.shift0 + tap, b);
-            }
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -171,7 +182,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TC_BM, TC_BN, MODE == MODE_TN, MODE == MODE_TN, EB == 2 ? 1 : 2);
+      constexpr uint32_t idesc = make_idesc(TC_BM, BN, MODE == MODE_TN, MODE == MODE_TN, EB == 2 ? 1 : 2);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -185,7 +196,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * TC_BN;
+        const uint32_t d_tmem = tmem_base + acc * BN;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -228,22 +239,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_BN;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       if (MODE == MODE_NT) {
         const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
         const int b = m_tile / p.t_tiles, t = (m_tile % p.t_tiles) * TC_BM + row;
         const bool row_ok = t < p.T;
         float* crow = p.C + ((size_t)b * p.T + t) * p.ldc;
 #pragma unroll 1
-        for (int c = 0; c < TC_BN / 32; ++c) {
+        for (int c = 0; c < BN / 32; ++c) {
           float v[32];
           tmem_ld32(t_addr + c * 32, v);
-          if (c == TC_BN / 32 - 1) {          // all TMEM reads of this accumulator are done
+          if (c == BN / 32 - 1) {          // all TMEM reads of this accumulator are done
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
           }
-          const int n0 = n_tile * TC_BN + c * 32;
+          const int n0 = n_tile * BN + c * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = n0 + j;
@@ -274,23 +285,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
             const float s1 = warp_colsum32(v, lane);
             const float s2 = warp_colsum32(sq, lane);
-            stat_s[(q * 2 + 0) * TC_BN + c * 32 + lane] = s1;
-            stat_s[(q * 2 + 1) * TC_BN + c * 32 + lane] = s2;
+            stat_s[(q * 2 + 0) * BN + c * 32 + lane] = s1;
+            stat_s[(q * 2 + 1) * BN + c * 32 + lane] = s2;
           }
         }
         if (p.stats != nullptr) {
           asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps
-          const int col = threadIdx.x - 64;                   // 0..127
-          const int n = n_tile * TC_BN + col;
-          if (n < p.N) {
-            double a = 0.0, bq = 0.0;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              a += (double)stat_s[(w * 2 + 0) * TC_BN + col];
-              bq += (double)stat_s[(w * 2 + 1) * TC_BN + col];
+          for (int cp = 0; cp < BN / 128; ++cp) {
+            const int col = threadIdx.x - 64 + cp * 128;       // 128 epilogue threads sweep the BN columns
+            const int n = n_tile * BN + col;
+            if (n < p.N) {
+              double a = 0.0, bq = 0.0;
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                a += (double)stat_s[(w * 2 + 0) * BN + col];
+                bq += (double)stat_s[(w * 2 + 1) * BN + col];
+              }
+              atomicAdd(p.stats + n, a);
+              atomicAdd(p.stats + p.N + n, bq);
             }
-            atomicAdd(p.stats + n, a);
-            atomicAdd(p.stats + p.N + n, bq);
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
@@ -300,15 +314,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int n = n_tile * TC_BM + row;
         float* orow = p.part + (((size_t)split * p.ntaps + tap) * p.N + n) * p.K;
 #pragma unroll 1
-        for (int c = 0; c < TC_BN / 32; ++c) {
+        for (int c = 0; c < BN / 32; ++c) {
           float v[32];
           tmem_ld32(t_addr + c * 32, v);
-          if (c == TC_BN / 32 - 1) {
+          if (c == BN / 32 - 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
           }
-          const int k0 = k_tile * TC_BN + c * 32;
+          const int k0 = k_tile * BN + c * 32;
           if (n < p.N) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -324,7 +338,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    tmem_dealloc(tmem_base, Cf::TMEM_COLS);
   }
 }
 
@@ -375,16 +389,37 @@ __global__ void cvt_pad_w_f32_kernel(const float* __restrict__ src, float* __res
 
 static int cvt_blocks(size_t total) { return (int)std::min<size_t>(ceil_div(total, (size_t)256), (size_t)num_sms() * 16); }
 
-static int ensure_smem_attr() {
-  static bool done = false;
-  if (!done) {
-    AVC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_NT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    AVC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_TN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    AVC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_NT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    AVC_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<MODE_TN, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    done = true;
+template <int MODE, int EB, int BN>
+static int tc_launch(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int grid, cudaStream_t st) {
+  static bool attr_done = false;
+  auto kern = tc_gemm_kernel<MODE, EB, BN>;
+  if (!attr_done) {
+    AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
+    attr_done = true;
   }
+  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(mA, mB, p);
+  AVC_LAUNCHED();
   return AVC_OK;
+}
+template <int MODE>
+static int tc_dispatch(int eb, int bn, const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int grid, cudaStream_t st) {
+  if (eb == 2) return bn == 256 ? tc_launch<MODE, 2, 256>(mA, mB, p, grid, st) : tc_launch<MODE, 2, 128>(mA, mB, p, grid, st);
+  return bn == 256 ? tc_launch<MODE, 4, 256>(mA, mB, p, grid, st) : tc_launch<MODE, 4, 128>(mA, mB, p, grid, st);
+}
+
+// tile-width choice: fewest (rounds x tile cost); a 256-wide tile costs ~1.41x a 128-wide one (smem-bound model)
+static int pick_bn(int row_tiles, int N) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("AVC_GEMM_BN");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 128 || forced == 256) return forced;
+  if (N <= 128) return 128;
+  const int sms = num_sms();
+  const double c128 = (double)ceil_div(row_tiles * ceil_div(N, 128), sms) * 1.0;
+  const double c256 = (double)ceil_div(row_tiles * ceil_div(N, 256), sms) * 1.41;
+  return c256 < c128 ? 256 : 128;
 }
 
 // fp32 -> padded fp32 staging for the tf32 path when the caller's strides are not 16-byte multiples
@@ -403,15 +438,16 @@ static inline bool direct_ok(const void* p, int ld) { return ((uintptr_t)p & 15)
 // eb = 2: both operands are staged as zero-padded bf16.  eb = 4: operands are read in place by TMA when
 // their row strides are 16-byte multiples (OOB zero fill covers K/N tails), otherwise staged as padded fp32.
 struct NtPlan {
-  int Kp, Np;
+  int Kp, Np, bn;
   bool stageA, stageW;
   size_t offA, offW, total;
 };
 static NtPlan nt_plan(const float* A, int lda, const float* W, int nB, int T, int N, int K, int ntaps, int eb) {
   NtPlan pl;
   const int row = 128 / eb;
+  pl.bn = pick_bn(nB * ceil_div(T, TC_BM), N);
   pl.Kp = round_up(K, row);
-  pl.Np = round_up(N, TC_BN);
+  pl.Np = round_up(N, pl.bn);
   pl.stageA = eb == 2 || !direct_ok(A, lda);
   pl.stageW = eb == 2 || !direct_ok(W, K);
   pl.offA = 0;
@@ -422,7 +458,7 @@ static NtPlan nt_plan(const float* A, int lda, const float* W, int nB, int T, in
 size_t gemm_nt_workspace_tc(int nB, int T, int N, int K, int ntaps, int eb) {
   // worst case (pointers unknown): assume staging
   const int row = 128 / eb;
-  const int Kp = round_up(K, row), Np = round_up(N, TC_BN);
+  const int Kp = round_up(K, row), Np = round_up(N, 256);
   return align256((size_t)nB * T * Kp * eb) + align256((size_t)ntaps * Np * Kp * eb);
 }
 
@@ -438,8 +474,7 @@ int gemm_nt_taps_tc(const float* A, int lda, const float* W, const float* bias, 
     set_error("avc_gemm_nt_taps(tensor): workspace %zu < %zu", ws_bytes, pl.total);
     return AVC_ERR_WORKSPACE;
   }
-  int rc = ensure_smem_attr();
-  if (rc) return rc;
+  int rc = 0;
   const size_t M = (size_t)nB * T;
   const int row = 128 / eb;
   const void* Aop = A;
@@ -462,18 +497,15 @@ int gemm_nt_taps_tc(const float* A, int lda, const float* W, const float* bias, 
   CUtensorMap mA, mB;
   rc = make_map3(&mA, Aop, a_k, T, nB, a_ld, (uint64_t)T * a_ld, row, TC_BM, eb);
   if (rc) return rc;
-  rc = make_map3(&mB, Wop, w_k, w_n, ntaps, w_ld, w_n * w_ld, row, TC_BN, eb);
+  rc = make_map3(&mB, Wop, w_k, w_n, ntaps, w_ld, w_n * w_ld, row, pl.bn, eb);
   if (rc) return rc;
   TcParams p{};
   p.nB = nB; p.T = T; p.ntaps = ntaps; p.shift0 = shift0; p.N = N; p.K = K;
-  p.t_tiles = ceil_div(T, TC_BM); p.n_tiles = pl.Np / TC_BN; p.kblocks = pl.Kp / row;
+  p.t_tiles = ceil_div(T, TC_BM); p.n_tiles = pl.Np / pl.bn; p.kblocks = pl.Kp / row;
   p.bias = bias; p.C = C; p.ldc = ldc; p.accumulate = accumulate; p.stats = stats;
   const int tiles = nB * p.t_tiles * p.n_tiles;
   const int grid = std::min(tiles, num_sms());
-  if (eb == 2) tc_gemm_kernel<MODE_NT, 2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mA, mB, p);
-  else tc_gemm_kernel<MODE_NT, 4><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mA, mB, p);
-  AVC_LAUNCHED();
-  return AVC_OK;
+  return tc_dispatch<MODE_NT>(eb, pl.bn, mA, mB, p, grid, st);
 }
 
 // ---- TN -------------------------------------------------------------------------------------------
@@ -494,16 +526,21 @@ static int tn_splits_tc(int rblocks, int tiles) {
 }
 
 struct TnPlan {
-  int Np, Kp, rs, rblocks, tiles, splits, rps;
+  int Np, Kp, rs, rblocks, tiles, splits, rps, bn;
   size_t off_y, off_x, off_part, total;
 };
 static TnPlan tn_plan(int nB, int T, int N, int K, int ntaps, int eb, bool stage_y, bool stage_x) {
   TnPlan pl;
+  pl.bn = (K % 256 == 0 || K > 640) ? 256 : 128;
+  {
+    const char* e = getenv("AVC_GEMM_BN");
+    if (e && (atoi(e) == 128 || atoi(e) == 256)) pl.bn = atoi(e);
+  }
   pl.Np = round_up(N, TC_BM);
-  pl.Kp = round_up(K, TC_BN);
+  pl.Kp = round_up(K, pl.bn);
   pl.rs = eb == 2 ? 64 : 32;
   pl.rblocks = nB * ceil_div(T, pl.rs);
-  pl.tiles = ntaps * (pl.Np / TC_BM) * (pl.Kp / TC_BN);
+  pl.tiles = ntaps * (pl.Np / TC_BM) * (pl.Kp / pl.bn);
   pl.splits = tn_splits_tc(pl.rblocks, pl.tiles);
   pl.rps = ceil_div(pl.rblocks, pl.splits);
   const size_t M = (size_t)nB * T;
@@ -529,8 +566,7 @@ int gemm_tn_taps_tc(const float* dY, int ldy, const float* X, int ldx, float* dW
     set_error("avc_gemm_tn_taps(tensor): workspace %zu < %zu", ws_bytes, pl.total);
     return AVC_ERR_WORKSPACE;
   }
-  int rc = ensure_smem_attr();
-  if (rc) return rc;
+  int rc = 0;
   const size_t M = (size_t)nB * T;
   const int row = 128 / eb;
   float* part = (float*)((uint8_t*)ws + pl.off_part);
@@ -558,13 +594,12 @@ int gemm_tn_taps_tc(const float* dY, int ldy, const float* X, int ldx, float* dW
   if (rc) return rc;
   TcParams p{};
   p.nB = nB; p.T = T; p.ntaps = ntaps; p.shift0 = shift0; p.N = N; p.K = K;
-  p.n_tiles = pl.Np / TC_BM; p.k_tiles = pl.Kp / TC_BN; p.splits = pl.splits; p.rblocks = pl.rblocks;
+  p.n_tiles = pl.Np / TC_BM; p.k_tiles = pl.Kp / pl.bn; p.splits = pl.splits; p.rblocks = pl.rblocks;
   p.rblocks_per_split = pl.rps; p.tbr = ceil_div(T, pl.rs); p.part = part;
   const int items = pl.tiles * pl.splits;
   const int grid = std::min(items, num_sms());
-  if (eb == 2) tc_gemm_kernel<MODE_TN, 2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mA, mB, p);
-  else tc_gemm_kernel<MODE_TN, 4><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mA, mB, p);
-  AVC_LAUNCHED();
+  rc = tc_dispatch<MODE_TN>(eb, pl.bn, mA, mB, p, grid, st);
+  if (rc) return rc;
   return launch_wgrad_reduce(part, dW, N, K, ntaps, pl.splits, out_mode, accumulate, st);
 }
 
