@@ -35,6 +35,7 @@ struct LstmTcParams {
   float* dP;            // bwd: out (nB,T,4H)
   __nv_bfloat16* xbuf;  // exchange buffer [2][nBpad][K]
   unsigned int* counters;  // [MT], zero-initialised
+  int exp_mode;            // experiment switch (AVC_LSTM_EXP): 0 none, 1 alternate two descriptors, 2 two half boxes
   unsigned long long* trace;  // optional per-step timestamps of CTA 0 (avc_debug_set_trace), else nullptr
 };
 
@@ -94,7 +95,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // all of them) is fetched ONCE per cluster -- each CTA loads 128/CL of its rows and multicasts them to its peers.
 template <bool BWD, int BN, int CL>
 __global__ void __launch_bounds__(LT_THREADS, 1)
-lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const LstmTcParams p) {
+lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
+               const __grid_constant__ CUtensorMap mapX2, const LstmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -155,9 +157,14 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_expect_tx(full_bar(stage), LT_STAGE);
-          if (CL == 1)
-            tma_load_3d(ring + stage * LT_STAGE, &mapX, full_bar(stage), kb * 64, row0, 0);
-          else
+          if (CL == 1) {
+            if (p.exp_mode == 2) {
+              tma_load_3d(ring + stage * LT_STAGE, &mapX2, full_bar(stage), kb * 64, row0, 0);
+              tma_load_3d(ring + stage * LT_STAGE + LT_STAGE / 2, &mapX2, full_bar(stage), kb * 64, row0 + 64, 0);
+            } else {
+              tma_load_3d(ring + stage * LT_STAGE, (p.exp_mode == 1 && (kb & 1)) ? &mapX2 : &mapX, full_bar(stage), kb * 64, row0, 0);
+            }
+          } else
             tma_load_3d_mc(ring + stage * LT_STAGE + crank * SLICE_ROWS * 128, &mapX, full_bar(stage), kb * 64,
                            row0 + crank * SLICE_ROWS, 0, cmask);
           if (kb == 0) LT_TRACE(1);
@@ -412,7 +419,7 @@ size_t lstm_tc_workspace(int nB, int T, int H, bool bwd) {
 }
 
 template <bool BWD, int BN, int CL>
-static int lt_launch(const CUtensorMap& mW, const CUtensorMap& mX, const LstmTcParams& p, const LtPlan& pl, cudaStream_t st) {
+static int lt_launch(const CUtensorMap& mW, const CUtensorMap& mX, const CUtensorMap& mX2, const LstmTcParams& p, const LtPlan& pl, cudaStream_t st) {
   auto kern = lstm_tc_kernel<BWD, BN, CL>;
   AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   cudaLaunchConfig_t cfg{};
@@ -444,17 +451,17 @@ static int lt_launch(const CUtensorMap& mW, const CUtensorMap& mX, const LstmTcP
     cfg.attrs = attrs;
     cfg.numAttrs = na;
   }
-  AVC_CUDA(cudaLaunchKernelEx(&cfg, kern, mW, mX, p));
+  AVC_CUDA(cudaLaunchKernelEx(&cfg, kern, mW, mX, mX2, p));
   g_launches.fetch_add(1);
   return AVC_OK;
 }
 
 template <bool BWD, int BN>
-static int lt_launch_cl(int cl, const CUtensorMap& mW, const CUtensorMap& mX, const LstmTcParams& p, const LtPlan& pl,
+static int lt_launch_cl(int cl, const CUtensorMap& mW, const CUtensorMap& mX, const CUtensorMap& mX2, const LstmTcParams& p, const LtPlan& pl,
                         cudaStream_t st) {
-  if (cl == 8) return lt_launch<BWD, BN, 8>(mW, mX, p, pl, st);
-  if (cl == 4) return lt_launch<BWD, BN, 4>(mW, mX, p, pl, st);
-  return lt_launch<BWD, BN, 1>(mW, mX, p, pl, st);
+  if (cl == 8) return lt_launch<BWD, BN, 8>(mW, mX, mX2, p, pl, st);
+  if (cl == 4) return lt_launch<BWD, BN, 4>(mW, mX, mX2, p, pl, st);
+  return lt_launch<BWD, BN, 1>(mW, mX, mX2, p, pl, st);
 }
 
 static int lt_cluster_size(int NT) {
@@ -490,7 +497,9 @@ int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh,
   AVC_LAUNCHED();
   const int nchunks = ceil_div(nB, pl.chunk);
   AVC_CUDA(cudaMemsetAsync(counters, 0, (size_t)nchunks * 64 * sizeof(unsigned), st));
-  CUtensorMap mW, mX;
+  CUtensorMap mW, mX, mX2;
+  const char* exp_env = getenv("AVC_LSTM_EXP");
+  const int exp_mode = exp_env ? atoi(exp_env) : 0;
   const int w_rows = bwd ? H : 4 * H;
   int rc = make_map3(&mW, Wb, pl.K, w_rows, 1, pl.K, (uint64_t)w_rows * pl.K, 64, pl.BN);
   if (rc) return rc;
@@ -512,13 +521,16 @@ int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh,
     p.xbuf = xbuf;
     p.counters = counters + ch * 64;
     p.trace = (ch == 0) ? g_trace : nullptr;
+    p.exp_mode = exp_mode;
     int cl = lt_cluster_size(p.NT);
     rc = make_map3(&mX, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, 128 / cl);
     if (rc) return rc;
+    rc = make_map3(&mX2, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, exp_mode == 2 ? 64 : 128 / cl);
+    if (rc) return rc;
     for (;;) {
-      if (bwd) rc = lt_launch_cl<true, 16>(cl, mW, mX, p, pl, st);
-      else if (pl.BN == 64) rc = lt_launch_cl<false, 64>(cl, mW, mX, p, pl, st);
-      else rc = lt_launch_cl<false, 32>(cl, mW, mX, p, pl, st);
+      if (bwd) rc = lt_launch_cl<true, 16>(cl, mW, mX, mX2, p, pl, st);
+      else if (pl.BN == 64) rc = lt_launch_cl<false, 64>(cl, mW, mX, mX2, p, pl, st);
+      else rc = lt_launch_cl<false, 32>(cl, mW, mX, mX2, p, pl, st);
       if (rc != AVC_ERR_UNSUPPORTED || cl == 1) break;
       cl = cl == 8 ? 4 : 1;                             // clusters do not fit: retry with a smaller cluster
       rc = make_map3(&mX, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, 128 / cl);
