@@ -372,6 +372,262 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// BPTT with the 4H-long reduction split over a cluster of 4 CTAs ("K-split").
+// The plain BPTT kernel above gives each CTA 16 hidden units and the whole K = 4H reduction, so every SM has to
+// ingest the full dG tile (128 x 4H bf16 = 1 MB at H=1024) every step -- r01 traces show that ingest (~60 GB/s per
+// SM) is what bounds the step.  Here a cluster owns 64 hidden units of one batch tile; CTA rank r multiplies the
+// r-th quarter of K (W slice 64 x H, resident; dG quarter 128 x H streamed: 256 KB), then the four partial
+// 128 x 64 tiles are reduce-scattered through distributed shared memory: rank r receives the three foreign
+// partials of ITS 16 units, adds its own, and runs the gate-gradient algebra for those units.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+constexpr int KS_UNITS = 64;   // hidden units per cluster
+constexpr int KS_CL = 4;       // cluster size = K split
+
+__global__ void __launch_bounds__(LT_THREADS, 1)
+lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const LstmTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const int T = p.T, H = p.H, G = 4 * p.H;
+  const int kblocks = H / 64;                               // this CTA's quarter of K = 4H
+  constexpr uint32_t w_block = KS_UNITS * 128;              // 8 KB
+  const uint32_t w_base = base;
+  const uint32_t ring = base + kblocks * w_block;
+  const uint32_t red_off = kblocks * w_block + p.stages * LT_STAGE;      // [3][128][16] fp32 = 24 KB
+  float* red = reinterpret_cast<float*>(gen + red_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + red_off + 3 * 128 * 16 * 4);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
+  const uint32_t w_bar = bar0 + 8u * 16, tfull = bar0 + 8u * 17, tempty = bar0 + 8u * 18, red_full = bar0 + 8u * 19;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t r = cluster_ctarank();                     // K quarter and unit quarter owned by this CTA
+  const int cluster_id = blockIdx.x / KS_CL;
+  const int UT = H / KS_UNITS;
+  const int ut = cluster_id % UT, mt = cluster_id / UT;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(w_bar, 1);
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    mbar_init(red_full, 3 * 4);                             // one arrive per epilogue warp of each of the 3 peers
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 64);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  unsigned* counter = p.counters + mt;
+  const unsigned per_step = (unsigned)(UT * KS_CL);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_bar, kblocks * w_block);
+      for (int kb = 0; kb < kblocks; ++kb)
+        tma_load_3d(w_base + kb * w_block, &mapW, w_bar, (int)r * H + kb * 64, ut * KS_UNITS, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 1; s < T; ++s) {
+        while (ld_acquire(counter) < (unsigned)s * per_step) {
+        }
+        fence_proxy_async();
+        const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), LT_STAGE);
+          tma_load_3d(ring + stage * LT_STAGE, &mapX, full_bar(stage), (int)r * H + kb * 64, row0, 0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, KS_UNITS, 0, 0);
+      mbar_wait(w_bar, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 0; s < T; ++s) {
+        mbar_wait(tempty, (s & 1) ^ 1);
+        tc_fence_after();
+        if (s == 0) {
+          mbar_arrive(tfull);
+          continue;
+        }
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = ring + stage * LT_STAGE, sb = w_base + kb * w_block;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc,
+                     (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int b = mt * 128 + row;
+    const bool live = b < p.nB;
+    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int U = 16;
+    const int u0 = ut * KS_UNITS + (int)r * U;              // the 16 units this CTA finalises
+    const uint32_t red_s = smem_u32(red);
+    float dc_rec[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) dc_rec[i] = 0.f;
+    for (int s = 0; s < T; ++s) {
+      const int t = p.reverse ? s : T - 1 - s;
+      const bool has_prev = s < T - 1;
+      const int t_prev = p.reverse ? t + 1 : t - 1;
+      const size_t rowi = (size_t)b * T + t;
+      float dh[U], ct[U], cp[U], g4[4 * U];
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < U; i += 4) {
+          *reinterpret_cast<float4*>(&dh[i]) = __ldg(reinterpret_cast<const float4*>(p.dH + rowi * p.lddh + u0 + i));
+          *reinterpret_cast<float4*>(&ct[i]) = __ldg(reinterpret_cast<const float4*>(p.c_seq + rowi * H + u0 + i));
+          if (has_prev)
+            *reinterpret_cast<float4*>(&cp[i]) =
+                __ldg(reinterpret_cast<const float4*>(p.c_seq + ((size_t)b * T + t_prev) * H + u0 + i));
+          else
+            cp[i] = cp[i + 1] = cp[i + 2] = cp[i + 3] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4 * U; j += 4)
+          *reinterpret_cast<float4*>(&g4[j]) = __ldg(reinterpret_cast<const float4*>(p.gates + rowi * G + 4 * u0 + j));
+      } else {
+#pragma unroll
+        for (int i = 0; i < U; ++i) dh[i] = ct[i] = cp[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4 * U; ++j) g4[j] = 0.f;
+      }
+      mbar_wait(tfull, s & 1);
+      tc_fence_after();
+      if (s > 0) {
+        // my partial 128 x 64 tile: keep quarter r, ship quarter qq to cluster rank qq
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float d[32];
+          tmem_ld32(t_addr + half * 32, d);
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const uint32_t qq = half * 2 + h2;
+            if (qq == r) {
+#pragma unroll
+              for (int i = 0; i < U; ++i) dh[i] += d[h2 * 16 + i];
+            } else {
+              const uint32_t slot = r < qq ? r : r - 1;        // my index among qq's three senders
+              const uint32_t dst = mapa_shared(red_s + ((slot * 128 + row) * 16) * 4, qq);
+#pragma unroll
+              for (int i = 0; i < U; i += 4)
+                st_cluster_f4(dst + i * 4, make_float4(d[h2 * 16 + i], d[h2 * 16 + i + 1], d[h2 * 16 + i + 2], d[h2 * 16 + i + 3]));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (uint32_t qq = 0; qq < KS_CL; ++qq)
+            if (qq != r) mbar_arrive_cluster(mapa_shared(red_full, qq));
+        }
+        mbar_wait_cluster(red_full, (s - 1) & 1);
+#pragma unroll
+        for (int src = 0; src < 3; ++src) {
+#pragma unroll
+          for (int i = 0; i < U; i += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(red + (src * 128 + row) * 16 + i);
+            dh[i] += v.x; dh[i + 1] += v.y; dh[i + 2] += v.z; dh[i + 3] += v.w;
+          }
+        }
+      } else {
+        tc_fence_before();
+      }
+      __nv_bfloat16 gb[4 * U];
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const float gi = g4[4 * i], gf = g4[4 * i + 1], gg = g4[4 * i + 2], go = g4[4 * i + 3];
+        const float tc = tanh_fast(ct[i]);
+        const float dc = fmaf(dh[i] * go, 1.f - tc * tc, dc_rec[i]);
+        const float di = dc * gg * gi * (1.f - gi);
+        const float df = dc * cp[i] * gf * (1.f - gf);
+        const float dg = dc * gi * (1.f - gg * gg);
+        const float dO = dh[i] * tc * go * (1.f - go);
+        dc_rec[i] = dc * gf;
+        g4[4 * i] = di; g4[4 * i + 1] = df; g4[4 * i + 2] = dg; g4[4 * i + 3] = dO;
+        gb[4 * i] = __float2bfloat16_rn(di); gb[4 * i + 1] = __float2bfloat16_rn(df);
+        gb[4 * i + 2] = __float2bfloat16_rn(dg); gb[4 * i + 3] = __float2bfloat16_rn(dO);
+      }
+      if (live) {
+        __nv_bfloat16* xb = p.xbuf + ((size_t)(s & 1) * p.nBpad + b) * (size_t)G + 4 * u0;
+#pragma unroll
+        for (int j = 0; j < 4 * U; j += 8)
+          *reinterpret_cast<uint4*>(xb + j) = *reinterpret_cast<const uint4*>(&gb[j]);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        fence_proxy_async();
+        __threadfence();
+        red_release_add(counter, 1u);
+      }
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 4 * U; j += 4)
+          *reinterpret_cast<float4*>(p.dP + rowi * G + 4 * u0 + j) = *reinterpret_cast<const float4*>(&g4[j]);
+      }
+      if (lane == 0) mbar_arrive(tempty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
 // fp32 -> bf16 copy of a weight matrix
 __global__ void cvt_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -415,7 +671,44 @@ static LtPlan lt_plan(int nB, int H, bool bwd) {
 }
 size_t lstm_tc_workspace(int nB, int T, int H, bool bwd) {
   (void)T;
-  return lt_plan(nB, H, bwd).total;
+  return lt_plan(nB, H, bwd).total;       // the K-split BPTT variant uses the same layout (xbuf [2][nBpad][4H], counters)
+}
+
+static bool bwd_ksplit_enabled(int H) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("AVC_LSTM_BWD_KSPLIT");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode != 0 && H % 64 == 0;
+}
+
+// K-split BPTT launch: clusters of 4 along x
+static int lt_launch_ks(const CUtensorMap& mW, const CUtensorMap& mX, LstmTcParams p, int H, cudaStream_t st) {
+  const size_t w_bytes = (size_t)KS_UNITS * H * 2;
+  const size_t fixed = 1024 + w_bytes + 3 * 128 * 16 * 4 + 256;
+  int stages = (int)((225 * 1024 - fixed) / LT_STAGE);
+  stages = std::min(8, std::max(2, stages));
+  const size_t smem = fixed + (size_t)stages * LT_STAGE;
+  p.stages = stages;
+  AVC_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.MT * (H / KS_UNITS) * KS_CL);
+  cfg.blockDim = dim3(LT_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = KS_CL;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;
+  attrs[1].val.cooperative = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  AVC_CUDA(cudaLaunchKernelEx(&cfg, lstm_tc_bwd_ks_kernel, mW, mX, p));
+  g_launches.fetch_add(1);
+  return AVC_OK;
 }
 
 template <bool BWD, int BN, int CL>
@@ -522,6 +815,16 @@ int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh,
     p.counters = counters + ch * 64;
     p.trace = (ch == 0) ? g_trace : nullptr;
     p.exp_mode = exp_mode;
+    if (bwd && bwd_ksplit_enabled(H)) {
+      CUtensorMap mWk;
+      rc = make_map3(&mWk, Wb, pl.K, w_rows, 1, pl.K, (uint64_t)w_rows * pl.K, 64, KS_UNITS);
+      if (rc) return rc;
+      rc = make_map3(&mX, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, 128);
+      if (rc) return rc;
+      rc = lt_launch_ks(mWk, mX, p, H, st);
+      if (rc) return rc;
+      continue;
+    }
     int cl = lt_cluster_size(p.NT);
     rc = make_map3(&mX, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, 128 / cl);
     if (rc) return rc;
