@@ -154,7 +154,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         LT_TRACE(0);
         fence_proxy_async();
         const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb0 = 0; kb0 < kblocks; ++kb0) {
+          const int kb = p.exp_mode == 3 ? (kb0 + nt * 5) % kblocks : kb0;   // stagger: CTAs sweep K from different offsets
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_expect_tx(full_bar(stage), LT_STAGE);
           if (CL == 1) {
@@ -167,7 +168,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           } else
             tma_load_3d_mc(ring + stage * LT_STAGE + crank * SLICE_ROWS * 128, &mapX, full_bar(stage), kb * 64,
                            row0 + crank * SLICE_ROWS, 0, cmask);
-          if (kb == 0) LT_TRACE(1);
+          if (kb0 == 0) LT_TRACE(1);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         LT_TRACE(2);
@@ -187,16 +188,17 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           mbar_arrive(tfull);               // h_{-1} = 0 / no later step: nothing to multiply
           continue;
         }
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb0 = 0; kb0 < kblocks; ++kb0) {
+          const int kb = p.exp_mode == 3 ? (kb0 + nt * 5) % kblocks : kb0;
           mbar_wait(full_bar(stage), phase);
-          if (kb == 0) LT_TRACE(3);
-          if (kb == kblocks - 1) LT_TRACE(4);
+          if (kb0 == 0) LT_TRACE(3);
+          if (kb0 == kblocks - 1) LT_TRACE(4);
           tc_fence_after();
           const uint32_t sa = ring + stage * LT_STAGE, sb = w_base + kb * w_block;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16(tmem_base, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc,
-                     (kb > 0 || k > 0) ? 1u : 0u);
+                     (kb0 > 0 || k > 0) ? 1u : 0u);
           if (CL == 1) umma_commit(empty_bar(stage));
           else umma_commit_mc(empty_bar(stage), cmask);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
