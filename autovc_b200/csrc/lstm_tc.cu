@@ -152,10 +152,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         while (ld_acquire(counter) < target) {
         }
         LT_TRACE(0);
-        fence_proxy_async();
+        if (p.exp_mode == 4) fence_proxy_async();   // writer-side proxy fence + release/acquire order the TMA reads
         const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
         for (int kb0 = 0; kb0 < kblocks; ++kb0) {
-          const int kb = p.exp_mode == 3 ? (kb0 + nt * 5) % kblocks : kb0;   // stagger: CTAs sweep K from different offsets
+          const int kb = kb0;
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_expect_tx(full_bar(stage), LT_STAGE);
           if (CL == 1) {
@@ -189,7 +189,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           continue;
         }
         for (int kb0 = 0; kb0 < kblocks; ++kb0) {
-          const int kb = p.exp_mode == 3 ? (kb0 + nt * 5) % kblocks : kb0;
+          const int kb = kb0;
           mbar_wait(full_bar(stage), phase);
           if (kb0 == 0) LT_TRACE(3);
           if (kb0 == kblocks - 1) LT_TRACE(4);
@@ -272,6 +272,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           red_release_add(counter, 1u);
           LT_TRACE(8);
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // bulk fp32 stores below must not queue ahead of that fence
         if (live) {
 #pragma unroll
           for (int j = 0; j < BN; j += 4)
@@ -355,6 +356,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           red_release_add(counter, 1u);
           LT_TRACE(8);
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // bulk fp32 stores below must not queue ahead of that fence
         if (live) {
 #pragma unroll
           for (int j = 0; j < 4 * U; j += 4)
@@ -468,7 +470,7 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
       for (int s = 1; s < T; ++s) {
         while (ld_acquire(counter) < (unsigned)s * per_step) {
         }
-        fence_proxy_async();
+        if (p.exp_mode == 4) fence_proxy_async();
         const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
@@ -612,6 +614,7 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
         __threadfence();
         red_release_add(counter, 1u);
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       if (live) {
 #pragma unroll
         for (int j = 0; j < 4 * U; j += 4)
