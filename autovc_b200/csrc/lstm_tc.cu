@@ -268,8 +268,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         asm volatile("bar.sync 1, 128;" ::: "memory");     // all 128 rows' slices are written (CTA scope)
         if (threadIdx.x == 64) {                             // one cumulative gpu-scope release for the CTA
           fence_proxy_async();
-          __threadfence();
-          red_release_add(counter, 1u);
+          red_release_add(counter, 1u);        // red.release.gpu is itself the cumulative gpu-scope release
           LT_TRACE(8);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");     // bulk fp32 stores below must not queue ahead of that fence
@@ -352,8 +351,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         asm volatile("bar.sync 1, 128;" ::: "memory");     // all 128 rows' slices are written (CTA scope)
         if (threadIdx.x == 64) {                             // one cumulative gpu-scope release for the CTA
           fence_proxy_async();
-          __threadfence();
-          red_release_add(counter, 1u);
+          red_release_add(counter, 1u);        // red.release.gpu is itself the cumulative gpu-scope release
           LT_TRACE(8);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");     // bulk fp32 stores below must not queue ahead of that fence
@@ -611,7 +609,6 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 64) {
         fence_proxy_async();
-        __threadfence();
         red_release_add(counter, 1u);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
