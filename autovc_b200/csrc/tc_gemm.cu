@@ -141,11 +141,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (MODE == MODE_NT) {
-      if (lane == 0) {
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        if (MODE == MODE_NT) {
           const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
           const int b = m_tile / p.t_tiles, t0 = (m_tile % p.t_tiles) * TC_BM;
           for (int it = 0; it < kiters; ++it) {
@@ -157,33 +157,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tma_load_3d(sa + TC_STAGE_A, &mapB, full_bar(stage), kb * Gm::ROW, n_tile * BN, tap);
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
-        }
-      }
-    } else {
-      // TN stages are built from NBOX_A + NBOX_B small boxes (one 128-byte row of channels each): the whole warp
-      // issues them in parallel, one box per lane (r01 ncu: a single issuing thread was the bottleneck, 491k TMA
-      // instructions per launch and 45% tensor-pipe activity)
-      constexpr int NBOX_A = Gm::NBOX, NBOX_B = BN / Gm::ROW;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TnItem wi = tn_decode(tile, p.k_tiles, p.n_tiles, p.ntaps);
-        const int rb0 = wi.split * p.rblocks_per_split;
-        const int rb1 = min(p.rblocks, rb0 + p.rblocks_per_split);
-        for (int rb = rb0; rb < rb1; ++rb) {
-          const int b = rb / p.tbr, t0 = (rb % p.tbr) * Gm::RS;
-          if (lane == 0) {
+        } else {
+          const TnItem wi = tn_decode(tile, p.k_tiles, p.n_tiles, p.ntaps);
+          const int split = wi.split, k_tile = wi.k_tile, n_tile = wi.n_tile, tap = wi.tap;
+          const int rb0 = split * p.rblocks_per_split;
+          const int rb1 = min(p.rblocks, rb0 + p.rblocks_per_split);
+          for (int rb = rb0; rb < rb1; ++rb) {
+            const int b = rb / p.tbr, t0 = (rb % p.tbr) * Gm::RS;
             mbar_wait(empty_bar(stage), phase ^ 1);
             mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
+            const uint32_t sa = stage0 + stage * TC_STAGE_BYTES;
+#pragma unroll
+            for (int h = 0; h < Gm::NBOX; ++h)
+              tma_load_3d(sa + h * Gm::BOX_BYTES, &mapA, full_bar(stage), n_tile * TC_BM + h * Gm::ROW, t0, b);
+#pragma unroll
+            for (int h = 0; h < BN / Gm::ROW; ++h)
+              tma_load_3d(sa + TC_STAGE_A + h * Gm::BOX_BYTES, &mapB, full_bar(stage), k_tile * BN + h * Gm::ROW,
+                          t0 + p.shift0 + tap, b);
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          const uint32_t sa = stage0 + stage * TC_STAGE_BYTES;
-          if (lane < NBOX_A)
-            tma_load_3d(sa + lane * Gm::BOX_BYTES, &mapA, full_bar(stage), wi.n_tile * TC_BM + lane * Gm::ROW, t0, b);
-          else if (lane < NBOX_A + NBOX_B)
-            tma_load_3d(sa + TC_STAGE_A + (lane - NBOX_A) * Gm::BOX_BYTES, &mapB, full_bar(stage),
-                        wi.k_tile * BN + (lane - NBOX_A) * Gm::ROW, t0 + p.shift0 + wi.tap, b);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
