@@ -278,6 +278,76 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_frontend_or_convert(args):
+    """Secondary legs (not the driver's default): `--workload frontend` = make_spect log-mel front-end alone
+    (HBM roofline, SURVEY 8(d): 1 480 320 algorithmic bytes per 10 s utterance); `--workload convert` =
+    BASELINE.json configs[4]: front-end -> pad to x32 -> eval forward with swapped embeddings, mel frames/sec."""
+    import numpy as np
+    import autovc_b200
+    from autovc_b200.conversion import convert, padded_frames
+    from autovc_b200.make_spect import Spect
+    from oracle import make_spect_ref as fref
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    n, L = args.utterances, 160000
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    env = 0.55 + 0.45 * torch.sin(torch.linspace(0, 60, L, device=dev))[None, :]
+    wav = (0.1 * torch.randn(n, L, generator=g, device=dev) * env).clamp(-1.0, 1.0 - 2 ** -15)
+    dither = torch.rand(n, L, generator=g, device=dev)
+    sp = Spect()
+    F_ = 1 + L // 256
+    peaks = measured_peaks()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    if args.workload == "frontend":
+        ms = timed(lambda: sp.logmel(wav, dither, None, max_frames=padded_frames(L)), args.steps, args.warmup)
+        alg_bytes = n * (4 * L + 4 * L + 4 * 80 * F_)
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        # CPU baseline: oracle restatement on a bounded sample, single process like the reference
+        k = min(8, n)
+        wc, dc = wav[:k].cpu().numpy(), dither[:k].double().cpu().numpy()
+        t0 = time.perf_counter()
+        for i in range(k):
+            fref.logmel_from_wav(wc[i], dc[i])
+        cpu_fps = k * F_ / (time.perf_counter() - t0)
+        line = {"metric": "log-mel front-end mel frames/sec", "value": n * F_ / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64 IIR + f32 FFT", "data": "synthetic",
+                "config": {"workload": f"make_spect front-end, {n} synthetic 10 s 16 kHz waveforms (inputs {2*n*L*4/1e9:.2f} GB > L2)"},
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                             "traffic": None, "peak_source": peaks["source"] + " hbm_gbs",
+                             "algorithmic_bytes_per_utterance": 4 * L + 4 * L + 4 * 80 * F_},
+                "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
+                                 "sample": f"{k} of the {n} utterances through oracle/make_spect_ref.py (scipy filtfilt + numpy rfft)"}}
+        print(json.dumps(line), flush=True)
+        return
+    torch.manual_seed(0)
+    G = autovc_b200.Generator(32, 256, 512, 32, precision=args.precision).to(dev)
+    e = F.normalize(torch.randn(n, 256, generator=torch.Generator().manual_seed(5)), dim=-1).to(dev) * 0.8
+    et = e.roll(1, 0).contiguous()
+    ms = timed(lambda: convert(G, sp, wav, dither, None, e, et, chunk=256), args.steps, max(1, args.warmup - 2))
+    mac = MAC_PER_FRAME[(32, 80)] - 3_481_600 - 73_728 * 0   # one encoder pass in conversion (SURVEY 8(d): 28 385 280 MAC/frame)
+    flops = 2.0 * 28_385_280 * n * padded_frames(L)
+    line = {"metric": "conversion mel frames/sec", "value": n * F_ / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"waveform -> log-mel -> pad to x32 -> Generator(32,256,512,32).eval() forward, {n} x 10 s utterances, chunks of 256"},
+            "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"], "traffic": None}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -291,7 +361,11 @@ def main():
     ap.add_argument("--freq", type=int, default=16)
     ap.add_argument("--cpu-sample-batch", dest="cpu_sample_batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "frontend", "convert"])
+    ap.add_argument("--utterances", type=int, default=1024, help="frontend/convert legs: number of 10 s utterances")
     args = ap.parse_args()
+    if args.workload != "train":
+        return run_frontend_or_convert(args)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
