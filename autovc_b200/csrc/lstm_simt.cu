@@ -45,11 +45,13 @@ __global__ void lstm_small_fwd_kernel(const float* __restrict__ P, const float* 
   float c = 0.f;
   const bool live = b < nB;
   const unsigned quad_base = ((threadIdx.y * blockDim.x + threadIdx.x) & 31) & ~3u;
+  float p_next = live ? P[((size_t)b * T + (reverse ? T - 1 : 0)) * G + j] : 0.f;
   for (int step = 0; step < T; ++step) {
     const int t = reverse ? (T - 1 - step) : step;
-    float acc = 0.f;
+    float acc = p_next;
+    if (live && step + 1 < T)       // software prefetch: the next step's pre-activation is independent of the recurrence
+      p_next = P[((size_t)b * T + (reverse ? t - 1 : t + 1)) * G + j];
     if (live) {
-      acc = P[((size_t)b * T + t) * G + j];
       const float* w = Ws + (size_t)j * (H + 1);
       const float* h = hs + ul * H;
 #pragma unroll 8
@@ -91,7 +93,6 @@ __global__ void lstm_small_bwd_kernel(const float* __restrict__ dH, int lddh, co
   }
   float* Ws = sm;                              // [G][H+1]   (row j = gate column, col = hidden unit)
   float* dgs = Ws + (size_t)G * (H + 1);       // [UPB][G]   dG of the step processed just before
-  float* dhs = dgs + (size_t)blockDim.y * G;   // [UPB][H]
   const int j = threadIdx.x, ul = threadIdx.y;
   const int b = blockIdx.x * blockDim.y + ul;
   const int u = j >> 2, g = j & 3;
@@ -101,29 +102,37 @@ __global__ void lstm_small_bwd_kernel(const float* __restrict__ dH, int lddh, co
   const bool live = b < nB;
   float dc_rec = 0.f;
   const unsigned quad_base = ((threadIdx.y * blockDim.x + threadIdx.x) & 31) & ~3u;
+  // operands of the step about to be processed, fetched one step ahead (they do not depend on the recurrence)
+  float a_n = 0.f, ct_n = 0.f, cp_n = 0.f, dH_n = 0.f;
+  auto fetch = [&](int step) {
+    const int t = reverse ? (T - 1 - step) : step;
+    const int t_prev = reverse ? t + 1 : t - 1;
+    a_n = gates[((size_t)b * T + t) * G + j];
+    ct_n = c_seq[((size_t)b * T + t) * H + u];
+    cp_n = (step > 0) ? c_seq[((size_t)b * T + t_prev) * H + u] : 0.f;
+    dH_n = dH[((size_t)b * T + t) * lddh + u];
+  };
+  if (live) fetch(T - 1);
   // BPTT visits timesteps in the opposite order of the forward walk
   for (int step = T - 1; step >= 0; --step) {
     const int t = reverse ? (T - 1 - step) : step;
-    const int t_prev = reverse ? t + 1 : t - 1;  // the step that fed c_{prev}, h_{prev}
-    // phase 1: dh[u] = dH[b,t,u] + sum_j' dG_next[j'] * W[j'][u]
-    if (j < H) {
-      float acc = live ? dH[((size_t)b * T + t) * lddh + j] : 0.f;
-      const float* dg = dgs + ul * G;
-      for (int jj = 0; jj < G; ++jj) acc = fmaf(dg[jj], Ws[(size_t)jj * (H + 1) + j], acc);
-      dhs[ul * H + j] = acc;
+    const float a = a_n, ct = ct_n, cp = cp_n, dHt = dH_n;
+    if (live && step > 0) fetch(step - 1);
+    // dh[u] = dH[b,t,u] + sum_j' dG_next[j'] * W[j'][u]: thread (u,g) sums the quarter j' in [g*H, (g+1)*H), quad-reduce
+    float part = 0.f;
+    {
+      const float* dg = dgs + ul * G + g * H;
+      const float* w = Ws + (size_t)(g * H) * (H + 1) + u;
+#pragma unroll 8
+      for (int jj = 0; jj < H; ++jj) part = fmaf(dg[jj], w[(size_t)jj * (H + 1)], part);
     }
-    __syncthreads();
-    float a = 0.f, ct = 0.f, cp = 0.f;
-    if (live) {
-      a = gates[((size_t)b * T + t) * G + j];
-      ct = c_seq[((size_t)b * T + t) * H + u];
-      cp = (step > 0) ? c_seq[((size_t)b * T + t_prev) * H + u] : 0.f;
-    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    const float dh = part + dHt;
     const float gi = __shfl_sync(0xffffffffu, a, quad_base + 0);
     const float gf = __shfl_sync(0xffffffffu, a, quad_base + 1);
     const float gg = __shfl_sync(0xffffffffu, a, quad_base + 2);
     const float go = __shfl_sync(0xffffffffu, a, quad_base + 3);
-    const float dh = dhs[ul * H + u];
     const float tc = tanhf(ct);
     const float dc = dh * go * (1.f - tc * tc) + dc_rec;
     float d;
@@ -132,6 +141,7 @@ __global__ void lstm_small_bwd_kernel(const float* __restrict__ dH, int lddh, co
     else if (g == 2) d = dc * gi * (1.f - gg * gg);
     else d = dh * tc * go * (1.f - go);
     dc_rec = dc * gf;
+    __syncthreads();                 // every thread has read the previous step's dgs
     dgs[ul * G + j] = d;
     if (live) dP[((size_t)b * T + t) * G + j] = d;
     __syncthreads();
