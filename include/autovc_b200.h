@@ -196,7 +196,10 @@ int avc_loss_bwd(const float* a, const float* b, size_t n, const float* gout, in
  * make_spect.py:76, supplied by the host so the stream matches); lengths[i] <= max_len;
  * out: (n_utt, max_frames, 80) float32, frames beyond 1 + lengths[i]/256 are zero-filled
  * (= conversion.py:40-44 pad_seq).  mel_basis: (513, 80) float32 (librosa.filters.mel^T).
- * filt: double[12] = Butterworth b[0..5], a[0..5]; zi: double[5] = scipy lfilter_zi(b, a).
+ * filt: double[18] = the Butterworth filter as 3 second-order sections, scipy layout (b0,b1,b2,1,a1,a2) per row
+ * (scipy.signal.tf2sos(b, a)); zi: double[6] = scipy.signal.sosfilt_zi(sos).  The cascade realisation is what makes a
+ * chunk-parallel IIR numerically possible; it matches scipy's (b, a)-form filtfilt to ~1e-6 on the waveform and to
+ * < 1e-7 on the log-mel output.  lengths[i] must be >= 513 (numpy's multi-bounce reflection is not reproduced).
  * workspace: avc_logmel_workspace_bytes(n_utt, max_len).
  */
 int avc_logmel_frontend(const float* wav, const float* dither, const int* lengths, int n_utt, int max_len,
