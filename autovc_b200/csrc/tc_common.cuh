@@ -39,6 +39,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // multicast variants (thread-block clusters): the box lands at the same CTA-relative smem offset of every CTA in
 // `mask` and completes tx bytes on the mbarrier at the same offset in each of them
 __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
@@ -171,6 +177,33 @@ static inline int make_map3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64
   return AVC_OK;
 }
 
+
+// 4-D map over a channels-last (nB, T, C) array with the channel axis split into groups of `row` elements (one 128-byte
+// swizzle row each): dims (row, T, C/row, nB).  A box (row, frames, ngroups, 1) then lands in shared memory as `ngroups`
+// consecutive [frames][row] blocks -- the MN-major operand tile of the weight-gradient GEMM in ONE TMA instruction
+// instead of one per 128-byte channel group.  Requires C % row == 0.
+static inline int make_map4_grouped(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t T, uint64_t nB, uint64_t ld_elems,
+                                    uint32_t row, uint32_t frames, uint32_t ngroups, int elem_bytes, bool atom32) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return AVC_ERR_CUDA;
+  }
+  cuuint64_t dims[4] = {row, T, C / row, nB};
+  cuuint64_t strides[3] = {ld_elems * elem_bytes, (cuuint64_t)row * elem_bytes, T * ld_elems * elem_bytes};
+  cuuint32_t box[4] = {row, frames, ngroups, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4,
+                   const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d grouped) failed with CUresult %d (C=%llu T=%llu row=%u frames=%u groups=%u)", (int)r,
+              (unsigned long long)C, (unsigned long long)T, row, frames, ngroups);
+    return AVC_ERR_CUDA;
+  }
+  return AVC_OK;
+}
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }

@@ -55,6 +55,7 @@ struct TcParams {
   double* stats;
   // TN
   int k_tiles, splits, rblocks, rblocks_per_split, tbr;   // tbr = ceil(T / frames-per-stage)
+  int grouped_a, grouped_b;   // operand fetched with one grouped 4-D box per stage (make_map4_grouped)
   float* part;
 };
 
@@ -167,13 +168,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             mbar_wait(empty_bar(stage), phase ^ 1);
             mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
             const uint32_t sa = stage0 + stage * TC_STAGE_BYTES;
+            // one TMA instruction per operand when the channel count is a multiple of the 128-byte row (a single
+            // thread issues ~1 TMA per 100 cycles: 12 small boxes per stage made the producer the bottleneck)
+            if (p.grouped_a) {
+              tma_load_4d(sa, &mapA, full_bar(stage), 0, t0, n_tile * Gm::NBOX, b);
+            } else {
 #pragma unroll
-            for (int h = 0; h < Gm::NBOX; ++h)
-              tma_load_3d(sa + h * Gm::BOX_BYTES, &mapA, full_bar(stage), n_tile * TC_BM + h * Gm::ROW, t0, b);
+              for (int h = 0; h < Gm::NBOX; ++h)
+                tma_load_3d(sa + h * Gm::BOX_BYTES, &mapA, full_bar(stage), n_tile * TC_BM + h * Gm::ROW, t0, b);
+            }
+            if (p.grouped_b) {
+              tma_load_4d(sa + TC_STAGE_A, &mapB, full_bar(stage), 0, t0 + p.shift0 + tap, k_tile * (BN / Gm::ROW), b);
+            } else {
 #pragma unroll
-            for (int h = 0; h < BN / Gm::ROW; ++h)
-              tma_load_3d(sa + TC_STAGE_A + h * Gm::BOX_BYTES, &mapB, full_bar(stage), k_tile * BN + h * Gm::ROW,
-                          t0 + p.shift0 + tap, b);
+              for (int h = 0; h < BN / Gm::ROW; ++h)
+                tma_load_3d(sa + TC_STAGE_A + h * Gm::BOX_BYTES, &mapB, full_bar(stage), k_tile * BN + h * Gm::ROW,
+                            t0 + p.shift0 + tap, b);
+            }
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -588,14 +599,19 @@ int gemm_tn_taps_tc(const float* dY, int ldy, const float* X, int ldx, float* dW
     Xop = dst; x_ld = pl.Kp; x_c = pl.Kp;
   }
   CUtensorMap mA, mB;
-  rc = make_map3(&mA, Yop, y_c, T, nB, y_ld, (uint64_t)T * y_ld, row, pl.rs, eb, eb == 4);
+  // grouped 4-D boxes need whole 128-byte channel groups and whole tiles (no partially out-of-range group)
+  const bool ga = (y_c % TC_BM) == 0, gb = (x_c % pl.bn) == 0;
+  if (ga) rc = make_map4_grouped(&mA, Yop, y_c, T, nB, y_ld, row, pl.rs, TC_BM / row, eb, eb == 4);
+  else rc = make_map3(&mA, Yop, y_c, T, nB, y_ld, (uint64_t)T * y_ld, row, pl.rs, eb, eb == 4);
   if (rc) return rc;
-  rc = make_map3(&mB, Xop, x_c, T, nB, x_ld, (uint64_t)T * x_ld, row, pl.rs, eb, eb == 4);
+  if (gb) rc = make_map4_grouped(&mB, Xop, x_c, T, nB, x_ld, row, pl.rs, pl.bn / row, eb, eb == 4);
+  else rc = make_map3(&mB, Xop, x_c, T, nB, x_ld, (uint64_t)T * x_ld, row, pl.rs, eb, eb == 4);
   if (rc) return rc;
   TcParams p{};
   p.nB = nB; p.T = T; p.ntaps = ntaps; p.shift0 = shift0; p.N = N; p.K = K;
   p.n_tiles = pl.Np / TC_BM; p.k_tiles = pl.Kp / pl.bn; p.splits = pl.splits; p.rblocks = pl.rblocks;
   p.rblocks_per_split = pl.rps; p.tbr = ceil_div(T, pl.rs); p.part = part;
+  p.grouped_a = ga; p.grouped_b = gb;
   const int items = pl.tiles * pl.splits;
   const int grid = std::min(items, num_sms());
   rc = tc_dispatch<MODE_TN>(eb, pl.bn, mA, mB, p, grid, st);
