@@ -27,12 +27,29 @@ col_reduce_kernel(const float* __restrict__ x, int ldx, const float* __restrict_
       mu = mean[c];
       rs = rstd[c];
     }
-    for (int r = r0 + threadIdx.y; r < r1; r += CR_ROWS) {
-      if (MODE == 0) {
+    if (MODE == 0) {
+      // four independent row streams per thread keep enough loads in flight to approach HBM speed
+      float a1 = 0.f, b1 = 0.f, a2 = 0.f, b2 = 0.f, a3 = 0.f, b3 = 0.f;
+      int r = r0 + threadIdx.y;
+      for (; r + 3 * CR_ROWS < r1; r += 4 * CR_ROWS) {
+        const float v0 = x[(size_t)r * ldx + c];
+        const float v1 = x[(size_t)(r + CR_ROWS) * ldx + c];
+        const float v2 = x[(size_t)(r + 2 * CR_ROWS) * ldx + c];
+        const float v3 = x[(size_t)(r + 3 * CR_ROWS) * ldx + c];
+        a += v0; b = fmaf(v0, v0, b);
+        a1 += v1; b1 = fmaf(v1, v1, b1);
+        a2 += v2; b2 = fmaf(v2, v2, b2);
+        a3 += v3; b3 = fmaf(v3, v3, b3);
+      }
+      for (; r < r1; r += CR_ROWS) {
         const float v = x[(size_t)r * ldx + c];
         a += v;
         b = fmaf(v, v, b);
-      } else {
+      }
+      a += a1 + a2 + a3;
+      b += b1 + b2 + b3;
+    } else {
+      for (int r = r0 + threadIdx.y; r < r1; r += CR_ROWS) {
         const size_t i = (size_t)r * C + c;
         float g = x[i];  // dz
         if (act == AVC_ACT_RELU) g = z[i] > 0.f ? g : 0.f;
