@@ -169,6 +169,91 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dz, const floa
   }
 }
 
+// float4 variant (C % 4 == 0, 16-byte aligned pointers): one channel lookup per four elements
+__global__ void bn_act_bwd_apply_vec4_kernel(const float4* __restrict__ dz, const float4* __restrict__ z,
+                                             const float4* __restrict__ y, const float* __restrict__ mean,
+                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                             const double* __restrict__ sums, float4* __restrict__ dy, size_t total4, int M,
+                                             int C, int act) {
+  const float invM = 1.0f / (float)M;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i * 4) % C);
+    const float4 d4 = dz[i], y4 = y[i];
+    float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act != AVC_ACT_NONE) z4 = z[i];
+    const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w}, zv[4] = {z4.x, z4.y, z4.z, z4.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float g = dv[j];
+      if (act == AVC_ACT_RELU) g = zv[j] > 0.f ? g : 0.f;
+      else if (act == AVC_ACT_TANH) g *= (1.f - zv[j] * zv[j]);
+      const float rs = rstd[c + j];
+      const float xh = (yv[j] - mean[c + j]) * rs;
+      const float sg = (float)sums[c + j] * invM, sgx = (float)sums[C + c + j] * invM;
+      o[j] = gamma[c + j] * rs * (g - sg - xh * sgx);
+    }
+    dy[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// float4 variant of the BN-backward column reduction: block = 32 column-quads x 8 row lanes
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_vec4_kernel(const float4* __restrict__ dz, const float4* __restrict__ z, const float4* __restrict__ y,
+                          const float* __restrict__ mean, const float* __restrict__ rstd, int M, int C, int rows_per_block,
+                          int act, double* __restrict__ out) {
+  __shared__ float sa[8][128 + 4], sb[8][128 + 4];
+  const int cq = blockIdx.x * 32 + threadIdx.x;      // column quad
+  const int c = cq * 4;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    float mu[4], rs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mu[j] = mean[c + j];
+      rs[j] = rstd[c + j];
+    }
+    const int C4 = C >> 2;
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      const size_t i = (size_t)r * C4 + cq;
+      const float4 d4 = dz[i], y4 = y[i];
+      float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (act != AVC_ACT_NONE) z4 = z[i];
+      const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w}, zv[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float g = dv[j];
+        if (act == AVC_ACT_RELU) g = zv[j] > 0.f ? g : 0.f;
+        else if (act == AVC_ACT_TANH) g *= (1.f - zv[j] * zv[j]);
+        a[j] += g;
+        b[j] = fmaf(g, (yv[j] - mu[j]) * rs[j], b[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sa[threadIdx.y][threadIdx.x * 4 + j] = a[j];
+    sb[threadIdx.y][threadIdx.x * 4 + j] = b[j];
+  }
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 128) {
+    const int cc = blockIdx.x * 128 + t;
+    if (cc < C) {
+      double da = 0.0, db = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        da += (double)sa[i][t];
+        db += (double)sb[i][t];
+      }
+      atomicAdd(out + cc, da);
+      atomicAdd(out + C + cc, db);
+    }
+  }
+}
+
 __global__ void bn_param_grad_kernel(const double* __restrict__ sums, float* __restrict__ dgamma,
                                      float* __restrict__ dbeta, int C, int accumulate) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -282,6 +367,17 @@ extern "C" int avc_bn_act_fwd(const float* y, const float* mean, const float* rs
 extern "C" int avc_bn_act_bwd_reduce(const float* dz, const float* z, const float* y, const float* mean,
                                      const float* rstd, double* sums, int M, int C, int act, void* stream) {
   AVC_REQUIRE(dz && z && y && mean && rstd && sums && M > 0 && C > 0, "avc_bn_act_bwd_reduce: bad arguments");
+  const bool vec = (C % 4 == 0) && (((uintptr_t)dz | (uintptr_t)z | (uintptr_t)y) % 16 == 0);
+  if (vec) {
+    const int cb = ceil_div(C, 128);
+    int rb = ceil_div(8 * num_sms(), cb);
+    int rpb = std::max(64, ceil_div(M, rb));
+    rb = ceil_div(M, rpb);
+    bn_bwd_reduce_vec4_kernel<<<dim3(cb, rb), dim3(32, 8), 0, as_stream(stream)>>>(
+        (const float4*)dz, (const float4*)z, (const float4*)y, mean, rstd, M, C, rpb, act, sums);
+    AVC_LAUNCHED();
+    return AVC_OK;
+  }
   dim3 grid;
   int rpb;
   col_reduce_grid(M, C, grid, rpb);
@@ -295,7 +391,12 @@ extern "C" int avc_bn_act_bwd_apply(const float* dz, const float* z, const float
                                     float* dbeta, int M, int C, int act, int accumulate, void* stream) {
   AVC_REQUIRE(dz && z && y && mean && rstd && gamma && sums && dy && M > 0 && C > 0, "avc_bn_act_bwd_apply: bad arguments");
   const size_t total = (size_t)M * C;
-  bn_act_bwd_apply_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(dz, z, y, mean, rstd, gamma, sums, dy, total, M, C, act);
+  const bool vec = (C % 4 == 0) && (((uintptr_t)dz | (uintptr_t)z | (uintptr_t)y | (uintptr_t)dy) % 16 == 0);
+  if (vec)
+    bn_act_bwd_apply_vec4_kernel<<<ew_blocks(total / 4), 256, 0, as_stream(stream)>>>(
+        (const float4*)dz, (const float4*)z, (const float4*)y, mean, rstd, gamma, sums, (float4*)dy, total / 4, M, C, act);
+  else
+    bn_act_bwd_apply_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(dz, z, y, mean, rstd, gamma, sums, dy, total, M, C, act);
   AVC_LAUNCHED();
   if (dgamma || dbeta) {
     bn_param_grad_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(sums, dgamma, dbeta, C, accumulate);
