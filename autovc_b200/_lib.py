@@ -12,7 +12,8 @@ from ctypes import c_double, c_float, c_int, c_size_t, c_ulonglong, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libautovc_b200.so")
 
-PREC_FP32, PREC_BF16, PREC_TF32 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_TF32, PREC_HALF = 0, 1, 2, 3
+FMT_FP32, FMT_BF16, FMT_FP16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 ACT_CODES = {"none": ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH}
 
@@ -43,6 +44,15 @@ SIGNATURES = {
     "avc_lstm_seq_bwd": (c_int, [P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
     "avc_lstm_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "avc_debug_set_trace": (None, [P]),
+    "avc_gemm_nt_taps_h": (c_int, [P, c_int, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, P, c_size_t, P]),
+    "avc_gemm_nt_h_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "avc_gemm_tn_taps_h": (c_int, [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
+    "avc_gemm_tn_h_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "avc_cast16": (c_int, [P, c_int, P, c_int, c_size_t, c_int, c_int, P]),
+    "avc_bn_act_fwd_h": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "avc_bn_act_bwd_apply_h": (c_int, [P, P, P, P, P, P, P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, P]),
+    "avc_lstm_seq_fwd_h": (c_int, [P, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
+    "avc_lstm_seq_bwd_h": (c_int, [P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, P, c_size_t, P]),
     "avc_concat_bcast": (c_int, [P, c_int, P, P, c_int, c_int, c_int, c_int, P]),
     "avc_codes_fwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),
     "avc_codes_bwd": (c_int, [P, P, c_int, c_int, c_int, c_int, P]),

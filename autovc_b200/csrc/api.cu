@@ -36,16 +36,19 @@ int lstm_seq_fwd_simt(const float*, const float*, float*, int, float*, float*, i
 int lstm_seq_bwd_simt(const float*, int, const float*, const float*, const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
 size_t lstm_bwd_workspace_simt(int, int, int);
 // tensor-core implementations (tc_gemm.cu)
-int gemm_nt_taps_tc(const float*, int, const float*, const float*, float*, int, int, int, int, int, int, int, double*, int, int, void*, size_t, cudaStream_t);
-int gemm_tn_taps_tc(const float*, int, const float*, int, float*, int, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
+int gemm_nt_taps_tc(const void*, int, int, const float*, const float*, float*, int, int, int, int, int, int, int, double*, int, int, int, void*, size_t, cudaStream_t);
+int gemm_tn_taps_tc(const void*, int, int, const void*, int, int, float*, int, int, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 size_t gemm_nt_workspace_tc(int, int, int, int, int, int);
+size_t gemm_nt_workspace_h(int, int, int, int, int, int);
+size_t gemm_tn_workspace_h(int, int, int, int, int, int, int);
 size_t gemm_tn_workspace_tc(int, int, int, int, int, int);
 // persistent tensor-core recurrences (lstm_tc.cu)
 bool lstm_tc_supported(int H);
 void lstm_tc_set_trace(unsigned long long* p);
 size_t lstm_tc_workspace(int nB, int T, int H, bool bwd);
 int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh, float* gates, float* c_seq, const float* dH,
-                int lddh, float* dP, int nB, int T, int H, int reverse, void* ws, size_t ws_bytes, cudaStream_t st);
+                int lddh, float* dP, int nB, int T, int H, int reverse, void* ws, size_t ws_bytes, cudaStream_t st,
+                void* aux16 = nullptr, int fmt16 = 0);
 
 }  // namespace avc
 
@@ -64,8 +67,8 @@ extern "C" int avc_gemm_nt_taps(const float* A, int lda, const float* W, const f
   if (prec == AVC_PREC_FP32)
     return gemm_nt_taps_simt(A, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate, as_stream(stream));
   if (prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32)
-    return gemm_nt_taps_tc(A, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate,
-                           prec == AVC_PREC_BF16 ? 2 : 4, workspace, workspace_bytes, as_stream(stream));
+    return gemm_nt_taps_tc(A, 0, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate,
+                           prec == AVC_PREC_BF16 ? 2 : 4, 1, workspace, workspace_bytes, as_stream(stream));
   set_error("avc_gemm_nt_taps: precision %d not available in this build", prec);
   return AVC_ERR_UNSUPPORTED;
 }
@@ -81,8 +84,8 @@ extern "C" int avc_gemm_tn_taps(const float* dY, int ldy, const float* X, int ld
     return gemm_tn_taps_simt(dY, ldy, X, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, accumulate, workspace,
                              workspace_bytes, as_stream(stream));
   if (prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32)
-    return gemm_tn_taps_tc(dY, ldy, X, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, accumulate,
-                           prec == AVC_PREC_BF16 ? 2 : 4, workspace, workspace_bytes, as_stream(stream));
+    return gemm_tn_taps_tc(dY, 0, ldy, X, 0, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, accumulate,
+                           prec == AVC_PREC_BF16 ? 2 : 4, 1, workspace, workspace_bytes, as_stream(stream));
   set_error("avc_gemm_tn_taps: precision %d not available in this build", prec);
   return AVC_ERR_UNSUPPORTED;
 }
@@ -140,3 +143,49 @@ extern "C" size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H, int prec) {
 }
 
 extern "C" void avc_debug_set_trace(unsigned long long* device_buffer) { lstm_tc_set_trace(device_buffer); }
+
+// ---- GEMMs on operands that already live in HBM as 16-bit (formats: 0 = fp32 (staged to half_fmt), 1 = bf16, 2 = fp16) ----
+extern "C" int avc_gemm_nt_taps_h(const void* A, int a_fmt, int lda, const float* W, const float* bias, float* C, int ldc, int nB,
+                                  int T, int N, int K, int ntaps, int shift0, double* chan_stats, int accumulate, int half_fmt,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  AVC_REQUIRE(A && W && C, "avc_gemm_nt_taps_h: null pointer");
+  AVC_REQUIRE(nB > 0 && T > 0 && N > 0 && K > 0 && ntaps > 0 && lda >= K && ldc >= N, "avc_gemm_nt_taps_h: bad shape");
+  AVC_REQUIRE(a_fmt >= 0 && a_fmt <= 2 && (half_fmt == 1 || half_fmt == 2), "avc_gemm_nt_taps_h: bad format code");
+  return gemm_nt_taps_tc(A, a_fmt, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate, 2, half_fmt,
+                         workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int avc_gemm_tn_taps_h(const void* dY, int y_fmt, int ldy, const void* X, int x_fmt, int ldx, float* dW, int nB, int T,
+                                  int N, int K, int ntaps, int shift0, int out_mode, int accumulate, int half_fmt, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  AVC_REQUIRE(dY && X && dW, "avc_gemm_tn_taps_h: null pointer");
+  AVC_REQUIRE(nB > 0 && T > 0 && N > 0 && K > 0 && ntaps > 0 && ldy >= N && ldx >= K, "avc_gemm_tn_taps_h: bad shape");
+  AVC_REQUIRE(out_mode == 0 || out_mode == 1 || (out_mode == 2 && ntaps == 1 && N % 4 == 0), "avc_gemm_tn_taps_h: bad out_mode");
+  AVC_REQUIRE(y_fmt >= 0 && y_fmt <= 2 && x_fmt >= 0 && x_fmt <= 2 && (half_fmt == 1 || half_fmt == 2), "avc_gemm_tn_taps_h: bad format code");
+  return gemm_tn_taps_tc(dY, y_fmt, ldy, X, x_fmt, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, accumulate, 2, half_fmt, workspace,
+                         workspace_bytes, as_stream(stream));
+}
+
+extern "C" size_t avc_gemm_nt_h_workspace_bytes(int nB, int T, int N, int K, int ntaps, int a_fmt) {
+  return gemm_nt_workspace_h(nB, T, N, K, ntaps, a_fmt);
+}
+extern "C" size_t avc_gemm_tn_h_workspace_bytes(int nB, int T, int N, int K, int ntaps, int y_fmt, int x_fmt) {
+  return gemm_tn_workspace_h(nB, T, N, K, ntaps, y_fmt, x_fmt);
+}
+
+// persistent recurrences that additionally emit the 16-bit operand copy the following GEMMs read ("half" mode)
+extern "C" int avc_lstm_seq_fwd_h(const float* P, const float* Whh_p, float* h_seq, int ldh, float* gates, float* c_seq, void* h16,
+                                  int fmt16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes, void* stream) {
+  AVC_REQUIRE(P && Whh_p && h_seq && gates && c_seq && h16, "avc_lstm_seq_fwd_h: null pointer");
+  AVC_REQUIRE(nB > 0 && T > 0 && lstm_tc_supported(H) && ldh >= H && ldh % 4 == 0 && (fmt16 == 1 || fmt16 == 2), "avc_lstm_seq_fwd_h: unsupported shape");
+  return lstm_seq_tc(false, Whh_p, P, h_seq, ldh, gates, c_seq, nullptr, 0, nullptr, nB, T, H, reverse, workspace, workspace_bytes,
+                     as_stream(stream), h16, fmt16);
+}
+
+extern "C" int avc_lstm_seq_bwd_h(const float* dH, int lddh, const float* Whh_pT, const float* gates, const float* c_seq, float* dP,
+                                  void* dP16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes, void* stream) {
+  AVC_REQUIRE(dH && Whh_pT && gates && c_seq && dP && dP16, "avc_lstm_seq_bwd_h: null pointer");
+  AVC_REQUIRE(nB > 0 && T > 0 && lstm_tc_supported(H) && lddh >= H && lddh % 4 == 0, "avc_lstm_seq_bwd_h: unsupported shape");
+  return lstm_seq_tc(true, Whh_pT, nullptr, nullptr, 0, const_cast<float*>(gates), const_cast<float*>(c_seq), dH, lddh, dP, nB, T, H,
+                     reverse, workspace, workspace_bytes, as_stream(stream), dP16, 1);
+}

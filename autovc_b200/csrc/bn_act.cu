@@ -1,9 +1,51 @@
 // Train/eval BatchNorm1d + activation (+ residual) forward/backward, channel reductions, losses.
 // Reference call sites: nn.BatchNorm1d model_vc_mel.py:57,:101,:139,:150,:160; F.relu :69,:115;
 // torch.tanh :165; residual :197; F.mse_loss / F.l1_loss solver_encoder.py:230,:233,:236.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace avc {
+
+// 16-bit stores for the "half" precision mode (fmt 1 = bf16, 2 = fp16): four values -> 8 bytes
+__device__ __forceinline__ uint2 pack4_16(float a, float b, float c, float d, int fmt) {
+  uint2 r;
+  if (fmt == 2) {
+    const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    r.x = *reinterpret_cast<const uint32_t*>(&lo);
+    r.y = *reinterpret_cast<const uint32_t*>(&hi);
+  } else {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    r.x = *reinterpret_cast<const uint32_t*>(&lo);
+    r.y = *reinterpret_cast<const uint32_t*>(&hi);
+  }
+  return r;
+}
+__device__ __forceinline__ uint16_t cvt1_16(float a, int fmt) {
+  if (fmt == 2) {
+    const __half h = __float2half_rn(a);
+    return *reinterpret_cast<const uint16_t*>(&h);
+  }
+  const __nv_bfloat16 h = __float2bfloat16_rn(a);
+  return *reinterpret_cast<const uint16_t*>(&h);
+}
+
+// dst16 (M, C) ld ldd  <-  src fp32 (M, C) ld lds
+__global__ void cast16_kernel(const float* __restrict__ src, int lds, uint16_t* __restrict__ dst, int ldd, size_t M, int C, int fmt) {
+  const size_t total = M * (size_t)C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / C;
+    const int c = (int)(i % C);
+    dst[r * ldd + c] = cvt1_16(src[r * lds + c], fmt);
+  }
+}
+__global__ void cast16_vec4_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, size_t total4, int fmt) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    dst[i] = pack4_16(v.x, v.y, v.z, v.w, fmt);
+  }
+}
 
 // ---------------------------------------------------------------------------------------
 // column reductions over (M, C): block = 32 columns x 8 row-lanes; fp32 per-thread partials over a
@@ -133,7 +175,8 @@ __global__ void bn_act_fwd_kernel(const float* __restrict__ y, const float* __re
 __global__ void bn_act_fwd_vec4_kernel(const float4* __restrict__ y, const float* __restrict__ mean,
                                        const float* __restrict__ rstd, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, const float4* __restrict__ res,
-                                       float4* __restrict__ z, size_t total4, int C, int act) {
+                                       float4* __restrict__ z, size_t total4, int C, int act,
+                                       uint2* __restrict__ z16 = nullptr, int fmt16 = 0) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)((i * 4) % C);
     const float4 v = y[i];
@@ -148,6 +191,7 @@ __global__ void bn_act_fwd_vec4_kernel(const float4* __restrict__ y, const float
       o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
     }
     z[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (z16) z16[i] = pack4_16(o[0], o[1], o[2], o[3], fmt16);
   }
 }
 
@@ -174,7 +218,7 @@ __global__ void bn_act_bwd_apply_vec4_kernel(const float4* __restrict__ dz, cons
                                              const float4* __restrict__ y, const float* __restrict__ mean,
                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
                                              const double* __restrict__ sums, float4* __restrict__ dy, size_t total4, int M,
-                                             int C, int act) {
+                                             int C, int act, uint2* __restrict__ dy16 = nullptr, int fmt16 = 0) {
   const float invM = 1.0f / (float)M;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)((i * 4) % C);
@@ -193,7 +237,8 @@ __global__ void bn_act_bwd_apply_vec4_kernel(const float4* __restrict__ dz, cons
       const float sg = (float)sums[c + j] * invM, sgx = (float)sums[C + c + j] * invM;
       o[j] = gamma[c + j] * rs * (g - sg - xh * sgx);
     }
-    dy[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (dy) dy[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (dy16) dy16[i] = pack4_16(o[0], o[1], o[2], o[3], fmt16);
   }
 }
 
@@ -449,5 +494,45 @@ extern "C" int avc_loss_bwd(const float* a, const float* b, size_t n, const floa
   AVC_REQUIRE(a && b && gout && (da || db) && n > 0, "avc_loss_bwd: bad arguments");
   loss_bwd_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(a, b, n, gout, is_l1, da, db, accumulate);
   AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+// ---- "half" mode producers: the same kernels additionally (or instead) emit the 16-bit operand copy the next GEMM reads ----
+extern "C" int avc_cast16(const float* src, int lds, void* dst, int ldd, size_t M, int C, int fmt, void* stream) {
+  AVC_REQUIRE(src && dst && M > 0 && C > 0 && lds >= C && ldd >= C && (fmt == 1 || fmt == 2), "avc_cast16: bad arguments");
+  const size_t total = M * (size_t)C;
+  if (lds == C && ldd == C && C % 4 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 8 == 0))
+    cast16_vec4_kernel<<<ew_blocks(total / 4), 256, 0, as_stream(stream)>>>((const float4*)src, (uint2*)dst, total / 4, fmt);
+  else
+    cast16_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(src, lds, (uint16_t*)dst, ldd, M, C, fmt);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_bn_act_fwd_h(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                                const float* residual, float* z, void* z16, int fmt16, int M, int C, int act, void* stream) {
+  AVC_REQUIRE(y && mean && rstd && gamma && beta && z && z16 && M > 0 && C > 0, "avc_bn_act_fwd_h: bad arguments");
+  AVC_REQUIRE(C % 4 == 0 && (fmt16 == 1 || fmt16 == 2), "avc_bn_act_fwd_h: C must be a multiple of 4");
+  const size_t total = (size_t)M * C;
+  bn_act_fwd_vec4_kernel<<<ew_blocks(total / 4), 256, 0, as_stream(stream)>>>(
+      (const float4*)y, mean, rstd, gamma, beta, (const float4*)residual, (float4*)z, total / 4, C, act, (uint2*)z16, fmt16);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_bn_act_bwd_apply_h(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
+                                      const float* gamma, const double* sums, float* dy, void* dy16, int fmt16, float* dgamma,
+                                      float* dbeta, int M, int C, int act, int accumulate, void* stream) {
+  AVC_REQUIRE(dz && z && y && mean && rstd && gamma && sums && (dy || dy16) && M > 0 && C > 0, "avc_bn_act_bwd_apply_h: bad arguments");
+  AVC_REQUIRE(C % 4 == 0 && (fmt16 == 1 || fmt16 == 2), "avc_bn_act_bwd_apply_h: C must be a multiple of 4");
+  const size_t total = (size_t)M * C;
+  bn_act_bwd_apply_vec4_kernel<<<ew_blocks(total / 4), 256, 0, as_stream(stream)>>>(
+      (const float4*)dz, (const float4*)z, (const float4*)y, mean, rstd, gamma, sums, (float4*)dy, total / 4, M, C, act,
+      (uint2*)dy16, fmt16);
+  AVC_LAUNCHED();
+  if (dgamma || dbeta) {
+    bn_param_grad_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(sums, dgamma, dbeta, C, accumulate);
+    AVC_LAUNCHED();
+  }
   return AVC_OK;
 }

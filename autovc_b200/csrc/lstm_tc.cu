@@ -15,6 +15,8 @@
 //   backward: CTA owns 16 hidden units of dh, K = 4H (dh = dG_{t+1} W_hh)
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace avc {
@@ -35,6 +37,9 @@ struct LstmTcParams {
   float* dP;            // bwd: out (nB,T,4H)
   __nv_bfloat16* xbuf;  // exchange buffer [2][nBpad][K]
   unsigned int* counters;  // [MT], zero-initialised
+  void* h16;            // fwd: optional 16-bit copy of h_seq (nB,T,H) contiguous, format fmt16 (1 bf16 / 2 fp16)
+  void* dP16;           // bwd: optional 16-bit copy of dP (nB,T,4H)
+  int fmt16;
   int exp_mode;            // experiment switch (AVC_LSTM_EXP): 0 none, 1 alternate two descriptors, 2 two half boxes
   unsigned long long* trace;  // optional per-step timestamps of CTA 0 (avc_debug_set_trace), else nullptr
 };
@@ -281,6 +286,22 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             *reinterpret_cast<float4*>(p.c_seq + rowi * H + u0 + i) = *reinterpret_cast<const float4*>(&c[i]);
             *reinterpret_cast<float4*>(p.h_seq + rowi * p.ldh + u0 + i) = *reinterpret_cast<const float4*>(&hf[i]);
           }
+          if (p.h16 != nullptr) {
+            uint16_t* h16 = reinterpret_cast<uint16_t*>(p.h16) + rowi * H + u0;
+            if (p.fmt16 == 2) {
+#pragma unroll
+              for (int i = 0; i < U; i += 4) {
+                const __half2 lo = __floats2half2_rn(hf[i], hf[i + 1]), hi = __floats2half2_rn(hf[i + 2], hf[i + 3]);
+                uint2 v;
+                v.x = *reinterpret_cast<const uint32_t*>(&lo);
+                v.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(h16 + i) = v;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < U; i += 4) *reinterpret_cast<uint2*>(h16 + i) = *reinterpret_cast<const uint2*>(&hb[i]);
+            }
+          }
         }
         if (lane == 0) mbar_arrive(tempty);
       }
@@ -359,6 +380,11 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 4 * U; j += 4)
             *reinterpret_cast<float4*>(p.dP + rowi * G + 4 * u0 + j) = *reinterpret_cast<const float4*>(&g4[j]);
+          if (p.dP16 != nullptr) {
+            __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(p.dP16) + rowi * G + 4 * u0;
+#pragma unroll
+            for (int j = 0; j < 4 * U; j += 8) *reinterpret_cast<uint4*>(d16 + j) = *reinterpret_cast<const uint4*>(&gb[j]);
+          }
         }
         if (lane == 0) mbar_arrive(tempty);
       }
@@ -616,6 +642,11 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
 #pragma unroll
         for (int j = 0; j < 4 * U; j += 4)
           *reinterpret_cast<float4*>(p.dP + rowi * G + 4 * u0 + j) = *reinterpret_cast<const float4*>(&g4[j]);
+        if (p.dP16 != nullptr) {
+          __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(p.dP16) + rowi * G + 4 * u0;
+#pragma unroll
+          for (int j = 0; j < 4 * U; j += 8) *reinterpret_cast<uint4*>(d16 + j) = *reinterpret_cast<const uint4*>(&gb[j]);
+        }
       }
       if (lane == 0) mbar_arrive(tempty);
     }
@@ -773,7 +804,7 @@ static int lt_cluster_size(int NT) {
 // W: fwd -> Whh_p (4H, H);  bwd -> Whh_pT (H, 4H)  (fp32, packed/interleaved)
 int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh, float* gates, float* c_seq,
                 const float* dH, int lddh, float* dP, int nB, int T, int H, int reverse, void* ws, size_t ws_bytes,
-                cudaStream_t st) {
+                cudaStream_t st, void* aux16, int fmt16) {
   const LtPlan pl = lt_plan(nB, H, bwd);
   if (!ws || ws_bytes < pl.total) {
     set_error("avc_lstm_seq_%s(bf16): workspace %zu < %zu", bwd ? "bwd" : "fwd", ws_bytes, pl.total);
@@ -817,6 +848,9 @@ int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh,
     p.counters = counters + ch * 64;
     p.trace = (ch == 0) ? g_trace : nullptr;
     p.exp_mode = exp_mode;
+    p.fmt16 = fmt16;
+    p.h16 = (!bwd && aux16) ? (void*)((uint16_t*)aux16 + (size_t)b0 * T * H) : nullptr;
+    p.dP16 = (bwd && aux16) ? (void*)((uint16_t*)aux16 + (size_t)b0 * T * G) : nullptr;
     if (bwd && bwd_ksplit_enabled(H)) {
       CUtensorMap mWk;
       rc = make_map3(&mWk, Wb, pl.K, w_rows, 1, pl.K, (uint64_t)w_rows * pl.K, 64, KS_UNITS);

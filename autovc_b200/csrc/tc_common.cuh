@@ -127,8 +127,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor bit layout): fmt 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32); D = f32
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, int fmt = 1) {
-  return (1u << 4) /*D=f32*/ | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn_major << 15) |
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major, int fmt = 1, int fmt_b = -1) {
+  return (1u << 4) /*D=f32*/ | ((uint32_t)fmt << 7) | ((uint32_t)(fmt_b < 0 ? fmt : fmt_b) << 10) | ((uint32_t)a_mn_major << 15) |
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -154,7 +154,7 @@ static inline PFN_encodeTiled get_encode() {
 
 // 3-D bf16 tensor map over a row-major (d2, d1, d0) array: d0 contiguous, 128B swizzle, zero OOB fill
 static inline int make_map3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
-                     uint64_t stride2_elems, uint32_t box0, uint32_t box1, int elem_bytes = 2, bool atom32 = false) {
+                     uint64_t stride2_elems, uint32_t box0, uint32_t box1, int elem_bytes = 2, bool atom32 = false, int ofmt = -1) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -165,7 +165,7 @@ static inline int make_map3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t es[3] = {1, 1, 1};
   // fp32 operands are fetched as TFLOAT32: the TMA unit rounds them to tf32 on the way into shared memory
-  CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, es,
+  CUresult r = enc(m, elem_bytes == 2 ? (ofmt == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -183,7 +183,7 @@ static inline int make_map3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64
 // consecutive [frames][row] blocks -- the MN-major operand tile of the weight-gradient GEMM in ONE TMA instruction
 // instead of one per 128-byte channel group.  Requires C % row == 0.
 static inline int make_map4_grouped(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t T, uint64_t nB, uint64_t ld_elems,
-                                    uint32_t row, uint32_t frames, uint32_t ngroups, int elem_bytes, bool atom32) {
+                                    uint32_t row, uint32_t frames, uint32_t ngroups, int elem_bytes, bool atom32, int ofmt = -1) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -193,7 +193,7 @@ static inline int make_map4_grouped(CUtensorMap* m, const void* ptr, uint64_t C,
   cuuint64_t strides[3] = {ld_elems * elem_bytes, (cuuint64_t)row * elem_bytes, T * ld_elems * elem_bytes};
   cuuint32_t box[4] = {row, frames, ngroups, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4,
+  CUresult r = enc(m, elem_bytes == 2 ? (ofmt == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4,
                    const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -14,6 +14,8 @@
 // fp32 per tile and accumulated in fp64.
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace avc {
@@ -56,6 +58,7 @@ struct TcParams {
   // TN
   int k_tiles, splits, rblocks, rblocks_per_split, tbr;   // tbr = ceil(T / frames-per-stage)
   int grouped_a, grouped_b;   // operand fetched with one grouped 4-D box per stage (make_map4_grouped)
+  uint32_t idesc;             // tcgen05 instruction descriptor (operand formats are chosen at run time)
   float* part;
 };
 
@@ -193,7 +196,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TC_BM, BN, MODE == MODE_TN, MODE == MODE_TN, EB == 2 ? 1 : 2);
+      const uint32_t idesc = p.idesc;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -357,8 +360,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // fp32 -> padded bf16 staging
 // ---------------------------------------------------------------------------------------------------
 // dst[r][c] (ld = Cp, bf16) = src[r][c] (ld = lds, fp32) for c < C, zero for C <= c < Cp; rows >= R_src are zero
+// 16-bit conversions of a pair of floats for the two half formats (1 = bf16, 2 = fp16)
+__device__ __forceinline__ uint32_t pack16(float a, float b, int fmt) {
+  if (fmt == 2) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint16_t to16(float a, int fmt) {
+  if (fmt == 2) {
+    const __half h = __float2half_rn(a);
+    return *reinterpret_cast<const uint16_t*>(&h);
+  }
+  const __nv_bfloat16 h = __float2bfloat16_rn(a);
+  return *reinterpret_cast<const uint16_t*>(&h);
+}
+
 __global__ void cvt_pad_bf16_kernel(const float* __restrict__ src, int lds, __nv_bfloat16* __restrict__ dst, int Cp,
-                                    size_t R_dst, size_t R_src, int C) {
+                                    size_t R_dst, size_t R_src, int C, int fmt = 1) {
   const size_t total = R_dst * (size_t)(Cp / 2);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t r = i / (Cp / 2);
@@ -368,12 +389,12 @@ __global__ void cvt_pad_bf16_kernel(const float* __restrict__ src, int lds, __nv
       if (c < C) a = src[r * lds + c];
       if (c + 1 < C) b = src[r * lds + c + 1];
     }
-    reinterpret_cast<__nv_bfloat162*>(dst)[i] = __floats2bfloat162_rn(a, b);
+    reinterpret_cast<uint32_t*>(dst)[i] = pack16(a, b, fmt);
   }
 }
 // weights [ntaps][N][K] fp32 -> [ntaps][Np][Kp] bf16, zero padded
 __global__ void cvt_pad_w_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int ntaps, int N, int K,
-                                      int Np, int Kp) {
+                                      int Np, int Kp, int fmt = 1) {
   const size_t total = (size_t)ntaps * Np * Kp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int k = (int)(i % Kp);
@@ -444,6 +465,9 @@ __global__ void cvt_pad_f32_kernel(const float* __restrict__ src, int lds, float
 }
 
 static inline bool direct_ok(const void* p, int ld) { return ((uintptr_t)p & 15) == 0 && (ld & 3) == 0; }
+static inline bool direct16_ok(const void* p, int ld) { return ((uintptr_t)p & 15) == 0 && (ld & 7) == 0; }
+// operand formats: 0 = fp32 in memory, 1 = bf16, 2 = fp16.  instruction format codes: f16 = 0, bf16 = 1, tf32 = 2
+static inline int ifmt_of(int ofmt16) { return ofmt16 == 2 ? 0 : 1; }
 
 // ---- NT -------------------------------------------------------------------------------------------
 // eb = 2: both operands are staged as zero-padded bf16.  eb = 4: operands are read in place by TMA when
@@ -453,13 +477,13 @@ struct NtPlan {
   bool stageA, stageW;
   size_t offA, offW, total;
 };
-static NtPlan nt_plan(const float* A, int lda, const float* W, int nB, int T, int N, int K, int ntaps, int eb) {
+static NtPlan nt_plan(const void* A, int a_fmt, int lda, const float* W, int nB, int T, int N, int K, int ntaps, int eb) {
   NtPlan pl;
   const int row = 128 / eb;
   pl.bn = pick_bn(nB * ceil_div(T, TC_BM), N);
   pl.Kp = round_up(K, row);
   pl.Np = round_up(N, pl.bn);
-  pl.stageA = eb == 2 || !direct_ok(A, lda);
+  pl.stageA = a_fmt == 0 && (eb == 2 || !direct_ok(A, lda));     // 16-bit operands are always read in place
   pl.stageW = eb == 2 || !direct_ok(W, K);
   pl.offA = 0;
   pl.offW = pl.stageA ? align256((size_t)nB * T * pl.Kp * eb) : 0;
@@ -473,14 +497,21 @@ size_t gemm_nt_workspace_tc(int nB, int T, int N, int K, int ntaps, int eb) {
   return align256((size_t)nB * T * Kp * eb) + align256((size_t)ntaps * Np * Kp * eb);
 }
 
-int gemm_nt_taps_tc(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int nB, int T, int N,
-                    int K, int ntaps, int shift0, double* stats, int accumulate, int eb, void* ws, size_t ws_bytes,
+// A: fp32 (a_fmt 0) or already 16-bit in HBM (a_fmt 1 = bf16, 2 = fp16; needs eb == 2).  fp32 operands of an
+// eb == 2 GEMM are staged to `half_fmt`.
+int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const float* W, const float* bias, float* C, int ldc, int nB, int T, int N,
+                    int K, int ntaps, int shift0, double* stats, int accumulate, int eb, int half_fmt, void* ws, size_t ws_bytes,
                     cudaStream_t st) {
+  const float* A = (const float*)Av;
+  if (a_fmt != 0 && (eb != 2 || !direct16_ok(Av, lda))) {
+    set_error("avc_gemm_nt_taps_h: 16-bit A needs a 16-byte aligned pointer and lda %% 8 == 0 (lda=%d)", lda);
+    return AVC_ERR_INVALID;
+  }
   if (stats && accumulate) {
     set_error("avc_gemm_nt_taps: chan_stats and accumulate are mutually exclusive");
     return AVC_ERR_UNSUPPORTED;
   }
-  const NtPlan pl = nt_plan(A, lda, W, nB, T, N, K, ntaps, eb);
+  const NtPlan pl = nt_plan(Av, a_fmt, lda, W, nB, T, N, K, ntaps, eb);
   if (pl.total > 0 && (!ws || ws_bytes < pl.total)) {
     set_error("avc_gemm_nt_taps(tensor): workspace %zu < %zu", ws_bytes, pl.total);
     return AVC_ERR_WORKSPACE;
@@ -488,32 +519,34 @@ int gemm_nt_taps_tc(const float* A, int lda, const float* W, const float* bias, 
   int rc = 0;
   const size_t M = (size_t)nB * T;
   const int row = 128 / eb;
-  const void* Aop = A;
+  const void* Aop = Av;
   const void* Wop = W;
   uint64_t a_ld = lda, a_k = K, w_k = K, w_n = N, w_ld = K;
+  const int fa = a_fmt != 0 ? a_fmt : half_fmt, fw = half_fmt;     // 16-bit formats of the two operands (eb == 2)
   if (pl.stageA) {
     void* dst = (uint8_t*)ws + pl.offA;
-    if (eb == 2) cvt_pad_bf16_kernel<<<cvt_blocks(M * (pl.Kp / 2)), 256, 0, st>>>(A, lda, (__nv_bfloat16*)dst, pl.Kp, M, M, K);
+    if (eb == 2) cvt_pad_bf16_kernel<<<cvt_blocks(M * (pl.Kp / 2)), 256, 0, st>>>(A, lda, (__nv_bfloat16*)dst, pl.Kp, M, M, K, fa);
     else cvt_pad_f32_kernel<<<cvt_blocks(M * pl.Kp), 256, 0, st>>>(A, lda, (float*)dst, pl.Kp, M, K);
     AVC_LAUNCHED();
     Aop = dst; a_ld = pl.Kp; a_k = pl.Kp;
   }
   if (pl.stageW) {
     void* dst = (uint8_t*)ws + pl.offW;
-    if (eb == 2) cvt_pad_w_bf16_kernel<<<cvt_blocks((size_t)ntaps * pl.Np * pl.Kp), 256, 0, st>>>(W, (__nv_bfloat16*)dst, ntaps, N, K, pl.Np, pl.Kp);
+    if (eb == 2) cvt_pad_w_bf16_kernel<<<cvt_blocks((size_t)ntaps * pl.Np * pl.Kp), 256, 0, st>>>(W, (__nv_bfloat16*)dst, ntaps, N, K, pl.Np, pl.Kp, fw);
     else cvt_pad_w_f32_kernel<<<cvt_blocks((size_t)ntaps * pl.Np * pl.Kp), 256, 0, st>>>(W, (float*)dst, ntaps, N, K, pl.Np, pl.Kp);
     AVC_LAUNCHED();
     Wop = dst; w_k = pl.Kp; w_n = pl.Np; w_ld = pl.Kp;
   }
   CUtensorMap mA, mB;
-  rc = make_map3(&mA, Aop, a_k, T, nB, a_ld, (uint64_t)T * a_ld, row, TC_BM, eb);
+  rc = make_map3(&mA, Aop, a_k, T, nB, a_ld, (uint64_t)T * a_ld, row, TC_BM, eb, false, fa);
   if (rc) return rc;
-  rc = make_map3(&mB, Wop, w_k, w_n, ntaps, w_ld, w_n * w_ld, row, pl.bn, eb);
+  rc = make_map3(&mB, Wop, w_k, w_n, ntaps, w_ld, w_n * w_ld, row, pl.bn, eb, false, fw);
   if (rc) return rc;
   TcParams p{};
   p.nB = nB; p.T = T; p.ntaps = ntaps; p.shift0 = shift0; p.N = N; p.K = K;
   p.t_tiles = ceil_div(T, TC_BM); p.n_tiles = pl.Np / pl.bn; p.kblocks = pl.Kp / row;
   p.bias = bias; p.C = C; p.ldc = ldc; p.accumulate = accumulate; p.stats = stats;
+  p.idesc = eb == 2 ? make_idesc(TC_BM, pl.bn, 0, 0, ifmt_of(fa), ifmt_of(fw)) : make_idesc(TC_BM, pl.bn, 0, 0, 2);
   const int tiles = nB * p.t_tiles * p.n_tiles;
   const int grid = std::min(tiles, num_sms());
   return tc_dispatch<MODE_NT>(eb, pl.bn, mA, mB, p, grid, st);
@@ -564,14 +597,29 @@ static TnPlan tn_plan(int nB, int T, int N, int K, int ntaps, int eb, bool stage
 size_t gemm_tn_workspace_tc(int nB, int T, int N, int K, int ntaps, int eb) {
   return tn_plan(nB, T, N, K, ntaps, eb, true, true).total;
 }
+size_t gemm_tn_workspace_h(int nB, int T, int N, int K, int ntaps, int y_fmt, int x_fmt) {
+  return tn_plan(nB, T, N, K, ntaps, 2, y_fmt == 0, x_fmt == 0).total;
+}
+size_t gemm_nt_workspace_h(int nB, int T, int N, int K, int ntaps, int a_fmt) {
+  const int Kp = round_up(K, 64), Np = round_up(N, 256);
+  return (a_fmt == 0 ? align256((size_t)nB * T * Kp * 2) : 0) + align256((size_t)ntaps * Np * Kp * 2);
+}
 
 int launch_wgrad_reduce(const float* part, float* dW, int N, int K, int ntaps, int splits, int out_mode, int accumulate,
                         cudaStream_t st);
 
-int gemm_tn_taps_tc(const float* dY, int ldy, const float* X, int ldx, float* dW, int nB, int T, int N, int K, int ntaps,
-                    int shift0, int out_mode, int accumulate, int eb, void* ws, size_t ws_bytes, cudaStream_t st) {
-  const bool stage_y = eb == 2 || !direct_ok(dY, ldy);
-  const bool stage_x = eb == 2 || !direct_ok(X, ldx);
+int gemm_tn_taps_tc(const void* dYv, int y_fmt, int ldy, const void* Xv, int x_fmt, int ldx, float* dW, int nB, int T, int N, int K,
+                    int ntaps, int shift0, int out_mode, int accumulate, int eb, int half_fmt, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
+  const float* dY = (const float*)dYv;
+  const float* X = (const float*)Xv;
+  if ((y_fmt != 0 && (eb != 2 || !direct16_ok(dYv, ldy))) || (x_fmt != 0 && (eb != 2 || !direct16_ok(Xv, ldx)))) {
+    set_error("avc_gemm_tn_taps_h: 16-bit operands need 16-byte aligned pointers and leading dimensions %% 8 == 0");
+    return AVC_ERR_INVALID;
+  }
+  const bool stage_y = y_fmt == 0 && (eb == 2 || !direct_ok(dY, ldy));
+  const bool stage_x = x_fmt == 0 && (eb == 2 || !direct_ok(X, ldx));
+  const int fy = y_fmt != 0 ? y_fmt : half_fmt, fx = x_fmt != 0 ? x_fmt : half_fmt;
   const TnPlan pl = tn_plan(nB, T, N, K, ntaps, eb, stage_y, stage_x);
   if (!ws || ws_bytes < pl.total) {
     set_error("avc_gemm_tn_taps(tensor): workspace %zu < %zu", ws_bytes, pl.total);
@@ -581,19 +629,19 @@ int gemm_tn_taps_tc(const float* dY, int ldy, const float* X, int ldx, float* dW
   const size_t M = (size_t)nB * T;
   const int row = 128 / eb;
   float* part = (float*)((uint8_t*)ws + pl.off_part);
-  const void* Yop = dY;
-  const void* Xop = X;
+  const void* Yop = dYv;
+  const void* Xop = Xv;
   uint64_t y_ld = ldy, y_c = N, x_ld = ldx, x_c = K;
   if (stage_y) {
     void* dst = (uint8_t*)ws + pl.off_y;
-    if (eb == 2) cvt_pad_bf16_kernel<<<cvt_blocks(M * (pl.Np / 2)), 256, 0, st>>>(dY, ldy, (__nv_bfloat16*)dst, pl.Np, M, M, N);
+    if (eb == 2) cvt_pad_bf16_kernel<<<cvt_blocks(M * (pl.Np / 2)), 256, 0, st>>>(dY, ldy, (__nv_bfloat16*)dst, pl.Np, M, M, N, fy);
     else cvt_pad_f32_kernel<<<cvt_blocks(M * pl.Np), 256, 0, st>>>(dY, ldy, (float*)dst, pl.Np, M, N);
     AVC_LAUNCHED();
     Yop = dst; y_ld = pl.Np; y_c = pl.Np;
   }
   if (stage_x) {
     void* dst = (uint8_t*)ws + pl.off_x;
-    if (eb == 2) cvt_pad_bf16_kernel<<<cvt_blocks(M * (pl.Kp / 2)), 256, 0, st>>>(X, ldx, (__nv_bfloat16*)dst, pl.Kp, M, M, K);
+    if (eb == 2) cvt_pad_bf16_kernel<<<cvt_blocks(M * (pl.Kp / 2)), 256, 0, st>>>(X, ldx, (__nv_bfloat16*)dst, pl.Kp, M, M, K, fx);
     else cvt_pad_f32_kernel<<<cvt_blocks(M * pl.Kp), 256, 0, st>>>(X, ldx, (float*)dst, pl.Kp, M, K);
     AVC_LAUNCHED();
     Xop = dst; x_ld = pl.Kp; x_c = pl.Kp;
@@ -601,17 +649,18 @@ int gemm_tn_taps_tc(const float* dY, int ldy, const float* X, int ldx, float* dW
   CUtensorMap mA, mB;
   // grouped 4-D boxes need whole 128-byte channel groups and whole tiles (no partially out-of-range group)
   const bool ga = (y_c % TC_BM) == 0, gb = (x_c % pl.bn) == 0;
-  if (ga) rc = make_map4_grouped(&mA, Yop, y_c, T, nB, y_ld, row, pl.rs, TC_BM / row, eb, eb == 4);
-  else rc = make_map3(&mA, Yop, y_c, T, nB, y_ld, (uint64_t)T * y_ld, row, pl.rs, eb, eb == 4);
+  if (ga) rc = make_map4_grouped(&mA, Yop, y_c, T, nB, y_ld, row, pl.rs, TC_BM / row, eb, eb == 4, fy);
+  else rc = make_map3(&mA, Yop, y_c, T, nB, y_ld, (uint64_t)T * y_ld, row, pl.rs, eb, eb == 4, fy);
   if (rc) return rc;
-  if (gb) rc = make_map4_grouped(&mB, Xop, x_c, T, nB, x_ld, row, pl.rs, pl.bn / row, eb, eb == 4);
-  else rc = make_map3(&mB, Xop, x_c, T, nB, x_ld, (uint64_t)T * x_ld, row, pl.rs, eb, eb == 4);
+  if (gb) rc = make_map4_grouped(&mB, Xop, x_c, T, nB, x_ld, row, pl.rs, pl.bn / row, eb, eb == 4, fx);
+  else rc = make_map3(&mB, Xop, x_c, T, nB, x_ld, (uint64_t)T * x_ld, row, pl.rs, eb, eb == 4, fx);
   if (rc) return rc;
   TcParams p{};
   p.nB = nB; p.T = T; p.ntaps = ntaps; p.shift0 = shift0; p.N = N; p.K = K;
   p.n_tiles = pl.Np / TC_BM; p.k_tiles = pl.Kp / pl.bn; p.splits = pl.splits; p.rblocks = pl.rblocks;
   p.rblocks_per_split = pl.rps; p.tbr = ceil_div(T, pl.rs); p.part = part;
   p.grouped_a = ga; p.grouped_b = gb;
+  p.idesc = eb == 2 ? make_idesc(TC_BM, pl.bn, 1, 1, ifmt_of(fy), ifmt_of(fx)) : make_idesc(TC_BM, pl.bn, 1, 1, 2);
   const int items = pl.tiles * pl.splits;
   const int grid = std::min(items, num_sms());
   rc = tc_dispatch<MODE_TN>(eb, pl.bn, mA, mB, p, grid, st);

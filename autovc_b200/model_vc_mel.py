@@ -14,7 +14,7 @@ the reference's transposes (model_vc_mel.py:64,:70,:112,:116,:196-197) exist her
 CPU path: parameters and inputs must live on a CUDA device.
 
 Extra (non-reference) constructor keywords: ``n_bins`` (80; 513 builds the model_vc_stft layer
-shapes) and ``precision`` ("fp32" | "bf16", also settable later through ``set_precision``).
+shapes) and ``precision`` ("fp32" | "tf32" | "half" | "bf16", also settable later through ``set_precision``).
 """
 from __future__ import annotations
 
@@ -25,9 +25,9 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import ACT_CODES, PREC_BF16, PREC_FP32
+from ._lib import ACT_CODES, PREC_BF16, PREC_FP32, PREC_HALF, PREC_TF32
 
-_PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": 2}
+_PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16, "tf32": PREC_TF32, "half": PREC_HALF}
 
 
 def _default_precision() -> str:
@@ -44,6 +44,8 @@ class LinearNorm(nn.Module):
         self.prec = PREC_FP32
 
     def forward(self, x):
+        if self.prec == PREC_HALF:
+            return ops.LinearH.apply(x, None, self.linear_layer.weight, self.linear_layer.bias)
         return ops.Linear.apply(x, self.linear_layer.weight, self.linear_layer.bias, self.prec)
 
 
@@ -66,25 +68,39 @@ class ConvNorm(nn.Module):
         raise RuntimeError("ConvNorm is fused with its BatchNorm and activation; call the owning block")
 
 
-def _conv_bn_act(block: nn.Sequential, x, act: str, residual=None, prec=PREC_FP32):
-    """act(BN(conv(x))) (+ residual) on channels-last x; bumps num_batches_tracked like nn.BatchNorm1d."""
+def _conv_bn_act(block: nn.Sequential, x, act: str, residual=None, prec=PREC_FP32, x16=None):
+    """act(BN(conv(x))) (+ residual) on channels-last x; bumps num_batches_tracked like nn.BatchNorm1d.
+    Returns (z, z16): z16 is the fp16 operand copy in half mode, else None."""
     conv, bn = block[0].conv, block[1]
     training = bn.training
-    z = ops.ConvBnAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
-                            ACT_CODES[act], training, prec)
+    if prec == PREC_HALF:
+        z, z16 = ops.ConvBnActH.apply(x, x16, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                      residual, ACT_CODES[act], training)
+        if z16.numel() == 0:
+            z16 = None
+    else:
+        z = ops.ConvBnAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
+                                ACT_CODES[act], training, prec)
+        z16 = None
     if training:
         bn.num_batches_tracked += 1
-    return z
+    return z, z16
 
 
-def _lstm(x, lstm: nn.LSTM, prec):
-    """Run an nn.LSTM's parameters through the LstmLayer kernels, layer by layer."""
+def _lstm(x, lstm: nn.LSTM, prec, x16=None):
+    """Run an nn.LSTM's parameters through the LstmLayer kernels, layer by layer.  Returns (h, h16)."""
+    H = lstm.hidden_size
+    half = prec == PREC_HALF and not lstm.bidirectional and 128 <= H <= 1024 and H % 64 == 0
     for l in range(lstm.num_layers):
         ws = []
         for suffix in (("", "_reverse") if lstm.bidirectional else ("",)):
             ws += [getattr(lstm, f"{n}_l{l}{suffix}") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
-        x = ops.LstmLayer.apply(x, prec, *ws)
-    return x
+        if half:
+            x, x16 = ops.LstmLayerH.apply(x, x16, *ws)
+        else:   # encoder BiLSTM (H = dim_neck): tiny GEMMs, fp32 recurrence; tf32 operands in half mode
+            x = ops.LstmLayer.apply(x, PREC_TF32 if prec == PREC_HALF else prec, *ws)
+            x16 = None
+    return x, x16
 
 
 class Encoder(nn.Module):
@@ -109,9 +125,10 @@ class Encoder(nn.Module):
         if x.dim() == 4:
             x = x.squeeze(1)
         h = ops.ConcatEmb.apply(x, c_org)
+        h16 = None
         for block in self.convolutions:
-            h = _conv_bn_act(block, h, "relu", prec=self.prec)
-        h = _lstm(h, self.lstm, self.prec)
+            h, h16 = _conv_bn_act(block, h, "relu", prec=self.prec, x16=h16)
+        h, _ = _lstm(h, self.lstm, self.prec)
         return ops.Codes.apply(h, self.dim_neck, self.freq)
 
     def forward(self, x, c_org):
@@ -135,11 +152,13 @@ class Decoder(nn.Module):
         self.linear_projection = LinearNorm(1024, n_bins)
 
     def forward(self, x):
-        h = _lstm(x, self.lstm1, self.prec)
+        h, h16 = _lstm(x, self.lstm1, self.prec)
         for block in self.convolutions:
-            h = _conv_bn_act(block, h, "relu", prec=self.prec)
-        h = _lstm(h, self.lstm2, self.prec)
+            h, h16 = _conv_bn_act(block, h, "relu", prec=self.prec, x16=h16)
+        h, h16 = _lstm(h, self.lstm2, self.prec, x16=h16)
         lin = self.linear_projection.linear_layer
+        if self.prec == PREC_HALF:
+            return ops.LinearH.apply(h, h16, lin.weight, lin.bias)
         return ops.Linear.apply(h, lin.weight, lin.bias, self.prec)
 
 
@@ -164,9 +183,10 @@ class Postnet(nn.Module):
     def channels_last(self, x, residual=None):
         """x (B,T,n_bins) -> postnet(x) (+ residual), channels-last."""
         n = len(self.convolutions)
+        x16 = None
         for i in range(n - 1):
-            x = _conv_bn_act(self.convolutions[i], x, "tanh", prec=self.prec)
-        return _conv_bn_act(self.convolutions[-1], x, "none", residual=residual, prec=self.prec)
+            x, x16 = _conv_bn_act(self.convolutions[i], x, "tanh", prec=self.prec, x16=x16)
+        return _conv_bn_act(self.convolutions[-1], x, "none", residual=residual, prec=self.prec, x16=x16)[0]
 
     def forward(self, x):
         # reference layout: channel-first (B, n_bins, T) in and out (model_vc_mel.py:163-169, :196)

@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import ACT_CODES, ACT_NONE, PREC_BF16, PREC_FP32, call, query
+from ._lib import ACT_CODES, ACT_NONE, FMT_BF16, FMT_FP16, FMT_FP32, PREC_BF16, PREC_FP32, PREC_HALF, PREC_TF32, call, query
 
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
@@ -34,8 +34,8 @@ def _check(*tensors):
             continue
         if not t.is_cuda:
             raise _lib.AvcError("autovc_b200 ops need CUDA tensors (there is no CPU fallback)")
-        if t.dtype != torch.float32:
-            raise _lib.AvcError(f"autovc_b200 ops take float32 tensors, got {t.dtype}")
+        if t.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            raise _lib.AvcError(f"autovc_b200 ops take float32 tensors (or their 16-bit operand copies), got {t.dtype}")
         if not t.is_contiguous():
             raise _lib.AvcError("autovc_b200 ops need contiguous tensors")
 
@@ -452,3 +452,207 @@ def mse_loss(a, b):
 
 def l1_loss(a, b):
     return _Loss.apply(a, b, True)
+
+
+# ======================================================================================
+# "half" mode (AVC_PREC_HALF): 16-bit operand copies travel next to the fp32 tensors
+# ======================================================================================
+_DT16 = {FMT_FP16: torch.float16, FMT_BF16: torch.bfloat16}
+
+
+def cast16(x: torch.Tensor, fmt: int) -> torch.Tensor:
+    """fp32 (..., C) contiguous -> 16-bit copy (fmt: FMT_FP16 forward operands, FMT_BF16 gradient operands)."""
+    C = x.shape[-1]
+    M = x.numel() // C
+    out = torch.empty(x.shape, dtype=_DT16[fmt], device=x.device)
+    call("avc_cast16", _p(x), C, _p(out), C, M, C, fmt, _stream())
+    return out
+
+
+def _operand(t32: torch.Tensor, t16: Optional[torch.Tensor], C: int, fmt: int):
+    """Pick what the tensor cores read: the 16-bit copy when it exists (or can be made) and is TMA-addressable
+    (C % 8 == 0), else the fp32 tensor, which the GEMM stages internally."""
+    if C % 8 != 0:
+        return t32, FMT_FP32
+    if t16 is None:
+        t16 = cast16(t32, fmt)
+    return t16, (FMT_FP16 if t16.dtype == torch.float16 else FMT_BF16)
+
+
+def gemm_nt_taps_h(A, a_fmt, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, half_fmt, stats=None, accumulate=False):
+    nbytes = query("avc_gemm_nt_h_workspace_bytes", nB, T, N, K, ntaps, a_fmt)
+    ws = _ws(nbytes, C.device)
+    call("avc_gemm_nt_taps_h", _p(A), a_fmt, lda, _p(W), _p(bias), _p(C), ldc, nB, T, N, K, ntaps, shift0, _p(stats),
+         int(accumulate), half_fmt, _p(ws), nbytes, _stream())
+
+
+def gemm_tn_taps_h(dY, y_fmt, ldy, X, x_fmt, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, half_fmt=FMT_BF16, accumulate=False):
+    nbytes = query("avc_gemm_tn_h_workspace_bytes", nB, T, N, K, ntaps, y_fmt, x_fmt)
+    ws = _ws(nbytes, dW.device)
+    call("avc_gemm_tn_taps_h", _p(dY), y_fmt, ldy, _p(X), x_fmt, ldx, _p(dW), nB, T, N, K, ntaps, shift0, out_mode,
+         int(accumulate), half_fmt, _p(ws), nbytes, _stream())
+
+
+class ConvBnActH(torch.autograd.Function):
+    """ConvBnAct for the half mode: (x, x16) -> (z, z16).  Forward operands fp16, gradient operands bf16."""
+
+    @staticmethod
+    def forward(ctx, x, x16, weight, bias, gamma, beta, running_mean, running_var, residual, act: int, training: bool):
+        x = x.contiguous()
+        _check(x, x16, weight, bias, gamma, beta, running_mean, running_var, residual)
+        if residual is not None and act != ACT_NONE:
+            raise _lib.AvcError("residual is only supported with act='none'")
+        B, T, Cin = x.shape
+        Cout, Cin_w, k = weight.shape
+        if Cin_w != Cin:
+            raise _lib.AvcError(f"conv: input has {Cin} channels, weight expects {Cin_w}")
+        M = B * T
+        wf, wd = pack_conv(weight)
+        A, a_fmt = _operand(x, x16, Cin, FMT_FP16)
+        y = torch.empty(B, T, Cout, device=x.device, dtype=torch.float32)
+        mean = torch.empty(Cout, device=x.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        stats = torch.zeros(2 * Cout, device=x.device, dtype=torch.float64) if training else None
+        gemm_nt_taps_h(A, a_fmt, Cin, wf, bias, y, Cout, B, T, Cout, Cin, k, -(k // 2), FMT_FP16, stats=stats)
+        if training:
+            call("avc_bn_finalize", _p(stats), M, Cout, BN_EPS, BN_MOMENTUM, _p(mean), _p(rstd), _p(running_mean),
+                 _p(running_var), _stream())
+        else:
+            call("avc_bn_eval_stats", _p(running_mean), _p(running_var), Cout, BN_EPS, _p(mean), _p(rstd), _stream())
+        z = torch.empty_like(y)
+        if Cout % 8 == 0:
+            z16 = torch.empty(B, T, Cout, device=x.device, dtype=torch.float16)
+            call("avc_bn_act_fwd_h", _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(z), _p(z16), FMT_FP16,
+                 M, Cout, act, _stream())
+        else:
+            z16 = torch.empty(0, device=x.device, dtype=torch.float16)
+            call("avc_bn_act_fwd", _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(z), M, Cout, act, _stream())
+        ctx.save_for_backward(A, weight, gamma, y, z, mean, rstd)
+        ctx.act, ctx.training, ctx.has_res, ctx.a_fmt, ctx.wd = act, training, residual is not None, a_fmt, wd
+        ctx.x_needs_grad = x.requires_grad
+        ctx.mark_non_differentiable(z16)
+        return z, z16
+
+    @staticmethod
+    def backward(ctx, dz, _dz16):
+        A, weight, gamma, y, z, mean, rstd = ctx.saved_tensors
+        if not ctx.training:
+            raise _lib.AvcError("backward through eval-mode BatchNorm is not on the supported path")
+        dz = dz.contiguous()
+        B, T, Cin = A.shape
+        Cout, _, k = weight.shape
+        M = B * T
+        sums = torch.zeros(2 * Cout, device=dz.device, dtype=torch.float64)
+        call("avc_bn_act_bwd_reduce", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(sums), M, Cout, ctx.act, _stream())
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        if Cout % 8 == 0:      # the gradient w.r.t. the conv output is only ever a GEMM operand: emit it as bf16 only
+            dy = torch.empty(B, T, Cout, device=dz.device, dtype=torch.bfloat16)
+            call("avc_bn_act_bwd_apply_h", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(gamma), _p(sums), _NULL, _p(dy), FMT_BF16,
+                 _p(dgamma), _p(dbeta), M, Cout, ctx.act, 0, _stream())
+            y_fmt = FMT_BF16
+        else:
+            dy = torch.empty_like(y)
+            call("avc_bn_act_bwd_apply", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(gamma), _p(sums), _p(dy), _p(dgamma),
+                 _p(dbeta), M, Cout, ctx.act, 0, _stream())
+            y_fmt = FMT_FP32
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(B, T, Cin, device=dz.device, dtype=torch.float32)
+            gemm_nt_taps_h(dy, y_fmt, Cout, ctx.wd, None, dx, Cin, B, T, Cin, Cout, k, -(k // 2), FMT_BF16)
+        dw = torch.empty_like(weight)
+        gemm_tn_taps_h(dy, y_fmt, Cout, A, ctx.a_fmt, Cin, dw, B, T, Cout, Cin, k, -(k // 2), out_mode=1)
+        db = torch.zeros(Cout, device=dz.device, dtype=torch.float32)
+        dres = dz if ctx.has_res else None
+        return dx, None, dw, db, dgamma, dbeta, None, None, dres, None, None
+
+
+class LstmLayerH(torch.autograd.Function):
+    """One unidirectional nn.LSTM layer in half mode: (x, x16) -> (h, h16).  Persistent recurrence kernels with 16-bit
+    side outputs; input projection on fp16 operands, gradient GEMMs on bf16 (dP) x fp16 (x, h)."""
+
+    @staticmethod
+    def forward(ctx, x, x16, w_ih, w_hh, b_ih, b_hh):
+        x = x.contiguous()
+        _check(x, x16, w_ih, w_hh, b_ih, b_hh)
+        B, T, I = x.shape
+        H = w_hh.shape[1]
+        G = 4 * H
+        wi_p, wi_pT = pack_lstm_w(w_ih)
+        wh_p, wh_pT = pack_lstm_w(w_hh)
+        b_p = pack_lstm_b(b_ih, b_hh)
+        A, a_fmt = _operand(x, x16, I, FMT_FP16)
+        Pre = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
+        gemm_nt_taps_h(A, a_fmt, I, wi_p, b_p, Pre, G, B, T, G, I, 1, 0, FMT_FP16)
+        out = torch.empty(B, T, H, device=x.device, dtype=torch.float32)
+        h16 = torch.empty(B, T, H, device=x.device, dtype=torch.float16)
+        gates = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
+        c_seq = torch.empty(B, T, H, device=x.device, dtype=torch.float32)
+        nbytes = query("avc_lstm_fwd_workspace_bytes", B, T, H, PREC_BF16)
+        ws = _ws(nbytes, x.device)
+        call("avc_lstm_seq_fwd_h", _p(Pre), _p(wh_p), _p(out), H, _p(gates), _p(c_seq), _p(h16), FMT_FP16, B, T, H, 0,
+             _p(ws), nbytes, _stream())
+        ctx.save_for_backward(A, h16, w_ih, w_hh, b_ih, gates, c_seq)
+        ctx.a_fmt, ctx.packs = a_fmt, (wi_pT, wh_pT)
+        ctx.mark_non_differentiable(h16)
+        return out, h16
+
+    @staticmethod
+    def backward(ctx, dout, _d16):
+        A, h16, w_ih, w_hh, b_ih, gates, c_seq = ctx.saved_tensors
+        wi_pT, wh_pT = ctx.packs
+        dout = dout.contiguous()
+        B, T, I = A.shape
+        H = w_hh.shape[1]
+        G = 4 * H
+        dP = torch.empty(B, T, G, device=dout.device, dtype=torch.float32)
+        dP16 = torch.empty(B, T, G, device=dout.device, dtype=torch.bfloat16)
+        nbytes = query("avc_lstm_bwd_workspace_bytes", B, T, H, PREC_BF16)
+        ws = _ws(nbytes, dout.device)
+        call("avc_lstm_seq_bwd_h", _p(dout), H, _p(wh_pT), _p(gates), _p(c_seq), _p(dP), _p(dP16), B, T, H, 0, _p(ws), nbytes,
+             _stream())
+        dw_ih = torch.empty_like(w_ih)
+        gemm_tn_taps_h(dP16, FMT_BF16, G, A, ctx.a_fmt, I, dw_ih, B, T, G, I, 1, 0, out_mode=2)
+        dw_hh = torch.empty_like(w_hh)
+        gemm_tn_taps_h(dP16, FMT_BF16, G, h16, FMT_FP16, H, dw_hh, B, T, G, H, 1, -1, out_mode=2)
+        db_ih = torch.empty_like(b_ih)
+        db_hh = torch.empty_like(b_ih)
+        colsum(dP, G, B * T, G, db_ih, db_hh, out_mode=2)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(B, T, I, device=dout.device, dtype=torch.float32)
+            gemm_nt_taps_h(dP16, FMT_BF16, G, wi_pT, None, dx, I, B, T, I, G, 1, 0, FMT_BF16)
+        return dx, None, dw_ih, dw_hh, db_ih, db_hh
+
+
+class LinearH(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, x16, weight, bias):
+        x = x.contiguous()
+        _check(x, x16, weight, bias)
+        B, T, K = x.shape
+        N = weight.shape[0]
+        A, a_fmt = _operand(x, x16, K, FMT_FP16)
+        y = torch.empty(B, T, N, device=x.device, dtype=torch.float32)
+        gemm_nt_taps_h(A, a_fmt, K, weight.detach(), bias, y, N, B, T, N, K, 1, 0, FMT_FP16)
+        ctx.save_for_backward(A, weight)
+        ctx.a_fmt = a_fmt
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        A, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        B, T, K = A.shape
+        N = weight.shape[0]
+        D, d_fmt = _operand(dy, None, N, FMT_BF16)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wT = transpose2d(weight, PackCache())
+            dx = torch.empty(B, T, K, device=dy.device, dtype=torch.float32)
+            gemm_nt_taps_h(D, d_fmt, N, wT, None, dx, K, B, T, K, N, 1, 0, FMT_BF16)
+        dw = torch.empty_like(weight)
+        gemm_tn_taps_h(D, d_fmt, N, A, ctx.a_fmt, K, dw, B, T, N, K, 1, 0, out_mode=0)
+        db = torch.empty(N, device=dy.device, dtype=torch.float32)
+        colsum(dy, N, B * T, N, db)
+        return dx, None, dw, db

@@ -37,7 +37,9 @@ extern "C" {
 
 #define AVC_VERSION 100
 
-enum { AVC_PREC_FP32 = 0, AVC_PREC_BF16 = 1, AVC_PREC_TF32 = 2 };
+enum { AVC_PREC_FP32 = 0, AVC_PREC_BF16 = 1, AVC_PREC_TF32 = 2, AVC_PREC_HALF = 3 };
+/* operand formats of the *_h entry points */
+enum { AVC_FMT_FP32 = 0, AVC_FMT_BF16 = 1, AVC_FMT_FP16 = 2 };
 enum { AVC_ACT_NONE = 0, AVC_ACT_RELU = 1, AVC_ACT_TANH = 2 };
 enum {
   AVC_OK = 0,
@@ -154,6 +156,38 @@ int avc_lstm_seq_bwd(const float* dH, int lddh, const float* Whh_p, const float*
                      float* dP, int nB, int T, int H, int reverse, int prec,
                      void* workspace, size_t workspace_bytes, void* stream);
 size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H, int prec);
+
+/* ---------------------------------------------------------------------------------------
+ * "half" mode (AVC_PREC_HALF): the GEMM operands already live in HBM as 16-bit copies that the PRODUCING kernels emit
+ * next to (or instead of) their fp32 results, so the tensor cores run at the 16-bit rate with no staging pass:
+ *   forward operands (activations, weights): fp16 -- 10 mantissa bits like tf32, half the bytes, twice the MMA rate;
+ *   gradient operands (dY, dP):              bf16 -- fp32's exponent range, no loss scaling needed;
+ *   mixed bf16 x fp16 products (weight gradients) are legal for kind::f16.  Accumulation, statistics, saved state: fp32.
+ * Operand format codes: AVC_FMT_FP32 (staged internally to `half_fmt`), AVC_FMT_BF16, AVC_FMT_FP16.  16-bit operands need
+ * 16-byte aligned pointers and leading dimensions that are multiples of 8 elements.
+ */
+int avc_gemm_nt_taps_h(const void* A, int a_fmt, int lda, const float* W, const float* bias, float* C, int ldc,
+                       int nB, int T, int N, int K, int ntaps, int shift0, double* chan_stats, int accumulate, int half_fmt,
+                       void* workspace, size_t workspace_bytes, void* stream);
+size_t avc_gemm_nt_h_workspace_bytes(int nB, int T, int N, int K, int ntaps, int a_fmt);
+int avc_gemm_tn_taps_h(const void* dY, int y_fmt, int ldy, const void* X, int x_fmt, int ldx, float* dW,
+                       int nB, int T, int N, int K, int ntaps, int shift0, int out_mode, int accumulate, int half_fmt,
+                       void* workspace, size_t workspace_bytes, void* stream);
+size_t avc_gemm_tn_h_workspace_bytes(int nB, int T, int N, int K, int ntaps, int y_fmt, int x_fmt);
+/* dst16 (M, C) ld ldd <- src fp32 (M, C) ld lds */
+int avc_cast16(const float* src, int lds, void* dst, int ldd, size_t M, int C, int fmt, void* stream);
+/* avc_bn_act_fwd that also writes z16 (C % 4 == 0) */
+int avc_bn_act_fwd_h(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                     const float* residual, float* z, void* z16, int fmt16, int M, int C, int act, void* stream);
+/* avc_bn_act_bwd_apply that writes dy16 (and fp32 dy only when dy != NULL) */
+int avc_bn_act_bwd_apply_h(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
+                           const float* gamma, const double* sums, float* dy, void* dy16, int fmt16, float* dgamma,
+                           float* dbeta, int M, int C, int act, int accumulate, void* stream);
+/* persistent recurrences (128 <= H <= 1024, H % 64 == 0) with a 16-bit side output: h16 (nB,T,H) / dP16 (nB,T,4H, bf16) */
+int avc_lstm_seq_fwd_h(const float* P, const float* Whh_p, float* h_seq, int ldh, float* gates, float* c_seq, void* h16,
+                       int fmt16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes, void* stream);
+int avc_lstm_seq_bwd_h(const float* dH, int lddh, const float* Whh_pT, const float* gates, const float* c_seq, float* dP,
+                       void* dP16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Profiling hook: when set to a device buffer of >= 16*T uint64, CTA 0 of the next persistent recurrence
  * launches records %globaltimer stamps per step (slot layout in lstm_tc.cu).  NULL disables it. */

@@ -136,7 +136,7 @@ def _rel_l2(a, b):
 
 
 @pytest.mark.parametrize("name", ["train_16_16_b16_t128", "train_16_16_b2_t128"])
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32", "half", "bf16"])
 def test_tensor_core_modes_within_rel_l2_gate(name, precision):
     """Reduced-precision tensor-core modes versus the reference's fp32 path.  The north_star gate for the
     reduced-precision mode is <= 1e-2 relative L2 on the outputs.  `tf32` (fp32 operands rounded to tf32 by

@@ -93,3 +93,53 @@ def test_tn_taps_tensor(nB, T, N, K, ntaps, shift0, mode, prec):
     dW32 = torch.empty_like(dW)
     ops.gemm_tn_taps(dY, N, X, K, dW32, nB, T, N, K, ntaps, shift0, out_mode=mode, prec=PREC_FP32)
     assert float((dW32 - dW).abs().max()) < 2e-2 * scale
+
+
+def _r16(x, dt):
+    return x.to(dt).double()
+
+
+@pytest.mark.parametrize("a_dt,w_fmt", [(torch.float16, 2), (torch.bfloat16, 1), (torch.bfloat16, 2)])
+def test_nt_taps_prestaged_16bit_operands(a_dt, w_fmt):
+    """'half' mode GEMM: A already 16-bit in HBM (read in place by TMA), W staged to w_fmt; includes the mixed
+    bf16 x fp16 product."""
+    from autovc_b200._lib import FMT_BF16, FMT_FP16
+    nB, T, N, K, ntaps = 3, 128, 512, 336, 5
+    A = _rand(nB * T, K, seed=1)
+    W = _rand(ntaps, N, K, seed=2) * 0.05
+    bias = _rand(N, seed=3)
+    A16 = A.to(a_dt).contiguous()
+    C = torch.empty(nB * T, N, device=DEV)
+    stats = torch.zeros(2 * N, dtype=torch.double, device=DEV)
+    ops.gemm_nt_taps_h(A16, FMT_FP16 if a_dt == torch.float16 else FMT_BF16, K, W, bias, C, N, nB, T, N, K, ntaps, -2, w_fmt, stats=stats)
+    w_dt = torch.float16 if w_fmt == 2 else torch.bfloat16
+    A3 = A16.double().view(nB, T, K)
+    ref = torch.zeros(nB, T, N, dtype=torch.double, device=DEV)
+    for tap in range(ntaps):
+        s = tap - 2
+        lo, hi = max(0, -s), min(T, T - s)
+        ref[:, lo:hi] += A3[:, lo + s:hi + s] @ _r16(W[tap], w_dt).t()
+    ref = (ref + bias.double()).view(nB * T, N)
+    scale = float(ref.abs().max())
+    assert float((C.double() - ref).abs().max()) < 3e-5 * scale * (K * ntaps / 256) ** 0.5
+    torch.testing.assert_close(stats[:N], ref.sum(0), rtol=1e-4, atol=1e-3 * scale)
+
+
+@pytest.mark.parametrize("y_dt,x_dt", [(torch.bfloat16, torch.float16), (torch.bfloat16, torch.bfloat16)])
+def test_tn_taps_prestaged_16bit_operands(y_dt, x_dt):
+    from autovc_b200._lib import FMT_BF16, FMT_FP16
+    nB, T, N, K, ntaps, shift0 = 2, 128, 512, 512, 5, -2
+    dY = _rand(nB * T, N, seed=4).to(y_dt).contiguous()
+    X = _rand(nB * T, K, seed=5).to(x_dt).contiguous()
+    dW = torch.empty(N, K, ntaps, device=DEV)
+    f = lambda dt: FMT_FP16 if dt == torch.float16 else FMT_BF16
+    ops.gemm_tn_taps_h(dY, f(y_dt), N, X, f(x_dt), K, dW, nB, T, N, K, ntaps, shift0, out_mode=1)
+    Y3, X3 = dY.double().view(nB, T, N), X.double().view(nB, T, K)
+    ref = torch.zeros(ntaps, N, K, dtype=torch.double, device=DEV)
+    for tap in range(ntaps):
+        s = shift0 + tap
+        lo, hi = max(0, -s), min(T, T - s)
+        ref[tap] = torch.einsum("btn,btk->nk", Y3[:, lo:hi], X3[:, lo + s:hi + s])
+    ref = ref.permute(1, 2, 0)
+    scale = float(ref.abs().max())
+    assert float((dW.double() - ref).abs().max()) < 3e-5 * scale
