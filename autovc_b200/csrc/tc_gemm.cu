@@ -401,7 +401,7 @@ __global__ void cvt_pad_w_bf16_kernel(const float* __restrict__ src, __nv_bfloat
     const int n = (int)((i / Kp) % Np);
     const int tap = (int)(i / ((size_t)Kp * Np));
     const float v = (n < N && k < K) ? src[((size_t)tap * N + n) * K + k] : 0.f;
-    dst[i] = __float2bfloat16_rn(v);
+    reinterpret_cast<uint16_t*>(dst)[i] = to16(v, fmt);
   }
 }
 
@@ -522,7 +522,7 @@ int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const float* W, const fl
   const void* Aop = Av;
   const void* Wop = W;
   uint64_t a_ld = lda, a_k = K, w_k = K, w_n = N, w_ld = K;
-  const int fa = a_fmt != 0 ? a_fmt : half_fmt, fw = half_fmt;     // 16-bit formats of the two operands (eb == 2)
+  const int fa = a_fmt != 0 ? a_fmt : half_fmt, fw = fa;            // weights are staged to A's 16-bit format (mixed formats trap)
   if (pl.stageA) {
     void* dst = (uint8_t*)ws + pl.offA;
     if (eb == 2) cvt_pad_bf16_kernel<<<cvt_blocks(M * (pl.Kp / 2)), 256, 0, st>>>(A, lda, (__nv_bfloat16*)dst, pl.Kp, M, M, K, fa);
@@ -620,6 +620,10 @@ int gemm_tn_taps_tc(const void* dYv, int y_fmt, int ldy, const void* Xv, int x_f
   const bool stage_y = y_fmt == 0 && (eb == 2 || !direct_ok(dY, ldy));
   const bool stage_x = x_fmt == 0 && (eb == 2 || !direct_ok(X, ldx));
   const int fy = y_fmt != 0 ? y_fmt : half_fmt, fx = x_fmt != 0 ? x_fmt : half_fmt;
+  if (eb == 2 && fy != fx) {   // tcgen05.mma kind::f16 traps (illegal instruction) on mixed bf16 x fp16 operands -- measured
+    set_error("avc_gemm_tn_taps_h: both operands must have the same 16-bit format");
+    return AVC_ERR_UNSUPPORTED;
+  }
   const TnPlan pl = tn_plan(nB, T, N, K, ntaps, eb, stage_y, stage_x);
   if (!ws || ws_bytes < pl.total) {
     set_error("avc_gemm_tn_taps(tensor): workspace %zu < %zu", ws_bytes, pl.total);

@@ -527,19 +527,18 @@ class ConvBnActH(torch.autograd.Function):
         else:
             z16 = torch.empty(0, device=x.device, dtype=torch.float16)
             call("avc_bn_act_fwd", _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(z), M, Cout, act, _stream())
-        ctx.save_for_backward(A, weight, gamma, y, z, mean, rstd)
-        ctx.act, ctx.training, ctx.has_res, ctx.a_fmt, ctx.wd = act, training, residual is not None, a_fmt, wd
-        ctx.x_needs_grad = x.requires_grad
+        ctx.save_for_backward(x, weight, gamma, y, z, mean, rstd)
+        ctx.act, ctx.training, ctx.has_res, ctx.wd = act, training, residual is not None, wd
         ctx.mark_non_differentiable(z16)
         return z, z16
 
     @staticmethod
     def backward(ctx, dz, _dz16):
-        A, weight, gamma, y, z, mean, rstd = ctx.saved_tensors
+        x, weight, gamma, y, z, mean, rstd = ctx.saved_tensors
         if not ctx.training:
             raise _lib.AvcError("backward through eval-mode BatchNorm is not on the supported path")
         dz = dz.contiguous()
-        B, T, Cin = A.shape
+        B, T, Cin = x.shape
         Cout, _, k = weight.shape
         M = B * T
         sums = torch.zeros(2 * Cout, device=dz.device, dtype=torch.float64)
@@ -561,7 +560,9 @@ class ConvBnActH(torch.autograd.Function):
             dx = torch.empty(B, T, Cin, device=dz.device, dtype=torch.float32)
             gemm_nt_taps_h(dy, y_fmt, Cout, ctx.wd, None, dx, Cin, B, T, Cin, Cout, k, -(k // 2), FMT_BF16)
         dw = torch.empty_like(weight)
-        gemm_tn_taps_h(dy, y_fmt, Cout, A, ctx.a_fmt, Cin, dw, B, T, Cout, Cin, k, -(k // 2), out_mode=1)
+        # both operands of a GEMM must share a 16-bit format: the activation gets a bf16 copy here (a 6 B/element pass)
+        X, x_fmt = _operand(x, None, Cin, FMT_BF16) if y_fmt == FMT_BF16 else (x, FMT_FP32)
+        gemm_tn_taps_h(dy, y_fmt, Cout, X, x_fmt, Cin, dw, B, T, Cout, Cin, k, -(k // 2), out_mode=1)   # fp32 operands are staged to bf16
         db = torch.zeros(Cout, device=dz.device, dtype=torch.float32)
         dres = dz if ctx.has_res else None
         return dx, None, dw, db, dgamma, dbeta, None, None, dres, None, None
@@ -592,17 +593,17 @@ class LstmLayerH(torch.autograd.Function):
         ws = _ws(nbytes, x.device)
         call("avc_lstm_seq_fwd_h", _p(Pre), _p(wh_p), _p(out), H, _p(gates), _p(c_seq), _p(h16), FMT_FP16, B, T, H, 0,
              _p(ws), nbytes, _stream())
-        ctx.save_for_backward(A, h16, w_ih, w_hh, b_ih, gates, c_seq)
-        ctx.a_fmt, ctx.packs = a_fmt, (wi_pT, wh_pT)
+        ctx.save_for_backward(x, out, w_ih, w_hh, b_ih, gates, c_seq)
+        ctx.packs = (wi_pT, wh_pT)
         ctx.mark_non_differentiable(h16)
         return out, h16
 
     @staticmethod
     def backward(ctx, dout, _d16):
-        A, h16, w_ih, w_hh, b_ih, gates, c_seq = ctx.saved_tensors
+        x, out, w_ih, w_hh, b_ih, gates, c_seq = ctx.saved_tensors
         wi_pT, wh_pT = ctx.packs
         dout = dout.contiguous()
-        B, T, I = A.shape
+        B, T, I = x.shape
         H = w_hh.shape[1]
         G = 4 * H
         dP = torch.empty(B, T, G, device=dout.device, dtype=torch.float32)
@@ -612,9 +613,10 @@ class LstmLayerH(torch.autograd.Function):
         call("avc_lstm_seq_bwd_h", _p(dout), H, _p(wh_pT), _p(gates), _p(c_seq), _p(dP), _p(dP16), B, T, H, 0, _p(ws), nbytes,
              _stream())
         dw_ih = torch.empty_like(w_ih)
-        gemm_tn_taps_h(dP16, FMT_BF16, G, A, ctx.a_fmt, I, dw_ih, B, T, G, I, 1, 0, out_mode=2)
+        X, x_fmt = _operand(x, None, I, FMT_BF16)
+        gemm_tn_taps_h(dP16, FMT_BF16, G, X, x_fmt, I, dw_ih, B, T, G, I, 1, 0, out_mode=2)
         dw_hh = torch.empty_like(w_hh)
-        gemm_tn_taps_h(dP16, FMT_BF16, G, h16, FMT_FP16, H, dw_hh, B, T, G, H, 1, -1, out_mode=2)
+        gemm_tn_taps_h(dP16, FMT_BF16, G, cast16(out, FMT_BF16), FMT_BF16, H, dw_hh, B, T, G, H, 1, -1, out_mode=2)
         db_ih = torch.empty_like(b_ih)
         db_hh = torch.empty_like(b_ih)
         colsum(dP, G, B * T, G, db_ih, db_hh, out_mode=2)
@@ -635,15 +637,14 @@ class LinearH(torch.autograd.Function):
         A, a_fmt = _operand(x, x16, K, FMT_FP16)
         y = torch.empty(B, T, N, device=x.device, dtype=torch.float32)
         gemm_nt_taps_h(A, a_fmt, K, weight.detach(), bias, y, N, B, T, N, K, 1, 0, FMT_FP16)
-        ctx.save_for_backward(A, weight)
-        ctx.a_fmt = a_fmt
+        ctx.save_for_backward(x, weight)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        A, weight = ctx.saved_tensors
+        x, weight = ctx.saved_tensors
         dy = dy.contiguous()
-        B, T, K = A.shape
+        B, T, K = x.shape
         N = weight.shape[0]
         D, d_fmt = _operand(dy, None, N, FMT_BF16)
         dx = None
@@ -652,7 +653,8 @@ class LinearH(torch.autograd.Function):
             dx = torch.empty(B, T, K, device=dy.device, dtype=torch.float32)
             gemm_nt_taps_h(D, d_fmt, N, wT, None, dx, K, B, T, K, N, 1, 0, FMT_BF16)
         dw = torch.empty_like(weight)
-        gemm_tn_taps_h(D, d_fmt, N, A, ctx.a_fmt, K, dw, B, T, N, K, 1, 0, out_mode=0)
+        X, x_fmt = _operand(x, None, K, FMT_BF16) if d_fmt == FMT_BF16 else (x, FMT_FP32)
+        gemm_tn_taps_h(D, d_fmt, N, X, x_fmt, K, dw, B, T, N, K, 1, 0, out_mode=0)
         db = torch.empty(N, device=dy.device, dtype=torch.float32)
         colsum(dy, N, B * T, N, db)
         return dx, None, dw, db

@@ -162,7 +162,8 @@ size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H, int prec);
  * next to (or instead of) their fp32 results, so the tensor cores run at the 16-bit rate with no staging pass:
  *   forward operands (activations, weights): fp16 -- 10 mantissa bits like tf32, half the bytes, twice the MMA rate;
  *   gradient operands (dY, dP):              bf16 -- fp32's exponent range, no loss scaling needed;
- *   mixed bf16 x fp16 products (weight gradients) are legal for kind::f16.  Accumulation, statistics, saved state: fp32.
+ *   both operands of one GEMM must share a format (kind::f16 traps on mixed bf16 x fp16 -- measured), so backward
+ *   GEMMs take bf16 copies of the forward activations made on the fly.  Accumulation, statistics, saved state: fp32.
  * Operand format codes: AVC_FMT_FP32 (staged internally to `half_fmt`), AVC_FMT_BF16, AVC_FMT_FP16.  16-bit operands need
  * 16-byte aligned pointers and leading dimensions that are multiples of 8 elements.
  */
