@@ -363,7 +363,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("AUTOVC_B200_PRECISION", "tf32"), choices=["fp32", "bf16", "tf32", "half"])
+    ap.add_argument("--precision", default=os.environ.get("AUTOVC_B200_PRECISION", "half"), choices=["fp32", "bf16", "tf32", "half"])
     ap.add_argument("--batch", type=int, default=256, help="crops per GPU")
     ap.add_argument("--len-crop", dest="len_crop", type=int, default=128)
     ap.add_argument("--dim-neck", dest="dim_neck", type=int, default=16)
