@@ -36,7 +36,8 @@ struct LstmTcParams {
   int lddh;
   float* dP;            // bwd: out (nB,T,4H)
   __nv_bfloat16* xbuf;  // exchange buffer [2][nBpad][K]
-  unsigned int* counters;  // [MT], zero-initialised
+  unsigned int* counters;  // [MT][64], zero-initialised: [mt][0] = whole-tile counter, or one counter per 64-column k-block
+  int kflags;              // 1: per-k-block release counters, consumers stream each k-block as soon as it is published
   void* h16;            // fwd: optional 16-bit copy of h_seq (nB,T,H) contiguous, format fmt16 (1 bf16 / 2 fp16)
   void* dP16;           // bwd: optional 16-bit copy of dP (nB,T,4H)
   int fmt16;
@@ -93,6 +94,54 @@ __device__ __forceinline__ unsigned long long gtime() {
   do {                                                                         \
     if (p.trace != nullptr && blockIdx.x == 0) p.trace[(size_t)s * 16 + (slot)] = gtime(); \
   } while (0)
+__device__ __forceinline__ uint4 ld_volatile_v4(const unsigned* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// Streams the `nkb` (<= 16) k-blocks [kb_first, kb_first + nkb) of the step's activation tile in the order in which their
+// producers publish them: one 64-byte poll reads all counters, every newly complete k-block is loaded at once and its index
+// is left in slot_kb[stage] for the MMA thread.  Hides the skew between the publishing CTAs behind the streaming.
+template <class IssueFn>
+__device__ __forceinline__ void stream_kblocks_as_published(const unsigned* cnt, unsigned target, int nkb, volatile int* slot_kb,
+                                                            int& stage, uint32_t& phase, int stages, uint32_t bar_full0,
+                                                            uint32_t bar_empty0, const IssueFn& issue) {
+  unsigned loaded = 0;
+  int nloaded = 0;
+  while (nloaded < nkb) {
+    unsigned c[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q * 4 < nkb) {
+        const uint4 v = ld_volatile_v4(cnt + q * 4);
+        c[q * 4] = v.x; c[q * 4 + 1] = v.y; c[q * 4 + 2] = v.z; c[q * 4 + 3] = v.w;
+      } else {
+        c[q * 4] = c[q * 4 + 1] = c[q * 4 + 2] = c[q * 4 + 3] = 0;
+      }
+    }
+    unsigned ready = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < nkb && c[k] >= target) ready |= 1u << k;
+    ready &= ~loaded;
+    if (ready == 0) continue;
+    fence_acq_rel_gpu();                       // order the TMA reads after the counter observations
+    while (ready) {
+      const int k = __ffs(ready) - 1;
+      ready &= ready - 1;
+      mbar_wait(bar_empty0 + 8u * stage, phase ^ 1);
+      slot_kb[stage] = k;
+      mbar_expect_tx(bar_full0 + 8u * stage, LT_STAGE);
+      issue(stage, k);
+      loaded |= 1u << k;
+      ++nloaded;
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+  }
+}
+
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 // BWD = false: BN = gate columns per CTA (64 or 32).  BWD = true: BN = hidden units per CTA (16).
@@ -116,6 +165,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
   const uint32_t w_bar = bar0 + 8u * 16, tfull = bar0 + 8u * 17, tempty = bar0 + 8u * 18;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  volatile int* slot_kb = reinterpret_cast<volatile int*>(bars + 20);     // [8] k-block index held by each ring slot
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = blockIdx.x % p.NT, mt = blockIdx.x / p.NT;
@@ -140,7 +190,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   if (CL > 1) cluster_sync_all();        // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  unsigned* counter = p.counters + mt;
+  unsigned* counter = p.counters + mt * 64;
+  const bool kflags = CL == 1 && !BWD && p.kflags != 0;
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
   constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1);
   constexpr int SLICE_ROWS = 128 / CL;
@@ -153,23 +204,27 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int s = 1; s < T; ++s) {
+        const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
+        if (kflags) {
+          constexpr int U_PUB = BN / 4;                            // units published per CTA -> 64 / U_PUB CTAs per k-block
+          stream_kblocks_as_published(counter, (unsigned)s * (64 / U_PUB), kblocks, slot_kb, stage, phase, p.stages,
+                                      full_bar(0), empty_bar(0), [&](int st, int kb) {
+                                        tma_load_3d(ring + st * LT_STAGE, &mapX, full_bar(st), kb * 64, row0, 0);
+                                      });
+          continue;
+        }
         const unsigned target = (unsigned)s * (unsigned)p.NT;     // every column tile has published step s-1
         while (ld_acquire(counter) < target) {
         }
         LT_TRACE(0);
         if (p.exp_mode == 4) fence_proxy_async();   // writer-side proxy fence + release/acquire order the TMA reads
-        const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
         for (int kb0 = 0; kb0 < kblocks; ++kb0) {
           const int kb = kb0;
           mbar_wait(empty_bar(stage), phase ^ 1);
+          slot_kb[stage] = kb;
           mbar_expect_tx(full_bar(stage), LT_STAGE);
           if (CL == 1) {
-            if (p.exp_mode == 2) {
-              tma_load_3d(ring + stage * LT_STAGE, &mapX2, full_bar(stage), kb * 64, row0, 0);
-              tma_load_3d(ring + stage * LT_STAGE + LT_STAGE / 2, &mapX2, full_bar(stage), kb * 64, row0 + 64, 0);
-            } else {
-              tma_load_3d(ring + stage * LT_STAGE, (p.exp_mode == 1 && (kb & 1)) ? &mapX2 : &mapX, full_bar(stage), kb * 64, row0, 0);
-            }
+            tma_load_3d(ring + stage * LT_STAGE, &mapX, full_bar(stage), kb * 64, row0, 0);
           } else
             tma_load_3d_mc(ring + stage * LT_STAGE + crank * SLICE_ROWS * 128, &mapX, full_bar(stage), kb * 64,
                            row0 + crank * SLICE_ROWS, 0, cmask);
@@ -194,8 +249,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           continue;
         }
         for (int kb0 = 0; kb0 < kblocks; ++kb0) {
-          const int kb = kb0;
           mbar_wait(full_bar(stage), phase);
+          const int kb = slot_kb[stage];
           if (kb0 == 0) LT_TRACE(3);
           if (kb0 == kblocks - 1) LT_TRACE(4);
           tc_fence_after();
@@ -273,7 +328,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         asm volatile("bar.sync 1, 128;" ::: "memory");     // all 128 rows' slices are written (CTA scope)
         if (threadIdx.x == 64) {                             // one cumulative gpu-scope release for the CTA
           fence_proxy_async();
-          red_release_add(counter, 1u);        // red.release.gpu is itself the cumulative gpu-scope release
+          red_release_add(kflags ? counter + (u0 >> 6) : counter, 1u);   // red.release.gpu is the cumulative gpu-scope release
           LT_TRACE(8);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");     // bulk fp32 stores below must not queue ahead of that fence
@@ -455,6 +510,7 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
   auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
   const uint32_t w_bar = bar0 + 8u * 16, tfull = bar0 + 8u * 17, tempty = bar0 + 8u * 18, red_full = bar0 + 8u * 19;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  volatile int* slot_kb = reinterpret_cast<volatile int*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t r = cluster_ctarank();                     // K quarter and unit quarter owned by this CTA
@@ -481,8 +537,9 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  unsigned* counter = p.counters + mt;
+  unsigned* counter = p.counters + mt * 64;
   const unsigned per_step = (unsigned)(UT * KS_CL);
+  const bool kflags = p.kflags != 0;     // counter[kb]: k-block kb of dG (64 gate columns) is published by exactly one CTA
 
   if (warp == 0) {
     if (lane == 0) {
@@ -492,12 +549,20 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       for (int s = 1; s < T; ++s) {
+        const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
+        if (kflags) {
+          stream_kblocks_as_published(counter + r * kblocks, (unsigned)s, kblocks, slot_kb, stage, phase, p.stages, full_bar(0),
+                                      empty_bar(0), [&](int st, int kb) {
+                                        tma_load_3d(ring + st * LT_STAGE, &mapX, full_bar(st), (int)r * H + kb * 64, row0, 0);
+                                      });
+          continue;
+        }
         while (ld_acquire(counter) < (unsigned)s * per_step) {
         }
         if (p.exp_mode == 4) fence_proxy_async();
-        const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
+          slot_kb[stage] = kb;
           mbar_expect_tx(full_bar(stage), LT_STAGE);
           tma_load_3d(ring + stage * LT_STAGE, &mapX, full_bar(stage), (int)r * H + kb * 64, row0, 0);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -517,14 +582,15 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
           mbar_arrive(tfull);
           continue;
         }
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb0 = 0; kb0 < kblocks; ++kb0) {
           mbar_wait(full_bar(stage), phase);
+          const int kb = slot_kb[stage];
           tc_fence_after();
           const uint32_t sa = ring + stage * LT_STAGE, sb = w_base + kb * w_block;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16(tmem_base, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc,
-                     (kb > 0 || k > 0) ? 1u : 0u);
+                     (kb0 > 0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(stage));
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -635,7 +701,7 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 64) {
         fence_proxy_async();
-        red_release_add(counter, 1u);
+        red_release_add(kflags ? counter + (u0 >> 4) : counter, 1u);   // dG columns 4*u0 .. 4*u0+63 = k-block u0/16
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (live) {
@@ -699,7 +765,7 @@ static LtPlan lt_plan(int nB, int H, bool bwd) {
   pl.off_x = align256((size_t)4 * H * H * 2);
   pl.off_cnt = pl.off_x + align256((size_t)2 * MT * 128 * pl.K * 2);
   const int nchunks = ceil_div(nB, pl.chunk);
-  pl.total = pl.off_cnt + align256((size_t)nchunks * 64 * sizeof(unsigned));
+  pl.total = pl.off_cnt + align256((size_t)nchunks * 128 * sizeof(unsigned));
   return pl;
 }
 size_t lstm_tc_workspace(int nB, int T, int H, bool bwd) {
@@ -822,7 +888,12 @@ int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh,
   cvt_bf16_kernel<<<(int)std::min<size_t>(ceil_div(wn, (size_t)256), (size_t)num_sms() * 8), 256, 0, st>>>(W, Wb, wn);
   AVC_LAUNCHED();
   const int nchunks = ceil_div(nB, pl.chunk);
-  AVC_CUDA(cudaMemsetAsync(counters, 0, (size_t)nchunks * 64 * sizeof(unsigned), st));
+  AVC_CUDA(cudaMemsetAsync(counters, 0, (size_t)nchunks * 128 * sizeof(unsigned), st));
+  static int kflags_mode = -1;
+  if (kflags_mode < 0) {
+    const char* e = getenv("AVC_LSTM_KFLAGS");
+    kflags_mode = e ? atoi(e) : 1;
+  }
   CUtensorMap mW, mX, mX2;
   const char* exp_env = getenv("AVC_LSTM_EXP");
   const int exp_mode = exp_env ? atoi(exp_env) : 0;
@@ -845,7 +916,8 @@ int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh,
     p.lddh = lddh;
     p.dP = dP ? dP + (size_t)b0 * T * G : nullptr;
     p.xbuf = xbuf;
-    p.counters = counters + ch * 64;
+    p.counters = counters + ch * 128;
+    p.kflags = (kflags_mode != 0 && H / 64 <= 16 && (H / 64) % 4 == 0 && pl.MTmax <= 2) ? 1 : 0;
     p.trace = (ch == 0) ? g_trace : nullptr;
     p.exp_mode = exp_mode;
     p.fmt16 = fmt16;
