@@ -892,7 +892,7 @@ int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh,
   static int kflags_mode = -1;
   if (kflags_mode < 0) {
     const char* e = getenv("AVC_LSTM_KFLAGS");
-    kflags_mode = e ? atoi(e) : 1;
+    kflags_mode = e ? atoi(e) : 0;   // measured neutral (r01): per-k-block counters stay opt-in
   }
   CUtensorMap mW, mX, mX2;
   const char* exp_env = getenv("AVC_LSTM_EXP");
