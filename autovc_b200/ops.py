@@ -530,6 +530,7 @@ class ConvBnActH(torch.autograd.Function):
         ctx.save_for_backward(x, weight, gamma, y, z, mean, rstd)
         ctx.act, ctx.training, ctx.has_res, ctx.wd = act, training, residual is not None, wd
         ctx.mark_non_differentiable(z16)
+        ctx.set_materialize_grads(False)      # no zero tensor for the 16-bit side output's (absent) gradient
         return z, z16
 
     @staticmethod
@@ -596,6 +597,7 @@ class LstmLayerH(torch.autograd.Function):
         ctx.save_for_backward(x, out, w_ih, w_hh, b_ih, gates, c_seq)
         ctx.packs = (wi_pT, wh_pT)
         ctx.mark_non_differentiable(h16)
+        ctx.set_materialize_grads(False)
         return out, h16
 
     @staticmethod

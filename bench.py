@@ -125,7 +125,7 @@ def run_reference(args):
 
 def workload_config(args, note=None):
     c = {"workload": f"AutoVC mel Generator train step (solver_encoder.py:228-300), dim_neck={args.dim_neck} dim_emb=256 dim_pre=512 "
-                     f"freq={args.freq}, synthetic 80-bin mel, batch {args.batch} per GPU, len_crop {args.len_crop}",
+                     f"freq={args.freq}, synthetic {args.n_bins}-bin {'mel' if args.n_bins == 80 else 'linear spectrogram'}, batch {args.batch} per GPU, len_crop {args.len_crop}",
          "global_batch": args.batch * args.gpus, "len_crop": args.len_crop, "precision": args.precision,
          "parallelism": f"dp{args.gpus}",
          "l2": "per-step working set (>5 GB of activations) far exceeds the 126 MB L2; no explicit flush"}
@@ -180,14 +180,17 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)
-    G = autovc_b200.Generator(args.dim_neck, 256, 512, args.freq, precision=args.precision).to(dev).train()
+    if args.n_bins == 513:      # BASELINE.json configs[3]: the model_vc_stft variant (its .model)
+        G = autovc_b200.GeneratorSTFT(args.dim_neck, 256, 512, args.freq, precision=args.precision).model.to(dev).train()
+    else:
+        G = autovc_b200.Generator(args.dim_neck, 256, 512, args.freq, precision=args.precision).to(dev).train()
     opt = torch.optim.Adam(G.parameters(), 1e-4)
     reducer = None
     if world > 1:
         solver.broadcast_parameters(G)
         reducer = solver.GradBucketReducer(G.parameters(), bucket_mb=25.0)
     B, T = args.batch, args.len_crop
-    x_host, e_host = synth_batch(B, T, 80, 256, 1234 + rank)
+    x_host, e_host = synth_batch(B, T, args.n_bins, 256, 1234 + rank)
     x_pin, e_pin = x_host.pin_memory(), e_host.pin_memory()
     x_dev, e_dev = x_host.to(dev), e_host.to(dev)
 
@@ -249,7 +252,7 @@ def run_ours(args):
     tot_ms = sum(f["ms"] for f in fam.values()) or 1.0
     top = max(fam.items(), key=lambda kv: kv[1]["ms"])
     peaks = measured_peaks()
-    step_flops = 6.0 * MAC_PER_FRAME[(args.dim_neck, 80)] * B * T
+    step_flops = 6.0 * MAC_PER_FRAME.get((args.dim_neck, args.n_bins), MAC_PER_FRAME[(16, 80)]) * B * T
     top_name, top_f = top
     achieved = top_f["flops"] / (top_f["ms"] * 1e-3) / 1e12 if top_f["ms"] > 0 else 0.0
     roofline = {
@@ -368,6 +371,7 @@ def main():
     ap.add_argument("--len-crop", dest="len_crop", type=int, default=128)
     ap.add_argument("--dim-neck", dest="dim_neck", type=int, default=16)
     ap.add_argument("--freq", type=int, default=16)
+    ap.add_argument("--n-bins", dest="n_bins", type=int, default=80, choices=[80, 513], help="513 = model_vc_stft variant (configs[3])")
     ap.add_argument("--cpu-sample-batch", dest="cpu_sample_batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "frontend", "convert"])
