@@ -38,6 +38,8 @@ SIGNATURES = {
     "avc_bn_act_fwd": (c_int, [P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "avc_bn_act_bwd_reduce": (c_int, [P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "avc_bn_act_bwd_apply": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "avc_bn_act_bwd_reduce_y": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
+    "avc_bn_act_bwd_apply_y": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, P]),
     "avc_colsum": (c_int, [P, c_int, c_int, c_int, P, P, c_int, c_int, P, c_size_t, P]),
     "avc_lstm_seq_fwd": (c_int, [P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
     "avc_lstm_fwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

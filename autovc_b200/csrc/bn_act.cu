@@ -151,6 +151,9 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ rmean, const floa
   rstd[c] = 1.0f / sqrtf(rvar[c] + eps);
 }
 
+// the one expression every forward AND every recomputing backward kernel uses for the BatchNorm affine map
+__device__ __forceinline__ float bn_affine(float y, float mu, float sc, float be) { return fmaf(y - mu, sc, be); }
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == AVC_ACT_RELU) return fmaxf(v, 0.f);
   if (act == AVC_ACT_TANH) return tanhf(v);
@@ -165,33 +168,9 @@ __global__ void bn_act_fwd_kernel(const float* __restrict__ y, const float* __re
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const float sc = rstd[c] * gamma[c];
-    float v = (y[i] - mean[c]) * sc + beta[c];
-    v = apply_act(v, act);
+    float v = apply_act(bn_affine(y[i], mean[c], sc, beta[c]), act);
     if (res) v += res[i];
     z[i] = v;
-  }
-}
-
-__global__ void bn_act_fwd_vec4_kernel(const float4* __restrict__ y, const float* __restrict__ mean,
-                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, const float4* __restrict__ res,
-                                       float4* __restrict__ z, size_t total4, int C, int act,
-                                       uint2* __restrict__ z16 = nullptr, int fmt16 = 0) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)((i * 4) % C);
-    const float4 v = y[i];
-    float o[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float sc = rstd[c + j] * gamma[c + j];
-      o[j] = apply_act((o[j] - mean[c + j]) * sc + beta[c + j], act);
-    }
-    if (res) {
-      const float4 r = res[i];
-      o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
-    }
-    z[i] = make_float4(o[0], o[1], o[2], o[3]);
-    if (z16) z16[i] = pack4_16(o[0], o[1], o[2], o[3], fmt16);
   }
 }
 
@@ -213,67 +192,128 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dz, const floa
   }
 }
 
-// float4 variant (C % 4 == 0, 16-byte aligned pointers): one channel lookup per four elements
-__global__ void bn_act_bwd_apply_vec4_kernel(const float4* __restrict__ dz, const float4* __restrict__ z,
-                                             const float4* __restrict__ y, const float* __restrict__ mean,
-                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                             const double* __restrict__ sums, float4* __restrict__ dy, size_t total4, int M,
-                                             int C, int act, uint2* __restrict__ dy16 = nullptr, int fmt16 = 0) {
-  const float invM = 1.0f / (float)M;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)((i * 4) % C);
-    const float4 d4 = dz[i], y4 = y[i];
-    float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (act != AVC_ACT_NONE) z4 = z[i];
-    const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w}, zv[4] = {z4.x, z4.y, z4.z, z4.w};
-    float o[4];
+// ---------------------------------------------------------------------------------------
+// Column-fixed variants (C % 4 == 0): block = 32 channel quads x 8 row lanes, each thread keeps the parameters of
+// ITS four channels in registers and walks down the rows with four independent row streams in flight.  The
+// grid-stride kernels above re-load 5 parameters per element and are L1-bound (r01b ncu: l1tex 83-90% busy, DRAM
+// 31-41%); these are bound by HBM.  With z == nullptr the activation is recomputed from y (bitwise the forward's
+// expression), which saves a whole (M, C) read in the two backward passes.
+// ---------------------------------------------------------------------------------------
+constexpr int BC_UNROLL = 4;
+
+__global__ void __launch_bounds__(256)
+bn_act_fwd_cols_kernel(const float4* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, const float4* __restrict__ res,
+                       float4* __restrict__ z, uint2* __restrict__ z16, int fmt16, int M, int C, int rows_per_block, int act) {
+  const int cq = blockIdx.x * 32 + threadIdx.x;
+  const int c = cq * 4;
+  if (c >= C) return;
+  float mu[4], sc[4], be[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float g = dv[j];
-      if (act == AVC_ACT_RELU) g = zv[j] > 0.f ? g : 0.f;
-      else if (act == AVC_ACT_TANH) g *= (1.f - zv[j] * zv[j]);
-      const float rs = rstd[c + j];
-      const float xh = (yv[j] - mean[c + j]) * rs;
-      const float sg = (float)sums[c + j] * invM, sgx = (float)sums[C + c + j] * invM;
-      o[j] = gamma[c + j] * rs * (g - sg - xh * sgx);
+  for (int j = 0; j < 4; ++j) {
+    mu[j] = mean[c + j];
+    sc[j] = rstd[c + j] * gamma[c + j];
+    be[j] = beta[c + j];
+  }
+  const int C4 = C >> 2;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  for (int r = r0 + threadIdx.y; r < r1; r += 8 * BC_UNROLL) {
+    float4 v[BC_UNROLL], rr[BC_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BC_UNROLL; ++u) {
+      const int ru = r + 8 * u;
+      if (ru < r1) {
+        v[u] = y[(size_t)ru * C4 + cq];
+        if (res) rr[u] = res[(size_t)ru * C4 + cq];
+      }
     }
-    if (dy) dy[i] = make_float4(o[0], o[1], o[2], o[3]);
-    if (dy16) dy16[i] = pack4_16(o[0], o[1], o[2], o[3], fmt16);
+#pragma unroll
+    for (int u = 0; u < BC_UNROLL; ++u) {
+      const int ru = r + 8 * u;
+      if (ru < r1) {
+        float o[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = apply_act(bn_affine(o[j], mu[j], sc[j], be[j]), act);
+        if (res) {
+          o[0] += rr[u].x; o[1] += rr[u].y; o[2] += rr[u].z; o[3] += rr[u].w;
+        }
+        const size_t i = (size_t)ru * C4 + cq;
+        z[i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (z16) z16[i] = pack4_16(o[0], o[1], o[2], o[3], fmt16);
+      }
+    }
   }
 }
 
-// float4 variant of the BN-backward column reduction: block = 32 column-quads x 8 row lanes
+// g = dz * act'(z) for four channels; z given, or recomputed from y when zv == nullptr
+__device__ __forceinline__ void bn_bwd_g4(const float4& d4, const float4& y4, const float4* zv, const float (&mu)[4],
+                                          const float (&rs)[4], const float (&sc)[4], const float (&be)[4], int act,
+                                          float (&g)[4], float (&xh)[4]) {
+  const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w};
+  float zz[4] = {0.f, 0.f, 0.f, 0.f};
+  if (act != AVC_ACT_NONE) {
+    if (zv) {
+      zz[0] = zv->x; zz[1] = zv->y; zz[2] = zv->z; zz[3] = zv->w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) zz[j] = apply_act(bn_affine(yv[j], mu[j], sc[j], be[j]), act);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float gg = dv[j];
+    if (act == AVC_ACT_RELU) gg = zz[j] > 0.f ? gg : 0.f;
+    else if (act == AVC_ACT_TANH) gg *= (1.f - zz[j] * zz[j]);
+    g[j] = gg;
+    xh[j] = (yv[j] - mu[j]) * rs[j];
+  }
+}
+
 __global__ void __launch_bounds__(256)
-bn_bwd_reduce_vec4_kernel(const float4* __restrict__ dz, const float4* __restrict__ z, const float4* __restrict__ y,
-                          const float* __restrict__ mean, const float* __restrict__ rstd, int M, int C, int rows_per_block,
-                          int act, double* __restrict__ out) {
+bn_bwd_reduce_cols_kernel(const float4* __restrict__ dz, const float4* __restrict__ z, const float4* __restrict__ y,
+                          const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, int M, int C, int rows_per_block, int act, double* __restrict__ out) {
   __shared__ float sa[8][128 + 4], sb[8][128 + 4];
-  const int cq = blockIdx.x * 32 + threadIdx.x;      // column quad
+  const int cq = blockIdx.x * 32 + threadIdx.x;
   const int c = cq * 4;
-  const int r0 = blockIdx.y * rows_per_block;
-  const int r1 = min(M, r0 + rows_per_block);
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
   float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
   if (c < C) {
-    float mu[4], rs[4];
+    float mu[4], rs[4], sc[4] = {0.f, 0.f, 0.f, 0.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       mu[j] = mean[c + j];
       rs[j] = rstd[c + j];
+      if (!z && act != AVC_ACT_NONE) {
+        sc[j] = rs[j] * gamma[c + j];
+        be[j] = beta[c + j];
+      }
     }
     const int C4 = C >> 2;
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
-      const size_t i = (size_t)r * C4 + cq;
-      const float4 d4 = dz[i], y4 = y[i];
-      float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (act != AVC_ACT_NONE) z4 = z[i];
-      const float dv[4] = {d4.x, d4.y, d4.z, d4.w}, yv[4] = {y4.x, y4.y, y4.z, y4.w}, zv[4] = {z4.x, z4.y, z4.z, z4.w};
+    const bool ldz = z != nullptr && act != AVC_ACT_NONE;
+    for (int r = r0 + threadIdx.y; r < r1; r += 8 * BC_UNROLL) {
+      float4 d4[BC_UNROLL], y4[BC_UNROLL], z4[BC_UNROLL];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float g = dv[j];
-        if (act == AVC_ACT_RELU) g = zv[j] > 0.f ? g : 0.f;
-        else if (act == AVC_ACT_TANH) g *= (1.f - zv[j] * zv[j]);
-        a[j] += g;
-        b[j] = fmaf(g, (yv[j] - mu[j]) * rs[j], b[j]);
+      for (int u = 0; u < BC_UNROLL; ++u) {
+        const int ru = r + 8 * u;
+        if (ru < r1) {
+          const size_t i = (size_t)ru * C4 + cq;
+          d4[u] = dz[i];
+          y4[u] = y[i];
+          if (ldz) z4[u] = z[i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < BC_UNROLL; ++u) {
+        if (r + 8 * u < r1) {
+          float g[4], xh[4];
+          bn_bwd_g4(d4[u], y4[u], ldz ? &z4[u] : nullptr, mu, rs, sc, be, act, g, xh);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            a[j] += g[j];
+            b[j] = fmaf(g[j], xh[j], b[j]);
+          }
+        }
       }
     }
   }
@@ -297,6 +337,115 @@ bn_bwd_reduce_vec4_kernel(const float4* __restrict__ dz, const float4* __restric
       atomicAdd(out + C + cc, db);
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_cols_kernel(const float4* __restrict__ dz, const float4* __restrict__ z, const float4* __restrict__ y,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, const double* __restrict__ sums, float4* __restrict__ dy,
+                         uint2* __restrict__ dy16, int fmt16, int M, int C, int rows_per_block, int act) {
+  const int cq = blockIdx.x * 32 + threadIdx.x;
+  const int c = cq * 4;
+  if (c >= C) return;
+  const float invM = 1.0f / (float)M;
+  float mu[4], rs[4], sc[4] = {0.f, 0.f, 0.f, 0.f}, be[4] = {0.f, 0.f, 0.f, 0.f}, gr[4], sg[4], sgx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mu[j] = mean[c + j];
+    rs[j] = rstd[c + j];
+    gr[j] = gamma[c + j] * rs[j];
+    sg[j] = (float)sums[c + j] * invM;
+    sgx[j] = (float)sums[C + c + j] * invM;
+    if (!z && act != AVC_ACT_NONE) {
+      sc[j] = rs[j] * gamma[c + j];
+      be[j] = beta[c + j];
+    }
+  }
+  const int C4 = C >> 2;
+  const bool ldz = z != nullptr && act != AVC_ACT_NONE;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  for (int r = r0 + threadIdx.y; r < r1; r += 8 * BC_UNROLL) {
+    float4 d4[BC_UNROLL], y4[BC_UNROLL], z4[BC_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BC_UNROLL; ++u) {
+      const int ru = r + 8 * u;
+      if (ru < r1) {
+        const size_t i = (size_t)ru * C4 + cq;
+        d4[u] = dz[i];
+        y4[u] = y[i];
+        if (ldz) z4[u] = z[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BC_UNROLL; ++u) {
+      const int ru = r + 8 * u;
+      if (ru < r1) {
+        float g[4], xh[4], o[4];
+        bn_bwd_g4(d4[u], y4[u], ldz ? &z4[u] : nullptr, mu, rs, sc, be, act, g, xh);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = gr[j] * (g[j] - sg[j] - xh[j] * sgx[j]);
+        const size_t i = (size_t)ru * C4 + cq;
+        if (dy) dy[i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (dy16) dy16[i] = pack4_16(o[0], o[1], o[2], o[3], fmt16);
+      }
+    }
+  }
+}
+
+// sum (and optionally sum of squares) of each column of x (M, C), row stride ldx4 float4s
+template <bool SQ>
+__global__ void __launch_bounds__(256)
+col_sums_cols_kernel(const float4* __restrict__ x, int ldx4, int M, int C, int rows_per_block, double* __restrict__ out) {
+  __shared__ float sa[8][128 + 4], sb[SQ ? 8 : 1][128 + 4];
+  const int cq = blockIdx.x * 32 + threadIdx.x;
+  const int c = cq * 4;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8 * BC_UNROLL) {
+      float4 v[BC_UNROLL];
+#pragma unroll
+      for (int u = 0; u < BC_UNROLL; ++u)
+        v[u] = (r + 8 * u < r1) ? x[(size_t)(r + 8 * u) * ldx4 + cq] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < BC_UNROLL; ++u) {
+        a[0] += v[u].x; a[1] += v[u].y; a[2] += v[u].z; a[3] += v[u].w;
+        if (SQ) {
+          b[0] = fmaf(v[u].x, v[u].x, b[0]); b[1] = fmaf(v[u].y, v[u].y, b[1]);
+          b[2] = fmaf(v[u].z, v[u].z, b[2]); b[3] = fmaf(v[u].w, v[u].w, b[3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sa[threadIdx.y][threadIdx.x * 4 + j] = a[j];
+    if (SQ) sb[threadIdx.y][threadIdx.x * 4 + j] = b[j];
+  }
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 128) {
+    const int cc = blockIdx.x * 128 + t;
+    if (cc < C) {
+      double da = 0.0, db = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        da += (double)sa[i][t];
+        if (SQ) db += (double)sb[i][t];
+      }
+      atomicAdd(out + cc, da);
+      if (SQ) atomicAdd(out + C + cc, db);
+    }
+  }
+}
+
+// grid for the column-fixed kernels: ceil(C/128) column blocks x enough row blocks for ~6 blocks per SM
+static void cols_grid(int M, int C, dim3& grid, int& rows_per_block) {
+  const int cb = ceil_div(C, 128);
+  int rb = std::max(1, ceil_div(6 * num_sms(), cb));
+  rows_per_block = std::max(8 * BC_UNROLL, ceil_div(ceil_div(M, rb), 8) * 8);
+  rb = ceil_div(M, rows_per_block);
+  grid = dim3(cb, rb);
 }
 
 __global__ void bn_param_grad_kernel(const double* __restrict__ sums, float* __restrict__ dgamma,
@@ -366,15 +515,28 @@ static int ew_blocks(size_t total) {
 
 using namespace avc;
 
-extern "C" int avc_channel_stats(const float* x, int ldx, int M, int C, double* stats, void* stream) {
-  AVC_REQUIRE(x && stats && M > 0 && C > 0 && ldx >= C, "avc_channel_stats: bad arguments");
-  dim3 grid;
-  int rpb;
-  col_reduce_grid(M, C, grid, rpb);
-  col_reduce_kernel<0><<<grid, dim3(CR_COLS, CR_ROWS), 0, as_stream(stream)>>>(x, ldx, nullptr, nullptr, nullptr, nullptr,
-                                                                              M, C, rpb, 0, stats);
+static inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+static int launch_col_sums(const float* x, int ldx, int M, int C, double* out, bool sq, cudaStream_t st) {
+  if (C % 4 == 0 && ldx % 4 == 0 && al16(x)) {
+    dim3 grid;
+    int rpb;
+    cols_grid(M, C, grid, rpb);
+    if (sq) col_sums_cols_kernel<true><<<grid, dim3(32, 8), 0, st>>>((const float4*)x, ldx / 4, M, C, rpb, out);
+    else col_sums_cols_kernel<false><<<grid, dim3(32, 8), 0, st>>>((const float4*)x, ldx / 4, M, C, rpb, out);
+  } else {
+    dim3 grid;
+    int rpb;
+    col_reduce_grid(M, C, grid, rpb);
+    col_reduce_kernel<0><<<grid, dim3(CR_COLS, CR_ROWS), 0, st>>>(x, ldx, nullptr, nullptr, nullptr, nullptr, M, C, rpb, 0, out);
+  }
   AVC_LAUNCHED();
   return AVC_OK;
+}
+
+extern "C" int avc_channel_stats(const float* x, int ldx, int M, int C, double* stats, void* stream) {
+  AVC_REQUIRE(x && stats && M > 0 && C > 0 && ldx >= C, "avc_channel_stats: bad arguments");
+  return launch_col_sums(x, ldx, M, C, stats, true, as_stream(stream));
 }
 
 extern "C" int avc_bn_finalize(const double* stats, int M, int C, float eps, float momentum, float* mean, float* rstd,
@@ -394,60 +556,114 @@ extern "C" int avc_bn_eval_stats(const float* running_mean, const float* running
   return AVC_OK;
 }
 
+static int bn_fwd_impl(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                       const float* residual, float* z, void* z16, int fmt16, int M, int C, int act, cudaStream_t st) {
+  const bool vec = (C % 4 == 0) && al16(y) && al16(z) && (!residual || al16(residual)) && (!z16 || ((uintptr_t)z16 & 7) == 0);
+  if (vec) {
+    dim3 grid;
+    int rpb;
+    cols_grid(M, C, grid, rpb);
+    bn_act_fwd_cols_kernel<<<grid, dim3(32, 8), 0, st>>>((const float4*)y, mean, rstd, gamma, beta, (const float4*)residual,
+                                                         (float4*)z, (uint2*)z16, fmt16, M, C, rpb, act);
+  } else {
+    if (z16) {
+      set_error("avc_bn_act_fwd_h: needs C %% 4 == 0 and 16-byte aligned tensors");
+      return AVC_ERR_INVALID;
+    }
+    const size_t total = (size_t)M * C;
+    bn_act_fwd_kernel<<<ew_blocks(total), 256, 0, st>>>(y, mean, rstd, gamma, beta, residual, z, total, C, act);
+  }
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
 extern "C" int avc_bn_act_fwd(const float* y, const float* mean, const float* rstd, const float* gamma,
                               const float* beta, const float* residual, float* z, int M, int C, int act, void* stream) {
   AVC_REQUIRE(y && mean && rstd && gamma && beta && z && M > 0 && C > 0, "avc_bn_act_fwd: bad arguments");
-  const size_t total = (size_t)M * C;
-  const bool vec = (C % 4 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)z % 16 == 0) &&
-                   (!residual || (uintptr_t)residual % 16 == 0);
-  if (vec)
-    bn_act_fwd_vec4_kernel<<<ew_blocks(total / 4), 256, 0, as_stream(stream)>>>(
-        (const float4*)y, mean, rstd, gamma, beta, (const float4*)residual, (float4*)z, total / 4, C, act);
-  else
-    bn_act_fwd_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(y, mean, rstd, gamma, beta, residual, z, total, C, act);
+  return bn_fwd_impl(y, mean, rstd, gamma, beta, residual, z, nullptr, 0, M, C, act, as_stream(stream));
+}
+
+// z may be NULL when gamma/beta are given and the tensors allow the float4 path: the activation is then recomputed from y
+static int bn_bwd_reduce_impl(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
+                              const float* gamma, const float* beta, double* sums, int M, int C, int act, cudaStream_t st) {
+  const bool vec = (C % 4 == 0) && al16(dz) && al16(y) && (!z || al16(z));
+  if (vec) {
+    dim3 grid;
+    int rpb;
+    cols_grid(M, C, grid, rpb);
+    const bool recompute = gamma && beta;
+    bn_bwd_reduce_cols_kernel<<<grid, dim3(32, 8), 0, st>>>((const float4*)dz, recompute ? nullptr : (const float4*)z,
+                                                            (const float4*)y, mean, rstd, gamma, beta, M, C, rpb, act, sums);
+    AVC_LAUNCHED();
+    return AVC_OK;
+  }
+  if (!z) {
+    set_error("avc_bn_act_bwd_reduce_y: z may only be NULL when C %% 4 == 0 and the tensors are 16-byte aligned");
+    return AVC_ERR_INVALID;
+  }
+  dim3 grid;
+  int rpb;
+  col_reduce_grid(M, C, grid, rpb);
+  col_reduce_kernel<1><<<grid, dim3(CR_COLS, CR_ROWS), 0, st>>>(dz, C, z, y, mean, rstd, M, C, rpb, act, sums);
   AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+static int bn_bwd_apply_impl(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
+                             const float* gamma, const float* beta, const double* sums, float* dy, void* dy16, int fmt16,
+                             float* dgamma, float* dbeta, int M, int C, int act, int accumulate, cudaStream_t st) {
+  const bool vec = (C % 4 == 0) && al16(dz) && al16(y) && (!z || al16(z)) && (!dy || al16(dy)) && (!dy16 || ((uintptr_t)dy16 & 7) == 0);
+  if (vec) {
+    dim3 grid;
+    int rpb;
+    cols_grid(M, C, grid, rpb);
+    bn_bwd_apply_cols_kernel<<<grid, dim3(32, 8), 0, st>>>((const float4*)dz, beta ? nullptr : (const float4*)z, (const float4*)y,
+                                                           mean, rstd, gamma, beta, sums, (float4*)dy, (uint2*)dy16, fmt16, M, C,
+                                                           rpb, act);
+  } else {
+    if (!z || dy16 || !dy) {
+      set_error("avc_bn_act_bwd_apply: the scalar path needs z and an fp32 dy (C %% 4 != 0 or unaligned tensors)");
+      return AVC_ERR_INVALID;
+    }
+    const size_t total = (size_t)M * C;
+    bn_act_bwd_apply_kernel<<<ew_blocks(total), 256, 0, st>>>(dz, z, y, mean, rstd, gamma, sums, dy, total, M, C, act);
+  }
+  AVC_LAUNCHED();
+  if (dgamma || dbeta) {
+    bn_param_grad_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, dgamma, dbeta, C, accumulate);
+    AVC_LAUNCHED();
+  }
   return AVC_OK;
 }
 
 extern "C" int avc_bn_act_bwd_reduce(const float* dz, const float* z, const float* y, const float* mean,
                                      const float* rstd, double* sums, int M, int C, int act, void* stream) {
   AVC_REQUIRE(dz && z && y && mean && rstd && sums && M > 0 && C > 0, "avc_bn_act_bwd_reduce: bad arguments");
-  const bool vec = (C % 4 == 0) && (((uintptr_t)dz | (uintptr_t)z | (uintptr_t)y) % 16 == 0);
-  if (vec) {
-    const int cb = ceil_div(C, 128);
-    int rb = ceil_div(8 * num_sms(), cb);
-    int rpb = std::max(64, ceil_div(M, rb));
-    rb = ceil_div(M, rpb);
-    bn_bwd_reduce_vec4_kernel<<<dim3(cb, rb), dim3(32, 8), 0, as_stream(stream)>>>(
-        (const float4*)dz, (const float4*)z, (const float4*)y, mean, rstd, M, C, rpb, act, sums);
-    AVC_LAUNCHED();
-    return AVC_OK;
-  }
-  dim3 grid;
-  int rpb;
-  col_reduce_grid(M, C, grid, rpb);
-  col_reduce_kernel<1><<<grid, dim3(CR_COLS, CR_ROWS), 0, as_stream(stream)>>>(dz, C, z, y, mean, rstd, M, C, rpb, act, sums);
-  AVC_LAUNCHED();
-  return AVC_OK;
+  return bn_bwd_reduce_impl(dz, z, y, mean, rstd, nullptr, nullptr, sums, M, C, act, as_stream(stream));
 }
 
 extern "C" int avc_bn_act_bwd_apply(const float* dz, const float* z, const float* y, const float* mean,
                                     const float* rstd, const float* gamma, const double* sums, float* dy, float* dgamma,
                                     float* dbeta, int M, int C, int act, int accumulate, void* stream) {
   AVC_REQUIRE(dz && z && y && mean && rstd && gamma && sums && dy && M > 0 && C > 0, "avc_bn_act_bwd_apply: bad arguments");
-  const size_t total = (size_t)M * C;
-  const bool vec = (C % 4 == 0) && (((uintptr_t)dz | (uintptr_t)z | (uintptr_t)y | (uintptr_t)dy) % 16 == 0);
-  if (vec)
-    bn_act_bwd_apply_vec4_kernel<<<ew_blocks(total / 4), 256, 0, as_stream(stream)>>>(
-        (const float4*)dz, (const float4*)z, (const float4*)y, mean, rstd, gamma, sums, (float4*)dy, total / 4, M, C, act);
-  else
-    bn_act_bwd_apply_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(dz, z, y, mean, rstd, gamma, sums, dy, total, M, C, act);
-  AVC_LAUNCHED();
-  if (dgamma || dbeta) {
-    bn_param_grad_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(sums, dgamma, dbeta, C, accumulate);
-    AVC_LAUNCHED();
-  }
-  return AVC_OK;
+  return bn_bwd_apply_impl(dz, z, y, mean, rstd, gamma, nullptr, sums, dy, nullptr, 0, dgamma, dbeta, M, C, act, accumulate,
+                           as_stream(stream));
+}
+
+extern "C" int avc_bn_act_bwd_reduce_y(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
+                                       const float* gamma, const float* beta, double* sums, int M, int C, int act, void* stream) {
+  AVC_REQUIRE(dz && y && mean && rstd && gamma && beta && sums && M > 0 && C > 0, "avc_bn_act_bwd_reduce_y: bad arguments");
+  return bn_bwd_reduce_impl(dz, z, y, mean, rstd, gamma, beta, sums, M, C, act, as_stream(stream));
+}
+
+extern "C" int avc_bn_act_bwd_apply_y(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
+                                      const float* gamma, const float* beta, const double* sums, float* dy, void* dy16, int fmt16,
+                                      float* dgamma, float* dbeta, int M, int C, int act, int accumulate, void* stream) {
+  AVC_REQUIRE(dz && y && mean && rstd && gamma && beta && sums && (dy || dy16) && M > 0 && C > 0,
+              "avc_bn_act_bwd_apply_y: bad arguments");
+  AVC_REQUIRE(!dy16 || fmt16 == 1 || fmt16 == 2, "avc_bn_act_bwd_apply_y: fmt16 must be 1 (bf16) or 2 (fp16)");
+  return bn_bwd_apply_impl(dz, z, y, mean, rstd, gamma, beta, sums, dy, dy16, fmt16, dgamma, dbeta, M, C, act, accumulate,
+                           as_stream(stream));
 }
 
 extern "C" int avc_colsum(const float* x, int ldx, int M, int C, float* out, float* out2, int out_mode, int accumulate,
@@ -460,12 +676,8 @@ extern "C" int avc_colsum(const float* x, int ldx, int M, int C, float* out, flo
   }
   cudaStream_t st = as_stream(stream);
   AVC_CUDA(cudaMemsetAsync(workspace, 0, 2 * sizeof(double) * (size_t)C, st));
-  dim3 grid;
-  int rpb;
-  col_reduce_grid(M, C, grid, rpb);
-  col_reduce_kernel<0><<<grid, dim3(CR_COLS, CR_ROWS), 0, st>>>(x, ldx, nullptr, nullptr, nullptr, nullptr, M, C, rpb, 0,
-                                                               (double*)workspace);
-  AVC_LAUNCHED();
+  const int rc = launch_col_sums(x, ldx, M, C, (double*)workspace, false, st);
+  if (rc) return rc;
   colsum_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const double*)workspace, out, out2, C, out_mode, accumulate);
   AVC_LAUNCHED();
   return AVC_OK;
@@ -513,11 +725,7 @@ extern "C" int avc_bn_act_fwd_h(const float* y, const float* mean, const float* 
                                 const float* residual, float* z, void* z16, int fmt16, int M, int C, int act, void* stream) {
   AVC_REQUIRE(y && mean && rstd && gamma && beta && z && z16 && M > 0 && C > 0, "avc_bn_act_fwd_h: bad arguments");
   AVC_REQUIRE(C % 4 == 0 && (fmt16 == 1 || fmt16 == 2), "avc_bn_act_fwd_h: C must be a multiple of 4");
-  const size_t total = (size_t)M * C;
-  bn_act_fwd_vec4_kernel<<<ew_blocks(total / 4), 256, 0, as_stream(stream)>>>(
-      (const float4*)y, mean, rstd, gamma, beta, (const float4*)residual, (float4*)z, total / 4, C, act, (uint2*)z16, fmt16);
-  AVC_LAUNCHED();
-  return AVC_OK;
+  return bn_fwd_impl(y, mean, rstd, gamma, beta, residual, z, z16, fmt16, M, C, act, as_stream(stream));
 }
 
 extern "C" int avc_bn_act_bwd_apply_h(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
@@ -525,14 +733,6 @@ extern "C" int avc_bn_act_bwd_apply_h(const float* dz, const float* z, const flo
                                       float* dbeta, int M, int C, int act, int accumulate, void* stream) {
   AVC_REQUIRE(dz && z && y && mean && rstd && gamma && sums && (dy || dy16) && M > 0 && C > 0, "avc_bn_act_bwd_apply_h: bad arguments");
   AVC_REQUIRE(C % 4 == 0 && (fmt16 == 1 || fmt16 == 2), "avc_bn_act_bwd_apply_h: C must be a multiple of 4");
-  const size_t total = (size_t)M * C;
-  bn_act_bwd_apply_vec4_kernel<<<ew_blocks(total / 4), 256, 0, as_stream(stream)>>>(
-      (const float4*)dz, (const float4*)z, (const float4*)y, mean, rstd, gamma, sums, (float4*)dy, total / 4, M, C, act,
-      (uint2*)dy16, fmt16);
-  AVC_LAUNCHED();
-  if (dgamma || dbeta) {
-    bn_param_grad_kernel<<<ceil_div(C, 128), 128, 0, as_stream(stream)>>>(sums, dgamma, dbeta, C, accumulate);
-    AVC_LAUNCHED();
-  }
-  return AVC_OK;
+  return bn_bwd_apply_impl(dz, z, y, mean, rstd, gamma, nullptr, sums, dy, dy16, fmt16, dgamma, dbeta, M, C, act, accumulate,
+                           as_stream(stream));
 }

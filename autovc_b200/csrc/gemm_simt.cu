@@ -165,6 +165,57 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
   }
 }
 
+// The split partials are summed in split order (deterministic), with the loads of several splits in flight.
+// out_mode 1 (conv weight (Cout, Cin, taps)): one thread owns one (n, k) and writes its `ntaps` consecutive outputs, so
+// both the partial reads (along k) and the stores (ntaps*4 contiguous bytes per thread) are coalesced.
+template <int NTAPS>
+__global__ void __launch_bounds__(256)
+wgrad_reduce_conv_kernel(const float* __restrict__ part, float* __restrict__ dW, size_t nk, int splits, int accumulate) {
+  const size_t total = nk * NTAPS;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nk; i += (size_t)gridDim.x * blockDim.x) {
+    float v[NTAPS];
+#pragma unroll
+    for (int t = 0; t < NTAPS; ++t) v[t] = 0.f;
+#pragma unroll 2
+    for (int s = 0; s < splits; ++s) {
+      float x[NTAPS];
+#pragma unroll
+      for (int t = 0; t < NTAPS; ++t) x[t] = part[(size_t)s * total + (size_t)t * nk + i];
+#pragma unroll
+      for (int t = 0; t < NTAPS; ++t) v[t] += x[t];
+    }
+#pragma unroll
+    for (int t = 0; t < NTAPS; ++t) {
+      const size_t o = i * NTAPS + t;
+      dW[o] = accumulate ? dW[o] + v[t] : v[t];
+    }
+  }
+}
+// out_mode 0 / 2 with K % 4 == 0: float4 along k
+__global__ void __launch_bounds__(256)
+wgrad_reduce_vec4_kernel(const float4* __restrict__ part, float* __restrict__ dW, int N, int K, int ntaps, int splits,
+                         int out_mode, int accumulate) {
+  const size_t total4 = (size_t)ntaps * N * K / 4;
+  const int K4 = K >> 2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int s = 0; s < splits; ++s) {
+      const float4 x = part[(size_t)s * total4 + i];
+      v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+    }
+    const int k = (int)(i % K4) * 4;
+    const int n = (int)((i / K4) % N);
+    const int tap = (int)(i / ((size_t)K4 * N));
+    float4* o = reinterpret_cast<float4*>(dW + wgrad_out_index(tap, n, k, N, K, ntaps, out_mode));
+    if (accumulate) {
+      const float4 old = *o;
+      v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+    }
+    *o = v;
+  }
+}
+
 static int tn_splits(int M, int N, int K, int ntaps) {
   const int tiles = ceil_div(N, SG_BN) * ceil_div(K, SG_BN) * ntaps;
   int splits = ceil_div(3 * num_sms(), tiles);
@@ -181,8 +232,19 @@ size_t gemm_tn_workspace_simt(int nB, int T, int N, int K, int ntaps) {
 int launch_wgrad_reduce(const float* part, float* dW, int N, int K, int ntaps, int splits, int out_mode, int accumulate,
                         cudaStream_t st) {
   const size_t total = (size_t)ntaps * N * K;
-  int blocks = (int)std::min<size_t>(ceil_div(total, (size_t)256), (size_t)num_sms() * 8);
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(part, dW, N, K, ntaps, splits, out_mode, accumulate);
+  const size_t cap = (size_t)num_sms() * 8;
+  if (out_mode == 1 && (ntaps == 5 || ntaps == 1)) {
+    const size_t nk = (size_t)N * K;
+    const int blocks = (int)std::min<size_t>(ceil_div(nk, (size_t)256), cap);
+    if (ntaps == 5) wgrad_reduce_conv_kernel<5><<<blocks, 256, 0, st>>>(part, dW, nk, splits, accumulate);
+    else wgrad_reduce_conv_kernel<1><<<blocks, 256, 0, st>>>(part, dW, nk, splits, accumulate);
+  } else if (out_mode != 1 && K % 4 == 0 && ((uintptr_t)part & 15) == 0 && ((uintptr_t)dW & 15) == 0) {
+    const int blocks = (int)std::min<size_t>(ceil_div(total / 4, (size_t)256), cap);
+    wgrad_reduce_vec4_kernel<<<blocks, 256, 0, st>>>((const float4*)part, dW, N, K, ntaps, splits, out_mode, accumulate);
+  } else {
+    const int blocks = (int)std::min<size_t>(ceil_div(total, (size_t)256), cap);
+    wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(part, dW, N, K, ntaps, splits, out_mode, accumulate);
+  }
   AVC_LAUNCHED();
   return AVC_OK;
 }

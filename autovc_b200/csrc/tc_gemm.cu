@@ -357,6 +357,220 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------------
+// MODE_NT on CTA pairs (tcgen05 cta_group::2): a cluster of two CTAs on neighbouring SMs owns a 256-row x 256-col
+// output tile.  Each CTA stages ITS 128 rows of A and ITS 128-row half of the W tile (32 KB per k block instead
+// of the 48 KB a lone CTA needs for 128x256), the leader's single thread issues M=256 MMAs that read both SMs'
+// shared memory and write both SMs' TMEM, and each CTA drains its own 128 x 256 accumulator half.  Per-SM operand
+// ingest -- what bounded the 1-CTA kernel (r01 ncu: tensor pipe 63%) -- drops by a third per MAC.
+// Barrier protocol (P = peer, L = leader; "mc" = tcgen05.commit multicast to both CTAs):
+//   full[s]  (L only, 1 arrival + 64 KB tx)  <- L's expect_tx, L's and P's TMA bytes
+//   empty[s] (each CTA, 1 arrival)           <- L's MMA commit mc   -> each CTA's producer refills its own slot
+//   tfull[a] (each CTA, 1 arrival)           <- L's MMA commit mc   -> each CTA's epilogue
+//   tempty[a](L only, 8 arrivals)            <- 4 epilogue warps of L (local) and of P (remote arrive)
+// ---------------------------------------------------------------------------------------------------
+struct Tc2Cfg {
+  static constexpr int BN = 256;                      // pair tile width
+  static constexpr int STAGE_B = 128 * 128;           // this CTA's half of the W tile: 128 rows x 128 B
+  static constexpr int STAGE_BYTES = TC_STAGE_A + STAGE_B;
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = 512;               // two 256-column fp32 accumulators
+  static constexpr int STAT_BYTES = 4 * 2 * BN * 4;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAT_BYTES + 256;
+};
+
+template <int EB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  using Cf = Tc2Cfg;
+  using Gm = TcGeom<EB>;
+  constexpr int BN = Cf::BN, ST = Cf::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t stage0 = base;
+  float* stat_s = reinterpret_cast<float*>(gen + ST * Cf::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + ST * Cf::STAGE_BYTES + Cf::STAT_BYTES);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (ST + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * ST + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * ST + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();           // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc_2cta(smem_u32(tmem_slot), Cf::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // both CTAs' barriers and TMEM exist before anyone signals
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_pairs = (p.nB * p.t_tiles + 1) >> 1;
+  const int total = m_pairs * p.n_tiles;             // pair tiles
+  const int kiters = p.ntaps * p.kblocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one thread in each CTA) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < total; tile += npairs) {
+        const int n_tile = tile % p.n_tiles, m_tile = (tile / p.n_tiles) * 2 + (int)rank;
+        // an odd tile count leaves the last pair's second half empty: b == nB is out of range and zero-filled
+        const int b = m_tile / p.t_tiles, t0 = (m_tile % p.t_tiles) * TC_BM;
+        for (int it = 0; it < kiters; ++it) {
+          const int tap = it / p.kblocks, kb = it - tap * p.kblocks;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cf::STAGE_BYTES);
+          const uint32_t fb = mapa_u32(full_bar(stage), 0);
+          const uint32_t sa = stage0 + stage * Cf::STAGE_BYTES;
+          tma_load_3d_2cta(sa, &mapA, fb, kb * Gm::ROW, t0 + p.shift0 + tap, b);
+          tma_load_3d_2cta(sa + TC_STAGE_A, &mapB, fb, kb * Gm::ROW, n_tile * BN + (int)rank * 128, tap);
+          if (++stage == ST) { stage = 0; phase ^= 1; }
+        }
+      }
+      // tail: every commit aimed at this CTA's empty barriers has landed before the CTA may exit
+      for (int s = 0; s < ST; ++s) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (++stage == ST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread of the leader CTA) =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = p.idesc;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total; tile += npairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);    // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = stage0 + stage * Cf::STAGE_BYTES, sb = sa + TC_STAGE_A;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_2cta<EB>(d_tmem, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc,
+                          (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2cta(empty_bar(stage), 3);
+          if (++stage == ST) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(tfull_bar(acc), 3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps: this CTA's 128 rows x 256 columns =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < total; tile += npairs) {
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const int n_tile = tile % p.n_tiles, m_tile = (tile / p.n_tiles) * 2 + (int)rank;
+      const int b = m_tile / p.t_tiles, t = (m_tile % p.t_tiles) * TC_BM + row;
+      const bool row_ok = t < p.T && b < p.nB;
+      float* crow = p.C + ((size_t)b * p.T + t) * p.ldc;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(t_addr + c * 32, v);
+        if (c == BN / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(tempty_leader0 + 8u * acc);
+        }
+        const int n0 = n_tile * BN + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + j;
+          float x = v[j] + ((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f);
+          v[j] = (row_ok && n < p.N) ? x : 0.f;
+        }
+        if (row_ok) {
+          if (n0 + 32 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              float4* dst = reinterpret_cast<float4*>(crow + n0 + j);
+              if (p.accumulate) {
+                const float4 old = *dst;
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              *dst = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < p.N) crow[n0 + j] = p.accumulate ? crow[n0 + j] + v[j] : v[j];
+          }
+        }
+        if (p.stats != nullptr) {
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+          const float s1 = warp_colsum32(v, lane);
+          const float s2 = warp_colsum32(sq, lane);
+          stat_s[(q * 2 + 0) * BN + c * 32 + lane] = s1;
+          stat_s[(q * 2 + 1) * BN + c * 32 + lane] = s2;
+        }
+      }
+      if (p.stats != nullptr) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int cp = 0; cp < BN / 128; ++cp) {
+          const int col = threadIdx.x - 64 + cp * 128;
+          const int n = n_tile * BN + col;
+          if (n < p.N) {
+            double a = 0.0, bq = 0.0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              a += (double)stat_s[(w * 2 + 0) * BN + col];
+              bq += (double)stat_s[(w * 2 + 1) * BN + col];
+            }
+            atomicAdd(p.stats + n, a);
+            atomicAdd(p.stats + p.N + n, bq);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // no CTA exits (or frees TMEM) while its peer may still touch it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cf::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // fp32 -> padded bf16 staging
 // ---------------------------------------------------------------------------------------------------
 // dst[r][c] (ld = Cp, bf16) = src[r][c] (ld = lds, fp32) for c < C, zero for C <= c < Cp; rows >= R_src are zero
@@ -432,6 +646,23 @@ static int tc_launch(const CUtensorMap& mA, const CUtensorMap& mB, const TcParam
   kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(mA, mB, p);
   AVC_LAUNCHED();
   return AVC_OK;
+}
+template <int EB>
+static int tc2_launch(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int grid, cudaStream_t st) {
+  static bool attr_done = false;
+  auto kern = tc_gemm2_nt_kernel<EB>;
+  if (!attr_done) {
+    AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  kern<<<grid, TC_THREADS, Tc2Cfg::SMEM_BYTES, st>>>(mA, mB, p);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+// AVC_GEMM_2CTA=0 keeps every NT GEMM on the single-CTA kernel
+static bool use_cta_pairs() {
+  const char* e = getenv("AVC_GEMM_2CTA");   // read per call so one process can compare both kernels
+  return e ? atoi(e) != 0 : true;
 }
 template <int MODE>
 static int tc_dispatch(int eb, int bn, const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int grid, cudaStream_t st) {
@@ -538,14 +769,21 @@ int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const float* W, const fl
     Wop = dst; w_k = pl.Kp; w_n = pl.Np; w_ld = pl.Kp;
   }
   CUtensorMap mA, mB;
+  const bool pairs = pl.bn == 256 && use_cta_pairs();
   rc = make_map3(&mA, Aop, a_k, T, nB, a_ld, (uint64_t)T * a_ld, row, TC_BM, eb, false, fa);
   if (rc) return rc;
-  rc = make_map3(&mB, Wop, w_k, w_n, ntaps, w_ld, w_n * w_ld, row, pl.bn, eb, false, fw);
+  rc = make_map3(&mB, Wop, w_k, w_n, ntaps, w_ld, w_n * w_ld, row, pairs ? 128 : pl.bn, eb, false, fw);
   if (rc) return rc;
   TcParams p{};
   p.nB = nB; p.T = T; p.ntaps = ntaps; p.shift0 = shift0; p.N = N; p.K = K;
   p.t_tiles = ceil_div(T, TC_BM); p.n_tiles = pl.Np / pl.bn; p.kblocks = pl.Kp / row;
   p.bias = bias; p.C = C; p.ldc = ldc; p.accumulate = accumulate; p.stats = stats;
+  if (pairs) {
+    p.idesc = eb == 2 ? make_idesc(256, 256, 0, 0, ifmt_of(fa), ifmt_of(fw)) : make_idesc(256, 256, 0, 0, 2);
+    const int pair_tiles = ceil_div(nB * p.t_tiles, 2) * p.n_tiles;
+    const int grid2 = 2 * std::min(pair_tiles, num_sms() / 2);
+    return eb == 2 ? tc2_launch<2>(mA, mB, p, grid2, st) : tc2_launch<4>(mA, mB, p, grid2, st);
+  }
   p.idesc = eb == 2 ? make_idesc(TC_BM, pl.bn, 0, 0, ifmt_of(fa), ifmt_of(fw)) : make_idesc(TC_BM, pl.bn, 0, 0, 2);
   const int tiles = nB * p.t_tiles * p.n_tiles;
   const int grid = std::min(tiles, num_sms());

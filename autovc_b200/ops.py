@@ -167,14 +167,14 @@ class ConvBnAct(torch.autograd.Function):
             call("avc_bn_eval_stats", _p(running_mean), _p(running_var), Cout, BN_EPS, _p(mean), _p(rstd), _stream())
         z = torch.empty_like(y)
         call("avc_bn_act_fwd", _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(z), M, Cout, act, _stream())
-        ctx.save_for_backward(x, weight, gamma, y, z, mean, rstd)
+        ctx.save_for_backward(x, weight, gamma, beta, y, z, mean, rstd)
         ctx.act, ctx.training, ctx.prec, ctx.has_res = act, training, prec, residual is not None
         ctx.wd = wd
         return z
 
     @staticmethod
     def backward(ctx, dz):
-        x, weight, gamma, y, z, mean, rstd = ctx.saved_tensors
+        x, weight, gamma, beta, y, z, mean, rstd = ctx.saved_tensors
         if not ctx.training:
             raise _lib.AvcError("backward through eval-mode BatchNorm is not on the supported path")
         dz = dz.contiguous()
@@ -183,12 +183,14 @@ class ConvBnAct(torch.autograd.Function):
         M = B * T
         prec = ctx.prec
         sums = torch.zeros(2 * Cout, device=x.device, dtype=torch.float64)
-        call("avc_bn_act_bwd_reduce", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(sums), M, Cout, ctx.act, _stream())
+        # act'(z) is recomputed from y where the float4 kernels apply (z is then not read)
+        call("avc_bn_act_bwd_reduce_y", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(sums), M, Cout,
+             ctx.act, _stream())
         dy = torch.empty_like(y)
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(gamma)
-        call("avc_bn_act_bwd_apply", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(gamma), _p(sums), _p(dy), _p(dgamma),
-             _p(dbeta), M, Cout, ctx.act, 0, _stream())
+        call("avc_bn_act_bwd_apply_y", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(sums), _p(dy), _NULL, 0,
+             _p(dgamma), _p(dbeta), M, Cout, ctx.act, 0, _stream())
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
@@ -527,7 +529,7 @@ class ConvBnActH(torch.autograd.Function):
         else:
             z16 = torch.empty(0, device=x.device, dtype=torch.float16)
             call("avc_bn_act_fwd", _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(z), M, Cout, act, _stream())
-        ctx.save_for_backward(x, weight, gamma, y, z, mean, rstd)
+        ctx.save_for_backward(x, weight, gamma, beta, y, z, mean, rstd)
         ctx.act, ctx.training, ctx.has_res, ctx.wd = act, training, residual is not None, wd
         ctx.mark_non_differentiable(z16)
         ctx.set_materialize_grads(False)      # no zero tensor for the 16-bit side output's (absent) gradient
@@ -535,7 +537,7 @@ class ConvBnActH(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dz, _dz16):
-        x, weight, gamma, y, z, mean, rstd = ctx.saved_tensors
+        x, weight, gamma, beta, y, z, mean, rstd = ctx.saved_tensors
         if not ctx.training:
             raise _lib.AvcError("backward through eval-mode BatchNorm is not on the supported path")
         dz = dz.contiguous()
@@ -543,18 +545,19 @@ class ConvBnActH(torch.autograd.Function):
         Cout, _, k = weight.shape
         M = B * T
         sums = torch.zeros(2 * Cout, device=dz.device, dtype=torch.float64)
-        call("avc_bn_act_bwd_reduce", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(sums), M, Cout, ctx.act, _stream())
+        call("avc_bn_act_bwd_reduce_y", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(sums), M, Cout,
+             ctx.act, _stream())
         dgamma = torch.empty_like(gamma)
         dbeta = torch.empty_like(gamma)
         if Cout % 8 == 0:      # the gradient w.r.t. the conv output is only ever a GEMM operand: emit it as bf16 only
             dy = torch.empty(B, T, Cout, device=dz.device, dtype=torch.bfloat16)
-            call("avc_bn_act_bwd_apply_h", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(gamma), _p(sums), _NULL, _p(dy), FMT_BF16,
-                 _p(dgamma), _p(dbeta), M, Cout, ctx.act, 0, _stream())
+            call("avc_bn_act_bwd_apply_y", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(sums), _NULL, _p(dy),
+                 FMT_BF16, _p(dgamma), _p(dbeta), M, Cout, ctx.act, 0, _stream())
             y_fmt = FMT_BF16
         else:
             dy = torch.empty_like(y)
-            call("avc_bn_act_bwd_apply", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(gamma), _p(sums), _p(dy), _p(dgamma),
-                 _p(dbeta), M, Cout, ctx.act, 0, _stream())
+            call("avc_bn_act_bwd_apply_y", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(sums), _p(dy), _NULL, 0,
+                 _p(dgamma), _p(dbeta), M, Cout, ctx.act, 0, _stream())
             y_fmt = FMT_FP32
         dx = None
         if ctx.needs_input_grad[0]:

@@ -124,6 +124,15 @@ int avc_bn_act_bwd_reduce(const float* dz, const float* z, const float* y, const
 int avc_bn_act_bwd_apply(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
                          const float* gamma, const double* sums, float* dy, float* dgamma, float* dbeta,
                          int M, int C, int act, int accumulate, void* stream);
+/* The same two passes with the activation RECOMPUTED from y (z = act((y-mean)*rstd*gamma+beta), the forward's own
+ * expression) instead of read back: one (M, C) read less per pass.  z may be NULL when C % 4 == 0 and all tensors
+ * are 16-byte aligned; otherwise it is required and read.  apply_y writes fp32 dy and/or a 16-bit copy dy16
+ * (fmt16: AVC_FMT_BF16 / AVC_FMT_FP16), either may be NULL. */
+int avc_bn_act_bwd_reduce_y(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
+                            const float* gamma, const float* beta, double* sums, int M, int C, int act, void* stream);
+int avc_bn_act_bwd_apply_y(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
+                           const float* gamma, const float* beta, const double* sums, float* dy, void* dy16, int fmt16,
+                           float* dgamma, float* dbeta, int M, int C, int act, int accumulate, void* stream);
 /* column sums of x (M, C) -> out (C), used for Linear / LSTM bias gradients.
  * out_mode 0: out[c]; 2: LSTM un-permute (c = u*4+g -> g*H+u), written to BOTH out and out2
  * when out2 != NULL (b_ih and b_hh receive the same gradient). */

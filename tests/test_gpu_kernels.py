@@ -141,3 +141,47 @@ def test_no_cpu_fallback():
     from autovc_b200 import AvcError
     with pytest.raises(AvcError):
         ops.mse_loss(torch.zeros(4), torch.zeros(4))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,C", [(4096, 512), (1000, 80), (333, 30), (77, 516)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_bn_backward_recompute_matches_z_read(M, C, act):
+    """avc_bn_act_bwd_{reduce,apply}_y (activation recomputed from y) == the z-reading entry points, bit for bit,
+    and the column-sum kernels agree with torch in fp64."""
+    from autovc_b200 import _lib
+    from autovc_b200.ops import _p, _stream, _NULL
+    y = _rand(M, C, seed=1)
+    dz = _rand(M, C, seed=2)
+    gamma, beta = _rand(C, seed=3) + 1.5, _rand(C, seed=4) * 0.3
+    stats = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
+    _lib.call("avc_channel_stats", _p(y), C, M, C, _p(stats), _stream())
+    torch.testing.assert_close(stats[:C], y.double().sum(0), rtol=1e-6, atol=1e-4)
+    torch.testing.assert_close(stats[C:], (y.double() ** 2).sum(0), rtol=1e-6, atol=1e-4)
+    mean, rstd = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    _lib.call("avc_bn_finalize", _p(stats), M, C, 1e-5, 0.1, _p(mean), _p(rstd), _NULL, _NULL, _stream())
+    z = torch.empty_like(y)
+    _lib.call("avc_bn_act_fwd", _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _NULL, _p(z), M, C, act, _stream())
+    pre = (y - mean) * (rstd * gamma) + beta
+    ref_z = {0: pre, 1: pre.clamp_min(0), 2: pre.tanh()}[act]
+    torch.testing.assert_close(z, ref_z, rtol=1e-5, atol=1e-5)
+    s_old = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
+    s_new = torch.zeros_like(s_old)
+    _lib.call("avc_bn_act_bwd_reduce", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(s_old), M, C, act, _stream())
+    # z may be omitted only on the float4 path
+    zarg = _NULL if C % 4 == 0 else _p(z)
+    _lib.call("avc_bn_act_bwd_reduce_y", _p(dz), zarg, _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(s_new), M, C, act, _stream())
+    torch.testing.assert_close(s_new, s_old, rtol=1e-12, atol=1e-9)     # same values, atomics in another order
+    dy_old, dy_new = torch.empty_like(y), torch.empty_like(y)
+    dg, db = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    _lib.call("avc_bn_act_bwd_apply", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(gamma), _p(s_old), _p(dy_old), _p(dg), _p(db),
+              M, C, act, 0, _stream())
+    dy16 = torch.empty(M, C, dtype=torch.bfloat16, device=DEV) if C % 4 == 0 else None
+    _lib.call("avc_bn_act_bwd_apply_y", _p(dz), zarg, _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(s_old), _p(dy_new),
+              _p(dy16), 1, _p(dg), _p(db), M, C, act, 0, _stream())
+    assert torch.equal(dy_new, dy_old)
+    if dy16 is not None:
+        assert torch.equal(dy16, dy_old.bfloat16())
+    if C % 4 != 0:
+        with pytest.raises(_lib.AvcError):
+            _lib.call("avc_bn_act_bwd_reduce_y", _p(dz), _NULL, _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(s_new), M, C, act, _stream())

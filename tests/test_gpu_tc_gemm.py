@@ -42,7 +42,9 @@ def _ref_nt(A, W, bias, nB, T, ntaps, shift0, prec=1):
 
 
 @pytest.mark.parametrize("nB,T,N,K,ntaps", [(2, 128, 512, 336, 5), (3, 128, 128, 64, 1), (2, 48, 130, 769, 5),
-                                            (4, 256, 80, 1024, 1), (1, 20, 64, 512, 1), (5, 64, 2048, 288, 1)])
+                                            (4, 256, 80, 1024, 1), (1, 20, 64, 512, 1), (5, 64, 2048, 288, 1),
+                                            # enough tiles for the 256-wide CTA-pair kernel: odd tile counts, ragged N / K / T
+                                            (40, 128, 640, 96, 5), (37, 100, 520, 72, 3), (75, 128, 256, 64, 1)])
 @pytest.mark.parametrize("prec", [1, 2])
 def test_nt_taps_tensor(nB, T, N, K, ntaps, prec):
     A = _rand(nB * T, K, seed=1)
