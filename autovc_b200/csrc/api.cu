@@ -36,7 +36,7 @@ int lstm_seq_fwd_simt(const float*, const float*, float*, int, float*, float*, i
 int lstm_seq_bwd_simt(const float*, int, const float*, const float*, const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
 size_t lstm_bwd_workspace_simt(int, int, int);
 // tensor-core implementations (tc_gemm.cu)
-int gemm_nt_taps_tc(const void*, int, int, const float*, const float*, float*, int, int, int, int, int, int, int, double*, int, int, int, void*, size_t, cudaStream_t);
+int gemm_nt_taps_tc(const void*, int, int, const void*, int, int, const float*, float*, int, int, int, int, int, int, int, double*, int, int, int, void*, size_t, cudaStream_t);
 int gemm_tn_taps_tc(const void*, int, int, const void*, int, int, float*, int, int, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
 size_t gemm_nt_workspace_tc(int, int, int, int, int, int);
 size_t gemm_nt_workspace_h(int, int, int, int, int, int);
@@ -46,9 +46,9 @@ size_t gemm_tn_workspace_tc(int, int, int, int, int, int);
 bool lstm_tc_supported(int H);
 void lstm_tc_set_trace(unsigned long long* p);
 size_t lstm_tc_workspace(int nB, int T, int H, bool bwd);
-int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh, float* gates, float* c_seq, const float* dH,
+int lstm_seq_tc(bool bwd, const void* W, const float* P, float* h_seq, int ldh, float* gates, float* c_seq, const float* dH,
                 int lddh, float* dP, int nB, int T, int H, int reverse, void* ws, size_t ws_bytes, cudaStream_t st,
-                void* aux16 = nullptr, int fmt16 = 0);
+                void* aux16 = nullptr, int fmt16 = 0, int w_fmt = 0);
 
 }  // namespace avc
 
@@ -67,7 +67,7 @@ extern "C" int avc_gemm_nt_taps(const float* A, int lda, const float* W, const f
   if (prec == AVC_PREC_FP32)
     return gemm_nt_taps_simt(A, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate, as_stream(stream));
   if (prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32)
-    return gemm_nt_taps_tc(A, 0, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate,
+    return gemm_nt_taps_tc(A, 0, lda, W, 0, K, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate,
                            prec == AVC_PREC_BF16 ? 2 : 4, 1, workspace, workspace_bytes, as_stream(stream));
   set_error("avc_gemm_nt_taps: precision %d not available in this build", prec);
   return AVC_ERR_UNSUPPORTED;
@@ -151,7 +151,17 @@ extern "C" int avc_gemm_nt_taps_h(const void* A, int a_fmt, int lda, const float
   AVC_REQUIRE(A && W && C, "avc_gemm_nt_taps_h: null pointer");
   AVC_REQUIRE(nB > 0 && T > 0 && N > 0 && K > 0 && ntaps > 0 && lda >= K && ldc >= N, "avc_gemm_nt_taps_h: bad shape");
   AVC_REQUIRE(a_fmt >= 0 && a_fmt <= 2 && (half_fmt == 1 || half_fmt == 2), "avc_gemm_nt_taps_h: bad format code");
-  return gemm_nt_taps_tc(A, a_fmt, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate, 2, half_fmt,
+  return gemm_nt_taps_tc(A, a_fmt, lda, W, 0, K, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate, 2, half_fmt,
+                         workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int avc_gemm_nt_taps_hw(const void* A, int a_fmt, int lda, const void* W16, int w_fmt, int ldw, const float* bias, float* C,
+                                   int ldc, int nB, int T, int N, int K, int ntaps, int shift0, double* chan_stats, int accumulate,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  AVC_REQUIRE(A && W16 && C, "avc_gemm_nt_taps_hw: null pointer");
+  AVC_REQUIRE(nB > 0 && T > 0 && N > 0 && K > 0 && ntaps > 0 && lda >= K && ldc >= N, "avc_gemm_nt_taps_hw: bad shape");
+  AVC_REQUIRE(a_fmt >= 0 && a_fmt <= 2 && (w_fmt == 1 || w_fmt == 2), "avc_gemm_nt_taps_hw: bad format code");
+  return gemm_nt_taps_tc(A, a_fmt, lda, W16, w_fmt, ldw, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate, 2, w_fmt,
                          workspace, workspace_bytes, as_stream(stream));
 }
 
@@ -174,18 +184,22 @@ extern "C" size_t avc_gemm_tn_h_workspace_bytes(int nB, int T, int N, int K, int
 }
 
 // persistent recurrences that additionally emit the 16-bit operand copy the following GEMMs read ("half" mode)
-extern "C" int avc_lstm_seq_fwd_h(const float* P, const float* Whh_p, float* h_seq, int ldh, float* gates, float* c_seq, void* h16,
-                                  int fmt16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int avc_lstm_seq_fwd_h(const float* P, const void* Whh_p, int w_fmt, float* h_seq, int ldh, float* gates, float* c_seq,
+                                  void* h16, int fmt16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
   AVC_REQUIRE(P && Whh_p && h_seq && gates && c_seq && h16, "avc_lstm_seq_fwd_h: null pointer");
   AVC_REQUIRE(nB > 0 && T > 0 && lstm_tc_supported(H) && ldh >= H && ldh % 4 == 0 && (fmt16 == 1 || fmt16 == 2), "avc_lstm_seq_fwd_h: unsupported shape");
+  AVC_REQUIRE(w_fmt == 0 || w_fmt == 1, "avc_lstm_seq_fwd_h: W_hh must be fp32 (0) or bf16 (1)");
   return lstm_seq_tc(false, Whh_p, P, h_seq, ldh, gates, c_seq, nullptr, 0, nullptr, nB, T, H, reverse, workspace, workspace_bytes,
-                     as_stream(stream), h16, fmt16);
+                     as_stream(stream), h16, fmt16, w_fmt);
 }
 
-extern "C" int avc_lstm_seq_bwd_h(const float* dH, int lddh, const float* Whh_pT, const float* gates, const float* c_seq, float* dP,
-                                  void* dP16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes, void* stream) {
+extern "C" int avc_lstm_seq_bwd_h(const float* dH, int lddh, const void* Whh_pT, int w_fmt, const float* gates, const float* c_seq,
+                                  float* dP, void* dP16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
   AVC_REQUIRE(dH && Whh_pT && gates && c_seq && dP && dP16, "avc_lstm_seq_bwd_h: null pointer");
   AVC_REQUIRE(nB > 0 && T > 0 && lstm_tc_supported(H) && lddh >= H && lddh % 4 == 0, "avc_lstm_seq_bwd_h: unsupported shape");
+  AVC_REQUIRE(w_fmt == 0 || w_fmt == 1, "avc_lstm_seq_bwd_h: W_hh^T must be fp32 (0) or bf16 (1)");
   return lstm_seq_tc(true, Whh_pT, nullptr, nullptr, 0, const_cast<float*>(gates), const_cast<float*>(c_seq), dH, lddh, dP, nB, T, H,
-                     reverse, workspace, workspace_bytes, as_stream(stream), dP16, 1);
+                     reverse, workspace, workspace_bytes, as_stream(stream), dP16, 1, w_fmt);
 }

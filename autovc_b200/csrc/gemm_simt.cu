@@ -1,4 +1,7 @@
 // fp32 CUDA-core implementations of the GEMM-with-taps family + weight packers.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "simt_gemm.cuh"
 
 namespace avc {
@@ -269,31 +272,73 @@ int gemm_tn_taps_simt(const float* dY, int ldy, const float* X, int ldx, float* 
 // ---------------------------------------------------------------------------------------
 // weight packers
 // ---------------------------------------------------------------------------------------
-__global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wd,
-                                        int Cout, int Cin, int ntaps) {
-  const size_t total = (size_t)Cout * Cin * ntaps;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int tap = (int)(i % ntaps);
-    const int ci = (int)((i / ntaps) % Cin);
-    const int co = (int)(i / ((size_t)ntaps * Cin));
-    const float v = w[i];
-    if (wf) wf[((size_t)tap * Cout + co) * Cin + ci] = v;
-    // dgrad: dX[t, ci] = sum_tap' sum_co dY[t + tap' - 2, co] * w[co, ci, 4 - tap']
-    if (wd) wd[((size_t)(ntaps - 1 - tap) * Cin + ci) * Cout + co] = v;
+// Output element: fmt 0 = fp32, 1 = bf16, 2 = fp16 (the 16-bit forms are what the tensor-core GEMMs read in place).
+__device__ __forceinline__ void pack_store(void* base, size_t idx, float v, int fmt) {
+  if (fmt == 0) {
+    reinterpret_cast<float*>(base)[idx] = v;
+  } else if (fmt == 2) {
+    const __half h = __float2half_rn(v);
+    reinterpret_cast<uint16_t*>(base)[idx] = *reinterpret_cast<const uint16_t*>(&h);
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    reinterpret_cast<uint16_t*>(base)[idx] = *reinterpret_cast<const uint16_t*>(&h);
   }
 }
 
-__global__ void pack_lstm_weight_kernel(const float* __restrict__ w, float* __restrict__ p, float* __restrict__ pT,
-                                        int H, int I) {
-  const size_t total = (size_t)4 * H * I;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % I);
-    const int row = (int)(i / I);  // g*H + u
-    const int g = row / H, u = row - g * H;
-    const int pr = u * 4 + g;
-    const float v = w[i];
-    if (p) p[(size_t)pr * I + k] = v;
-    if (pT) pT[(size_t)k * 4 * H + pr] = v;
+// Conv1d weight (Cout, Cin, taps) -> fwd [tap][Cout][ldf] and dgrad [taps-1-tap][Cin][ldd] (taps flipped; dX[t, ci] =
+// sum_tap' sum_co dY[t + tap' - pad, co] * w[co, ci, taps-1-tap']).  One block moves a 32 co x 32 ci x taps tile through
+// shared memory, so the global reads are runs of 32*taps floats and the writes runs of 32 elements; columns between the
+// logical width and the leading dimension are zero-filled.
+template <int NT_>   // taps known at compile time (0 = runtime value): constant trip counts let the loads be issued back to back
+__global__ void __launch_bounds__(256)
+pack_conv_tiled_kernel(const float* __restrict__ w, void* __restrict__ wf, int ldf, int fmt_f, void* __restrict__ wd, int ldd,
+                       int fmt_d, int Cout, int Cin, int ntaps_rt) {
+  extern __shared__ float pk_tile[];                 // [32][32 * ntaps + 1]
+  const int ntaps = NT_ > 0 ? NT_ : ntaps_rt;
+  const int span = 32 * ntaps, row = span + 1;
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+#pragma unroll 4
+  for (int e = threadIdx.x; e < 32 * span; e += 256) {
+    const int co_l = e / span, j = e - co_l * span;
+    const int co = co0 + co_l, ci = ci0 + j / ntaps;
+    pk_tile[co_l * row + j] = (co < Cout && ci < Cin) ? __ldg(w + ((size_t)co * Cin + ci0) * ntaps + j) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int e = threadIdx.x; e < ntaps * 1024; e += 256) {
+    const int a = e & 31, b = (e >> 5) & 31, tap = e >> 10;
+    if (wf) {                                        // lanes along ci
+      const int ci = ci0 + a, co = co0 + b;
+      if (co < Cout && ci < ldf) pack_store(wf, ((size_t)tap * Cout + co) * ldf + ci, pk_tile[b * row + a * ntaps + tap], fmt_f);
+    }
+    if (wd) {                                        // lanes along co
+      const int co = co0 + a, ci = ci0 + b;
+      if (ci < Cin && co < ldd)
+        pack_store(wd, ((size_t)(ntaps - 1 - tap) * Cin + ci) * ldd + co, pk_tile[a * row + b * ntaps + tap], fmt_d);
+    }
+  }
+}
+
+// nn.LSTM weight (4H, I), rows g*H+u -> gate-interleaved p [u*4+g][ldp] and its transpose pT [k][ldpT]
+__global__ void __launch_bounds__(256)
+pack_lstm_tiled_kernel(const float* __restrict__ w, void* __restrict__ p, int ldp, int fmt_p, void* __restrict__ pT, int ldpT,
+                       int fmt_pT, int H, int I) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, pr0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int G = 4 * H;
+  for (int i = ty; i < 32; i += 8) {
+    const int pr = pr0 + i, k = k0 + tx;
+    const float v = (pr < G && k < I) ? w[((size_t)(pr & 3) * H + (pr >> 2)) * I + k] : 0.f;
+    tile[i][tx] = v;
+    if (p && pr < G && k < ldp) pack_store(p, (size_t)pr * ldp + k, v, fmt_p);
+  }
+  __syncthreads();
+  if (pT) {
+    for (int i = ty; i < 32; i += 8) {
+      const int k = k0 + i, pr = pr0 + tx;
+      if (k < I && pr < ldpT) pack_store(pT, (size_t)k * ldpT + pr, pr < G ? tile[tx][i] : 0.f, fmt_pT);
+    }
   }
 }
 
@@ -324,23 +369,53 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 
 using namespace avc;
 
+static int pack_conv_impl(const float* w, void* wf, int ldf, int fmt_f, void* wd, int ldd, int fmt_d, int Cout, int Cin, int ntaps,
+                          cudaStream_t st) {
+  const size_t smem = (size_t)32 * (32 * ntaps + 1) * sizeof(float);
+  if (smem > 48 * 1024) {
+    set_error("avc_pack_conv_weight: %d taps exceed the packer's shared-memory tile", ntaps);
+    return AVC_ERR_UNSUPPORTED;
+  }
+  const dim3 grid(ceil_div(std::max(Cin, ldf), 32), ceil_div(std::max(Cout, ldd), 32));
+  if (ntaps == 5) pack_conv_tiled_kernel<5><<<grid, 256, smem, st>>>(w, wf, ldf, fmt_f, wd, ldd, fmt_d, Cout, Cin, ntaps);
+  else if (ntaps == 1) pack_conv_tiled_kernel<1><<<grid, 256, smem, st>>>(w, wf, ldf, fmt_f, wd, ldd, fmt_d, Cout, Cin, ntaps);
+  else pack_conv_tiled_kernel<0><<<grid, 256, smem, st>>>(w, wf, ldf, fmt_f, wd, ldd, fmt_d, Cout, Cin, ntaps);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
 extern "C" int avc_pack_conv_weight(const float* w, float* w_fwd, float* w_dgrad, int Cout, int Cin, int ntaps,
                                     void* stream) {
   AVC_REQUIRE(w && (w_fwd || w_dgrad) && Cout > 0 && Cin > 0 && ntaps > 0, "avc_pack_conv_weight: bad arguments");
-  const size_t total = (size_t)Cout * Cin * ntaps;
-  int blocks = (int)std::min<size_t>(ceil_div(total, (size_t)256), (size_t)num_sms() * 8);
-  pack_conv_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, w_fwd, w_dgrad, Cout, Cin, ntaps);
+  return pack_conv_impl(w, w_fwd, Cin, 0, w_dgrad, Cout, 0, Cout, Cin, ntaps, as_stream(stream));
+}
+
+extern "C" int avc_pack_conv_weight_h(const float* w, void* w_fwd, int ldf, int fmt_f, void* w_dgrad, int ldd, int fmt_d, int Cout,
+                                      int Cin, int ntaps, void* stream) {
+  AVC_REQUIRE(w && (w_fwd || w_dgrad) && Cout > 0 && Cin > 0 && ntaps > 0, "avc_pack_conv_weight_h: bad arguments");
+  AVC_REQUIRE((!w_fwd || ldf >= Cin) && (!w_dgrad || ldd >= Cout) && fmt_f >= 0 && fmt_f <= 2 && fmt_d >= 0 && fmt_d <= 2,
+              "avc_pack_conv_weight_h: bad leading dimension or format");
+  return pack_conv_impl(w, w_fwd, w_fwd ? ldf : Cin, fmt_f, w_dgrad, w_dgrad ? ldd : Cout, fmt_d, Cout, Cin, ntaps, as_stream(stream));
+}
+
+static int pack_lstm_impl(const float* w, void* p, int ldp, int fmt_p, void* pT, int ldpT, int fmt_pT, int H, int I, cudaStream_t st) {
+  pack_lstm_tiled_kernel<<<dim3(ceil_div(std::max(I, ldp), 32), ceil_div(std::max(4 * H, ldpT), 32)), 256, 0, st>>>(
+      w, p, ldp, fmt_p, pT, ldpT, fmt_pT, H, I);
   AVC_LAUNCHED();
   return AVC_OK;
 }
 
 extern "C" int avc_pack_lstm_weight(const float* w, float* out_p, float* out_pT, int H, int I, void* stream) {
   AVC_REQUIRE(w && (out_p || out_pT) && H > 0 && I > 0, "avc_pack_lstm_weight: bad arguments");
-  const size_t total = (size_t)4 * H * I;
-  int blocks = (int)std::min<size_t>(ceil_div(total, (size_t)256), (size_t)num_sms() * 8);
-  pack_lstm_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w, out_p, out_pT, H, I);
-  AVC_LAUNCHED();
-  return AVC_OK;
+  return pack_lstm_impl(w, out_p, I, 0, out_pT, 4 * H, 0, H, I, as_stream(stream));
+}
+
+extern "C" int avc_pack_lstm_weight_h(const float* w, void* out_p, int ldp, int fmt_p, void* out_pT, int ldpT, int fmt_pT, int H, int I,
+                                      void* stream) {
+  AVC_REQUIRE(w && (out_p || out_pT) && H > 0 && I > 0, "avc_pack_lstm_weight_h: bad arguments");
+  AVC_REQUIRE((!out_p || ldp >= I) && (!out_pT || ldpT >= 4 * H) && fmt_p >= 0 && fmt_p <= 2 && fmt_pT >= 0 && fmt_pT <= 2,
+              "avc_pack_lstm_weight_h: bad leading dimension or format");
+  return pack_lstm_impl(w, out_p, out_p ? ldp : I, fmt_p, out_pT, out_pT ? ldpT : 4 * H, fmt_pT, H, I, as_stream(stream));
 }
 
 extern "C" int avc_pack_lstm_bias(const float* b_ih, const float* b_hh, float* out, int H, void* stream) {

@@ -868,9 +868,10 @@ static int lt_cluster_size(int NT) {
 }
 
 // W: fwd -> Whh_p (4H, H);  bwd -> Whh_pT (H, 4H)  (fp32, packed/interleaved)
-int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh, float* gates, float* c_seq,
+// w_fmt 0: W is fp32 and converted to bf16 here; 1: W is already bf16 (avc_pack_lstm_weight_h) and read in place
+int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh, float* gates, float* c_seq,
                 const float* dH, int lddh, float* dP, int nB, int T, int H, int reverse, void* ws, size_t ws_bytes,
-                cudaStream_t st, void* aux16, int fmt16) {
+                cudaStream_t st, void* aux16, int fmt16, int w_fmt) {
   const LtPlan pl = lt_plan(nB, H, bwd);
   if (!ws || ws_bytes < pl.total) {
     set_error("avc_lstm_seq_%s(bf16): workspace %zu < %zu", bwd ? "bwd" : "fwd", ws_bytes, pl.total);
@@ -881,12 +882,21 @@ int lstm_seq_tc(bool bwd, const float* W, const float* P, float* h_seq, int ldh,
     return AVC_ERR_UNSUPPORTED;
   }
   uint8_t* w8 = (uint8_t*)ws;
-  __nv_bfloat16* Wb = (__nv_bfloat16*)(w8 + pl.off_w);
+  const __nv_bfloat16* Wb = (const __nv_bfloat16*)(w8 + pl.off_w);
   __nv_bfloat16* xbuf = (__nv_bfloat16*)(w8 + pl.off_x);
   unsigned* counters = (unsigned*)(w8 + pl.off_cnt);
-  const size_t wn = (size_t)4 * H * H;
-  cvt_bf16_kernel<<<(int)std::min<size_t>(ceil_div(wn, (size_t)256), (size_t)num_sms() * 8), 256, 0, st>>>(W, Wb, wn);
-  AVC_LAUNCHED();
+  if (w_fmt == 0) {
+    const size_t wn = (size_t)4 * H * H;
+    cvt_bf16_kernel<<<(int)std::min<size_t>(ceil_div(wn, (size_t)256), (size_t)num_sms() * 8), 256, 0, st>>>(
+        (const float*)Wv, (__nv_bfloat16*)(w8 + pl.off_w), wn);
+    AVC_LAUNCHED();
+  } else {
+    if (w_fmt != 1 || ((uintptr_t)Wv & 15) != 0) {
+      set_error("avc_lstm_seq_*_h: a pre-packed W_hh must be bf16 (w_fmt 1) and 16-byte aligned");
+      return AVC_ERR_INVALID;
+    }
+    Wb = (const __nv_bfloat16*)Wv;
+  }
   const int nchunks = ceil_div(nB, pl.chunk);
   AVC_CUDA(cudaMemsetAsync(counters, 0, (size_t)nchunks * 128 * sizeof(unsigned), st));
   static int kflags_mode = -1;

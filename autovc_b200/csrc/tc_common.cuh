@@ -96,6 +96,31 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
   if (EB == 2) umma_f16(tmem_d, da, db, idesc, accumulate);
   else umma_tf32(tmem_d, da, db, idesc, accumulate);
 }
+// ---- shared -> global tile stores through the TMA unit (bulk async-group completion) ----
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---- cta_group::2 (a CTA pair drives one 256-row MMA; operands and the accumulator are split across both SMs) ----
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   uint32_t r;
@@ -222,6 +247,28 @@ static inline int make_map3(CUtensorMap* m, const void* ptr, uint64_t d0, uint64
   return AVC_OK;
 }
 
+
+// 3-D fp32 map of an OUTPUT (d2, d1, d0) array for TMA stores / reduce-adds: box (32 columns = one 128-byte swizzle row, box1 rows)
+static inline int make_map3_out_f32(CUtensorMap* m, void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                                    uint64_t stride2_elems, uint32_t box1) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return AVC_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_elems * 4, stride2_elems * 4};
+  cuuint32_t box[3] = {32, box1, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(output) failed with CUresult %d (dims %llu,%llu,%llu)", (int)r, (unsigned long long)d0,
+              (unsigned long long)d1, (unsigned long long)d2);
+    return AVC_ERR_CUDA;
+  }
+  return AVC_OK;
+}
 
 // 4-D map over a channels-last (nB, T, C) array with the channel axis split into groups of `row` elements (one 128-byte
 // swizzle row each): dims (row, T, C/row, nB).  A box (row, frames, ngroups, 1) then lands in shared memory as `ngroups`

@@ -59,6 +59,7 @@ struct TcParams {
   int k_tiles, splits, rblocks, rblocks_per_split, tbr;   // tbr = ceil(T / frames-per-stage)
   int grouped_a, grouped_b;   // operand fetched with one grouped 4-D box per stage (make_map4_grouped)
   uint32_t idesc;             // tcgen05 instruction descriptor (operand formats are chosen at run time)
+  int tma_store;              // NT pair kernel: C leaves through shared memory + TMA stores (needs ldc % 4 == 0, 16-byte aligned C)
   float* part;
 };
 
@@ -372,15 +373,17 @@ struct Tc2Cfg {
   static constexpr int BN = 256;                      // pair tile width
   static constexpr int STAGE_B = 128 * 128;           // this CTA's half of the W tile: 128 rows x 128 B
   static constexpr int STAGE_BYTES = TC_STAGE_A + STAGE_B;
-  static constexpr int STAGES = 6;
+  static constexpr int STAGES = 5;
   static constexpr int TMEM_COLS = 512;               // two 256-column fp32 accumulators
   static constexpr int STAT_BYTES = 4 * 2 * BN * 4;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAT_BYTES + 256;
+  static constexpr int EPI_BYTES = 4 * 2 * 4096;      // per epilogue warp: two 32-row x 32-column fp32 staging tiles
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAT_BYTES + EPI_BYTES + 256;
 };
 
 template <int EB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   const __grid_constant__ CUtensorMap mapC, const TcParams p) {
   using Cf = Tc2Cfg;
   using Gm = TcGeom<EB>;
   constexpr int BN = Cf::BN, ST = Cf::STAGES;
@@ -390,7 +393,8 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   uint8_t* gen = smem_raw + (base - raw);
   const uint32_t stage0 = base;
   float* stat_s = reinterpret_cast<float*>(gen + ST * Cf::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + ST * Cf::STAGE_BYTES + Cf::STAT_BYTES);
+  const uint32_t epi0 = base + ST * Cf::STAGE_BYTES + Cf::STAT_BYTES;                   // 1024-byte aligned (128B swizzle atoms)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + ST * Cf::STAGE_BYTES + Cf::STAT_BYTES + Cf::EPI_BYTES);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (ST + s); };
@@ -405,6 +409,7 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&mapC) : "memory");
     for (int s = 0; s < ST; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -481,9 +486,9 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
   } else {
     // ===================== epilogue warps: this CTA's 128 rows x 256 columns =====================
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
+    const int q = warp & 3;                  // TMEM lane quadrant = rows [32q, 32q + 32) of this CTA's half tile
     const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0);
+    const uint32_t epi_w = epi0 + (uint32_t)(warp - 2) * 8192u;   // this warp's two staging tiles
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < total; tile += npairs) {
@@ -491,7 +496,7 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       const int n_tile = tile % p.n_tiles, m_tile = (tile / p.n_tiles) * 2 + (int)rank;
-      const int b = m_tile / p.t_tiles, t = (m_tile % p.t_tiles) * TC_BM + row;
+      const int b = m_tile / p.t_tiles, t_blk = (m_tile % p.t_tiles) * TC_BM + q * 32, t = t_blk + lane;
       const bool row_ok = t < p.T && b < p.nB;
       float* crow = p.C + ((size_t)b * p.T + t) * p.ldc;
 #pragma unroll 1
@@ -510,32 +515,61 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           float x = v[j] + ((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f);
           v[j] = (row_ok && n < p.N) ? x : 0.f;
         }
-        if (row_ok) {
-          if (n0 + 32 <= p.N && (p.ldc & 3) == 0) {
+        if (p.tma_store) {
+          // registers -> swizzled shared tile -> one TMA store (or reduce-add) of 32 rows x 128 B; rows >= T and columns
+          // >= N are clipped by the TMA unit.  Thread = row: 16-byte chunk j of row r sits at chunk j ^ (r & 7).
+          const uint32_t buf = epi_w + (uint32_t)(c & 1) * 4096u;
+          if (lane == 0) bulk_wait_read<1>();            // the store issued two chunks ago has drained this tile
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              float4* dst = reinterpret_cast<float4*>(crow + n0 + j);
-              if (p.accumulate) {
-                const float4 old = *dst;
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-              }
-              *dst = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < p.N) crow[n0 + j] = p.accumulate ? crow[n0 + j] + v[j] : v[j];
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(buf + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.accumulate) tma_reduce_add_3d(&mapC, buf, n0, t_blk, b);
+            else tma_store_3d(&mapC, buf, n0, t_blk, b);
+            bulk_commit();
           }
-        }
-        if (p.stats != nullptr) {
-          float sq[32];
+          if (p.stats != nullptr) {                      // lane = column: walk down the 32 rows of the staged tile
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-          const float s1 = warp_colsum32(v, lane);
-          const float s2 = warp_colsum32(sq, lane);
-          stat_s[(q * 2 + 0) * BN + c * 32 + lane] = s1;
-          stat_s[(q * 2 + 1) * BN + c * 32 + lane] = s2;
+            for (int r = 0; r < 32; ++r) {
+              const float x = ld_shared_f32(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+              s1 += x;
+              s2 = fmaf(x, x, s2);
+            }
+            stat_s[(q * 2 + 0) * BN + c * 32 + lane] = s1;
+            stat_s[(q * 2 + 1) * BN + c * 32 + lane] = s2;
+          }
+        } else {
+          if (row_ok) {
+            if (n0 + 32 <= p.N && (p.ldc & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                float4* dst = reinterpret_cast<float4*>(crow + n0 + j);
+                if (p.accumulate) {
+                  const float4 old = *dst;
+                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *dst = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < p.N) crow[n0 + j] = p.accumulate ? crow[n0 + j] + v[j] : v[j];
+            }
+          }
+          if (p.stats != nullptr) {
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+            const float s1 = warp_colsum32(v, lane);
+            const float s2 = warp_colsum32(sq, lane);
+            stat_s[(q * 2 + 0) * BN + c * 32 + lane] = s1;
+            stat_s[(q * 2 + 1) * BN + c * 32 + lane] = s2;
+          }
         }
       }
       if (p.stats != nullptr) {
@@ -559,6 +593,7 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store && lane == 0) bulk_wait_all();       // the staged tiles must be read out before the CTA's smem goes away
   }
 
   tc_fence_before();
@@ -648,14 +683,14 @@ static int tc_launch(const CUtensorMap& mA, const CUtensorMap& mB, const TcParam
   return AVC_OK;
 }
 template <int EB>
-static int tc2_launch(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int grid, cudaStream_t st) {
+static int tc2_launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mC, const TcParams& p, int grid, cudaStream_t st) {
   static bool attr_done = false;
   auto kern = tc_gemm2_nt_kernel<EB>;
   if (!attr_done) {
     AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  kern<<<grid, TC_THREADS, Tc2Cfg::SMEM_BYTES, st>>>(mA, mB, p);
+  kern<<<grid, TC_THREADS, Tc2Cfg::SMEM_BYTES, st>>>(mA, mB, mC, p);
   AVC_LAUNCHED();
   return AVC_OK;
 }
@@ -708,14 +743,14 @@ struct NtPlan {
   bool stageA, stageW;
   size_t offA, offW, total;
 };
-static NtPlan nt_plan(const void* A, int a_fmt, int lda, const float* W, int nB, int T, int N, int K, int ntaps, int eb) {
+static NtPlan nt_plan(const void* A, int a_fmt, int lda, const void* W, int w_fmt, int nB, int T, int N, int K, int ntaps, int eb) {
   NtPlan pl;
   const int row = 128 / eb;
   pl.bn = pick_bn(nB * ceil_div(T, TC_BM), N);
   pl.Kp = round_up(K, row);
   pl.Np = round_up(N, pl.bn);
   pl.stageA = a_fmt == 0 && (eb == 2 || !direct_ok(A, lda));     // 16-bit operands are always read in place
-  pl.stageW = eb == 2 || !direct_ok(W, K);
+  pl.stageW = w_fmt == 0 && (eb == 2 || !direct_ok(W, K));
   pl.offA = 0;
   pl.offW = pl.stageA ? align256((size_t)nB * T * pl.Kp * eb) : 0;
   pl.total = pl.offW + (pl.stageW ? align256((size_t)ntaps * pl.Np * pl.Kp * eb) : 0);
@@ -730,19 +765,33 @@ size_t gemm_nt_workspace_tc(int nB, int T, int N, int K, int ntaps, int eb) {
 
 // A: fp32 (a_fmt 0) or already 16-bit in HBM (a_fmt 1 = bf16, 2 = fp16; needs eb == 2).  fp32 operands of an
 // eb == 2 GEMM are staged to `half_fmt`.
-int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const float* W, const float* bias, float* C, int ldc, int nB, int T, int N,
-                    int K, int ntaps, int shift0, double* stats, int accumulate, int eb, int half_fmt, void* ws, size_t ws_bytes,
-                    cudaStream_t st) {
+// W: fp32 [ntaps][N][K] (w_fmt 0; staged like A), or pre-packed 16-bit [ntaps][N][ldw] (w_fmt 1/2, ldw % 8 == 0, read in place;
+// a 16-bit A must then have the same format, an fp32 A is staged to it).
+int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const void* Wv, int w_fmt, int ldw, const float* bias, float* C, int ldc,
+                    int nB, int T, int N, int K, int ntaps, int shift0, double* stats, int accumulate, int eb, int half_fmt, void* ws,
+                    size_t ws_bytes, cudaStream_t st) {
   const float* A = (const float*)Av;
+  const float* W = (const float*)Wv;
   if (a_fmt != 0 && (eb != 2 || !direct16_ok(Av, lda))) {
     set_error("avc_gemm_nt_taps_h: 16-bit A needs a 16-byte aligned pointer and lda %% 8 == 0 (lda=%d)", lda);
     return AVC_ERR_INVALID;
+  }
+  if (w_fmt != 0) {
+    if (eb != 2 || !direct16_ok(Wv, ldw) || ldw < K) {
+      set_error("avc_gemm_nt_taps_hw: 16-bit W needs a 16-byte aligned pointer and ldw %% 8 == 0, ldw >= K (ldw=%d)", ldw);
+      return AVC_ERR_INVALID;
+    }
+    if (a_fmt != 0 && a_fmt != w_fmt) {   // tcgen05.mma kind::f16 traps on mixed bf16 x fp16 operands
+      set_error("avc_gemm_nt_taps_hw: A and W must share one 16-bit format");
+      return AVC_ERR_UNSUPPORTED;
+    }
+    half_fmt = w_fmt;
   }
   if (stats && accumulate) {
     set_error("avc_gemm_nt_taps: chan_stats and accumulate are mutually exclusive");
     return AVC_ERR_UNSUPPORTED;
   }
-  const NtPlan pl = nt_plan(Av, a_fmt, lda, W, nB, T, N, K, ntaps, eb);
+  const NtPlan pl = nt_plan(Av, a_fmt, lda, Wv, w_fmt, nB, T, N, K, ntaps, eb);
   if (pl.total > 0 && (!ws || ws_bytes < pl.total)) {
     set_error("avc_gemm_nt_taps(tensor): workspace %zu < %zu", ws_bytes, pl.total);
     return AVC_ERR_WORKSPACE;
@@ -752,7 +801,7 @@ int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const float* W, const fl
   const int row = 128 / eb;
   const void* Aop = Av;
   const void* Wop = W;
-  uint64_t a_ld = lda, a_k = K, w_k = K, w_n = N, w_ld = K;
+  uint64_t a_ld = lda, a_k = K, w_k = K, w_n = N, w_ld = w_fmt != 0 ? ldw : K;
   const int fa = a_fmt != 0 ? a_fmt : half_fmt, fw = fa;            // weights are staged to A's 16-bit format (mixed formats trap)
   if (pl.stageA) {
     void* dst = (uint8_t*)ws + pl.offA;
@@ -782,7 +831,14 @@ int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const float* W, const fl
     p.idesc = eb == 2 ? make_idesc(256, 256, 0, 0, ifmt_of(fa), ifmt_of(fw)) : make_idesc(256, 256, 0, 0, 2);
     const int pair_tiles = ceil_div(nB * p.t_tiles, 2) * p.n_tiles;
     const int grid2 = 2 * std::min(pair_tiles, num_sms() / 2);
-    return eb == 2 ? tc2_launch<2>(mA, mB, p, grid2, st) : tc2_launch<4>(mA, mB, p, grid2, st);
+    CUtensorMap mC = mA;                    // placeholder when the direct-store epilogue is used
+    static const bool tma_epi = getenv("AVC_GEMM_TMA_STORE") ? atoi(getenv("AVC_GEMM_TMA_STORE")) != 0 : true;
+    p.tma_store = tma_epi && (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0);
+    if (p.tma_store) {
+      rc = make_map3_out_f32(&mC, C, N, T, nB, ldc, (uint64_t)T * ldc, 32);
+      if (rc) return rc;
+    }
+    return eb == 2 ? tc2_launch<2>(mA, mB, mC, p, grid2, st) : tc2_launch<4>(mA, mB, mC, p, grid2, st);
   }
   p.idesc = eb == 2 ? make_idesc(TC_BM, pl.bn, 0, 0, ifmt_of(fa), ifmt_of(fw)) : make_idesc(TC_BM, pl.bn, 0, 0, 2);
   const int tiles = nB * p.t_tiles * p.n_tiles;

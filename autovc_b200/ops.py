@@ -119,6 +119,45 @@ def pack_lstm_w(weight: torch.Tensor, cache: PackCache = _GLOBAL_CACHE):
     return cache.get("lstm_w", weight, build)
 
 
+def _ld8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+_T16 = {FMT_BF16: torch.bfloat16, FMT_FP16: torch.float16}
+
+
+def pack_conv_h(weight: torch.Tensor, cache: PackCache = _GLOBAL_CACHE):
+    """(Cout, Cin, k) -> fp16 fwd [k][Cout][ld8(Cin)] and bf16 dgrad [k][Cin][ld8(Cout)] (taps flipped), the layouts the
+    half-mode GEMMs read in place (forward operands fp16, gradient operands bf16)."""
+    def build():
+        Cout, Cin, k = weight.shape
+        w = weight.detach()
+        wf = torch.empty(k, Cout, _ld8(Cin), device=w.device, dtype=torch.float16)
+        wd = torch.empty(k, Cin, _ld8(Cout), device=w.device, dtype=torch.bfloat16)
+        call("avc_pack_conv_weight_h", _p(w), _p(wf), _ld8(Cin), FMT_FP16, _p(wd), _ld8(Cout), FMT_BF16, Cout, Cin, k, _stream())
+        return wf, wd
+    return cache.get("conv_h", weight, build)
+
+
+def pack_lstm_w_h(weight: torch.Tensor, fmt_p: int, cache: PackCache = _GLOBAL_CACHE):
+    """(4H, I) -> gate-interleaved (4H, ld8(I)) in `fmt_p` and its bf16 transpose (I, 4H)."""
+    def build():
+        G, I = weight.shape
+        w = weight.detach()
+        p = torch.empty(G, _ld8(I), device=w.device, dtype=_T16[fmt_p])
+        pT = torch.empty(I, G, device=w.device, dtype=torch.bfloat16)
+        call("avc_pack_lstm_weight_h", _p(w), _p(p), _ld8(I), fmt_p, _p(pT), G, FMT_BF16, G // 4, I, _stream())
+        return p, pT
+    return cache.get(("lstm_w_h", fmt_p), weight, build)
+
+
+def gemm_nt_taps_hw(A, a_fmt, lda, W16, w_fmt, ldw, bias, C, ldc, nB, T, N, K, ntaps, shift0, stats=None, accumulate=False):
+    nbytes = query("avc_gemm_nt_h_workspace_bytes", nB, T, N, K, ntaps, a_fmt) if a_fmt == FMT_FP32 else 0
+    ws = _ws(nbytes, C.device) if nbytes else None
+    call("avc_gemm_nt_taps_hw", _p(A), a_fmt, lda, _p(W16), w_fmt, ldw, _p(bias), _p(C), ldc, nB, T, N, K, ntaps, shift0,
+         _p(stats), int(accumulate), _p(ws), nbytes, _stream())
+
+
 def pack_lstm_b(b_ih: torch.Tensor, b_hh: torch.Tensor, cache: PackCache = _GLOBAL_CACHE):
     def build():
         out = torch.empty_like(b_ih)
@@ -509,13 +548,13 @@ class ConvBnActH(torch.autograd.Function):
         if Cin_w != Cin:
             raise _lib.AvcError(f"conv: input has {Cin} channels, weight expects {Cin_w}")
         M = B * T
-        wf, wd = pack_conv(weight)
+        wf, wd = pack_conv_h(weight)
         A, a_fmt = _operand(x, x16, Cin, FMT_FP16)
         y = torch.empty(B, T, Cout, device=x.device, dtype=torch.float32)
         mean = torch.empty(Cout, device=x.device, dtype=torch.float32)
         rstd = torch.empty_like(mean)
         stats = torch.zeros(2 * Cout, device=x.device, dtype=torch.float64) if training else None
-        gemm_nt_taps_h(A, a_fmt, Cin, wf, bias, y, Cout, B, T, Cout, Cin, k, -(k // 2), FMT_FP16, stats=stats)
+        gemm_nt_taps_hw(A, a_fmt, Cin, wf, FMT_FP16, wf.shape[-1], bias, y, Cout, B, T, Cout, Cin, k, -(k // 2), stats=stats)
         if training:
             call("avc_bn_finalize", _p(stats), M, Cout, BN_EPS, BN_MOMENTUM, _p(mean), _p(rstd), _p(running_mean),
                  _p(running_var), _stream())
@@ -562,7 +601,7 @@ class ConvBnActH(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, T, Cin, device=dz.device, dtype=torch.float32)
-            gemm_nt_taps_h(dy, y_fmt, Cout, ctx.wd, None, dx, Cin, B, T, Cin, Cout, k, -(k // 2), FMT_BF16)
+            gemm_nt_taps_hw(dy, y_fmt, Cout, ctx.wd, FMT_BF16, ctx.wd.shape[-1], None, dx, Cin, B, T, Cin, Cout, k, -(k // 2))
         dw = torch.empty_like(weight)
         # both operands of a GEMM must share a 16-bit format: the activation gets a bf16 copy here (a 6 B/element pass)
         X, x_fmt = _operand(x, None, Cin, FMT_BF16) if y_fmt == FMT_BF16 else (x, FMT_FP32)
@@ -583,19 +622,19 @@ class LstmLayerH(torch.autograd.Function):
         B, T, I = x.shape
         H = w_hh.shape[1]
         G = 4 * H
-        wi_p, wi_pT = pack_lstm_w(w_ih)
-        wh_p, wh_pT = pack_lstm_w(w_hh)
+        wi_p, wi_pT = pack_lstm_w_h(w_ih, FMT_FP16)      # projection operands fp16, dX operands bf16
+        wh_p, wh_pT = pack_lstm_w_h(w_hh, FMT_BF16)      # the recurrences run on bf16
         b_p = pack_lstm_b(b_ih, b_hh)
         A, a_fmt = _operand(x, x16, I, FMT_FP16)
         Pre = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
-        gemm_nt_taps_h(A, a_fmt, I, wi_p, b_p, Pre, G, B, T, G, I, 1, 0, FMT_FP16)
+        gemm_nt_taps_hw(A, a_fmt, I, wi_p, FMT_FP16, wi_p.shape[-1], b_p, Pre, G, B, T, G, I, 1, 0)
         out = torch.empty(B, T, H, device=x.device, dtype=torch.float32)
         h16 = torch.empty(B, T, H, device=x.device, dtype=torch.float16)
         gates = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
         c_seq = torch.empty(B, T, H, device=x.device, dtype=torch.float32)
         nbytes = query("avc_lstm_fwd_workspace_bytes", B, T, H, PREC_BF16)
         ws = _ws(nbytes, x.device)
-        call("avc_lstm_seq_fwd_h", _p(Pre), _p(wh_p), _p(out), H, _p(gates), _p(c_seq), _p(h16), FMT_FP16, B, T, H, 0,
+        call("avc_lstm_seq_fwd_h", _p(Pre), _p(wh_p), FMT_BF16, _p(out), H, _p(gates), _p(c_seq), _p(h16), FMT_FP16, B, T, H, 0,
              _p(ws), nbytes, _stream())
         ctx.save_for_backward(x, out, w_ih, w_hh, b_ih, gates, c_seq)
         ctx.packs = (wi_pT, wh_pT)
@@ -615,8 +654,8 @@ class LstmLayerH(torch.autograd.Function):
         dP16 = torch.empty(B, T, G, device=dout.device, dtype=torch.bfloat16)
         nbytes = query("avc_lstm_bwd_workspace_bytes", B, T, H, PREC_BF16)
         ws = _ws(nbytes, dout.device)
-        call("avc_lstm_seq_bwd_h", _p(dout), H, _p(wh_pT), _p(gates), _p(c_seq), _p(dP), _p(dP16), B, T, H, 0, _p(ws), nbytes,
-             _stream())
+        call("avc_lstm_seq_bwd_h", _p(dout), H, _p(wh_pT), FMT_BF16, _p(gates), _p(c_seq), _p(dP), _p(dP16), B, T, H, 0, _p(ws),
+             nbytes, _stream())
         dw_ih = torch.empty_like(w_ih)
         X, x_fmt = _operand(x, None, I, FMT_BF16)
         gemm_tn_taps_h(dP16, FMT_BF16, G, X, x_fmt, I, dw_ih, B, T, G, I, 1, 0, out_mode=2)
@@ -628,7 +667,7 @@ class LstmLayerH(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, T, I, device=dout.device, dtype=torch.float32)
-            gemm_nt_taps_h(dP16, FMT_BF16, G, wi_pT, None, dx, I, B, T, I, G, 1, 0, FMT_BF16)
+            gemm_nt_taps_hw(dP16, FMT_BF16, G, wi_pT, FMT_BF16, G, None, dx, I, B, T, I, G, 1, 0)
         return dx, None, dw_ih, dw_hh, db_ih, db_hh
 
 

@@ -148,11 +148,14 @@ def kernel_flops(name, a):
     if name in ("avc_gemm_nt_taps_h", "avc_gemm_tn_taps_h"):
         nB, T, N, K, taps = a[7], a[8], a[9], a[10], a[11]
         return 2.0 * nB * T * N * K * taps
+    if name == "avc_gemm_nt_taps_hw":
+        nB, T, N, K, taps = a[9], a[10], a[11], a[12], a[13]
+        return 2.0 * nB * T * N * K * taps
     if name == "avc_lstm_seq_fwd_h":
-        nB, T, H = a[8], a[9], a[10]
+        nB, T, H = a[9], a[10], a[11]
         return 2.0 * nB * T * 4 * H * H
     if name == "avc_lstm_seq_bwd_h":
-        nB, T, H = a[7], a[8], a[9]
+        nB, T, H = a[8], a[9], a[10]
         return 2.0 * nB * T * 4 * H * H
     if name == "avc_lstm_seq_fwd":
         nB, T, H = a[6], a[7], a[8]

@@ -194,10 +194,24 @@ int avc_bn_act_bwd_apply_h(const float* dz, const float* z, const float* y, cons
                            const float* gamma, const double* sums, float* dy, void* dy16, int fmt16, float* dgamma,
                            float* dbeta, int M, int C, int act, int accumulate, void* stream);
 /* persistent recurrences (128 <= H <= 1024, H % 64 == 0) with a 16-bit side output: h16 (nB,T,H) / dP16 (nB,T,4H, bf16) */
-int avc_lstm_seq_fwd_h(const float* P, const float* Whh_p, float* h_seq, int ldh, float* gates, float* c_seq, void* h16,
+/* w_fmt: AVC_FMT_FP32 = Whh_p / Whh_pT are the fp32 packings of avc_pack_lstm_weight (converted per call);
+ *        AVC_FMT_BF16 = the bf16 packings of avc_pack_lstm_weight_h (ld = H resp. 4H), read in place. */
+int avc_lstm_seq_fwd_h(const float* P, const void* Whh_p, int w_fmt, float* h_seq, int ldh, float* gates, float* c_seq, void* h16,
                        int fmt16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes, void* stream);
-int avc_lstm_seq_bwd_h(const float* dH, int lddh, const float* Whh_pT, const float* gates, const float* c_seq, float* dP,
+int avc_lstm_seq_bwd_h(const float* dH, int lddh, const void* Whh_pT, int w_fmt, const float* gates, const float* c_seq, float* dP,
                        void* dP16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes, void* stream);
+/* Weight packers that write the 16-bit (or fp32: fmt 0) layouts the tensor-core GEMMs read IN PLACE, with a leading
+ * dimension (ldf >= Cin, ldd >= Cout, ldp >= I, ldpT >= 4H; multiples of 8 for 16-bit) whose tail columns are zero-filled:
+ *   w_fwd [tap][Cout][ldf], w_dgrad [taps-1-tap][Cin][ldd];  out_p [u*4+g][ldp], out_pT [k][ldpT].  Either output may be NULL. */
+int avc_pack_conv_weight_h(const float* w, void* w_fwd, int ldf, int fmt_f, void* w_dgrad, int ldd, int fmt_d, int Cout, int Cin,
+                           int ntaps, void* stream);
+int avc_pack_lstm_weight_h(const float* w, void* out_p, int ldp, int fmt_p, void* out_pT, int ldpT, int fmt_pT, int H, int I,
+                           void* stream);
+/* avc_gemm_nt_taps_h with W already packed as 16-bit [ntaps][N][ldw] (w_fmt bf16/fp16, ldw % 8 == 0): no per-call
+ * staging of W.  A: fp32 (staged to w_fmt) or 16-bit of the SAME format.  Workspace: avc_gemm_nt_h_workspace_bytes. */
+int avc_gemm_nt_taps_hw(const void* A, int a_fmt, int lda, const void* W16, int w_fmt, int ldw, const float* bias, float* C, int ldc,
+                        int nB, int T, int N, int K, int ntaps, int shift0, double* chan_stats, int accumulate,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* Profiling hook: when set to a device buffer of >= 16*T uint64, CTA 0 of the next persistent recurrence
  * launches records %globaltimer stamps per step (slot layout in lstm_tc.cu).  NULL disables it. */

@@ -145,3 +145,69 @@ def test_tn_taps_prestaged_16bit_operands(y_dt, x_dt):
     ref = ref.permute(1, 2, 0)
     scale = float(ref.abs().max())
     assert float((dW.double() - ref).abs().max()) < 3e-5 * scale
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Cout,Cin,k", [(512, 336, 5), (80, 512, 5), (40, 30, 3), (512, 80, 1)])
+def test_pack_conv_weight_h_layouts(Cout, Cin, k):
+    """avc_pack_conv_weight(_h): fwd [tap][Cout][ld] / dgrad [k-1-tap][Cin][ld], fp32 and 16-bit, zero-filled tails."""
+    from autovc_b200 import _lib
+    from autovc_b200.ops import _p, _stream
+    w = _rand(Cout, Cin, k, seed=5)
+    wf32 = torch.empty(k, Cout, Cin, device=DEV)
+    wd32 = torch.empty(k, Cin, Cout, device=DEV)
+    _lib.call("avc_pack_conv_weight", _p(w), _p(wf32), _p(wd32), Cout, Cin, k, _stream())
+    assert torch.equal(wf32, w.permute(2, 0, 1).contiguous())
+    assert torch.equal(wd32, w.flip(2).permute(2, 1, 0).contiguous())
+    ldf, ldd = (Cin + 7) // 8 * 8, (Cout + 7) // 8 * 8
+    wf = torch.full((k, Cout, ldf), 7.0, device=DEV, dtype=torch.float16)
+    wd = torch.full((k, Cin, ldd), 7.0, device=DEV, dtype=torch.bfloat16)
+    _lib.call("avc_pack_conv_weight_h", _p(w), _p(wf), ldf, 2, _p(wd), ldd, 1, Cout, Cin, k, _stream())
+    assert torch.equal(wf[..., :Cin], wf32.half()) and float(wf[..., Cin:].abs().sum()) == 0.0
+    assert torch.equal(wd[..., :Cout], wd32.bfloat16()) and float(wd[..., Cout:].abs().sum()) == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,I", [(1024, 512), (16, 30), (512, 288)])
+def test_pack_lstm_weight_h_layouts(H, I):
+    from autovc_b200 import _lib
+    from autovc_b200.ops import _p, _stream
+    w = _rand(4 * H, I, seed=6)
+    ref = w.view(4, H, I).permute(1, 0, 2).reshape(4 * H, I).contiguous()       # row u*4+g
+    p32, pT32 = torch.empty(4 * H, I, device=DEV), torch.empty(I, 4 * H, device=DEV)
+    _lib.call("avc_pack_lstm_weight", _p(w), _p(p32), _p(pT32), H, I, _stream())
+    assert torch.equal(p32, ref) and torch.equal(pT32, ref.t().contiguous())
+    ldp = (I + 7) // 8 * 8
+    p16 = torch.full((4 * H, ldp), 7.0, device=DEV, dtype=torch.float16)
+    pT16 = torch.full((I, 4 * H), 7.0, device=DEV, dtype=torch.bfloat16)
+    _lib.call("avc_pack_lstm_weight_h", _p(w), _p(p16), ldp, 2, _p(pT16), 4 * H, 1, H, I, _stream())
+    assert torch.equal(p16[:, :I], ref.half()) and float(p16[:, I:].abs().sum()) == 0.0
+    assert torch.equal(pT16, ref.t().contiguous().bfloat16())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nB,T,N,K,ntaps", [(40, 128, 640, 96, 5), (3, 100, 130, 200, 3), (4, 128, 2048, 288, 1)])
+def test_nt_taps_prepacked_weight_equals_staged(nB, T, N, K, ntaps):
+    """avc_gemm_nt_taps_hw (W packed once as 16-bit) == avc_gemm_nt_taps_h (W staged per call), bit for bit."""
+    A = _rand(nB * T, K, seed=1).half()
+    W = _rand(ntaps, N, K, seed=2) * 0.05
+    bias = _rand(N, seed=3)
+    shift0 = -(ntaps // 2)
+    C1 = torch.empty(nB * T, N, device=DEV)
+    C2 = torch.empty_like(C1)
+    s1 = torch.zeros(2 * N, dtype=torch.double, device=DEV)
+    s2 = torch.zeros_like(s1)
+    ops.gemm_nt_taps_h(A, 2, K, W, bias, C1, N, nB, T, N, K, ntaps, shift0, 2, stats=s1)
+    ldw = (K + 7) // 8 * 8
+    W16 = torch.zeros(ntaps, N, ldw, device=DEV, dtype=torch.float16)
+    W16[..., :K] = W.half()
+    ops.gemm_nt_taps_hw(A, 2, K, W16, 2, ldw, bias, C2, N, nB, T, N, K, ntaps, shift0, stats=s2)
+    assert torch.equal(C1, C2)
+    torch.testing.assert_close(s1, s2, rtol=1e-12, atol=1e-9)
+    # an fp32 A is staged to W's format
+    C3 = torch.empty_like(C1)
+    ops.gemm_nt_taps_hw(A.float(), 0, K, W16, 2, ldw, bias, C3, N, nB, T, N, K, ntaps, shift0)
+    assert torch.equal(C1, C3)
+    # mixed 16-bit formats are refused (tcgen05 kind::f16 would trap)
+    with pytest.raises(Exception):
+        ops.gemm_nt_taps_hw(A.bfloat16(), 1, K, W16, 2, ldw, bias, C3, N, nB, T, N, K, ntaps, shift0)
