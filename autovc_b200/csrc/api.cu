@@ -45,6 +45,7 @@ size_t gemm_tn_workspace_tc(int, int, int, int, int, int);
 // persistent tensor-core recurrences (lstm_tc.cu)
 bool lstm_tc_supported(int H);
 void lstm_tc_set_trace(unsigned long long* p);
+void tc_gemm_set_trace(unsigned long long* p);
 size_t lstm_tc_workspace(int nB, int T, int H, bool bwd);
 int lstm_seq_tc(bool bwd, const void* W, const float* P, float* h_seq, int ldh, float* gates, float* c_seq, const float* dH,
                 int lddh, float* dP, int nB, int T, int H, int reverse, void* ws, size_t ws_bytes, cudaStream_t st,
@@ -142,7 +143,10 @@ extern "C" size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H, int prec) {
   return lstm_bwd_workspace_simt(nB, T, H);
 }
 
-extern "C" void avc_debug_set_trace(unsigned long long* device_buffer) { lstm_tc_set_trace(device_buffer); }
+extern "C" void avc_debug_set_trace(unsigned long long* device_buffer) {
+  lstm_tc_set_trace(device_buffer);
+  tc_gemm_set_trace(device_buffer);
+}
 
 // ---- GEMMs on operands that already live in HBM as 16-bit (formats: 0 = fp32 (staged to half_fmt), 1 = bf16, 2 = fp16) ----
 extern "C" int avc_gemm_nt_taps_h(const void* A, int a_fmt, int lda, const float* W, const float* bias, float* C, int ldc, int nB,

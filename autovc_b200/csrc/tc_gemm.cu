@@ -59,6 +59,8 @@ struct TcParams {
   int k_tiles, splits, rblocks, rblocks_per_split, tbr;   // tbr = ceil(T / frames-per-stage)
   int grouped_a, grouped_b;   // operand fetched with one grouped 4-D box per stage (make_map4_grouped)
   uint32_t idesc;             // tcgen05 instruction descriptor (operand formats are chosen at run time)
+  unsigned long long* trace;  // avc_debug_set_trace: %globaltimer stamps of pair 0's leader, 8 slots per tile (first 64 tiles)
+  int dbg;                    // AVC_GEMM_EPI_DEBUG (measurement only): 1 = skip the TMA store issue, 2 = also skip the smem staging
   int tma_store;              // NT pair kernel: C leaves through shared memory + TMA stores (needs ldc % 4 == 0, 16-byte aligned C)
   float* part;
 };
@@ -369,6 +371,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 //   tfull[a] (each CTA, 1 arrival)           <- L's MMA commit mc   -> each CTA's epilogue
 //   tempty[a](L only, 8 arrivals)            <- 4 epilogue warps of L (local) and of P (remote arrive)
 // ---------------------------------------------------------------------------------------------------
+// trace slots per tile of pair 0 / leader: 0 producer slot free, 1 loads issued, 2 accumulator free (MMA), 3 operands landed,
+// 4 MMAs issued, 5 epilogue woke, 6 first chunk done, 7 accumulator released
+#define TC2_TRACE(slot)                                                                                          \
+  do {                                                                                                           \
+    if (p.trace != nullptr && blockIdx.x == 0 && iter < 64) {                                                    \
+      unsigned long long t_;                                                                                     \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                     \
+      p.trace[iter * 8 + (slot)] = t_;                                                                           \
+    }                                                                                                            \
+  } while (0)
+
+// chunk-level stamps of tile #4 (steady state): p.trace[512 + 4 * chunk + k]; k: 0 TMEM read, 1 bias/mask, 2 staged, 3 store issued
+#define TC2_CTRACE(k)                                                                                            \
+  do {                                                                                                           \
+    if (p.trace != nullptr && blockIdx.x == 0 && iter == 4 && threadIdx.x == 64) {                               \
+      unsigned long long t_;                                                                                     \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                     \
+      p.trace[512 + c * 4 + (k)] = t_;                                                                           \
+    }                                                                                                            \
+  } while (0)
+
 struct Tc2Cfg {
   static constexpr int BN = 256;                      // pair tile width
   static constexpr int STAGE_B = 128 * 128;           // this CTA's half of the W tile: 128 rows x 128 B
@@ -377,7 +400,8 @@ struct Tc2Cfg {
   static constexpr int TMEM_COLS = 512;               // two 256-column fp32 accumulators
   static constexpr int STAT_BYTES = 4 * 2 * BN * 4;
   static constexpr int EPI_BYTES = 4 * 2 * 4096;      // per epilogue warp: two 32-row x 32-column fp32 staging tiles
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAT_BYTES + EPI_BYTES + 256;
+  static constexpr int BIAS_BYTES = 4 * BN * 4;       // per epilogue warp: the tile's 256 bias values
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAT_BYTES + EPI_BYTES + BIAS_BYTES + 256;
 };
 
 template <int EB>
@@ -394,7 +418,8 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   const uint32_t stage0 = base;
   float* stat_s = reinterpret_cast<float*>(gen + ST * Cf::STAGE_BYTES);
   const uint32_t epi0 = base + ST * Cf::STAGE_BYTES + Cf::STAT_BYTES;                   // 1024-byte aligned (128B swizzle atoms)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + ST * Cf::STAGE_BYTES + Cf::STAT_BYTES + Cf::EPI_BYTES);
+  const uint32_t bias0 = epi0 + Cf::EPI_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + ST * Cf::STAGE_BYTES + Cf::STAT_BYTES + Cf::EPI_BYTES + Cf::BIAS_BYTES);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (ST + s); };
@@ -436,13 +461,15 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < total; tile += npairs) {
+      int iter = 0;
+      for (int tile = pair; tile < total; tile += npairs, ++iter) {
         const int n_tile = tile % p.n_tiles, m_tile = (tile / p.n_tiles) * 2 + (int)rank;
         // an odd tile count leaves the last pair's second half empty: b == nB is out of range and zero-filled
         const int b = m_tile / p.t_tiles, t0 = (m_tile % p.t_tiles) * TC_BM;
         for (int it = 0; it < kiters; ++it) {
           const int tap = it / p.kblocks, kb = it - tap * p.kblocks;
           mbar_wait(empty_bar(stage), phase ^ 1);
+          if (it == 0) TC2_TRACE(0);
           if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cf::STAGE_BYTES);
           const uint32_t fb = mapa_u32(full_bar(stage), 0);
           const uint32_t sa = stage0 + stage * Cf::STAGE_BYTES;
@@ -450,6 +477,7 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           tma_load_3d_2cta(sa + TC_STAGE_A, &mapB, fb, kb * Gm::ROW, n_tile * BN + (int)rank * 128, tap);
           if (++stage == ST) { stage = 0; phase ^= 1; }
         }
+        TC2_TRACE(1);
       }
       // tail: every commit aimed at this CTA's empty barriers has landed before the CTA may exit
       for (int s = 0; s < ST; ++s) {
@@ -465,13 +493,16 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = pair; tile < total; tile += npairs) {
+      int iter = 0;
+      for (int tile = pair; tile < total; tile += npairs, ++iter) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);    // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
+        TC2_TRACE(2);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (it == kiters - 1) TC2_TRACE(3);
           const uint32_t sa = stage0 + stage * Cf::STAGE_BYTES, sb = sa + TC_STAGE_A;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
@@ -481,6 +512,7 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           if (++stage == ST) { stage = 0; phase ^= 1; }
         }
         umma_commit_2cta(tfull_bar(acc), 3);
+        TC2_TRACE(4);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -491,46 +523,83 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const uint32_t epi_w = epi0 + (uint32_t)(warp - 2) * 8192u;   // this warp's two staging tiles
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = pair; tile < total; tile += npairs) {
+    int iter = 0;
+    for (int tile = pair; tile < total; tile += npairs, ++iter) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      if (threadIdx.x == 64) TC2_TRACE(5);
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       const int n_tile = tile % p.n_tiles, m_tile = (tile / p.n_tiles) * 2 + (int)rank;
       const int b = m_tile / p.t_tiles, t_blk = (m_tile % p.t_tiles) * TC_BM + q * 32, t = t_blk + lane;
       const bool row_ok = t < p.T && b < p.nB;
+      const bool rows_full = t_blk + 32 <= p.T && b < p.nB;       // warp-uniform: no row of this warp's block is clipped
       float* crow = p.C + ((size_t)b * p.T + t) * p.ldc;
+      // A lone warp per scheduler is issue-bound (r01b trace: ~500 instructions and 0.9 us per 32-column chunk with per-element
+      // bias loads and masks), so the common case -- full chunk, nothing to zero for the BN sums -- takes a short path: the
+      // tile's bias values are parked in shared memory once and added with 8 vector loads per chunk.
+      const uint32_t bias_w = bias0 + (uint32_t)(warp - 2) * (BN * 4);
+      if (p.tma_store && p.bias != nullptr) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) {
+          const int n = n_tile * BN + i * 32 + lane;
+          st_shared_f32(bias_w + (i * 32 + lane) * 4, n < p.N ? __ldg(p.bias + n) : 0.f);
+        }
+        __syncwarp();
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         float v[32];
         tmem_ld32(t_addr + c * 32, v);
+        TC2_CTRACE(0);
         if (c == BN / 32 - 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_remote(tempty_leader0 + 8u * acc);
+          if (lane == 0) mbar_arrive_remote_relaxed(tempty_leader0 + 8u * acc);   // the TMEM reads have completed (wait::ld)
+          if (threadIdx.x == 64) TC2_TRACE(7);
         }
+        if (c == 1 && threadIdx.x == 64) TC2_TRACE(6);
         const int n0 = n_tile * BN + c * 32;
+        const bool fast = p.tma_store && n0 + 32 <= p.N && (rows_full || p.stats == nullptr);
+        if (fast) {
+          if (p.bias != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + j;
-          float x = v[j] + ((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f);
-          v[j] = (row_ok && n < p.N) ? x : 0.f;
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = ld_shared_v4(bias_w + (c * 32 + j * 4) * 4);
+              v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + j;
+            float x = v[j] + ((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f);
+            v[j] = (row_ok && n < p.N) ? x : 0.f;
+          }
         }
+        TC2_CTRACE(1);
         if (p.tma_store) {
           // registers -> swizzled shared tile -> one TMA store (or reduce-add) of 32 rows x 128 B; rows >= T and columns
           // >= N are clipped by the TMA unit.  Thread = row: 16-byte chunk j of row r sits at chunk j ^ (r & 7).
           const uint32_t buf = epi_w + (uint32_t)(c & 1) * 4096u;
           if (lane == 0) bulk_wait_read<1>();            // the store issued two chunks ago has drained this tile
           __syncwarp();
+          if (p.dbg < 2) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            st_shared_v4(buf + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          fence_async_smem();
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(buf + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            fence_async_smem();
+          } else if (v[0] == 123.456f) {
+            st_shared_v4(buf, v[1], v[2], v[3], v[31]);
+          }
           __syncwarp();
-          if (lane == 0) {
+          TC2_CTRACE(2);
+          if (lane == 0 && p.dbg < 1) {
             if (p.accumulate) tma_reduce_add_3d(&mapC, buf, n0, t_blk, b);
             else tma_store_3d(&mapC, buf, n0, t_blk, b);
             bulk_commit();
           }
+          TC2_CTRACE(3);
           if (p.stats != nullptr) {                      // lane = column: walk down the 32 rows of the staged tile
             float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -682,6 +751,9 @@ static int tc_launch(const CUtensorMap& mA, const CUtensorMap& mB, const TcParam
   AVC_LAUNCHED();
   return AVC_OK;
 }
+static unsigned long long* g_gemm_trace = nullptr;
+void tc_gemm_set_trace(unsigned long long* p) { g_gemm_trace = p; }
+
 template <int EB>
 static int tc2_launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mC, const TcParams& p, int grid, cudaStream_t st) {
   static bool attr_done = false;
@@ -834,6 +906,8 @@ int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const void* Wv, int w_fm
     CUtensorMap mC = mA;                    // placeholder when the direct-store epilogue is used
     static const bool tma_epi = getenv("AVC_GEMM_TMA_STORE") ? atoi(getenv("AVC_GEMM_TMA_STORE")) != 0 : true;
     p.tma_store = tma_epi && (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0);
+    p.dbg = getenv("AVC_GEMM_EPI_DEBUG") ? atoi(getenv("AVC_GEMM_EPI_DEBUG")) : 0;
+    p.trace = g_gemm_trace;
     if (p.tma_store) {
       rc = make_map3_out_f32(&mC, C, N, T, nB, ldc, (uint64_t)T * ldc, 32);
       if (rc) return rc;
