@@ -198,73 +198,94 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      mbar_expect_tx(w_bar, kblocks * w_block);
-      for (int kb = 0; kb < kblocks; ++kb) tma_load_3d(w_base + kb * w_block, &mapW, w_bar, kb * 64, nt * BN, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int s = 1; s < T; ++s) {
-        const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
-        if (kflags) {
+    // The whole warp walks the loops (warp-uniform operands stay in uniform registers); one elected lane issues.  Issuing
+    // from inside `if (lane == 0)` costs an ELECT/R2UR loop of ~20 dependent instructions per TMA / tcgen05.mma.
+    if (kflags) {
+      if (lane == 0) {
+        mbar_expect_tx(w_bar, kblocks * w_block);
+        for (int kb = 0; kb < kblocks; ++kb) tma_load_3d(w_base + kb * w_block, &mapW, w_bar, kb * 64, nt * BN, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int s = 1; s < T; ++s) {
+          const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
           constexpr int U_PUB = BN / 4;                            // units published per CTA -> 64 / U_PUB CTAs per k-block
           stream_kblocks_as_published(counter, (unsigned)s * (64 / U_PUB), kblocks, slot_kb, stage, phase, p.stages,
                                       full_bar(0), empty_bar(0), [&](int st, int kb) {
                                         tma_load_3d(ring + st * LT_STAGE, &mapX, full_bar(st), kb * 64, row0, 0);
                                       });
-          continue;
         }
+      }
+    } else {
+      if (elect_one()) {
+        mbar_expect_tx(w_bar, kblocks * w_block);
+        for (int kb = 0; kb < kblocks; ++kb) tma_load_3d(w_base + kb * w_block, &mapW, w_bar, kb * 64, nt * BN, 0);
+      }
+      __syncwarp();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 1; s < T; ++s) {
+        const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
         const unsigned target = (unsigned)s * (unsigned)p.NT;     // every column tile has published step s-1
-        while (ld_acquire(counter) < target) {
+        if (lane == 0) {
+          while (ld_acquire(counter) < target) {
+          }
+          LT_TRACE(0);
+          if (p.exp_mode == 4) fence_proxy_async();   // writer-side proxy fence + release/acquire order the TMA reads
         }
-        LT_TRACE(0);
-        if (p.exp_mode == 4) fence_proxy_async();   // writer-side proxy fence + release/acquire order the TMA reads
-        for (int kb0 = 0; kb0 < kblocks; ++kb0) {
-          const int kb = kb0;
+        __syncwarp();
+        for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          slot_kb[stage] = kb;
-          mbar_expect_tx(full_bar(stage), LT_STAGE);
-          if (CL == 1) {
-            tma_load_3d(ring + stage * LT_STAGE, &mapX, full_bar(stage), kb * 64, row0, 0);
-          } else
-            tma_load_3d_mc(ring + stage * LT_STAGE + crank * SLICE_ROWS * 128, &mapX, full_bar(stage), kb * 64,
-                           row0 + crank * SLICE_ROWS, 0, cmask);
-          if (kb0 == 0) LT_TRACE(1);
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(stage), LT_STAGE);
+            if (CL == 1) {
+              tma_load_3d(ring + stage * LT_STAGE, &mapX, full_bar(stage), kb * 64, row0, 0);
+            } else
+              tma_load_3d_mc(ring + stage * LT_STAGE + crank * SLICE_ROWS * 128, &mapX, full_bar(stage), kb * 64,
+                             row0 + crank * SLICE_ROWS, 0, cmask);
+            if (kb == 0) LT_TRACE(1);
+            if (kb == kblocks - 1) LT_TRACE(2);
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        LT_TRACE(2);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-      mbar_wait(w_bar, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int s = 0; s < T; ++s) {
-        mbar_wait(tempty, (s & 1) ^ 1);
+    constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+    mbar_wait(w_bar, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int s = 0; s < T; ++s) {
+      mbar_wait(tempty, (s & 1) ^ 1);
+      tc_fence_after();
+      if (s == 0) {
+        if (elect_one()) mbar_arrive(tfull);               // h_{-1} = 0 / no later step: nothing to multiply
+        __syncwarp();
+        continue;
+      }
+      for (int kb0 = 0; kb0 < kblocks; ++kb0) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        if (s == 0) {
-          mbar_arrive(tfull);               // h_{-1} = 0 / no later step: nothing to multiply
-          continue;
-        }
-        for (int kb0 = 0; kb0 < kblocks; ++kb0) {
-          mbar_wait(full_bar(stage), phase);
-          const int kb = slot_kb[stage];
+        int kb = kb0;                                      // k-blocks arrive in order unless they are streamed as published
+        if (kflags) kb = slot_kb[stage];
+        const uint32_t sa = ring + stage * LT_STAGE, sb = w_base + kb * w_block;
+        if (elect_one()) {
           if (kb0 == 0) LT_TRACE(3);
           if (kb0 == kblocks - 1) LT_TRACE(4);
-          tc_fence_after();
-          const uint32_t sa = ring + stage * LT_STAGE, sb = w_base + kb * w_block;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16(tmem_base, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc,
                      (kb0 > 0 || k > 0) ? 1u : 0u);
           if (CL == 1) umma_commit(empty_bar(stage));
           else umma_commit_mc(empty_bar(stage), cmask);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (kb0 == kblocks - 1) {
+            umma_commit(tfull);
+            LT_TRACE(5);
+          }
         }
-        umma_commit(tfull);
-        LT_TRACE(5);
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -542,59 +563,79 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
   const bool kflags = p.kflags != 0;     // counter[kb]: k-block kb of dG (64 gate columns) is published by exactly one CTA
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(w_bar, kblocks * w_block);
-      for (int kb = 0; kb < kblocks; ++kb)
-        tma_load_3d(w_base + kb * w_block, &mapW, w_bar, (int)r * H + kb * 64, ut * KS_UNITS, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int s = 1; s < T; ++s) {
-        const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
-        if (kflags) {
+    // whole-warp loops, one elected lane issues (see lstm_tc_kernel)
+    if (kflags) {
+      if (lane == 0) {
+        mbar_expect_tx(w_bar, kblocks * w_block);
+        for (int kb = 0; kb < kblocks; ++kb)
+          tma_load_3d(w_base + kb * w_block, &mapW, w_bar, (int)r * H + kb * 64, ut * KS_UNITS, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int s = 1; s < T; ++s) {
+          const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
           stream_kblocks_as_published(counter + r * kblocks, (unsigned)s, kblocks, slot_kb, stage, phase, p.stages, full_bar(0),
                                       empty_bar(0), [&](int st, int kb) {
                                         tma_load_3d(ring + st * LT_STAGE, &mapX, full_bar(st), (int)r * H + kb * 64, row0, 0);
                                       });
-          continue;
         }
-        while (ld_acquire(counter) < (unsigned)s * per_step) {
+      }
+    } else {
+      if (elect_one()) {
+        mbar_expect_tx(w_bar, kblocks * w_block);
+        for (int kb = 0; kb < kblocks; ++kb)
+          tma_load_3d(w_base + kb * w_block, &mapW, w_bar, (int)r * H + kb * 64, ut * KS_UNITS, 0);
+      }
+      __syncwarp();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int s = 1; s < T; ++s) {
+        const int row0 = ((s - 1) & 1) * p.nBpad + mt * 128;
+        if (lane == 0) {
+          while (ld_acquire(counter) < (unsigned)s * per_step) {
+          }
+          if (p.exp_mode == 4) fence_proxy_async();
         }
-        if (p.exp_mode == 4) fence_proxy_async();
+        __syncwarp();
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          slot_kb[stage] = kb;
-          mbar_expect_tx(full_bar(stage), LT_STAGE);
-          tma_load_3d(ring + stage * LT_STAGE, &mapX, full_bar(stage), (int)r * H + kb * 64, row0, 0);
+          if (elect_one()) {
+            mbar_expect_tx(full_bar(stage), LT_STAGE);
+            tma_load_3d(ring + stage * LT_STAGE, &mapX, full_bar(stage), (int)r * H + kb * 64, row0, 0);
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(128, KS_UNITS, 0, 0);
-      mbar_wait(w_bar, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int s = 0; s < T; ++s) {
-        mbar_wait(tempty, (s & 1) ^ 1);
+    constexpr uint32_t idesc = make_idesc(128, KS_UNITS, 0, 0);
+    mbar_wait(w_bar, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int s = 0; s < T; ++s) {
+      mbar_wait(tempty, (s & 1) ^ 1);
+      tc_fence_after();
+      if (s == 0) {
+        if (elect_one()) mbar_arrive(tfull);
+        __syncwarp();
+        continue;
+      }
+      for (int kb0 = 0; kb0 < kblocks; ++kb0) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        if (s == 0) {
-          mbar_arrive(tfull);
-          continue;
-        }
-        for (int kb0 = 0; kb0 < kblocks; ++kb0) {
-          mbar_wait(full_bar(stage), phase);
-          const int kb = slot_kb[stage];
-          tc_fence_after();
-          const uint32_t sa = ring + stage * LT_STAGE, sb = w_base + kb * w_block;
+        int kb = kb0;
+        if (kflags) kb = slot_kb[stage];
+        const uint32_t sa = ring + stage * LT_STAGE, sb = w_base + kb * w_block;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16(tmem_base, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc,
                      (kb0 > 0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(stage));
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (kb0 == kblocks - 1) umma_commit(tfull);
         }
-        umma_commit(tfull);
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {

@@ -96,6 +96,20 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
   if (EB == 2) umma_f16(tmem_d, da, db, idesc, accumulate);
   else umma_tf32(tmem_d, da, db, idesc, accumulate);
 }
+// One lane of a fully active warp.  Role warps run their loops with ALL lanes (warp-uniform control flow and operands,
+// which the compiler keeps in uniform registers) and only predicate the asynchronous instruction itself on this: issuing
+// from inside `if (lane == 0)` costs an ELECT/R2UR.BROADCAST loop of ~20 instructions per tcgen05.mma (r01b SASS), about
+// as long as a 128x256x16 MMA runs.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- shared -> global tile stores through the TMA unit (bulk async-group completion) ----
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src), "r"(c0),
@@ -154,6 +168,12 @@ __device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const CUtensorMap
   asm volatile(
       "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
       "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2cta(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 template <int EB>

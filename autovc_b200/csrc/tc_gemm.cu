@@ -147,8 +147,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -158,10 +158,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int it = 0; it < kiters; ++it) {
             const int tap = it / p.kblocks, kb = it - tap * p.kblocks;
             mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
-            const uint32_t sa = stage0 + stage * TC_STAGE_BYTES;
-            tma_load_3d(sa, &mapA, full_bar(stage), kb * Gm::ROW, t0 + p.shift0 + tap, b);
-            tma_load_3d(sa + TC_STAGE_A, &mapB, full_bar(stage), kb * Gm::ROW, n_tile * BN, tap);
+            if (elect_one()) {
+              mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
+              const uint32_t sa = stage0 + stage * TC_STAGE_BYTES;
+              tma_load_3d(sa, &mapA, full_bar(stage), kb * Gm::ROW, t0 + p.shift0 + tap, b);
+              tma_load_3d(sa + TC_STAGE_A, &mapB, full_bar(stage), kb * Gm::ROW, n_tile * BN, tap);
+            }
+            __syncwarp();
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
         } else {
@@ -172,33 +175,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int rb = rb0; rb < rb1; ++rb) {
             const int b = rb / p.tbr, t0 = (rb % p.tbr) * Gm::RS;
             mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
-            const uint32_t sa = stage0 + stage * TC_STAGE_BYTES;
-            // one TMA instruction per operand when the channel count is a multiple of the 128-byte row (a single
-            // thread issues ~1 TMA per 100 cycles: 12 small boxes per stage made the producer the bottleneck)
-            if (p.grouped_a) {
-              tma_load_4d(sa, &mapA, full_bar(stage), 0, t0, n_tile * Gm::NBOX, b);
-            } else {
+            if (elect_one()) {
+              mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
+              const uint32_t sa = stage0 + stage * TC_STAGE_BYTES;
+              // one TMA instruction per operand when the channel count is a multiple of the 128-byte row (a single
+              // thread issues ~1 TMA per 100 cycles: 12 small boxes per stage made the producer the bottleneck)
+              if (p.grouped_a) {
+                tma_load_4d(sa, &mapA, full_bar(stage), 0, t0, n_tile * Gm::NBOX, b);
+              } else {
 #pragma unroll
-              for (int h = 0; h < Gm::NBOX; ++h)
-                tma_load_3d(sa + h * Gm::BOX_BYTES, &mapA, full_bar(stage), n_tile * TC_BM + h * Gm::ROW, t0, b);
-            }
-            if (p.grouped_b) {
-              tma_load_4d(sa + TC_STAGE_A, &mapB, full_bar(stage), 0, t0 + p.shift0 + tap, k_tile * (BN / Gm::ROW), b);
-            } else {
+                for (int h = 0; h < Gm::NBOX; ++h)
+                  tma_load_3d(sa + h * Gm::BOX_BYTES, &mapA, full_bar(stage), n_tile * TC_BM + h * Gm::ROW, t0, b);
+              }
+              if (p.grouped_b) {
+                tma_load_4d(sa + TC_STAGE_A, &mapB, full_bar(stage), 0, t0 + p.shift0 + tap, k_tile * (BN / Gm::ROW), b);
+              } else {
 #pragma unroll
-              for (int h = 0; h < BN / Gm::ROW; ++h)
-                tma_load_3d(sa + TC_STAGE_A + h * Gm::BOX_BYTES, &mapB, full_bar(stage), k_tile * BN + h * Gm::ROW,
-                            t0 + p.shift0 + tap, b);
+                for (int h = 0; h < BN / Gm::ROW; ++h)
+                  tma_load_3d(sa + TC_STAGE_A + h * Gm::BOX_BYTES, &mapB, full_bar(stage), k_tile * BN + h * Gm::ROW,
+                              t0 + p.shift0 + tap, b);
+              }
             }
+            __syncwarp();
             if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+    {
       const uint32_t idesc = p.idesc;
       int stage = 0;
       uint32_t phase = 0;
@@ -218,27 +224,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = stage0 + stage * TC_STAGE_BYTES, sb = sa + TC_STAGE_A;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint64_t da, db;
-            if (MODE == MODE_NT) {
-              // K-major: 128-byte rows, 8-row groups 1024 B apart; one MMA's K slice is 32 B further along the row
-              da = make_desc(sa + k * 32, 16, 1024);
-              db = make_desc(sb + k * 32, 16, 1024);
-            } else {
-              // MN-major: each frame is a 128-byte row of ROW channels; 8-frame groups 1024 B apart (SBO), the
-              // next ROW-channel box of the tile BOX_BYTES further (LBO); one MMA's K slice = KMMA frames
-              // (32-bit operands: the only MN-major layout is SWIZZLE_128B_BASE32B -- 32-byte swizzle atoms, 4-frame
-              //  groups 512 B apart -- which the TMA map produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
-              da = make_desc(sa + k * Gm::KMMA * 128, Gm::BOX_BYTES, EB == 2 ? 1024 : 512, EB == 2 ? 2 : 1);
-              db = make_desc(sb + k * Gm::KMMA * 128, Gm::BOX_BYTES, EB == 2 ? 1024 : 512, EB == 2 ? 2 : 1);
+            for (int k = 0; k < 4; ++k) {
+              uint64_t da, db;
+              if (MODE == MODE_NT) {
+                // K-major: 128-byte rows, 8-row groups 1024 B apart; one MMA's K slice is 32 B further along the row
+                da = make_desc(sa + k * 32, 16, 1024);
+                db = make_desc(sb + k * 32, 16, 1024);
+              } else {
+                // MN-major: each frame is a 128-byte row of ROW channels; 8-frame groups 1024 B apart (SBO), the
+                // next ROW-channel box of the tile BOX_BYTES further (LBO); one MMA's K slice = KMMA frames
+                // (32-bit operands: the only MN-major layout is SWIZZLE_128B_BASE32B -- 32-byte swizzle atoms, 4-frame
+                //  groups 512 B apart -- which the TMA map produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                da = make_desc(sa + k * Gm::KMMA * 128, Gm::BOX_BYTES, EB == 2 ? 1024 : 512, EB == 2 ? 2 : 1);
+                db = make_desc(sb + k * Gm::KMMA * 128, Gm::BOX_BYTES, EB == 2 ? 1024 : 512, EB == 2 ? 2 : 1);
+              }
+              umma<EB>(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
             }
-            umma<EB>(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_commit(empty_bar(stage));                // frees the smem slot when these MMAs retire
+            if (it == iters - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
           }
-          umma_commit(empty_bar(stage));                // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(acc));                    // accumulator complete -> epilogue
+        if (iters == 0) {                                 // an empty split still hands its (untouched) accumulator on
+          if (elect_one()) umma_commit(tfull_bar(acc));
+          __syncwarp();
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -457,8 +470,8 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   const int kiters = p.ntaps * p.kblocks;
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread in each CTA) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -469,15 +482,18 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         for (int it = 0; it < kiters; ++it) {
           const int tap = it / p.kblocks, kb = it - tap * p.kblocks;
           mbar_wait(empty_bar(stage), phase ^ 1);
-          if (it == 0) TC2_TRACE(0);
-          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cf::STAGE_BYTES);
-          const uint32_t fb = mapa_u32(full_bar(stage), 0);
-          const uint32_t sa = stage0 + stage * Cf::STAGE_BYTES;
-          tma_load_3d_2cta(sa, &mapA, fb, kb * Gm::ROW, t0 + p.shift0 + tap, b);
-          tma_load_3d_2cta(sa + TC_STAGE_A, &mapB, fb, kb * Gm::ROW, n_tile * BN + (int)rank * 128, tap);
+          if (elect_one()) {
+            if (it == 0) TC2_TRACE(0);
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cf::STAGE_BYTES);
+            const uint32_t fb = mapa_u32(full_bar(stage), 0);
+            const uint32_t sa = stage0 + stage * Cf::STAGE_BYTES;
+            tma_load_3d_2cta(sa, &mapA, fb, kb * Gm::ROW, t0 + p.shift0 + tap, b);
+            tma_load_3d_2cta(sa + TC_STAGE_A, &mapB, fb, kb * Gm::ROW, n_tile * BN + (int)rank * 128, tap);
+            if (it == kiters - 1) TC2_TRACE(1);
+          }
+          __syncwarp();
           if (++stage == ST) { stage = 0; phase ^= 1; }
         }
-        TC2_TRACE(1);
       }
       // tail: every commit aimed at this CTA's empty barriers has landed before the CTA may exit
       for (int s = 0; s < ST; ++s) {
@@ -486,8 +502,8 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread of the leader CTA) =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (leader CTA; whole warp loops, one elected lane issues) =====================
+    if (rank == 0) {
       const uint32_t idesc = p.idesc;
       int stage = 0;
       uint32_t phase = 0;
@@ -497,22 +513,27 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       for (int tile = pair; tile < total; tile += npairs, ++iter) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);    // both CTAs' epilogues have drained this accumulator
         tc_fence_after();
-        TC2_TRACE(2);
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int it = 0; it < kiters; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          if (it == kiters - 1) TC2_TRACE(3);
           const uint32_t sa = stage0 + stage * Cf::STAGE_BYTES, sb = sa + TC_STAGE_A;
+          if (elect_one()) {
+            if (it == 0) TC2_TRACE(2);
+            if (it == kiters - 1) TC2_TRACE(3);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_2cta<EB>(d_tmem, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc,
-                          (it > 0 || k > 0) ? 1u : 0u);
-          umma_commit_2cta(empty_bar(stage), 3);
+            for (int k = 0; k < 4; ++k)
+              umma_2cta<EB>(d_tmem, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc,
+                            (it > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2cta(empty_bar(stage), 3);
+            if (it == kiters - 1) {
+              umma_commit_2cta(tfull_bar(acc), 3);
+              TC2_TRACE(4);
+            }
+          }
+          __syncwarp();
           if (++stage == ST) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2cta(tfull_bar(acc), 3);
-        TC2_TRACE(4);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -675,6 +696,173 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------
+// MODE_TN on CTA pairs: dW tile = 256 dY channels (two 128-channel tiles, one per CTA) x 256 X channels.  Each CTA stages
+// ITS 128 dY channels and ITS 128-channel half of the X tile per 64-frame block: 32 KB per stage instead of 48 KB.  Needs
+// whole grouped boxes (channel counts multiples of the tiles) and an even number of 128-channel dY tiles.  Barrier protocol
+// as in tc_gemm2_nt_kernel; partials are written with direct stores (the epilogue is far from the critical path here).
+// ---------------------------------------------------------------------------------------------------
+template <int EB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_gemm2_tn_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  using Gm = TcGeom<EB>;
+  constexpr int BN = 256, ST = 6, STAGE_BYTES = 32768;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const uint32_t stage0 = base;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + ST * STAGE_BYTES);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (ST + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * ST + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * ST + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    for (int s = 0; s < ST; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc_2cta(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_pairs = p.n_tiles >> 1;                         // pairs of 128-channel dY tiles
+  const int total = p.ntaps * n_pairs * p.k_tiles * p.splits;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = pair; item < total; item += npairs) {
+      const TnItem wi = tn_decode(item, p.k_tiles, n_pairs, p.ntaps);
+      const int n_tile = wi.n_tile * 2 + (int)rank;
+      const int rb0 = wi.split * p.rblocks_per_split;
+      const int rb1 = min(p.rblocks, rb0 + p.rblocks_per_split);
+      for (int rb = rb0; rb < rb1; ++rb) {
+        const int b = rb / p.tbr, t0 = (rb % p.tbr) * Gm::RS;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+          const uint32_t fb = mapa_u32(full_bar(stage), 0);
+          const uint32_t sa = stage0 + stage * STAGE_BYTES;
+          tma_load_4d_2cta(sa, &mapA, fb, 0, t0, n_tile * Gm::NBOX, b);
+          tma_load_4d_2cta(sa + TC_STAGE_A, &mapB, fb, 0, t0 + p.shift0 + wi.tap, wi.k_tile * (BN / Gm::ROW) + (int)rank * Gm::NBOX, b);
+        }
+        __syncwarp();
+        if (++stage == ST) { stage = 0; phase ^= 1; }
+      }
+    }
+    for (int s = 0; s < ST; ++s) {                             // tail: all commits to this CTA's empty barriers have landed
+      mbar_wait(empty_bar(stage), phase ^ 1);
+      if (++stage == ST) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = p.idesc;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = pair; item < total; item += npairs) {
+        const int split = tn_decode(item, p.k_tiles, n_pairs, p.ntaps).split;
+        const int rb0 = split * p.rblocks_per_split;
+        const int iters = max(0, min(p.rblocks, rb0 + p.rblocks_per_split) - rb0);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = stage0 + stage * STAGE_BYTES, sb = sa + TC_STAGE_A;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_2cta<EB>(d_tmem, make_desc(sa + k * Gm::KMMA * 128, Gm::BOX_BYTES, EB == 2 ? 1024 : 512, EB == 2 ? 2 : 1),
+                            make_desc(sb + k * Gm::KMMA * 128, Gm::BOX_BYTES, EB == 2 ? 1024 : 512, EB == 2 ? 2 : 1), idesc,
+                            (it > 0 || k > 0) ? 1u : 0u);
+            umma_commit_2cta(empty_bar(stage), 3);
+            if (it == iters - 1) umma_commit_2cta(tfull_bar(acc), 3);
+          }
+          __syncwarp();
+          if (++stage == ST) { stage = 0; phase ^= 1; }
+        }
+        if (iters == 0) {
+          if (elect_one()) umma_commit_2cta(tfull_bar(acc), 3);
+          __syncwarp();
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = pair; item < total; item += npairs) {
+      const TnItem wi = tn_decode(item, p.k_tiles, n_pairs, p.ntaps);
+      const bool has_work = wi.split * p.rblocks_per_split < p.rblocks;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const int n = (wi.n_tile * 2 + (int)rank) * TC_BM + row;
+      float* orow = p.part + (((size_t)wi.split * p.ntaps + wi.tap) * p.N + n) * p.K;
+      const bool vec = (p.K & 3) == 0;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        float v[32];
+        tmem_ld32(t_addr + c * 32, v);
+        if (c == BN / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote_relaxed(tempty_leader0 + 8u * acc);
+        }
+        const int k0 = wi.k_tile * BN + c * 32;
+        if (n < p.N) {
+          if (!has_work) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          if (vec && k0 + 32 <= p.K) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + k0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (k0 + j < p.K) orow[k0 + j] = v[j];
+          }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // fp32 -> padded bf16 staging
 // ---------------------------------------------------------------------------------------------------
 // dst[r][c] (ld = Cp, bf16) = src[r][c] (ld = lds, fp32) for c < C, zero for C <= c < Cp; rows >= R_src are zero
@@ -770,6 +958,19 @@ static int tc2_launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtens
 static bool use_cta_pairs() {
   const char* e = getenv("AVC_GEMM_2CTA");   // read per call so one process can compare both kernels
   return e ? atoi(e) != 0 : true;
+}
+template <int EB>
+static int tc2_tn_launch(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int grid, cudaStream_t st) {
+  static bool attr_done = false;
+  constexpr int SMEM = 1024 + 6 * 32768 + 256;
+  auto kern = tc_gemm2_tn_kernel<EB>;
+  if (!attr_done) {
+    AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_done = true;
+  }
+  kern<<<grid, TC_THREADS, SMEM, st>>>(mA, mB, p);
+  AVC_LAUNCHED();
+  return AVC_OK;
 }
 template <int MODE>
 static int tc_dispatch(int eb, int bn, const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int grid, cudaStream_t st) {
@@ -1024,7 +1225,9 @@ int gemm_tn_taps_tc(const void* dYv, int y_fmt, int ldy, const void* Xv, int x_f
   if (ga) rc = make_map4_grouped(&mA, Yop, y_c, T, nB, y_ld, row, pl.rs, TC_BM / row, eb, eb == 4, fy);
   else rc = make_map3(&mA, Yop, y_c, T, nB, y_ld, (uint64_t)T * y_ld, row, pl.rs, eb, eb == 4, fy);
   if (rc) return rc;
-  if (gb) rc = make_map4_grouped(&mB, Xop, x_c, T, nB, x_ld, row, pl.rs, pl.bn / row, eb, eb == 4, fx);
+  // CTA pairs (256 dY channels x 256 X channels per pair tile): whole grouped boxes and an even number of dY tiles
+  const bool pairs = use_cta_pairs() && pl.bn == 256 && ga && gb && ((pl.Np / TC_BM) % 2 == 0);
+  if (gb) rc = make_map4_grouped(&mB, Xop, x_c, T, nB, x_ld, row, pl.rs, (pairs ? 128 : pl.bn) / row, eb, eb == 4, fx);
   else rc = make_map3(&mB, Xop, x_c, T, nB, x_ld, (uint64_t)T * x_ld, row, pl.rs, eb, eb == 4, fx);
   if (rc) return rc;
   TcParams p{};
@@ -1034,8 +1237,14 @@ int gemm_tn_taps_tc(const void* dYv, int y_fmt, int ldy, const void* Xv, int x_f
   p.grouped_a = ga; p.grouped_b = gb;
   p.idesc = eb == 2 ? make_idesc(TC_BM, pl.bn, 1, 1, ifmt_of(fy), ifmt_of(fx)) : make_idesc(TC_BM, pl.bn, 1, 1, 2);
   const int items = pl.tiles * pl.splits;
-  const int grid = std::min(items, num_sms());
-  rc = tc_dispatch<MODE_TN>(eb, pl.bn, mA, mB, p, grid, st);
+  if (pairs) {
+    p.idesc = eb == 2 ? make_idesc(256, 256, 1, 1, ifmt_of(fy), ifmt_of(fx)) : make_idesc(256, 256, 1, 1, 2);
+    const int grid2 = 2 * std::min(items / 2, num_sms() / 2);
+    rc = eb == 2 ? tc2_tn_launch<2>(mA, mB, p, grid2, st) : tc2_tn_launch<4>(mA, mB, p, grid2, st);
+  } else {
+    const int grid = std::min(items, num_sms());
+    rc = tc_dispatch<MODE_TN>(eb, pl.bn, mA, mB, p, grid, st);
+  }
   if (rc) return rc;
   return launch_wgrad_reduce(part, dW, N, K, ntaps, pl.splits, out_mode, accumulate, st);
 }

@@ -12,14 +12,15 @@ from autovc_b200._lib import FMT_FP16  # noqa: E402
 B, T = 256, 128
 M = B * T
 N, K = int(sys.argv[1]) if len(sys.argv) > 1 else 4096, int(sys.argv[2]) if len(sys.argv) > 2 else 64
+TAPS = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 A = torch.randn(M, K, device="cuda").half()
-W = (torch.randn(1, N, K, device="cuda") * 0.05).half()
+W = (torch.randn(TAPS, N, K, device="cuda") * 0.05).half()
 C = torch.empty(M, N, device="cuda")
 for _ in range(3):
-    ops.gemm_nt_taps_hw(A, FMT_FP16, K, W, FMT_FP16, K, None, C, N, B, T, N, K, 1, 0)
+    ops.gemm_nt_taps_hw(A, FMT_FP16, K, W, FMT_FP16, K, None, C, N, B, T, N, K, TAPS, -(TAPS // 2))
 trace = torch.zeros(1024, dtype=torch.int64, device="cuda")
 _lib.load().avc_debug_set_trace(ctypes.c_void_p(trace.data_ptr()))
-ops.gemm_nt_taps_hw(A, FMT_FP16, K, W, FMT_FP16, K, None, C, N, B, T, N, K, 1, 0)
+ops.gemm_nt_taps_hw(A, FMT_FP16, K, W, FMT_FP16, K, None, C, N, B, T, N, K, TAPS, -(TAPS // 2))
 torch.cuda.synchronize()
 _lib.load().avc_debug_set_trace(ctypes.c_void_p(0))
 full = trace.cpu()

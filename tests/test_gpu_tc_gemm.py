@@ -69,7 +69,8 @@ def test_nt_taps_tensor(nB, T, N, K, ntaps, prec):
 
 @pytest.mark.parametrize("nB,T,N,K,ntaps,shift0,mode", [(2, 128, 512, 336, 5, -2, 1), (3, 64, 64, 512, 1, 0, 2),
                                                         (2, 48, 130, 769, 5, -2, 1), (4, 128, 4096, 1024, 1, -1, 2),
-                                                        (4, 128, 2048, 512, 1, 1, 2), (3, 100, 80, 1024, 1, 0, 0)])
+                                                        (4, 128, 2048, 512, 1, 1, 2), (3, 100, 80, 1024, 1, 0, 0),
+                                                        (8, 128, 512, 512, 5, -2, 1), (5, 96, 256, 768, 3, -1, 0)])
 @pytest.mark.parametrize("prec", [1, 2])
 def test_tn_taps_tensor(nB, T, N, K, ntaps, shift0, mode, prec):
     dY = _rand(nB * T, N, seed=4)
