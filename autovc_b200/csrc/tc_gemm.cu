@@ -274,22 +274,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
         const int b = m_tile / p.t_tiles, t = (m_tile % p.t_tiles) * TC_BM + row;
         const bool row_ok = t < p.T;
+        const bool rows_partial = (m_tile % p.t_tiles) * TC_BM + TC_BM > p.T;   // tile-uniform
         float* crow = p.C + ((size_t)b * p.T + t) * p.ldc;
+        // chunks that lie entirely beyond column N are not even read (N = 64 or 80 in a 128-wide tile), and full chunks
+        // skip the per-element masks: a lone epilogue warp per scheduler is issue-bound (see tc_gemm2_nt_kernel)
+        const int nchunks = min(BN / 32, (p.N - n_tile * BN + 31) >> 5);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < nchunks; ++c) {
           float v[32];
           tmem_ld32(t_addr + c * 32, v);
-          if (c == BN / 32 - 1) {          // all TMEM reads of this accumulator are done
+          if (c == nchunks - 1) {          // all TMEM reads of this accumulator are done
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
           }
           const int n0 = n_tile * BN + c * 32;
+          if (n0 + 32 <= p.N) {
+            if (p.bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + j;
-            float x = v[j] + ((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f);
-            v[j] = (row_ok && n < p.N) ? x : 0.f;
+              for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + j);
+            }
+            if (rows_partial && p.stats != nullptr && !row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + j;
+              float x = v[j] + ((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f);
+              v[j] = (row_ok && n < p.N) ? x : 0.f;
+            }
           }
           if (row_ok) {
             if (n0 + 32 <= p.N && (p.ldc & 3) == 0) {
@@ -353,10 +368,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (lane == 0) mbar_arrive(tempty_bar(acc));
           }
           const int k0 = k_tile * BN + c * 32;
-          if (n < p.N) {
+          if (n < p.N && k0 < p.K) {
+            if (!has_work) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (k0 + j < p.K) orow[k0 + j] = has_work ? v[j] : 0.f;
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            if ((p.K & 3) == 0 && k0 + 32 <= p.K) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(orow + k0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (k0 + j < p.K) orow[k0 + j] = v[j];
+            }
           }
         }
       }
@@ -409,10 +434,11 @@ struct Tc2Cfg {
   static constexpr int BN = 256;                      // pair tile width
   static constexpr int STAGE_B = 128 * 128;           // this CTA's half of the W tile: 128 rows x 128 B
   static constexpr int STAGE_BYTES = TC_STAGE_A + STAGE_B;
-  static constexpr int STAGES = 5;
+  static constexpr int STAGES = 5;                    // 6 stages with one staging tile per warp measured no faster
   static constexpr int TMEM_COLS = 512;               // two 256-column fp32 accumulators
   static constexpr int STAT_BYTES = 4 * 2 * BN * 4;
-  static constexpr int EPI_BYTES = 4 * 2 * 4096;      // per epilogue warp: two 32-row x 32-column fp32 staging tiles
+  static constexpr int EPI_BUFS = 2;                  // staging tiles per epilogue warp
+  static constexpr int EPI_BYTES = 4 * EPI_BUFS * 4096;   // per epilogue warp: 32-row x 32-column fp32 staging tiles
   static constexpr int BIAS_BYTES = 4 * BN * 4;       // per epilogue warp: the tile's 256 bias values
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAT_BYTES + EPI_BYTES + BIAS_BYTES + 256;
 };
@@ -541,7 +567,7 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     // ===================== epilogue warps: this CTA's 128 rows x 256 columns =====================
     const int q = warp & 3;                  // TMEM lane quadrant = rows [32q, 32q + 32) of this CTA's half tile
     const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0);
-    const uint32_t epi_w = epi0 + (uint32_t)(warp - 2) * 8192u;   // this warp's two staging tiles
+    const uint32_t epi_w = epi0 + (uint32_t)(warp - 2) * (Cf::EPI_BUFS * 4096u);   // this warp's staging tile(s)
     int acc = 0;
     uint32_t acc_phase = 0;
     int iter = 0;
@@ -602,8 +628,8 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         if (p.tma_store) {
           // registers -> swizzled shared tile -> one TMA store (or reduce-add) of 32 rows x 128 B; rows >= T and columns
           // >= N are clipped by the TMA unit.  Thread = row: 16-byte chunk j of row r sits at chunk j ^ (r & 7).
-          const uint32_t buf = epi_w + (uint32_t)(c & 1) * 4096u;
-          if (lane == 0) bulk_wait_read<1>();            // the store issued two chunks ago has drained this tile
+          const uint32_t buf = epi_w + (uint32_t)(c & (Cf::EPI_BUFS - 1)) * 4096u;
+          if (lane == 0) bulk_wait_read<Cf::EPI_BUFS - 1>();   // the store that last used this tile has drained it
           __syncwarp();
           if (p.dbg < 2) {
 #pragma unroll
