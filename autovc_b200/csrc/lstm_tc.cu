@@ -41,9 +41,38 @@ struct LstmTcParams {
   void* h16;            // fwd: optional 16-bit copy of h_seq (nB,T,H) contiguous, format fmt16 (1 bf16 / 2 fp16)
   void* dP16;           // bwd: optional 16-bit copy of dP (nB,T,4H)
   int fmt16;
+  int wide;                // every row-per-thread tensor is 32-byte aligned (pointer and row stride): use 256-bit accesses
+  int out_tma;             // the saved tensors leave through shared staging tiles + TMA stores (maps in LtOutMaps)
   int exp_mode;            // experiment switch (AVC_LSTM_EXP): 0 none, 1 alternate two descriptors, 2 two half boxes
   unsigned long long* trace;  // optional per-step timestamps of CTA 0 (avc_debug_set_trace), else nullptr
 };
+
+// tensor maps of the tensors a recurrence saves / emits per step (TMA stores from a shared staging tile)
+struct alignas(64) LtOutMaps {
+  CUtensorMap gates;   // fwd: (G, T, nB) fp32, box (32, 1, 32), 128B swizzle     bwd: dP (same shape)
+  CUtensorMap c;       // fwd: c_seq (H, T, nB) fp32, box (U, 1, 32)
+  CUtensorMap h;       // fwd: h_seq (H, T, nB; row stride ldh) fp32, box (U, 1, 32)
+  CUtensorMap h16;     // fwd: h16 (H, T, nB) 16-bit, box (U, 1, 32)              bwd: dP16 (G, T, nB), box (64, 1, 32)
+};
+constexpr int LT_OUT_STAGE = 16384;      // 4 epilogue warps x 4 KB
+
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256).  The epilogues read and write row-per-thread tiles: every lane
+// touches its own row, so the load/store path is paid per request, and 32-byte requests (one full sector) halve them.
+__device__ __forceinline__ void ldg_nc_v8(const float* p, float* v) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+               "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void stg_v8f(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+               "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
 
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -93,6 +122,13 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define LT_TRACE(slot)                                                         \
   do {                                                                         \
     if (p.trace != nullptr && blockIdx.x == 0) p.trace[(size_t)s * 16 + (slot)] = gtime(); \
+  } while (0)
+// all-CTA stamps for steps 64..67 (skew analysis): p.trace[16*T + (cta*4 + (s-64))*2 + k], k = 0 barrier passed, 1 published;
+// the SM id of each CTA goes to p.trace[16*T + 8*gridDim.x + cta]
+#define LT_TRACE_ALL(k)                                                                        \
+  do {                                                                                         \
+    if (p.trace != nullptr && s >= 64 && s < 68)                                               \
+      p.trace[(size_t)16 * T + ((size_t)blockIdx.x * 4 + (s - 64)) * 2 + (k)] = gtime();       \
   } while (0)
 __device__ __forceinline__ uint4 ld_volatile_v4(const unsigned* p) {
   uint4 v;
@@ -150,7 +186,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <bool BWD, int BN, int CL>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX,
-               const __grid_constant__ CUtensorMap mapX2, const LstmTcParams p) {
+               const __grid_constant__ CUtensorMap mapX2, const __grid_constant__ LtOutMaps om, const LstmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -159,13 +195,15 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
   const uint32_t w_block = BN * 128;                       // bytes of one resident weight k-block
   const uint32_t w_base = base;
   const uint32_t ring = base + kblocks * w_block;          // multiples of 1024 (BN*128 with BN >= 16 and kblocks even)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + kblocks * w_block + p.stages * LT_STAGE);
+  const uint32_t out_stage = ring + p.stages * LT_STAGE;   // staging tiles of the saved tensors (when p.out_tma), 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + kblocks * w_block + p.stages * LT_STAGE + (p.out_tma ? LT_OUT_STAGE : 0));
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (8 + s); };
   const uint32_t w_bar = bar0 + 8u * 16, tfull = bar0 + 8u * 17, tempty = bar0 + 8u * 18;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
   volatile int* slot_kb = reinterpret_cast<volatile int*>(bars + 20);     // [8] k-block index held by each ring slot
+  const uint32_t go_bar = bar0 + 8u * 24;     // producer -> epilogue: "the loads of the next step are issued" (see the epilogue)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = blockIdx.x % p.NT, mt = blockIdx.x / p.NT;
@@ -182,6 +220,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
     mbar_init(w_bar, 1);
     mbar_init(tfull, 1);
     mbar_init(tempty, 4);
+    mbar_init(go_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
@@ -213,6 +252,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
                                       full_bar(0), empty_bar(0), [&](int st, int kb) {
                                         tma_load_3d(ring + st * LT_STAGE, &mapX, full_bar(st), kb * 64, row0, 0);
                                       });
+          mbar_arrive(go_bar);
         }
       }
     } else {
@@ -230,6 +270,12 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           while (ld_acquire(counter) < target) {
           }
           LT_TRACE(0);
+          LT_TRACE_ALL(0);
+          if (p.trace != nullptr && s == 64) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            p.trace[(size_t)16 * T + (size_t)8 * gridDim.x + blockIdx.x] = smid;
+          }
           if (p.exp_mode == 4) fence_proxy_async();   // writer-side proxy fence + release/acquire order the TMA reads
         }
         __syncwarp();
@@ -243,7 +289,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
               tma_load_3d_mc(ring + stage * LT_STAGE + crank * SLICE_ROWS * 128, &mapX, full_bar(stage), kb * 64,
                              row0 + crank * SLICE_ROWS, 0, cmask);
             if (kb == 0) LT_TRACE(1);
-            if (kb == kblocks - 1) LT_TRACE(2);
+            if (kb == kblocks - 1) {
+              LT_TRACE(2);
+              mbar_arrive(go_bar);          // every load of this step is in flight: the epilogue may use the LSU again
+            }
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -306,9 +355,14 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         const size_t rowi = (size_t)b * T + t;
         float pre[BN];
         if (live) {
+          if (p.wide) {
 #pragma unroll
-          for (int j = 0; j < BN; j += 4)
-            *reinterpret_cast<float4*>(&pre[j]) = __ldg(reinterpret_cast<const float4*>(p.P + rowi * G + n0 + j));
+            for (int j = 0; j < BN; j += 8) ldg_nc_v8(p.P + rowi * G + n0 + j, &pre[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN; j += 4)
+              *reinterpret_cast<float4*>(&pre[j]) = __ldg(reinterpret_cast<const float4*>(p.P + rowi * G + n0 + j));
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < BN; ++j) pre[j] = 0.f;
@@ -324,7 +378,11 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           for (int j = 0; j < BN; ++j) pre[j] += d[j];
         }
         tc_fence_before();
-        __nv_bfloat16 hb[U];
+        if (!BWD) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty);       // the accumulator is in registers: the next step's MMAs may overwrite it
+        }
+        alignas(32) __nv_bfloat16 hb[U];
         float hf[U];
 #pragma unroll
         for (int i = 0; i < U; ++i) {
@@ -341,9 +399,12 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         // The (much larger) fp32 tensors saved for BPTT are stored after the release, off the critical path.
         if (live) {
           __nv_bfloat16* xb = p.xbuf + ((size_t)(s & 1) * p.nBpad + b) * p.K + u0;
+          if (U == 16) {                                   // 32 bytes: one request
+            stg_v8(xb, reinterpret_cast<const uint32_t*>(hb));
+          } else {
 #pragma unroll
-          for (int i = 0; i < U; i += 4)
-            *reinterpret_cast<uint2*>(xb + i) = *reinterpret_cast<const uint2*>(&hb[i]);
+            for (int i = 0; i < U; i += 8) *reinterpret_cast<uint4*>(xb + i) = *reinterpret_cast<const uint4*>(&hb[i]);
+          }
         }
         if (threadIdx.x == 64) LT_TRACE(7);
         asm volatile("bar.sync 1, 128;" ::: "memory");     // all 128 rows' slices are written (CTA scope)
@@ -351,9 +412,79 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           fence_proxy_async();
           red_release_add(kflags ? counter + (u0 >> 6) : counter, 1u);   // red.release.gpu is the cumulative gpu-scope release
           LT_TRACE(8);
+          LT_TRACE_ALL(1);
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");     // bulk fp32 stores below must not queue ahead of that fence
-        if (live) {
+        // The tensors saved for BPTT (48 KB per CTA and step, row-per-thread stores) occupy the SM's load/store path for
+        // ~2-4 us.  Issued right after the publish they sit in front of the producer's ld.acquire polls: the all-CTA trace
+        // (scripts/bench_lstm.py) showed the LAST publisher of a step noticing the completed barrier up to 4.6 us late, every
+        // step, which set the period.  They are therefore held back until the producer has seen the barrier and issued the
+        // next step's loads, and then overlap with the streaming.
+        if ((p.exp_mode & 16) && s + 1 < T) mbar_wait(go_bar, s & 1);
+        if (p.out_tma) {
+          // Saved tensors: registers -> this warp's 4 KB staging tile -> TMA store, in four rounds.  As plain row-per-thread
+          // stores (3300 16-byte requests per CTA and step) they held the SM's load/store path for ~4 us right when the
+          // producer polls for the next step: the LAST publisher of every step noticed the completed barrier up to 4.6 us
+          // late (all-CTA trace, scripts/bench_lstm.py) and 12.3 us steps ran in 9.2 us without them.  Rows of padded
+          // utterances (b >= nB) are clipped by the TMA unit.
+          const uint32_t buf = out_stage + (uint32_t)(warp - 2) * 4096u;
+          const int brow = mt * 128 + q * 32;
+#pragma unroll
+          for (int half = 0; half < BN / 32; ++half) {                 // gates: 32 columns (one 128-byte swizzle row) per round
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(buf + lane * 128 + ((j ^ (lane & 7)) << 4), pre[half * 32 + 4 * j], pre[half * 32 + 4 * j + 1],
+                           pre[half * 32 + 4 * j + 2], pre[half * 32 + 4 * j + 3]);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&om.gates, buf, n0 + half * 32, t, brow);
+              bulk_commit();
+            }
+          }
+          if (lane == 0) bulk_wait_read<0>();                            // c_t and h_t: two [32][U] fp32 tiles
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < U; i += 4) {
+            st_shared_v4(buf + lane * (U * 4) + i * 4, c[i], c[i + 1], c[i + 2], c[i + 3]);
+            st_shared_v4(buf + 2048 + lane * (U * 4) + i * 4, hf[i], hf[i + 1], hf[i + 2], hf[i + 3]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&om.c, buf, u0, t, brow);
+            tma_store_3d(&om.h, buf + 2048, u0, t, brow);
+            bulk_commit();
+          }
+          if (p.h16 != nullptr) {                                        // 16-bit copy of h_t: one [32][U] tile
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < U; i += 8) {
+              uint32_t w[4];
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                if (p.fmt16 == 2) {
+                  const __half2 v2 = __floats2half2_rn(hf[i + 2 * k2], hf[i + 2 * k2 + 1]);
+                  w[k2] = *reinterpret_cast<const uint32_t*>(&v2);
+                } else {
+                  w[k2] = (uint32_t)*reinterpret_cast<const uint16_t*>(&hb[i + 2 * k2]) |
+                          ((uint32_t)*reinterpret_cast<const uint16_t*>(&hb[i + 2 * k2 + 1]) << 16);
+                }
+              }
+              st_shared_v4(buf + lane * (U * 2) + i * 2, __uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]),
+                           __uint_as_float(w[3]));
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&om.h16, buf, u0, t, brow);
+              bulk_commit();
+            }
+          }
+        } else if (live && !(p.exp_mode & 8)) {
 #pragma unroll
           for (int j = 0; j < BN; j += 4)
             *reinterpret_cast<float4*>(p.gates + rowi * G + n0 + j) = *reinterpret_cast<const float4*>(&pre[j]);
@@ -379,8 +510,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             }
           }
         }
-        if (lane == 0) mbar_arrive(tempty);
       }
+      if (p.out_tma && lane == 0) bulk_wait_all();      // the staged tiles are read out before the CTA's smem goes away
     } else {
       constexpr int U = BN;                      // 16 hidden units
       const int u0 = nt * U;
@@ -647,29 +778,51 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
     constexpr int U = 16;
     const int u0 = ut * KS_UNITS + (int)r * U;              // the 16 units this CTA finalises
     const uint32_t red_s = smem_u32(red);
-    float dc_rec[U];
+    float dc_rec[U], c_carry[U];
 #pragma unroll
-    for (int i = 0; i < U; ++i) dc_rec[i] = 0.f;
+    for (int i = 0; i < U; ++i) dc_rec[i] = c_carry[i] = 0.f;
     for (int s = 0; s < T; ++s) {
       const int t = p.reverse ? s : T - 1 - s;
       const bool has_prev = s < T - 1;
       const int t_prev = p.reverse ? t + 1 : t - 1;
       const size_t rowi = (size_t)b * T + t;
       float dh[U], ct[U], cp[U], g4[4 * U];
-      if (live) {
+      if (live && !(p.exp_mode & 32)) {
+        // c_t of this step is c_{t_prev} of the previous one (kept in registers): one c_seq read per step
+        if (s == 0) {
 #pragma unroll
-        for (int i = 0; i < U; i += 4) {
-          *reinterpret_cast<float4*>(&dh[i]) = __ldg(reinterpret_cast<const float4*>(p.dH + rowi * p.lddh + u0 + i));
-          *reinterpret_cast<float4*>(&ct[i]) = __ldg(reinterpret_cast<const float4*>(p.c_seq + rowi * H + u0 + i));
-          if (has_prev)
-            *reinterpret_cast<float4*>(&cp[i]) =
-                __ldg(reinterpret_cast<const float4*>(p.c_seq + ((size_t)b * T + t_prev) * H + u0 + i));
-          else
-            cp[i] = cp[i + 1] = cp[i + 2] = cp[i + 3] = 0.f;
+          for (int i = 0; i < U; i += 4)
+            *reinterpret_cast<float4*>(&ct[i]) = __ldg(reinterpret_cast<const float4*>(p.c_seq + rowi * H + u0 + i));
+        } else {
+#pragma unroll
+          for (int i = 0; i < U; ++i) ct[i] = c_carry[i];
+        }
+        if (p.wide) {
+#pragma unroll
+          for (int i = 0; i < U; i += 8) {
+            ldg_nc_v8(p.dH + rowi * p.lddh + u0 + i, &dh[i]);
+            if (has_prev) ldg_nc_v8(p.c_seq + ((size_t)b * T + t_prev) * H + u0 + i, &cp[i]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4 * U; j += 8) ldg_nc_v8(p.gates + rowi * G + 4 * u0 + j, &g4[j]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < U; i += 4) {
+            *reinterpret_cast<float4*>(&dh[i]) = __ldg(reinterpret_cast<const float4*>(p.dH + rowi * p.lddh + u0 + i));
+            if (has_prev)
+              *reinterpret_cast<float4*>(&cp[i]) =
+                  __ldg(reinterpret_cast<const float4*>(p.c_seq + ((size_t)b * T + t_prev) * H + u0 + i));
+          }
+#pragma unroll
+          for (int j = 0; j < 4 * U; j += 4)
+            *reinterpret_cast<float4*>(&g4[j]) = __ldg(reinterpret_cast<const float4*>(p.gates + rowi * G + 4 * u0 + j));
+        }
+        if (!has_prev) {
+#pragma unroll
+          for (int i = 0; i < U; ++i) cp[i] = 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 4 * U; j += 4)
-          *reinterpret_cast<float4*>(&g4[j]) = __ldg(reinterpret_cast<const float4*>(p.gates + rowi * G + 4 * u0 + j));
+        for (int i = 0; i < U; ++i) c_carry[i] = cp[i];
       } else {
 #pragma unroll
         for (int i = 0; i < U; ++i) dh[i] = ct[i] = cp[i] = 0.f;
@@ -718,7 +871,7 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
       } else {
         tc_fence_before();
       }
-      __nv_bfloat16 gb[4 * U];
+      alignas(32) __nv_bfloat16 gb[4 * U];
 #pragma unroll
       for (int i = 0; i < U; ++i) {
         const float gi = g4[4 * i], gf = g4[4 * i + 1], gg = g4[4 * i + 2], go = g4[4 * i + 3];
@@ -736,8 +889,7 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
       if (live) {
         __nv_bfloat16* xb = p.xbuf + ((size_t)(s & 1) * p.nBpad + b) * (size_t)G + 4 * u0;
 #pragma unroll
-        for (int j = 0; j < 4 * U; j += 8)
-          *reinterpret_cast<uint4*>(xb + j) = *reinterpret_cast<const uint4*>(&gb[j]);
+        for (int j = 0; j < 4 * U; j += 16) stg_v8(xb + j, reinterpret_cast<const uint32_t*>(&gb[j]));
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 64) {
@@ -745,14 +897,24 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
         red_release_add(kflags ? counter + (u0 >> 4) : counter, 1u);   // dG columns 4*u0 .. 4*u0+63 = k-block u0/16
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (live) {
+      if (live && !(p.exp_mode & 8)) {
+        if (p.wide) {
 #pragma unroll
-        for (int j = 0; j < 4 * U; j += 4)
-          *reinterpret_cast<float4*>(p.dP + rowi * G + 4 * u0 + j) = *reinterpret_cast<const float4*>(&g4[j]);
+          for (int j = 0; j < 4 * U; j += 8) stg_v8f(p.dP + rowi * G + 4 * u0 + j, &g4[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4 * U; j += 4)
+            *reinterpret_cast<float4*>(p.dP + rowi * G + 4 * u0 + j) = *reinterpret_cast<const float4*>(&g4[j]);
+        }
         if (p.dP16 != nullptr) {
           __nv_bfloat16* d16 = reinterpret_cast<__nv_bfloat16*>(p.dP16) + rowi * G + 4 * u0;
+          if (p.wide) {
 #pragma unroll
-          for (int j = 0; j < 4 * U; j += 8) *reinterpret_cast<uint4*>(d16 + j) = *reinterpret_cast<const uint4*>(&gb[j]);
+            for (int j = 0; j < 4 * U; j += 16) stg_v8(d16 + j, reinterpret_cast<const uint32_t*>(&gb[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4 * U; j += 8) *reinterpret_cast<uint4*>(d16 + j) = *reinterpret_cast<const uint4*>(&gb[j]);
+          }
         }
       }
       if (lane == 0) mbar_arrive(tempty);
@@ -786,7 +948,7 @@ static int fwd_bn(int H) { return H >= 1024 ? 64 : 32; }
 
 struct LtPlan {
   int BN, NT, MTmax, K, stages;
-  size_t smem, w_bytes, off_w, off_x, off_cnt, total;
+  size_t smem, w_bytes, out_stage, off_w, off_x, off_cnt, total;
   int chunk;   // utterances per launch
 };
 static LtPlan lt_plan(int nB, int H, bool bwd) {
@@ -796,10 +958,11 @@ static LtPlan lt_plan(int nB, int H, bool bwd) {
   pl.NT = bwd ? H / 16 : 4 * H / pl.BN;
   pl.MTmax = std::max(1, num_sms() / pl.NT);
   pl.w_bytes = (size_t)pl.BN * pl.K * 2;
-  const size_t budget = 225 * 1024;
-  int stages = (int)((budget - 1024 - 256 - pl.w_bytes) / LT_STAGE);
+  pl.out_stage = bwd ? 0 : LT_OUT_STAGE;          // forward: staging tiles for the TMA stores of the saved tensors
+  const size_t budget = 227 * 1024;
+  int stages = (int)((budget - 1024 - 256 - pl.w_bytes - pl.out_stage) / LT_STAGE);
   pl.stages = std::min(8, std::max(2, stages));
-  pl.smem = 1024 + pl.w_bytes + (size_t)pl.stages * LT_STAGE + 256;
+  pl.smem = 1024 + pl.w_bytes + (size_t)pl.stages * LT_STAGE + pl.out_stage + 256;
   pl.chunk = std::min(nB, pl.MTmax * 128);
   const int MT = ceil_div(pl.chunk, 128);
   pl.off_w = 0;
@@ -852,7 +1015,8 @@ static int lt_launch_ks(const CUtensorMap& mW, const CUtensorMap& mX, LstmTcPara
 }
 
 template <bool BWD, int BN, int CL>
-static int lt_launch(const CUtensorMap& mW, const CUtensorMap& mX, const CUtensorMap& mX2, const LstmTcParams& p, const LtPlan& pl, cudaStream_t st) {
+static int lt_launch(const CUtensorMap& mW, const CUtensorMap& mX, const CUtensorMap& mX2, const LtOutMaps& om, const LstmTcParams& p,
+                     const LtPlan& pl, cudaStream_t st) {
   auto kern = lstm_tc_kernel<BWD, BN, CL>;
   AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   cudaLaunchConfig_t cfg{};
@@ -884,17 +1048,17 @@ static int lt_launch(const CUtensorMap& mW, const CUtensorMap& mX, const CUtenso
     cfg.attrs = attrs;
     cfg.numAttrs = na;
   }
-  AVC_CUDA(cudaLaunchKernelEx(&cfg, kern, mW, mX, mX2, p));
+  AVC_CUDA(cudaLaunchKernelEx(&cfg, kern, mW, mX, mX2, om, p));
   g_launches.fetch_add(1);
   return AVC_OK;
 }
 
 template <bool BWD, int BN>
-static int lt_launch_cl(int cl, const CUtensorMap& mW, const CUtensorMap& mX, const CUtensorMap& mX2, const LstmTcParams& p, const LtPlan& pl,
-                        cudaStream_t st) {
-  if (cl == 8) return lt_launch<BWD, BN, 8>(mW, mX, mX2, p, pl, st);
-  if (cl == 4) return lt_launch<BWD, BN, 4>(mW, mX, mX2, p, pl, st);
-  return lt_launch<BWD, BN, 1>(mW, mX, mX2, p, pl, st);
+static int lt_launch_cl(int cl, const CUtensorMap& mW, const CUtensorMap& mX, const CUtensorMap& mX2, const LtOutMaps& om,
+                        const LstmTcParams& p, const LtPlan& pl, cudaStream_t st) {
+  if (cl == 8) return lt_launch<BWD, BN, 8>(mW, mX, mX2, om, p, pl, st);
+  if (cl == 4) return lt_launch<BWD, BN, 4>(mW, mX, mX2, om, p, pl, st);
+  return lt_launch<BWD, BN, 1>(mW, mX, mX2, om, p, pl, st);
 }
 
 static int lt_cluster_size(int NT) {
@@ -972,6 +1136,10 @@ int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh,
     p.trace = (ch == 0) ? g_trace : nullptr;
     p.exp_mode = exp_mode;
     p.fmt16 = fmt16;
+    {
+      auto al32 = [](const void* q) { return ((uintptr_t)q & 31) == 0; };
+      p.wide = al32(p.P) && al32(p.gates) && al32(p.c_seq) && al32(p.dH) && al32(p.dP) && (lddh % 8 == 0) && (H % 8 == 0);
+    }
     p.h16 = (!bwd && aux16) ? (void*)((uint16_t*)aux16 + (size_t)b0 * T * H) : nullptr;
     p.dP16 = (bwd && aux16) ? (void*)((uint16_t*)aux16 + (size_t)b0 * T * G) : nullptr;
     if (bwd && bwd_ksplit_enabled(H)) {
@@ -989,10 +1157,25 @@ int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh,
     if (rc) return rc;
     rc = make_map3(&mX2, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, exp_mode == 2 ? 64 : 128 / cl);
     if (rc) return rc;
+    // forward: the saved tensors leave through TMA stores (needs 16-byte aligned tensors; ldh % 4 == 0 is an API precondition)
+    LtOutMaps om{};
+    om.gates = om.c = om.h = om.h16 = mW;
+    static const bool out_tma_env = getenv("AVC_LSTM_OUT_TMA") ? atoi(getenv("AVC_LSTM_OUT_TMA")) != 0 : true;
+    p.out_tma = 0;
+    if (!bwd && out_tma_env && pl.out_stage > 0 && (((uintptr_t)p.gates | (uintptr_t)p.c_seq | (uintptr_t)p.h_seq | (uintptr_t)p.h16) & 15) == 0) {
+      const int U = pl.BN / 4;
+      const uint64_t Tn = (uint64_t)T;
+      rc = make_map3_store(&om.gates, p.gates, 4, G, Tn, nb, G, Tn * G, 32, 1, 32, true);
+      if (!rc) rc = make_map3_store(&om.c, p.c_seq, 4, H, Tn, nb, H, Tn * H, U, 1, 32, false);
+      if (!rc) rc = make_map3_store(&om.h, p.h_seq, 4, H, Tn, nb, ldh, Tn * ldh, U, 1, 32, false);
+      if (!rc && p.h16) rc = make_map3_store(&om.h16, p.h16, 2, H, Tn, nb, H, Tn * H, U, 1, 32, false);
+      if (rc) return rc;
+      p.out_tma = 1;
+    }
     for (;;) {
-      if (bwd) rc = lt_launch_cl<true, 16>(cl, mW, mX, mX2, p, pl, st);
-      else if (pl.BN == 64) rc = lt_launch_cl<false, 64>(cl, mW, mX, mX2, p, pl, st);
-      else rc = lt_launch_cl<false, 32>(cl, mW, mX, mX2, p, pl, st);
+      if (bwd) rc = lt_launch_cl<true, 16>(cl, mW, mX, mX2, om, p, pl, st);
+      else if (pl.BN == 64) rc = lt_launch_cl<false, 64>(cl, mW, mX, mX2, om, p, pl, st);
+      else rc = lt_launch_cl<false, 32>(cl, mW, mX, mX2, om, p, pl, st);
       if (rc != AVC_ERR_UNSUPPORTED || cl == 1) break;
       cl = cl == 8 ? 4 : 1;                             // clusters do not fit: retry with a smaller cluster
       rc = make_map3(&mX, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, 128 / cl);

@@ -302,6 +302,31 @@ static inline int make_map3_out_f32(CUtensorMap* m, void* ptr, uint64_t d0, uint
   return AVC_OK;
 }
 
+// 3-D map of an OUTPUT (d2, d1, d0) array for TMA stores with an arbitrary element size / box and optional 128B swizzle
+// (the inner box, box0 * elem_bytes, must be a multiple of 16 bytes; 128 bytes when swizzled)
+static inline int make_map3_store(CUtensorMap* m, void* ptr, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                                  uint64_t stride1_elems, uint64_t stride2_elems, uint32_t box0, uint32_t box1, uint32_t box2,
+                                  bool swizzle128) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return AVC_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_elems * elem_bytes, stride2_elems * elem_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, ptr, dims, strides, box,
+                   es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(store) failed with CUresult %d (dims %llu,%llu,%llu box %u,%u,%u)", (int)r,
+              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, box0, box1, box2);
+    return AVC_ERR_CUDA;
+  }
+  return AVC_OK;
+}
+
 // 4-D map over a channels-last (nB, T, C) array with the channel axis split into groups of `row` elements (one 128-byte
 // swizzle row each): dims (row, T, C/row, nB).  A box (row, frames, ngroups, 1) then lands in shared memory as `ngroups`
 // consecutive [frames][row] blocks -- the MN-major operand tile of the weight-gradient GEMM in ONE TMA instruction

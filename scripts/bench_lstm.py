@@ -55,7 +55,7 @@ nf = _lib.query("avc_lstm_fwd_workspace_bytes", B, T, H, prec); wf = _ws(nf, dev
 nb = _lib.query("avc_lstm_bwd_workspace_bytes", B, T, H, prec); wb = _ws(nb, dev)
 names = ["barrier", "tma0", "tmaN", "land0", "landN", "mma_issued", "epi_wake", "math_done", "published"]
 for which in ("fwd", "bwd"):
-    trace = torch.zeros(16 * T, dtype=torch.int64, device=dev)
+    trace = torch.zeros(16 * T + 9 * 1024, dtype=torch.int64, device=dev)
     _lib.load().avc_debug_set_trace(ctypes.c_void_p(trace.data_ptr()))
     if which == "fwd":
         _lib.call("avc_lstm_seq_fwd", _p(P), _p(W), _p(h), H, _p(gates), _p(c), B, T, H, 0, prec, _p(wf), nf, _stream())
@@ -63,7 +63,8 @@ for which in ("fwd", "bwd"):
         _lib.call("avc_lstm_seq_bwd", _p(dH), H, _p(W), _p(WT), _p(gates), _p(c), _p(dP), B, T, H, 0, prec, _p(wb), nb, _stream())
     torch.cuda.synchronize()
     _lib.load().avc_debug_set_trace(ctypes.c_void_p(0))
-    tr = trace.cpu().view(T, 16)[:, :9].double()
+    full = trace.cpu()
+    tr = full[:16 * T].view(T, 16)[:, :9].double()
     # steps 20..100: offsets of each event relative to the previous step's 'published'
     rows = []
     for s in range(20, 100):
@@ -72,3 +73,22 @@ for which in ("fwd", "bwd"):
     import numpy as np
     med = np.median(np.array(rows), axis=0)
     print(which, "median us after previous publish:", {n: round(float(v), 2) for n, v in zip(names, med)}, flush=True)
+    if which == "fwd":
+        ncta = 128
+        allc = full[16 * T:16 * T + ncta * 8].view(ncta, 4, 2).double()
+        smid = full[16 * T + 8 * ncta:16 * T + 9 * ncta]
+        for tile in range(2):
+            sl = slice(tile * 64, tile * 64 + 64)
+            for st in range(1, 4):
+                pub_prev, bar, pub = allc[sl, st - 1, 1], allc[sl, st, 0], allc[sl, st, 1]
+                t0, t1 = pub_prev.min(), pub_prev.max()
+                print(f"tile {tile} step {64 + st}: publish spread {float((t1 - t0) / 1e3):.2f} us (median {float((pub_prev.median() - t0) / 1e3):.2f}) | "
+                      f"barrier pass after LAST publish min/med/max {float((bar.min() - t1) / 1e3):.2f}/{float((bar.median() - t1) / 1e3):.2f}/"
+                      f"{float((bar.max() - t1) / 1e3):.2f} | next publish after barrier pass min/med/max "
+                      f"{float((pub - bar).min() / 1e3):.2f}/{float((pub - bar).median() / 1e3):.2f}/{float((pub - bar).max() / 1e3):.2f}")
+            lat = torch.stack([(allc[sl, st, 0] - allc[sl, st - 1, 1].max()) / 1e3 for st in range(1, 4)], 1)   # (64, 3)
+            o2 = torch.argsort(lat.mean(1))
+            print("   detection latency by cta (cta, smid, us x3):", [(int(i) + tile * 64, int(smid[int(i) + tile * 64]), [round(float(v), 1) for v in lat[i]]) for i in o2[::5]])
+            order = torch.argsort(allc[sl, 1, 1])
+            pp = allc[sl, 1, 1]
+            print("   publish order (cta, smid, us):", [(int(i) + tile * 64, int(smid[int(i) + tile * 64]), round(float((pp[i] - pp.min()) / 1e3), 2)) for i in order[::6]])
