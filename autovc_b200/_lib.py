@@ -41,6 +41,7 @@ SIGNATURES = {
     "avc_bn_act_bwd_reduce_y": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, P]),
     "avc_bn_act_bwd_apply_y": (c_int, [P, P, P, P, P, P, P, P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, P]),
     "avc_colsum": (c_int, [P, c_int, c_int, c_int, P, P, c_int, c_int, P, c_size_t, P]),
+    "avc_colsum16": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, c_size_t, P]),
     "avc_lstm_seq_fwd": (c_int, [P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
     "avc_lstm_fwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "avc_lstm_seq_bwd": (c_int, [P, c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),

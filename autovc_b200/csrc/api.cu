@@ -201,7 +201,7 @@ extern "C" int avc_lstm_seq_fwd_h(const float* P, const void* Whh_p, int w_fmt, 
 extern "C" int avc_lstm_seq_bwd_h(const float* dH, int lddh, const void* Whh_pT, int w_fmt, const float* gates, const float* c_seq,
                                   float* dP, void* dP16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes,
                                   void* stream) {
-  AVC_REQUIRE(dH && Whh_pT && gates && c_seq && dP && dP16, "avc_lstm_seq_bwd_h: null pointer");
+  AVC_REQUIRE(dH && Whh_pT && gates && c_seq && dP16, "avc_lstm_seq_bwd_h: null pointer");   // dP (fp32) is optional
   AVC_REQUIRE(nB > 0 && T > 0 && lstm_tc_supported(H) && lddh >= H && lddh % 4 == 0, "avc_lstm_seq_bwd_h: unsupported shape");
   AVC_REQUIRE(w_fmt == 0 || w_fmt == 1, "avc_lstm_seq_bwd_h: W_hh^T must be fp32 (0) or bf16 (1)");
   return lstm_seq_tc(true, Whh_pT, nullptr, nullptr, 0, const_cast<float*>(gates), const_cast<float*>(c_seq), dH, lddh, dP, nB, T, H,

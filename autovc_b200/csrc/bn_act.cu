@@ -439,6 +439,48 @@ col_sums_cols_kernel(const float4* __restrict__ x, int ldx4, int M, int C, int r
   }
 }
 
+// column sums of a 16-bit (bf16 / fp16) matrix, row stride ldx4 groups of four elements
+__global__ void __launch_bounds__(256)
+col_sums16_cols_kernel(const uint2* __restrict__ x, int ldx4, int M, int C, int rows_per_block, int fmt, double* __restrict__ out) {
+  __shared__ float sa[8][128 + 4];
+  const int cq = blockIdx.x * 32 + threadIdx.x;
+  const int c = cq * 4;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    for (int r = r0 + threadIdx.y; r < r1; r += 8 * BC_UNROLL) {
+      uint2 v[BC_UNROLL];
+#pragma unroll
+      for (int u = 0; u < BC_UNROLL; ++u) v[u] = (r + 8 * u < r1) ? x[(size_t)(r + 8 * u) * ldx4 + cq] : make_uint2(0u, 0u);
+#pragma unroll
+      for (int u = 0; u < BC_UNROLL; ++u) {
+        float2 lo, hi;
+        if (fmt == 2) {
+          lo = __half22float2(*reinterpret_cast<const __half2*>(&v[u].x));
+          hi = __half22float2(*reinterpret_cast<const __half2*>(&v[u].y));
+        } else {
+          lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[u].x));
+          hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v[u].y));
+        }
+        a[0] += lo.x; a[1] += lo.y; a[2] += hi.x; a[3] += hi.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sa[threadIdx.y][threadIdx.x * 4 + j] = a[j];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 128) {
+    const int cc = blockIdx.x * 128 + t;
+    if (cc < C) {
+      double da = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) da += (double)sa[i][t];
+      atomicAdd(out + cc, da);
+    }
+  }
+}
+
 // grid for the column-fixed kernels: ceil(C/128) column blocks x enough row blocks for ~6 blocks per SM
 static void cols_grid(int M, int C, dim3& grid, int& rows_per_block) {
   const int cb = ceil_div(C, 128);
@@ -678,6 +720,27 @@ extern "C" int avc_colsum(const float* x, int ldx, int M, int C, float* out, flo
   AVC_CUDA(cudaMemsetAsync(workspace, 0, 2 * sizeof(double) * (size_t)C, st));
   const int rc = launch_col_sums(x, ldx, M, C, (double*)workspace, false, st);
   if (rc) return rc;
+  colsum_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const double*)workspace, out, out2, C, out_mode, accumulate);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_colsum16(const void* x16, int fmt, int ldx, int M, int C, float* out, float* out2, int out_mode, int accumulate,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  AVC_REQUIRE(x16 && out && M > 0 && C > 0 && ldx >= C && (fmt == 1 || fmt == 2), "avc_colsum16: bad arguments");
+  AVC_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ((uintptr_t)x16 & 7) == 0, "avc_colsum16: needs C, ldx multiples of 4 and an 8-byte aligned input");
+  AVC_REQUIRE(out_mode == 0 || out_mode == 2, "avc_colsum16: bad out_mode");
+  if (!workspace || workspace_bytes < 2 * sizeof(double) * (size_t)C) {
+    set_error("avc_colsum16: workspace too small");
+    return AVC_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  AVC_CUDA(cudaMemsetAsync(workspace, 0, 2 * sizeof(double) * (size_t)C, st));
+  dim3 grid;
+  int rpb;
+  cols_grid(M, C, grid, rpb);
+  col_sums16_cols_kernel<<<grid, dim3(32, 8), 0, st>>>((const uint2*)x16, ldx / 4, M, C, rpb, fmt, (double*)workspace);
+  AVC_LAUNCHED();
   colsum_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const double*)workspace, out, out2, C, out_mode, accumulate);
   AVC_LAUNCHED();
   return AVC_OK;

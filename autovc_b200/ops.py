@@ -68,6 +68,11 @@ def colsum(x, ldx, M, C, out, out2=None, out_mode=0, accumulate=False):
     call("avc_colsum", _p(x), ldx, M, C, _p(out), _p(out2), out_mode, int(accumulate), _p(ws), ws.numel() * 8, _stream())
 
 
+def colsum16(x16, fmt, ldx, M, C, out, out2=None, out_mode=0, accumulate=False):
+    ws = torch.empty(2 * C, dtype=torch.float64, device=x16.device)
+    call("avc_colsum16", _p(x16), fmt, ldx, M, C, _p(out), _p(out2), out_mode, int(accumulate), _p(ws), ws.numel() * 8, _stream())
+
+
 class PackCache:
     """Packed copies of the weights so the two encoder passes of one step pack once.
 
@@ -650,11 +655,11 @@ class LstmLayerH(torch.autograd.Function):
         B, T, I = x.shape
         H = w_hh.shape[1]
         G = 4 * H
-        dP = torch.empty(B, T, G, device=dout.device, dtype=torch.float32)
+        # the gate gradient is only ever a GEMM operand / reduced over rows: emit it as bf16 only (no fp32 dP tensor)
         dP16 = torch.empty(B, T, G, device=dout.device, dtype=torch.bfloat16)
         nbytes = query("avc_lstm_bwd_workspace_bytes", B, T, H, PREC_BF16)
         ws = _ws(nbytes, dout.device)
-        call("avc_lstm_seq_bwd_h", _p(dout), H, _p(wh_pT), FMT_BF16, _p(gates), _p(c_seq), _p(dP), _p(dP16), B, T, H, 0, _p(ws),
+        call("avc_lstm_seq_bwd_h", _p(dout), H, _p(wh_pT), FMT_BF16, _p(gates), _p(c_seq), _NULL, _p(dP16), B, T, H, 0, _p(ws),
              nbytes, _stream())
         dw_ih = torch.empty_like(w_ih)
         X, x_fmt = _operand(x, None, I, FMT_BF16)
@@ -663,7 +668,7 @@ class LstmLayerH(torch.autograd.Function):
         gemm_tn_taps_h(dP16, FMT_BF16, G, cast16(out, FMT_BF16), FMT_BF16, H, dw_hh, B, T, G, H, 1, -1, out_mode=2)
         db_ih = torch.empty_like(b_ih)
         db_hh = torch.empty_like(b_ih)
-        colsum(dP, G, B * T, G, db_ih, db_hh, out_mode=2)
+        colsum16(dP16, FMT_BF16, G, B * T, G, db_ih, db_hh, out_mode=2)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, T, I, device=dout.device, dtype=torch.float32)

@@ -139,6 +139,11 @@ int avc_bn_act_bwd_apply_y(const float* dz, const float* z, const float* y, cons
 int avc_colsum(const float* x, int ldx, int M, int C, float* out, float* out2, int out_mode, int accumulate,
                void* workspace, size_t workspace_bytes, void* stream);
 
+/* avc_colsum over a 16-bit (AVC_FMT_BF16 / AVC_FMT_FP16) matrix: C, ldx multiples of 4 (half mode: LSTM bias gradients
+ * from the bf16 copy of dP, the same operand the weight-gradient GEMMs read). */
+int avc_colsum16(const void* x16, int fmt, int ldx, int M, int C, float* out, float* out2, int out_mode, int accumulate,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * LSTM recurrences, nn.LSTM at model_vc_mel.py:61/:73 (encoder BiLSTM), :90/:111 (lstm1),
  * :104/:118 (lstm2).  P = x W_ih^T + b_ih + b_hh is computed by avc_gemm_nt_taps with the
@@ -198,6 +203,7 @@ int avc_bn_act_bwd_apply_h(const float* dz, const float* z, const float* y, cons
  *        AVC_FMT_BF16 = the bf16 packings of avc_pack_lstm_weight_h (ld = H resp. 4H), read in place. */
 int avc_lstm_seq_fwd_h(const float* P, const void* Whh_p, int w_fmt, float* h_seq, int ldh, float* gates, float* c_seq, void* h16,
                        int fmt16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes, void* stream);
+/* (dP, the fp32 gate-gradient tensor, may be NULL: only dP16 is then written) */
 int avc_lstm_seq_bwd_h(const float* dH, int lddh, const void* Whh_pT, int w_fmt, const float* gates, const float* c_seq, float* dP,
                        void* dP16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes, void* stream);
 /* Weight packers that write the 16-bit (or fp32: fmt 0) layouts the tensor-core GEMMs read IN PLACE, with a leading

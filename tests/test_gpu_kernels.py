@@ -185,3 +185,19 @@ def test_bn_backward_recompute_matches_z_read(M, C, act):
     if C % 4 != 0:
         with pytest.raises(_lib.AvcError):
             _lib.call("avc_bn_act_bwd_reduce_y", _p(dz), _NULL, _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(s_new), M, C, act, _stream())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,C,dt,fmt", [(4096, 4096, torch.bfloat16, 1), (1000, 64, torch.float16, 2), (77, 516, torch.bfloat16, 1)])
+def test_colsum16(M, C, dt, fmt):
+    """avc_colsum16: column sums of a 16-bit matrix, plain and with the LSTM un-permute (c = u*4+g -> g*H+u)."""
+    from autovc_b200 import ops
+    x = (_rand(M, C, seed=9) * 0.1).to(dt)
+    out = torch.empty(C, device=DEV)
+    ops.colsum16(x, fmt, C, M, C, out)
+    torch.testing.assert_close(out, x.double().sum(0).float(), rtol=1e-5, atol=1e-5)
+    o1, o2 = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    ops.colsum16(x, fmt, C, M, C, o1, o2, out_mode=2)
+    ref = x.double().sum(0).view(C // 4, 4).t().reshape(-1).float()
+    torch.testing.assert_close(o1, ref, rtol=1e-5, atol=1e-5)
+    assert torch.equal(o1, o2)
