@@ -354,6 +354,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
         const int t = p.reverse ? T - 1 - s : s;
         const size_t rowi = (size_t)b * T + t;
         float pre[BN];
+        if ((p.exp_mode & 64) && s > 0) mbar_wait(go_bar, (s - 1) & 1);   // experiment: P loads only after the step's TMA loads are issued
         if (live) {
           if (p.wide) {
 #pragma unroll

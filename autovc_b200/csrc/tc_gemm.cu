@@ -1152,7 +1152,10 @@ static int tn_splits_tc(int rblocks, int tiles) {
   const int sms = num_sms();
   int best = 1;
   double best_eff = 0.0;
-  for (int s = 1; s <= 16; ++s) {
+  // few output tiles (the encoder BiLSTM's 64 x 512 / 64 x 16 weight gradients are ONE tile over 32768 rows) need many row
+  // splits to occupy the chip; large outputs stop early through the efficiency test below
+  const int max_splits = tiles <= 4 ? 64 : 16;
+  for (int s = 1; s <= max_splits; ++s) {
     if (s > 1 && rblocks / s < 8) break;
     const int items = tiles * s;
     const double eff = (double)items / ((double)ceil_div(items, sms) * sms);

@@ -31,10 +31,8 @@ def tn(N, K, ntaps):
     torch.cuda.synchronize()
 
 
-for pairs in ("0", "1"):
-    os.environ["AVC_GEMM_2CTA"] = pairs
-    nt(512, 512, 5, False)      # conv dgrad
-    nt(512, 512, 5, True)       # conv fwd + BN sums
-    nt(4096, 512, 1, False)     # LSTM input projection (store-heavy)
-tn(512, 512, 5)                 # conv wgrad
-tn(4096, 1024, 1)               # dW_hh
+nt(512, 512, 5, False)      # conv dgrad
+nt(512, 512, 5, True)       # conv fwd + BN sums
+nt(4096, 512, 1, False)     # LSTM input projection (store-heavy)
+tn(512, 512, 5)             # conv wgrad
+tn(4096, 1024, 1)           # dW_hh

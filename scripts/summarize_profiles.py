@@ -33,6 +33,10 @@ if os.path.exists(path):
     for r in csv.DictReader(io.StringIO("".join(lines))):
         if r.get("Metric Name") == "gpu__time_duration.sum":
             rows.append((short(r["Kernel Name"]), r["Grid Size"], r["Block Size"], float(r["Metric Value"])))
+    # exactly one step: from one L1-loss forward kernel (once per step) to the next
+    marks = [i for i, r in enumerate(rows) if r[0].startswith("loss_fwd_kernel<1>") or r[0].startswith("loss_fwd_kernel<true>")]
+    if len(marks) >= 2:
+        rows = rows[marks[0]:marks[1]]
     agg = OrderedDict()
     for k, g, b, ns in rows:
         a = agg.setdefault(k, [0, 0.0, set()])
