@@ -13,6 +13,7 @@
 //
 //   forward : CTA owns BN gate columns (BN/4 hidden units, gate-interleaved), K = H
 //   backward: CTA owns 16 hidden units of dh, K = 4H (dh = dG_{t+1} W_hh)
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <cuda_fp16.h>
@@ -644,6 +645,9 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 constexpr int KS_UNITS = 64;   // hidden units per cluster
 constexpr int KS_CL = 4;       // cluster size = K split
 
+// PAIRS = 2: the cluster holds TWO unit tiles (8 CTAs); the two CTAs with the same K quarter stream the same dG quarter, so each
+// loads half of its rows and multicasts them to both (TMA multicast), halving the L2 requests per CTA.
+template <int PAIRS>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const LstmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -666,17 +670,21 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
   volatile int* slot_kb = reinterpret_cast<volatile int*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t r = cluster_ctarank();                     // K quarter and unit quarter owned by this CTA
-  const int cluster_id = blockIdx.x / KS_CL;
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t r = crank & 3;                             // K quarter and unit quarter owned by this CTA
+  const uint32_t ug = crank >> 2;                           // which unit tile of the cluster (always 0 when PAIRS == 1)
+  const int cluster_id = blockIdx.x / (KS_CL * PAIRS);
   const int UT = H / KS_UNITS;
-  const int ut = cluster_id % UT, mt = cluster_id / UT;
+  const int ut = (cluster_id % (UT / PAIRS)) * PAIRS + (int)ug, mt = cluster_id / (UT / PAIRS);
+  constexpr int SLICE_ROWS = 128 / PAIRS;                   // rows of the activation tile this CTA loads (and multicasts)
+  const uint16_t mc_mask = (uint16_t)((1u << r) | (PAIRS == 2 ? (1u << (4 + r)) : 0u));
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), PAIRS);     // both CTAs that receive a multicast slot must have consumed it
     }
     mbar_init(w_bar, 1);
     mbar_init(tfull, 1);
@@ -692,7 +700,7 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   unsigned* counter = p.counters + mt * 64;
   const unsigned per_step = (unsigned)(UT * KS_CL);
-  const bool kflags = p.kflags != 0;     // counter[kb]: k-block kb of dG (64 gate columns) is published by exactly one CTA
+  const bool kflags = PAIRS == 1 && p.kflags != 0;     // counter[kb]: k-block kb of dG (64 gate columns) is published by exactly one CTA
 
   if (warp == 0) {
     // whole-warp loops, one elected lane issues (see lstm_tc_kernel)
@@ -732,7 +740,11 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
           mbar_wait(empty_bar(stage), phase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(full_bar(stage), LT_STAGE);
-            tma_load_3d(ring + stage * LT_STAGE, &mapX, full_bar(stage), (int)r * H + kb * 64, row0, 0);
+            if (PAIRS == 1)
+              tma_load_3d(ring + stage * LT_STAGE, &mapX, full_bar(stage), (int)r * H + kb * 64, row0, 0);
+            else
+              tma_load_3d_mc(ring + stage * LT_STAGE + ug * SLICE_ROWS * 128, &mapX, full_bar(stage), (int)r * H + kb * 64,
+                             row0 + (int)ug * SLICE_ROWS, 0, mc_mask);
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -763,7 +775,8 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
           for (int k = 0; k < 4; ++k)
             umma_f16(tmem_base, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc,
                      (kb0 > 0 || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(stage));
+          if (PAIRS == 1) umma_commit(empty_bar(stage));
+          else umma_commit_mc(empty_bar(stage), mc_mask);
           if (kb0 == kblocks - 1) umma_commit(tfull);
         }
         __syncwarp();
@@ -846,7 +859,7 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
               for (int i = 0; i < U; ++i) dh[i] += d[h2 * 16 + i];
             } else {
               const uint32_t slot = r < qq ? r : r - 1;        // my index among qq's three senders
-              const uint32_t dst = mapa_shared(red_s + ((slot * 128 + row) * 16) * 4, qq);
+              const uint32_t dst = mapa_shared(red_s + ((slot * 128 + row) * 16) * 4, (ug << 2) | qq);
 #pragma unroll
               for (int i = 0; i < U; i += 4)
                 st_cluster_f4(dst + i * 4, make_float4(d[h2 * 16 + i], d[h2 * 16 + i + 1], d[h2 * 16 + i + 2], d[h2 * 16 + i + 3]));
@@ -858,7 +871,7 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
         if (lane == 0) {
 #pragma unroll
           for (uint32_t qq = 0; qq < KS_CL; ++qq)
-            if (qq != r) mbar_arrive_cluster(mapa_shared(red_full, qq));
+            if (qq != r) mbar_arrive_cluster(mapa_shared(red_full, (ug << 2) | qq));
         }
         mbar_wait_cluster(red_full, (s - 1) & 1);
 #pragma unroll
@@ -990,14 +1003,10 @@ static bool bwd_ksplit_enabled(int H) {
 }
 
 // K-split BPTT launch: clusters of 4 along x
-static int lt_launch_ks(const CUtensorMap& mW, const CUtensorMap& mX, LstmTcParams p, int H, cudaStream_t st) {
-  const size_t w_bytes = (size_t)KS_UNITS * H * 2;
-  const size_t fixed = 1024 + w_bytes + 3 * 128 * 16 * 4 + 256;
-  int stages = (int)((225 * 1024 - fixed) / LT_STAGE);
-  stages = std::min(8, std::max(2, stages));
-  const size_t smem = fixed + (size_t)stages * LT_STAGE;
-  p.stages = stages;
-  AVC_CUDA(cudaFuncSetAttribute(lstm_tc_bwd_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <int PAIRS>
+static int lt_launch_ks_t(const CUtensorMap& mW, const CUtensorMap& mX, LstmTcParams p, int H, size_t smem, cudaStream_t st) {
+  auto kern = lstm_tc_bwd_ks_kernel<PAIRS>;
+  AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.MT * (H / KS_UNITS) * KS_CL);
   cfg.blockDim = dim3(LT_THREADS);
@@ -1005,16 +1014,58 @@ static int lt_launch_ks(const CUtensorMap& mW, const CUtensorMap& mX, LstmTcPara
   cfg.stream = st;
   cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
-  attrs[0].val.clusterDim.x = KS_CL;
+  attrs[0].val.clusterDim.x = KS_CL * PAIRS;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
   attrs[1].id = cudaLaunchAttributeCooperative;
   attrs[1].val.cooperative = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 2;
-  AVC_CUDA(cudaLaunchKernelEx(&cfg, lstm_tc_bwd_ks_kernel, mW, mX, p));
+  if (PAIRS > 1) {      // all clusters must be co-resident (the CTAs spin on each other's counters)
+    int max_clusters = 0;
+    cfg.numAttrs = 1;
+    const cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg);
+    if (oe != cudaSuccess || max_clusters * KS_CL * PAIRS < (int)cfg.gridDim.x) {
+      if (getenv("AVC_DEBUG")) fprintf(stderr, "lstm bwd: clusters of 8 rejected (%s, max %d clusters, grid %u)\n", cudaGetErrorString(oe), max_clusters, cfg.gridDim.x);
+      (void)cudaGetLastError();
+      return AVC_ERR_UNSUPPORTED;
+    }
+    cfg.numAttrs = 2;
+  }
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mW, mX, p);
+  if (e != cudaSuccess && PAIRS > 1) {
+    if (getenv("AVC_DEBUG")) fprintf(stderr, "lstm bwd: cluster-8 launch failed: %s\n", cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return AVC_ERR_UNSUPPORTED;         // the caller retries with clusters of 4
+  }
+  AVC_CUDA(e);
   g_launches.fetch_add(1);
   return AVC_OK;
+}
+
+// K-split BPTT launch: clusters of 4 (or 8 = two unit tiles sharing the activation stream by multicast) along x
+static int lt_launch_ks(const CUtensorMap& mW, const CUtensorMap& mX, const CUtensorMap& mXhalf, LstmTcParams p, int H, cudaStream_t st) {
+  const size_t w_bytes = (size_t)KS_UNITS * H * 2;
+  const size_t fixed = 1024 + w_bytes + 3 * 128 * 16 * 4 + 256;
+  int stages = (int)((225 * 1024 - fixed) / LT_STAGE);
+  stages = std::min(8, std::max(2, stages));
+  const size_t smem = fixed + (size_t)stages * LT_STAGE;
+  p.stages = stages;
+  static int mc = -1;
+  if (mc < 0) {
+    const char* e = getenv("AVC_LSTM_BWD_MC");
+    mc = e ? atoi(e) : 1;
+  }
+  // 16 clusters of 8 (H = 1024 at two batch tiles) do not fit the B200's GPCs at one CTA per SM (occupancy query: 15); smaller
+  // grids do.  Remember per grid size whether the launch was refused.
+  static bool refused[64] = {};
+  const int gidx = std::min(63, p.MT * (H / KS_UNITS) / 2);
+  if (mc != 0 && (H / KS_UNITS) % 2 == 0 && !refused[gidx]) {
+    const int rc = lt_launch_ks_t<2>(mW, mXhalf, p, H, smem, st);
+    if (rc != AVC_ERR_UNSUPPORTED) return rc;
+    refused[gidx] = true;
+  }
+  return lt_launch_ks_t<1>(mW, mX, p, H, smem, st);
 }
 
 template <bool BWD, int BN, int CL>
@@ -1153,7 +1204,9 @@ int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh,
       if (rc) return rc;
       rc = make_map3(&mX, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, 128);
       if (rc) return rc;
-      rc = lt_launch_ks(mWk, mX, p, H, st);
+      rc = make_map3(&mX2, xbuf, pl.K, (uint64_t)2 * p.nBpad, 1, pl.K, (uint64_t)2 * p.nBpad * pl.K, 64, 64);
+      if (rc) return rc;
+      rc = lt_launch_ks(mWk, mX, mX2, p, H, st);
       if (rc) return rc;
       continue;
     }
