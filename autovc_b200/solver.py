@@ -49,12 +49,74 @@ def train_step(G, optimizer, x_real, emb_org, lambda_cd: float = 1.0, reducer: "
         for k, v in zip(("x_identic", "x_identic_psnt", "code_real", "code_reconst"), outs):
             result[k] = v.detach()
     optimizer.step()                                                            # :300
+    if sync_losses == "async":
+        # the four scalars go to pinned host memory without blocking the host; the caller reads them through the handle
+        # (typically one step later, when it logs) -- the GPU queue then never runs dry between steps
+        result["losses"] = AsyncLosses(torch.stack([g_loss.detach(), l_id.detach(), l_id_psnt.detach(), l_cd.detach()]))
+        return result
     if sync_losses:
         vals = torch.stack([g_loss.detach(), l_id.detach(), l_id_psnt.detach(), l_cd.detach()]).tolist()
     else:
         vals = [g_loss.detach(), l_id.detach(), l_id_psnt.detach(), l_cd.detach()]
     result.update({"g_loss": vals[0], "L_id": vals[1], "L_id_psnt": vals[2], "L_cd": vals[3]})
     return result
+
+
+class AsyncLosses:
+    """Device -> pinned-host copy of a step's loss scalars (solver_encoder.py:315-317 reads them with ``.item()``) that does
+    not stall the host: ``values()`` waits for the copy and returns [g_loss, L_id, L_id_psnt, L_cd] as floats."""
+
+    _pool: List[torch.Tensor] = []
+
+    def __init__(self, dev_vals: torch.Tensor):
+        self.host = AsyncLosses._pool.pop() if AsyncLosses._pool else torch.empty(4, dtype=torch.float32).pin_memory()
+        self.host.copy_(dev_vals, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def values(self) -> List[float]:
+        self.event.synchronize()
+        out = self.host.tolist()
+        AsyncLosses._pool.append(self.host)
+        return out
+
+
+class HostBatchPrefetcher:
+    """Double-buffered host -> device staging of the (x_real, emb_org) batches a loader hands over in pinned memory
+    (the reference copies them synchronously with ``.to(self.device)``, solver_encoder.py:203-204).
+
+    ``put(x_pin, e_pin)`` enqueues the copy of the NEXT batch on a side stream; ``get()`` makes the compute stream wait
+    for the oldest enqueued batch and returns its device tensors.  With one batch in flight the copy of step n+1 runs
+    under the kernels of step n instead of in front of them."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._slots = [None, None]      # device buffers, reused
+        self._queue = []                # (slot, event)
+        self._next = 0
+
+    def put(self, x_pin: torch.Tensor, e_pin: torch.Tensor):
+        slot = self._next
+        self._next ^= 1
+        bufs = self._slots[slot]
+        if bufs is None or bufs[0].shape != x_pin.shape or bufs[1].shape != e_pin.shape:
+            bufs = (torch.empty(x_pin.shape, dtype=x_pin.dtype, device=self.device),
+                    torch.empty(e_pin.shape, dtype=e_pin.dtype, device=self.device))
+            self._slots[slot] = bufs
+        # the slot's previous contents may still be read by kernels of the step that used it
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            bufs[0].copy_(x_pin, non_blocking=True)
+            bufs[1].copy_(e_pin, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._queue.append((slot, ev))
+
+    def get(self):
+        slot, ev = self._queue.pop(0)
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        return self._slots[slot]
 
 
 class GradBucketReducer:

@@ -200,10 +200,20 @@ def run_ours(args):
     def step_resident():
         return solver.train_step(G, opt, x_dev, e_dev, reducer=reducer, sync_losses=False)
 
+    prefetch = solver.HostBatchPrefetcher(dev)
+    prefetch.put(x_pin, e_pin)
+    pending = [None]
+
     def step_e2e():
-        xd = x_pin.to(dev, non_blocking=True)
-        ed = e_pin.to(dev, non_blocking=True)
-        return solver.train_step(G, opt, xd, ed, reducer=reducer, sync_losses=True)      # D2H of the losses, like :315-317
+        # every step copies one batch from pinned host memory (the copy of the NEXT step's batch is enqueued on a side
+        # stream before this step's kernels, so K timed steps contain K host->device copies) and reads the losses back
+        xd, ed = prefetch.get()
+        prefetch.put(x_pin, e_pin)
+        # D2H of the losses every step (like :315-317), into pinned memory; the host reads step n's values while step n+1
+        # is already queued, so the GPU never waits for the host between steps
+        res = solver.train_step(G, opt, xd, ed, reducer=reducer, sync_losses="async")
+        prev, pending[0] = pending[0], res["losses"]
+        return prev.values() if prev is not None else None
 
     def barrier():
         if world > 1:

@@ -167,3 +167,18 @@ def test_tensor_core_modes_within_rel_l2_gate(name, precision):
         if abs(d[2] - ref[i][2]) > (0.08 if precision == "tf32" else 0.25) * ref[i][2] + 1e-9:
             bad.append((n, d[2], ref[i][2]))
     assert not bad, bad
+
+
+@pytest.mark.gpu
+def test_host_batch_prefetcher_hands_over_batches_in_order():
+    from autovc_b200.solver import HostBatchPrefetcher
+    pf = HostBatchPrefetcher("cuda")
+    xs = [torch.full((4, 8, 80), float(i)).pin_memory() for i in range(5)]
+    es = [torch.full((4, 256), float(-i)).pin_memory() for i in range(5)]
+    pf.put(xs[0], es[0])
+    for i in range(5):
+        xd, ed = pf.get()
+        if i + 1 < 5:
+            pf.put(xs[i + 1], es[i + 1])
+        y = (xd * 2).sum() + ed.sum()          # consume on the compute stream
+        assert float(y) == float(xs[i].sum() * 2 + es[i].sum())
