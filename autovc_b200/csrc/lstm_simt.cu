@@ -149,6 +149,143 @@ __global__ void lstm_small_bwd_kernel(const float* __restrict__ dH, int lddh, co
 }
 
 // ---------------------------------------------------------------------------------------
+// H = 16 / 32 (the encoder BiLSTM of the two published configurations): same arithmetic in the same order as the generic
+// kernels above, but the thread's W_hh row lives in registers, the recurrent vector is exchanged through a double-buffered
+// shared tile read with 128-bit loads, and a step needs ONE block barrier instead of two.
+// ---------------------------------------------------------------------------------------
+template <int HT>
+__global__ void __launch_bounds__(256)
+lstm_small_fwd_kernel_t(const float* __restrict__ P, const float* __restrict__ Whh_p, float* __restrict__ h_seq, int ldh,
+                        float* __restrict__ gates, float* __restrict__ c_seq, int nB, int T, int reverse) {
+  constexpr int H = HT, G = 4 * HT, UPB = 256 / G;
+  __shared__ __align__(16) float hs[2][UPB][HT];
+  if (reverse == 2) {
+    const int d = blockIdx.y;
+    P += (size_t)d * nB * T * G;
+    Whh_p += (size_t)d * G * H;
+    gates += (size_t)d * nB * T * G;
+    c_seq += (size_t)d * nB * T * H;
+    h_seq += d * H;
+    reverse = d;
+  }
+  const int j = threadIdx.x, ul = threadIdx.y;
+  const int b = blockIdx.x * UPB + ul;
+  const int u = j >> 2, g = j & 3;
+  float w[HT];
+#pragma unroll
+  for (int k = 0; k < HT; ++k) w[k] = Whh_p[(size_t)j * H + k];
+  if (j < H) hs[0][ul][j] = 0.f;
+  __syncthreads();
+  float c = 0.f;
+  const bool live = b < nB;
+  const unsigned quad_base = ((threadIdx.y * blockDim.x + threadIdx.x) & 31) & ~3u;
+  float p_next = live ? P[((size_t)b * T + (reverse ? T - 1 : 0)) * G + j] : 0.f;
+  for (int step = 0; step < T; ++step) {
+    const int t = reverse ? (T - 1 - step) : step;
+    const int cur = step & 1;
+    float acc = p_next;
+    if (live && step + 1 < T) p_next = P[((size_t)b * T + (reverse ? t - 1 : t + 1)) * G + j];
+    const float4* h4 = reinterpret_cast<const float4*>(hs[cur][ul]);
+#pragma unroll
+    for (int k = 0; k < HT; k += 4) {
+      const float4 hv = h4[k >> 2];
+      acc = fmaf(w[k], hv.x, acc);
+      acc = fmaf(w[k + 1], hv.y, acc);
+      acc = fmaf(w[k + 2], hv.z, acc);
+      acc = fmaf(w[k + 3], hv.w, acc);
+    }
+    const float a = (g == 2) ? tanhf(acc) : sigmoidf_acc(acc);
+    const float gi = __shfl_sync(0xffffffffu, a, quad_base + 0);
+    const float gf = __shfl_sync(0xffffffffu, a, quad_base + 1);
+    const float gg = __shfl_sync(0xffffffffu, a, quad_base + 2);
+    const float go = __shfl_sync(0xffffffffu, a, quad_base + 3);
+    c = gf * c + gi * gg;
+    const float h_new = go * tanhf(c);
+    if (g == 0) hs[cur ^ 1][ul][u] = h_new;
+    if (live) {
+      gates[((size_t)b * T + t) * G + j] = a;
+      if (g == 0) {
+        h_seq[((size_t)b * T + t) * ldh + u] = h_new;
+        c_seq[((size_t)b * T + t) * H + u] = c;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int HT>
+__global__ void __launch_bounds__(256)
+lstm_small_bwd_kernel_t(const float* __restrict__ dH, int lddh, const float* __restrict__ Whh_p, const float* __restrict__ gates,
+                        const float* __restrict__ c_seq, float* __restrict__ dP, int nB, int T, int reverse) {
+  constexpr int H = HT, G = 4 * HT, UPB = 256 / G;
+  __shared__ __align__(16) float dgs[2][UPB][G];
+  if (reverse == 2) {
+    const int d = blockIdx.y;
+    dH += d * H;
+    Whh_p += (size_t)d * G * H;
+    gates += (size_t)d * nB * T * G;
+    c_seq += (size_t)d * nB * T * H;
+    dP += (size_t)d * nB * T * G;
+    reverse = d;
+  }
+  const int j = threadIdx.x, ul = threadIdx.y;
+  const int b = blockIdx.x * UPB + ul;
+  const int u = j >> 2, g = j & 3;
+  float w[HT];                                  // W[g*H + jj][u]: the quarter of the reduction this thread sums
+#pragma unroll
+  for (int jj = 0; jj < HT; ++jj) w[jj] = Whh_p[(size_t)(g * H + jj) * H + u];
+  dgs[0][ul][j] = 0.f;
+  __syncthreads();
+  const bool live = b < nB;
+  float dc_rec = 0.f;
+  const unsigned quad_base = ((threadIdx.y * blockDim.x + threadIdx.x) & 31) & ~3u;
+  float a_n = 0.f, ct_n = 0.f, cp_n = 0.f, dH_n = 0.f;
+  auto fetch = [&](int step) {
+    const int t = reverse ? (T - 1 - step) : step;
+    const int t_prev = reverse ? t + 1 : t - 1;
+    a_n = gates[((size_t)b * T + t) * G + j];
+    ct_n = c_seq[((size_t)b * T + t) * H + u];
+    cp_n = (step > 0) ? c_seq[((size_t)b * T + t_prev) * H + u] : 0.f;
+    dH_n = dH[((size_t)b * T + t) * lddh + u];
+  };
+  if (live) fetch(T - 1);
+  int cur = 0;
+  for (int step = T - 1; step >= 0; --step, cur ^= 1) {
+    const int t = reverse ? (T - 1 - step) : step;
+    const float a = a_n, ct = ct_n, cp = cp_n, dHt = dH_n;
+    if (live && step > 0) fetch(step - 1);
+    float part = 0.f;
+    const float4* dg4 = reinterpret_cast<const float4*>(&dgs[cur][ul][g * H]);
+#pragma unroll
+    for (int jj = 0; jj < HT; jj += 4) {
+      const float4 dv = dg4[jj >> 2];
+      part = fmaf(dv.x, w[jj], part);
+      part = fmaf(dv.y, w[jj + 1], part);
+      part = fmaf(dv.z, w[jj + 2], part);
+      part = fmaf(dv.w, w[jj + 3], part);
+    }
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    const float dh = part + dHt;
+    const float gi = __shfl_sync(0xffffffffu, a, quad_base + 0);
+    const float gf = __shfl_sync(0xffffffffu, a, quad_base + 1);
+    const float gg = __shfl_sync(0xffffffffu, a, quad_base + 2);
+    const float go = __shfl_sync(0xffffffffu, a, quad_base + 3);
+    const float tc = tanhf(ct);
+    const float dc = dh * go * (1.f - tc * tc) + dc_rec;
+    float d;
+    if (g == 0) d = dc * gg * gi * (1.f - gi);
+    else if (g == 1) d = dc * cp * gf * (1.f - gf);
+    else if (g == 2) d = dc * gi * (1.f - gg * gg);
+    else d = dh * tc * go * (1.f - go);
+    dc_rec = dc * gf;
+    dgs[cur ^ 1][ul][j] = d;
+    if (live) dP[((size_t)b * T + t) * G + j] = d;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // large H: one launch per timestep
 // ---------------------------------------------------------------------------------------
 // gates tile: rows = utterances, cols = interleaved gate columns
@@ -245,6 +382,14 @@ lstm_step_bwd_kernel(const float* __restrict__ dH, int lddh, const float* __rest
 int lstm_seq_fwd_simt(const float* P, const float* Whh_p, float* h_seq, int ldh, float* gates, float* c_seq, int nB,
                       int T, int H, int reverse, cudaStream_t st) {
   const int G = 4 * H;
+  if (H == 16 || H == 32) {
+    const int upb = 256 / G;
+    const dim3 grid(ceil_div(nB, upb), reverse == 2 ? 2 : 1), block(G, upb);
+    if (H == 16) lstm_small_fwd_kernel_t<16><<<grid, block, 0, st>>>(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, reverse);
+    else lstm_small_fwd_kernel_t<32><<<grid, block, 0, st>>>(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, reverse);
+    AVC_LAUNCHED();
+    return AVC_OK;
+  }
   if (H <= SMALL_H_MAX && H % 8 == 0) {
     int upb = std::max(1, 256 / G);
     const size_t smem = ((size_t)G * (H + 1) + (size_t)upb * H) * sizeof(float);
@@ -274,6 +419,14 @@ int lstm_seq_bwd_simt(const float* dH, int lddh, const float* Whh_p, const float
                       const float* c_seq, float* dP, int nB, int T, int H, int reverse, void* ws, size_t ws_bytes,
                       cudaStream_t st) {
   const int G = 4 * H;
+  if (H == 16 || H == 32) {
+    const int upb = 256 / G;
+    const dim3 grid(ceil_div(nB, upb), reverse == 2 ? 2 : 1), block(G, upb);
+    if (H == 16) lstm_small_bwd_kernel_t<16><<<grid, block, 0, st>>>(dH, lddh, Whh_p, gates, c_seq, dP, nB, T, reverse);
+    else lstm_small_bwd_kernel_t<32><<<grid, block, 0, st>>>(dH, lddh, Whh_p, gates, c_seq, dP, nB, T, reverse);
+    AVC_LAUNCHED();
+    return AVC_OK;
+  }
   if (H <= SMALL_H_MAX && H % 8 == 0) {
     int upb = std::max(1, 256 / G);
     const size_t smem = ((size_t)G * (H + 1) + (size_t)upb * G + (size_t)upb * H) * sizeof(float);
