@@ -4,10 +4,12 @@ Public surface mirrors the reference's modules for this path:
   autovc_b200.model_vc_mel.Generator     <- model_vc_mel.Generator
   autovc_b200.model_vc_stft.GeneratorSTFT <- model_vc_stft.GeneratorSTFT
   autovc_b200.make_spect.Spect / logmel   <- make_spect.Spect (spmel branch)
+  autovc_b200.optim.FusedAdam             <- torch.optim.Adam as solver_encoder.py:130 configures it (one-launch step)
   autovc_b200.solver                      <- the step maths of solver_encoder.Solver.train + data parallelism
 """
 from ._lib import AvcError, LIB_PATH, launch_count, load  # noqa: F401
 from .model_vc_mel import Generator  # noqa: F401
 from .model_vc_stft import GeneratorSTFT  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 
-__all__ = ["Generator", "GeneratorSTFT", "AvcError", "load", "launch_count", "LIB_PATH"]
+__all__ = ["Generator", "GeneratorSTFT", "FusedAdam", "AvcError", "load", "launch_count", "LIB_PATH"]

@@ -187,7 +187,7 @@ def run_ours(args):
         G = autovc_b200.GeneratorSTFT(args.dim_neck, 256, 512, args.freq, precision=args.precision).model.to(dev).train()
     else:
         G = autovc_b200.Generator(args.dim_neck, 256, 512, args.freq, precision=args.precision).to(dev).train()
-    opt = torch.optim.Adam(G.parameters(), 1e-4)
+    opt = autovc_b200.FusedAdam(G.parameters(), 1e-4)      # solver_encoder.py:130's Adam, one-launch step
     reducer = None
     if world > 1:
         solver.broadcast_parameters(G)

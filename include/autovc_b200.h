@@ -251,6 +251,19 @@ int avc_loss_bwd(const float* a, const float* b, size_t n, const float* gout, in
                  float* da, float* db, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Optimizer step, solver_encoder.py:130 (torch.optim.Adam(G.parameters(), lr): betas (0.9, 0.999), eps 1e-8, no weight
+ * decay, no amsgrad) and :300 (.step()).  ONE launch updates every parameter tensor:
+ *   g' = grad_scale * g;  m += (1-beta1)(g' - m);  v = beta2 v + (1-beta2) g'^2;
+ *   p -= lr/(1-beta1^step) * m / (sqrt(v)/sqrt(1-beta2^step) + eps)      (torch's _multi_tensor_adam, fp32)
+ * table : device array of n_tensors records {float* p; const float* g; float* m; float* v; uint64 n;} (40 bytes each);
+ * chunks: device array of int2 {tensor index, chunk index within the tensor}, one entry per avc_adam_chunk_elems()
+ *         elements of every tensor (static for a given parameter list);  step is 1-based.
+ * grad_scale folds the 1/world_size of a summed data-parallel gradient (1.0 otherwise). */
+int avc_adam_chunk_elems(void);
+int avc_adam_step(const void* table, const void* chunks, int nchunks, double lr, double beta1, double beta2, double eps,
+                  int step, float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * make_spect front-end, make_spect.py:72-83 (spmel branch) + :30-48:
  *   y = filtfilt(butter(5, 30 Hz HP), wav) [fp64, scipy odd-extension padlen 18, lfilter_zi]
  *   wav' = 0.96*y + (dither - 0.5)*1e-6
