@@ -52,9 +52,9 @@ SIGNATURES = {
     "avc_gemm_tn_taps_h": (c_int, [P, c_int, c_int, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
     "avc_gemm_tn_h_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "avc_cast16": (c_int, [P, c_int, P, c_int, c_size_t, c_int, c_int, P]),
-    "avc_bn_act_fwd_h": (c_int, [P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "avc_bn_act_fwd_h": (c_int, [P, P, P, P, P, P, P, P, c_int, P, c_int, c_int, c_int, c_int, P]),
     "avc_bn_act_bwd_apply_h": (c_int, [P, P, P, P, P, P, P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, P]),
-    "avc_lstm_seq_fwd_h": (c_int, [P, P, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_size_t, P]),
+    "avc_lstm_seq_fwd_h": (c_int, [P, P, c_int, P, c_int, P, P, P, c_int, P, c_int, c_int, c_int, c_int, P, c_size_t, P]),
     "avc_lstm_seq_bwd_h": (c_int, [P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, P, c_size_t, P]),
     "avc_pack_conv_weight_h": (c_int, [P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, P]),
     "avc_pack_lstm_weight_h": (c_int, [P, P, c_int, c_int, P, c_int, c_int, c_int, c_int, P]),

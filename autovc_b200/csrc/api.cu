@@ -49,7 +49,7 @@ void tc_gemm_set_trace(unsigned long long* p);
 size_t lstm_tc_workspace(int nB, int T, int H, bool bwd);
 int lstm_seq_tc(bool bwd, const void* W, const float* P, float* h_seq, int ldh, float* gates, float* c_seq, const float* dH,
                 int lddh, float* dP, int nB, int T, int H, int reverse, void* ws, size_t ws_bytes, cudaStream_t st,
-                void* aux16 = nullptr, int fmt16 = 0, int w_fmt = 0);
+                void* aux16 = nullptr, int fmt16 = 0, int w_fmt = 0, void* aux16b = nullptr);
 
 }  // namespace avc
 
@@ -189,13 +189,13 @@ extern "C" size_t avc_gemm_tn_h_workspace_bytes(int nB, int T, int N, int K, int
 
 // persistent recurrences that additionally emit the 16-bit operand copy the following GEMMs read ("half" mode)
 extern "C" int avc_lstm_seq_fwd_h(const float* P, const void* Whh_p, int w_fmt, float* h_seq, int ldh, float* gates, float* c_seq,
-                                  void* h16, int fmt16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes,
-                                  void* stream) {
+                                  void* h16, int fmt16, void* h16b, int nB, int T, int H, int reverse, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
   AVC_REQUIRE(P && Whh_p && h_seq && gates && c_seq && h16, "avc_lstm_seq_fwd_h: null pointer");
   AVC_REQUIRE(nB > 0 && T > 0 && lstm_tc_supported(H) && ldh >= H && ldh % 4 == 0 && (fmt16 == 1 || fmt16 == 2), "avc_lstm_seq_fwd_h: unsupported shape");
   AVC_REQUIRE(w_fmt == 0 || w_fmt == 1, "avc_lstm_seq_fwd_h: W_hh must be fp32 (0) or bf16 (1)");
   return lstm_seq_tc(false, Whh_p, P, h_seq, ldh, gates, c_seq, nullptr, 0, nullptr, nB, T, H, reverse, workspace, workspace_bytes,
-                     as_stream(stream), h16, fmt16, w_fmt);
+                     as_stream(stream), h16, fmt16, w_fmt, h16b);
 }
 
 extern "C" int avc_lstm_seq_bwd_h(const float* dH, int lddh, const void* Whh_pT, int w_fmt, const float* gates, const float* c_seq,

@@ -204,7 +204,8 @@ constexpr int BC_UNROLL = 4;
 __global__ void __launch_bounds__(256)
 bn_act_fwd_cols_kernel(const float4* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
                        const float* __restrict__ gamma, const float* __restrict__ beta, const float4* __restrict__ res,
-                       float4* __restrict__ z, uint2* __restrict__ z16, int fmt16, int M, int C, int rows_per_block, int act) {
+                       float4* __restrict__ z, uint2* __restrict__ z16, int fmt16, uint2* __restrict__ z16b, int fmt16b, int M, int C,
+                       int rows_per_block, int act) {
   const int cq = blockIdx.x * 32 + threadIdx.x;
   const int c = cq * 4;
   if (c >= C) return;
@@ -238,8 +239,9 @@ bn_act_fwd_cols_kernel(const float4* __restrict__ y, const float* __restrict__ m
           o[0] += rr[u].x; o[1] += rr[u].y; o[2] += rr[u].z; o[3] += rr[u].w;
         }
         const size_t i = (size_t)ru * C4 + cq;
-        z[i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (z) z[i] = make_float4(o[0], o[1], o[2], o[3]);
         if (z16) z16[i] = pack4_16(o[0], o[1], o[2], o[3], fmt16);
+        if (z16b) z16b[i] = pack4_16(o[0], o[1], o[2], o[3], fmt16b);
       }
     }
   }
@@ -599,16 +601,18 @@ extern "C" int avc_bn_eval_stats(const float* running_mean, const float* running
 }
 
 static int bn_fwd_impl(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                       const float* residual, float* z, void* z16, int fmt16, int M, int C, int act, cudaStream_t st) {
-  const bool vec = (C % 4 == 0) && al16(y) && al16(z) && (!residual || al16(residual)) && (!z16 || ((uintptr_t)z16 & 7) == 0);
+                       const float* residual, float* z, void* z16, int fmt16, int M, int C, int act, cudaStream_t st,
+                       void* z16b = nullptr, int fmt16b = 0) {
+  const bool vec = (C % 4 == 0) && al16(y) && (!z || al16(z)) && (!residual || al16(residual)) && (!z16 || ((uintptr_t)z16 & 7) == 0) &&
+                   (!z16b || ((uintptr_t)z16b & 7) == 0);
   if (vec) {
     dim3 grid;
     int rpb;
     cols_grid(M, C, grid, rpb);
     bn_act_fwd_cols_kernel<<<grid, dim3(32, 8), 0, st>>>((const float4*)y, mean, rstd, gamma, beta, (const float4*)residual,
-                                                         (float4*)z, (uint2*)z16, fmt16, M, C, rpb, act);
+                                                         (float4*)z, (uint2*)z16, fmt16, (uint2*)z16b, fmt16b, M, C, rpb, act);
   } else {
-    if (z16) {
+    if (z16 || z16b || !z) {
       set_error("avc_bn_act_fwd_h: needs C %% 4 == 0 and 16-byte aligned tensors");
       return AVC_ERR_INVALID;
     }
@@ -785,10 +789,11 @@ extern "C" int avc_cast16(const float* src, int lds, void* dst, int ldd, size_t 
 }
 
 extern "C" int avc_bn_act_fwd_h(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                                const float* residual, float* z, void* z16, int fmt16, int M, int C, int act, void* stream) {
-  AVC_REQUIRE(y && mean && rstd && gamma && beta && z && z16 && M > 0 && C > 0, "avc_bn_act_fwd_h: bad arguments");
-  AVC_REQUIRE(C % 4 == 0 && (fmt16 == 1 || fmt16 == 2), "avc_bn_act_fwd_h: C must be a multiple of 4");
-  return bn_fwd_impl(y, mean, rstd, gamma, beta, residual, z, z16, fmt16, M, C, act, as_stream(stream));
+                                const float* residual, float* z, void* z16, int fmt16, void* z16b, int fmt16b, int M, int C, int act,
+                                void* stream) {
+  AVC_REQUIRE(y && mean && rstd && gamma && beta && z16 && M > 0 && C > 0, "avc_bn_act_fwd_h: bad arguments");   // z (fp32) is optional
+  AVC_REQUIRE(C % 4 == 0 && (fmt16 == 1 || fmt16 == 2) && (!z16b || fmt16b == 1 || fmt16b == 2), "avc_bn_act_fwd_h: C must be a multiple of 4");
+  return bn_fwd_impl(y, mean, rstd, gamma, beta, residual, z, z16, fmt16, M, C, act, as_stream(stream), z16b, fmt16b);
 }
 
 extern "C" int avc_bn_act_bwd_apply_h(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,

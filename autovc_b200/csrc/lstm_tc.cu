@@ -41,6 +41,7 @@ struct LstmTcParams {
   int kflags;              // 1: per-k-block release counters, consumers stream each k-block as soon as it is published
   void* h16;            // fwd: optional 16-bit copy of h_seq (nB,T,H) contiguous, format fmt16 (1 bf16 / 2 fp16)
   void* dP16;           // bwd: optional 16-bit copy of dP (nB,T,4H)
+  void* h16b;           // fwd: optional bf16 copy of h_seq (nB,T,H) contiguous, next to h16 (the weight-gradient GEMMs' operand)
   int fmt16;
   int wide;                // every row-per-thread tensor is 32-byte aligned (pointer and row stride): use 256-bit accesses
   int out_tma;             // the saved tensors leave through shared staging tiles + TMA stores (maps in LtOutMaps)
@@ -54,6 +55,7 @@ struct alignas(64) LtOutMaps {
   CUtensorMap c;       // fwd: c_seq (H, T, nB) fp32, box (U, 1, 32)
   CUtensorMap h;       // fwd: h_seq (H, T, nB; row stride ldh) fp32, box (U, 1, 32)
   CUtensorMap h16;     // fwd: h16 (H, T, nB) 16-bit, box (U, 1, 32)              bwd: dP16 (G, T, nB), box (64, 1, 32)
+  CUtensorMap h16b;    // fwd: h16b (H, T, nB) bf16, box (U, 1, 32)
 };
 constexpr int LT_OUT_STAGE = 16384;      // 4 epilogue warps x 4 KB
 
@@ -478,11 +480,17 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
               }
               st_shared_v4(buf + lane * (U * 2) + i * 2, __uint_as_float(w[0]), __uint_as_float(w[1]), __uint_as_float(w[2]),
                            __uint_as_float(w[3]));
+              if (p.h16b != nullptr) {                                     // bf16 copy: a second [32][U] tile, same round
+                const uint4 hv = *reinterpret_cast<const uint4*>(&hb[i]);
+                st_shared_v4(buf + 2048 + lane * (U * 2) + i * 2, __uint_as_float(hv.x), __uint_as_float(hv.y), __uint_as_float(hv.z),
+                             __uint_as_float(hv.w));
+              }
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
               tma_store_3d(&om.h16, buf, u0, t, brow);
+              if (p.h16b != nullptr) tma_store_3d(&om.h16b, buf + 2048, u0, t, brow);
               bulk_commit();
             }
           }
@@ -510,6 +518,11 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
 #pragma unroll
               for (int i = 0; i < U; i += 4) *reinterpret_cast<uint2*>(h16 + i) = *reinterpret_cast<const uint2*>(&hb[i]);
             }
+          }
+          if (p.h16b != nullptr) {
+            uint16_t* h16b = reinterpret_cast<uint16_t*>(p.h16b) + rowi * H + u0;
+#pragma unroll
+            for (int i = 0; i < U; i += 4) *reinterpret_cast<uint2*>(h16b + i) = *reinterpret_cast<const uint2*>(&hb[i]);
           }
         }
       }
@@ -1132,7 +1145,7 @@ static int lt_cluster_size(int NT) {
 // w_fmt 0: W is fp32 and converted to bf16 here; 1: W is already bf16 (avc_pack_lstm_weight_h) and read in place
 int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh, float* gates, float* c_seq,
                 const float* dH, int lddh, float* dP, int nB, int T, int H, int reverse, void* ws, size_t ws_bytes,
-                cudaStream_t st, void* aux16, int fmt16, int w_fmt) {
+                cudaStream_t st, void* aux16, int fmt16, int w_fmt, void* aux16b) {
   const LtPlan pl = lt_plan(nB, H, bwd);
   if (!ws || ws_bytes < pl.total) {
     set_error("avc_lstm_seq_%s(bf16): workspace %zu < %zu", bwd ? "bwd" : "fwd", ws_bytes, pl.total);
@@ -1198,6 +1211,7 @@ int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh,
     }
     p.h16 = (!bwd && aux16) ? (void*)((uint16_t*)aux16 + (size_t)b0 * T * H) : nullptr;
     p.dP16 = (bwd && aux16) ? (void*)((uint16_t*)aux16 + (size_t)b0 * T * G) : nullptr;
+    p.h16b = (!bwd && aux16 && aux16b) ? (void*)((uint16_t*)aux16b + (size_t)b0 * T * H) : nullptr;
     if (bwd && bwd_ksplit_enabled(H)) {
       CUtensorMap mWk;
       rc = make_map3(&mWk, Wb, pl.K, w_rows, 1, pl.K, (uint64_t)w_rows * pl.K, 64, KS_UNITS);
@@ -1217,16 +1231,17 @@ int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh,
     if (rc) return rc;
     // forward: the saved tensors leave through TMA stores (needs 16-byte aligned tensors; ldh % 4 == 0 is an API precondition)
     LtOutMaps om{};
-    om.gates = om.c = om.h = om.h16 = mW;
+    om.gates = om.c = om.h = om.h16 = om.h16b = mW;
     static const bool out_tma_env = getenv("AVC_LSTM_OUT_TMA") ? atoi(getenv("AVC_LSTM_OUT_TMA")) != 0 : true;
     p.out_tma = 0;
-    if (!bwd && out_tma_env && pl.out_stage > 0 && (((uintptr_t)p.gates | (uintptr_t)p.c_seq | (uintptr_t)p.h_seq | (uintptr_t)p.h16) & 15) == 0) {
+    if (!bwd && out_tma_env && pl.out_stage > 0 && (((uintptr_t)p.gates | (uintptr_t)p.c_seq | (uintptr_t)p.h_seq | (uintptr_t)p.h16 | (uintptr_t)p.h16b) & 15) == 0) {
       const int U = pl.BN / 4;
       const uint64_t Tn = (uint64_t)T;
       rc = make_map3_store(&om.gates, p.gates, 4, G, Tn, nb, G, Tn * G, 32, 1, 32, true);
       if (!rc) rc = make_map3_store(&om.c, p.c_seq, 4, H, Tn, nb, H, Tn * H, U, 1, 32, false);
       if (!rc) rc = make_map3_store(&om.h, p.h_seq, 4, H, Tn, nb, ldh, Tn * ldh, U, 1, 32, false);
       if (!rc && p.h16) rc = make_map3_store(&om.h16, p.h16, 2, H, Tn, nb, H, Tn * H, U, 1, 32, false);
+      if (!rc && p.h16b) rc = make_map3_store(&om.h16b, p.h16b, 2, H, Tn, nb, H, Tn * H, U, 1, 32, false);
       if (rc) return rc;
       p.out_tma = 1;
     }

@@ -45,7 +45,7 @@ class LinearNorm(nn.Module):
 
     def forward(self, x):
         if self.prec == PREC_HALF:
-            return ops.LinearH.apply(x, None, self.linear_layer.weight, self.linear_layer.bias)
+            return ops.LinearH.apply(x, None, None, self.linear_layer.weight, self.linear_layer.bias)
         return ops.Linear.apply(x, self.linear_layer.weight, self.linear_layer.bias, self.prec)
 
 
@@ -68,27 +68,30 @@ class ConvNorm(nn.Module):
         raise RuntimeError("ConvNorm is fused with its BatchNorm and activation; call the owning block")
 
 
-def _conv_bn_act(block: nn.Sequential, x, act: str, residual=None, prec=PREC_FP32, x16=None):
+def _conv_bn_act(block: nn.Sequential, x, act: str, residual=None, prec=PREC_FP32, x16=None, x16b=None, need_z32=True):
     """act(BN(conv(x))) (+ residual) on channels-last x; bumps num_batches_tracked like nn.BatchNorm1d.
-    Returns (z, z16): z16 is the fp16 operand copy in half mode, else None."""
+    Returns (z, z16, z16b): the fp16 / bf16 operand copies in half mode, else None.  ``need_z32=False`` (half mode only):
+    the caller promises that nothing reads the fp32 activation, which is then not written (z is the autograd carrier)."""
     conv, bn = block[0].conv, block[1]
     training = bn.training
+    z16 = z16b = None
     if prec == PREC_HALF:
-        z, z16 = ops.ConvBnActH.apply(x, x16, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                      residual, ACT_CODES[act], training)
-        if z16.numel() == 0:
-            z16 = None
+        Cout = conv.weight.shape[0]
+        z, z16, z16b = ops.ConvBnActH.apply(x, x16, x16b, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
+                                            bn.running_var, residual, ACT_CODES[act], training,
+                                            need_z32 or Cout % 8 != 0 or not training)
+        z16 = z16 if z16.numel() else None
+        z16b = z16b if z16b.numel() else None
     else:
         z = ops.ConvBnAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
                                 ACT_CODES[act], training, prec)
-        z16 = None
     if training:
         bn.num_batches_tracked += 1
-    return z, z16
+    return z, z16, z16b
 
 
-def _lstm(x, lstm: nn.LSTM, prec, x16=None):
-    """Run an nn.LSTM's parameters through the LstmLayer kernels, layer by layer.  Returns (h, h16)."""
+def _lstm(x, lstm: nn.LSTM, prec, x16=None, x16b=None):
+    """Run an nn.LSTM's parameters through the LstmLayer kernels, layer by layer.  Returns (h, h16, h16b)."""
     H = lstm.hidden_size
     half = prec == PREC_HALF and not lstm.bidirectional and 128 <= H <= 1024 and H % 64 == 0
     for l in range(lstm.num_layers):
@@ -96,11 +99,12 @@ def _lstm(x, lstm: nn.LSTM, prec, x16=None):
         for suffix in (("", "_reverse") if lstm.bidirectional else ("",)):
             ws += [getattr(lstm, f"{n}_l{l}{suffix}") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
         if half:
-            x, x16 = ops.LstmLayerH.apply(x, x16, *ws)
+            x, x16, x16b = ops.LstmLayerH.apply(x, x16, x16b, *ws)
+            x16b = x16b if x16b.numel() else None
         else:   # encoder BiLSTM (H = dim_neck): tiny GEMMs, fp32 recurrence; tf32 operands in half mode
             x = ops.LstmLayer.apply(x, PREC_TF32 if prec == PREC_HALF else prec, *ws)
-            x16 = None
-    return x, x16
+            x16 = x16b = None
+    return x, x16, x16b
 
 
 class Encoder(nn.Module):
@@ -125,10 +129,12 @@ class Encoder(nn.Module):
         if x.dim() == 4:
             x = x.squeeze(1)
         h = ops.ConcatEmb.apply(x, c_org)
-        h16 = None
-        for block in self.convolutions:
-            h, h16 = _conv_bn_act(block, h, "relu", prec=self.prec, x16=h16)
-        h, _ = _lstm(h, self.lstm, self.prec)
+        h16 = h16b = None
+        n = len(self.convolutions)
+        for i, block in enumerate(self.convolutions):
+            # the BiLSTM reads the last conv's activation in fp32; the inner ones are only ever 16-bit GEMM operands
+            h, h16, h16b = _conv_bn_act(block, h, "relu", prec=self.prec, x16=h16, x16b=h16b, need_z32=(i == n - 1))
+        h, _, _ = _lstm(h, self.lstm, self.prec)
         return ops.Codes.apply(h, self.dim_neck, self.freq)
 
     def forward(self, x, c_org):
@@ -152,13 +158,17 @@ class Decoder(nn.Module):
         self.linear_projection = LinearNorm(1024, n_bins)
 
     def forward(self, x):
-        h, h16 = _lstm(x, self.lstm1, self.prec)
-        for block in self.convolutions:
-            h, h16 = _conv_bn_act(block, h, "relu", prec=self.prec, x16=h16)
-        h, h16 = _lstm(h, self.lstm2, self.prec, x16=h16)
+        h, h16, h16b = _lstm(x, self.lstm1, self.prec)
+        # half mode: lstm2 (persistent kernels, H = 1024) reads the 16-bit copies only -> no fp32 activation in between
+        lstm2_half = self.prec == PREC_HALF and 128 <= self.lstm2.hidden_size <= 1024 and self.lstm2.hidden_size % 64 == 0
+        n = len(self.convolutions)
+        for i, block in enumerate(self.convolutions):
+            h, h16, h16b = _conv_bn_act(block, h, "relu", prec=self.prec, x16=h16, x16b=h16b,
+                                        need_z32=(i == n - 1 and not lstm2_half))
+        h, h16, h16b = _lstm(h, self.lstm2, self.prec, x16=h16, x16b=h16b)
         lin = self.linear_projection.linear_layer
         if self.prec == PREC_HALF:
-            return ops.LinearH.apply(h, h16, lin.weight, lin.bias)
+            return ops.LinearH.apply(h, h16, h16b, lin.weight, lin.bias)
         return ops.Linear.apply(h, lin.weight, lin.bias, self.prec)
 
 
@@ -183,10 +193,10 @@ class Postnet(nn.Module):
     def channels_last(self, x, residual=None):
         """x (B,T,n_bins) -> postnet(x) (+ residual), channels-last."""
         n = len(self.convolutions)
-        x16 = None
+        x16 = x16b = None
         for i in range(n - 1):
-            x, x16 = _conv_bn_act(self.convolutions[i], x, "tanh", prec=self.prec, x16=x16)
-        return _conv_bn_act(self.convolutions[-1], x, "none", residual=residual, prec=self.prec, x16=x16)[0]
+            x, x16, x16b = _conv_bn_act(self.convolutions[i], x, "tanh", prec=self.prec, x16=x16, x16b=x16b, need_z32=False)
+        return _conv_bn_act(self.convolutions[-1], x, "none", residual=residual, prec=self.prec, x16=x16, x16b=x16b)[0]
 
     def forward(self, x):
         # reference layout: channel-first (B, n_bins, T) in and out (model_vc_mel.py:163-169, :196)

@@ -540,12 +540,16 @@ def gemm_tn_taps_h(dY, y_fmt, ldy, X, x_fmt, ldx, dW, nB, T, N, K, ntaps, shift0
 
 
 class ConvBnActH(torch.autograd.Function):
-    """ConvBnAct for the half mode: (x, x16) -> (z, z16).  Forward operands fp16, gradient operands bf16."""
+    """ConvBnAct for the half mode: (x, x16, x16b) -> (z, z16, z16b).  Forward operands fp16 (x16 / z16), gradient operands
+    bf16 (x16b / z16b: the activation copy the NEXT layer's weight-gradient GEMM reads, emitted here by the producing kernel
+    instead of being cast in backward).  With ``need_z32=False`` the fp32 activation is not written at all: ``z`` is then only
+    the autograd carrier (allocated, never filled) and every consumer must read the 16-bit copies."""
 
     @staticmethod
-    def forward(ctx, x, x16, weight, bias, gamma, beta, running_mean, running_var, residual, act: int, training: bool):
+    def forward(ctx, x, x16, x16b, weight, bias, gamma, beta, running_mean, running_var, residual, act: int, training: bool,
+                need_z32: bool = True):
         x = x.contiguous()
-        _check(x, x16, weight, bias, gamma, beta, running_mean, running_var, residual)
+        _check(x, x16, x16b, weight, bias, gamma, beta, running_mean, running_var, residual)
         if residual is not None and act != ACT_NONE:
             raise _lib.AvcError("residual is only supported with act='none'")
         B, T, Cin = x.shape
@@ -568,24 +572,35 @@ class ConvBnActH(torch.autograd.Function):
         z = torch.empty_like(y)
         if Cout % 8 == 0:
             z16 = torch.empty(B, T, Cout, device=x.device, dtype=torch.float16)
-            call("avc_bn_act_fwd_h", _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(z), _p(z16), FMT_FP16,
-                 M, Cout, act, _stream())
+            # the bf16 copy only serves the next layer's weight-gradient GEMM: skipped when nothing here needs a gradient
+            z16b = torch.empty(B, T, Cout, device=x.device, dtype=torch.bfloat16) if (training and any(ctx.needs_input_grad)) else None
+            call("avc_bn_act_fwd_h", _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(z) if need_z32 else _NULL,
+                 _p(z16), FMT_FP16, _p(z16b), FMT_BF16, M, Cout, act, _stream())
+            if z16b is None:
+                z16b = torch.empty(0, device=x.device, dtype=torch.bfloat16)
         else:
+            if not need_z32:
+                raise _lib.AvcError("need_z32=False needs Cout % 8 == 0 (the 16-bit copies are the only output then)")
             z16 = torch.empty(0, device=x.device, dtype=torch.float16)
+            z16b = torch.empty(0, device=x.device, dtype=torch.bfloat16)
             call("avc_bn_act_fwd", _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(residual), _p(z), M, Cout, act, _stream())
-        ctx.save_for_backward(x, weight, gamma, beta, y, z, mean, rstd)
+        # backward needs x only as the weight-gradient operand: keep the bf16 copy when the producer supplied one
+        xb = x16b if (x16b is not None and x16b.numel() == x.numel()) else None
+        # act'(z) is recomputed from y in backward where the float4 kernels apply (Cout % 4 == 0): z is then not saved
+        ctx.save_for_backward(x if xb is None else None, xb, weight, gamma, beta, y, mean, rstd, z if Cout % 4 != 0 else None)
+        ctx.x_shape = tuple(x.shape)
         ctx.act, ctx.training, ctx.has_res, ctx.wd = act, training, residual is not None, wd
-        ctx.mark_non_differentiable(z16)
-        ctx.set_materialize_grads(False)      # no zero tensor for the 16-bit side output's (absent) gradient
-        return z, z16
+        ctx.mark_non_differentiable(z16, z16b)
+        ctx.set_materialize_grads(False)      # no zero tensors for the 16-bit side outputs' (absent) gradients
+        return z, z16, z16b
 
     @staticmethod
-    def backward(ctx, dz, _dz16):
-        x, weight, gamma, beta, y, z, mean, rstd = ctx.saved_tensors
+    def backward(ctx, dz, _dz16, _dz16b):
+        x, xb, weight, gamma, beta, y, mean, rstd, z = ctx.saved_tensors
         if not ctx.training:
             raise _lib.AvcError("backward through eval-mode BatchNorm is not on the supported path")
         dz = dz.contiguous()
-        B, T, Cin = x.shape
+        B, T, Cin = ctx.x_shape
         Cout, _, k = weight.shape
         M = B * T
         sums = torch.zeros(2 * Cout, device=dz.device, dtype=torch.float64)
@@ -608,22 +623,28 @@ class ConvBnActH(torch.autograd.Function):
             dx = torch.empty(B, T, Cin, device=dz.device, dtype=torch.float32)
             gemm_nt_taps_hw(dy, y_fmt, Cout, ctx.wd, FMT_BF16, ctx.wd.shape[-1], None, dx, Cin, B, T, Cin, Cout, k, -(k // 2))
         dw = torch.empty_like(weight)
-        # both operands of a GEMM must share a 16-bit format: the activation gets a bf16 copy here (a 6 B/element pass)
-        X, x_fmt = _operand(x, None, Cin, FMT_BF16) if y_fmt == FMT_BF16 else (x, FMT_FP32)
+        # both operands of a GEMM must share a 16-bit format: bf16 copy of the activation from its producer, else cast here
+        if y_fmt == FMT_BF16:
+            X, x_fmt = (xb, FMT_BF16) if xb is not None else _operand(x, None, Cin, FMT_BF16)
+        else:
+            if x is None:
+                raise _lib.AvcError("conv backward: fp32 input was not saved")
+            X, x_fmt = x, FMT_FP32
         gemm_tn_taps_h(dy, y_fmt, Cout, X, x_fmt, Cin, dw, B, T, Cout, Cin, k, -(k // 2), out_mode=1)   # fp32 operands are staged to bf16
         db = torch.zeros(Cout, device=dz.device, dtype=torch.float32)
         dres = dz if ctx.has_res else None
-        return dx, None, dw, db, dgamma, dbeta, None, None, dres, None, None
+        return dx, None, None, dw, db, dgamma, dbeta, None, None, dres, None, None, None
 
 
 class LstmLayerH(torch.autograd.Function):
-    """One unidirectional nn.LSTM layer in half mode: (x, x16) -> (h, h16).  Persistent recurrence kernels with 16-bit
-    side outputs; input projection on fp16 operands, gradient GEMMs on bf16 (dP) x fp16 (x, h)."""
+    """One unidirectional nn.LSTM layer in half mode: (x, x16, x16b) -> (h, h16, h16b).  Persistent recurrence kernels with
+    16-bit side outputs (fp16: the next forward GEMM's operand; bf16: the weight-gradient GEMMs' operand); input projection on
+    fp16 operands, gradient GEMMs on bf16 (dP) x bf16 (x, h)."""
 
     @staticmethod
-    def forward(ctx, x, x16, w_ih, w_hh, b_ih, b_hh):
+    def forward(ctx, x, x16, x16b, w_ih, w_hh, b_ih, b_hh):
         x = x.contiguous()
-        _check(x, x16, w_ih, w_hh, b_ih, b_hh)
+        _check(x, x16, x16b, w_ih, w_hh, b_ih, b_hh)
         B, T, I = x.shape
         H = w_hh.shape[1]
         G = 4 * H
@@ -635,24 +656,29 @@ class LstmLayerH(torch.autograd.Function):
         gemm_nt_taps_hw(A, a_fmt, I, wi_p, FMT_FP16, wi_p.shape[-1], b_p, Pre, G, B, T, G, I, 1, 0)
         out = torch.empty(B, T, H, device=x.device, dtype=torch.float32)
         h16 = torch.empty(B, T, H, device=x.device, dtype=torch.float16)
+        h16b = torch.empty(B, T, H, device=x.device, dtype=torch.bfloat16) if any(ctx.needs_input_grad) else None
         gates = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
         c_seq = torch.empty(B, T, H, device=x.device, dtype=torch.float32)
         nbytes = query("avc_lstm_fwd_workspace_bytes", B, T, H, PREC_BF16)
         ws = _ws(nbytes, x.device)
-        call("avc_lstm_seq_fwd_h", _p(Pre), _p(wh_p), FMT_BF16, _p(out), H, _p(gates), _p(c_seq), _p(h16), FMT_FP16, B, T, H, 0,
-             _p(ws), nbytes, _stream())
-        ctx.save_for_backward(x, out, w_ih, w_hh, b_ih, gates, c_seq)
+        call("avc_lstm_seq_fwd_h", _p(Pre), _p(wh_p), FMT_BF16, _p(out), H, _p(gates), _p(c_seq), _p(h16), FMT_FP16, _p(h16b),
+             B, T, H, 0, _p(ws), nbytes, _stream())
+        xb = x16b if (x16b is not None and x16b.numel() == x.numel()) else None
+        ctx.save_for_backward(x if xb is None else None, xb, h16b, w_ih, w_hh, b_ih, gates, c_seq)
+        ctx.x_shape = tuple(x.shape)
         ctx.packs = (wi_pT, wh_pT)
-        ctx.mark_non_differentiable(h16)
+        if h16b is None:
+            h16b = torch.empty(0, device=x.device, dtype=torch.bfloat16)
+        ctx.mark_non_differentiable(h16, h16b)
         ctx.set_materialize_grads(False)
-        return out, h16
+        return out, h16, h16b
 
     @staticmethod
-    def backward(ctx, dout, _d16):
-        x, out, w_ih, w_hh, b_ih, gates, c_seq = ctx.saved_tensors
+    def backward(ctx, dout, _d16, _d16b):
+        x, xb, h16b, w_ih, w_hh, b_ih, gates, c_seq = ctx.saved_tensors
         wi_pT, wh_pT = ctx.packs
         dout = dout.contiguous()
-        B, T, I = x.shape
+        B, T, I = ctx.x_shape
         H = w_hh.shape[1]
         G = 4 * H
         # the gate gradient is only ever a GEMM operand / reduced over rows: emit it as bf16 only (no fp32 dP tensor)
@@ -662,10 +688,10 @@ class LstmLayerH(torch.autograd.Function):
         call("avc_lstm_seq_bwd_h", _p(dout), H, _p(wh_pT), FMT_BF16, _p(gates), _p(c_seq), _NULL, _p(dP16), B, T, H, 0, _p(ws),
              nbytes, _stream())
         dw_ih = torch.empty_like(w_ih)
-        X, x_fmt = _operand(x, None, I, FMT_BF16)
+        X, x_fmt = (xb, FMT_BF16) if xb is not None else _operand(x, None, I, FMT_BF16)
         gemm_tn_taps_h(dP16, FMT_BF16, G, X, x_fmt, I, dw_ih, B, T, G, I, 1, 0, out_mode=2)
         dw_hh = torch.empty_like(w_hh)
-        gemm_tn_taps_h(dP16, FMT_BF16, G, cast16(out, FMT_BF16), FMT_BF16, H, dw_hh, B, T, G, H, 1, -1, out_mode=2)
+        gemm_tn_taps_h(dP16, FMT_BF16, G, h16b, FMT_BF16, H, dw_hh, B, T, G, H, 1, -1, out_mode=2)
         db_ih = torch.empty_like(b_ih)
         db_hh = torch.empty_like(b_ih)
         colsum16(dP16, FMT_BF16, G, B * T, G, db_ih, db_hh, out_mode=2)
@@ -673,27 +699,29 @@ class LstmLayerH(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, T, I, device=dout.device, dtype=torch.float32)
             gemm_nt_taps_hw(dP16, FMT_BF16, G, wi_pT, FMT_BF16, G, None, dx, I, B, T, I, G, 1, 0)
-        return dx, None, dw_ih, dw_hh, db_ih, db_hh
+        return dx, None, None, dw_ih, dw_hh, db_ih, db_hh
 
 
 class LinearH(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, x16, weight, bias):
+    def forward(ctx, x, x16, x16b, weight, bias):
         x = x.contiguous()
-        _check(x, x16, weight, bias)
+        _check(x, x16, x16b, weight, bias)
         B, T, K = x.shape
         N = weight.shape[0]
         A, a_fmt = _operand(x, x16, K, FMT_FP16)
         y = torch.empty(B, T, N, device=x.device, dtype=torch.float32)
         gemm_nt_taps_h(A, a_fmt, K, weight.detach(), bias, y, N, B, T, N, K, 1, 0, FMT_FP16)
-        ctx.save_for_backward(x, weight)
+        xb = x16b if (x16b is not None and x16b.numel() == x.numel()) else None
+        ctx.save_for_backward(x if xb is None else None, xb, weight)
+        ctx.x_shape = tuple(x.shape)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, xb, weight = ctx.saved_tensors
         dy = dy.contiguous()
-        B, T, K = x.shape
+        B, T, K = ctx.x_shape
         N = weight.shape[0]
         D, d_fmt = _operand(dy, None, N, FMT_BF16)
         dx = None
@@ -702,8 +730,11 @@ class LinearH(torch.autograd.Function):
             dx = torch.empty(B, T, K, device=dy.device, dtype=torch.float32)
             gemm_nt_taps_h(D, d_fmt, N, wT, None, dx, K, B, T, K, N, 1, 0, FMT_BF16)
         dw = torch.empty_like(weight)
-        X, x_fmt = _operand(x, None, K, FMT_BF16) if d_fmt == FMT_BF16 else (x, FMT_FP32)
+        if d_fmt == FMT_BF16:
+            X, x_fmt = (xb, FMT_BF16) if xb is not None else _operand(x, None, K, FMT_BF16)
+        else:
+            X, x_fmt = (x, FMT_FP32) if x is not None else (xb, FMT_BF16)
         gemm_tn_taps_h(D, d_fmt, N, X, x_fmt, K, dw, B, T, N, K, 1, 0, out_mode=0)
         db = torch.empty(N, device=dy.device, dtype=torch.float32)
         colsum(dy, N, B * T, N, db)
-        return dx, None, dw, db
+        return dx, None, None, dw, db

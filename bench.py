@@ -152,7 +152,7 @@ def kernel_flops(name, a):
         nB, T, N, K, taps = a[9], a[10], a[11], a[12], a[13]
         return 2.0 * nB * T * N * K * taps
     if name == "avc_lstm_seq_fwd_h":
-        nB, T, H = a[9], a[10], a[11]
+        nB, T, H = a[10], a[11], a[12]
         return 2.0 * nB * T * 4 * H * H
     if name == "avc_lstm_seq_bwd_h":
         nB, T, H = a[8], a[9], a[10]

@@ -191,9 +191,12 @@ int avc_gemm_tn_taps_h(const void* dY, int y_fmt, int ldy, const void* X, int x_
 size_t avc_gemm_tn_h_workspace_bytes(int nB, int T, int N, int K, int ntaps, int y_fmt, int x_fmt);
 /* dst16 (M, C) ld ldd <- src fp32 (M, C) ld lds */
 int avc_cast16(const float* src, int lds, void* dst, int ldd, size_t M, int C, int fmt, void* stream);
-/* avc_bn_act_fwd that also writes z16 (C % 4 == 0) */
+/* avc_bn_act_fwd that also writes the 16-bit operand copies (C % 4 == 0): z16 in fmt16 (forward operand of the next GEMM)
+ * and, when z16b != NULL, a second copy in fmt16b (the bf16 operand of the next layer's weight-gradient GEMM).
+ * z (fp32) may be NULL when no consumer reads the activation in fp32. */
 int avc_bn_act_fwd_h(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                     const float* residual, float* z, void* z16, int fmt16, int M, int C, int act, void* stream);
+                     const float* residual, float* z, void* z16, int fmt16, void* z16b, int fmt16b, int M, int C, int act,
+                     void* stream);
 /* avc_bn_act_bwd_apply that writes dy16 (and fp32 dy only when dy != NULL) */
 int avc_bn_act_bwd_apply_h(const float* dz, const float* z, const float* y, const float* mean, const float* rstd,
                            const float* gamma, const double* sums, float* dy, void* dy16, int fmt16, float* dgamma,
@@ -201,8 +204,9 @@ int avc_bn_act_bwd_apply_h(const float* dz, const float* z, const float* y, cons
 /* persistent recurrences (128 <= H <= 1024, H % 64 == 0) with a 16-bit side output: h16 (nB,T,H) / dP16 (nB,T,4H, bf16) */
 /* w_fmt: AVC_FMT_FP32 = Whh_p / Whh_pT are the fp32 packings of avc_pack_lstm_weight (converted per call);
  *        AVC_FMT_BF16 = the bf16 packings of avc_pack_lstm_weight_h (ld = H resp. 4H), read in place. */
+/* h16b (optional, may be NULL): a bf16 copy of h next to h16 -- the operand of the dW_hh / next layer's dW_ih GEMMs. */
 int avc_lstm_seq_fwd_h(const float* P, const void* Whh_p, int w_fmt, float* h_seq, int ldh, float* gates, float* c_seq, void* h16,
-                       int fmt16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes, void* stream);
+                       int fmt16, void* h16b, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes, void* stream);
 /* (dP, the fp32 gate-gradient tensor, may be NULL: only dP16 is then written) */
 int avc_lstm_seq_bwd_h(const float* dH, int lddh, const void* Whh_pT, int w_fmt, const float* gates, const float* c_seq, float* dP,
                        void* dP16, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes, void* stream);

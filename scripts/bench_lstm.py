@@ -30,7 +30,7 @@ for (B, T, H) in [(256, 128, 1024), (256, 128, 512), (128, 256, 1024)]:
     dP16 = torch.empty(B, T, G, device=dev, dtype=torch.bfloat16)
     Wb, WTb = W.bfloat16(), WT.bfloat16()
     def fwd_h():     # half mode: pre-packed bf16 W_hh, fp16 copy of h
-        _lib.call("avc_lstm_seq_fwd_h", _p(P), _p(Wb), 1, _p(h), H, _p(gates), _p(c), _p(h16), 2, B, T, H, 0, _p(wf), nf, _stream())
+        _lib.call("avc_lstm_seq_fwd_h", _p(P), _p(Wb), 1, _p(h), H, _p(gates), _p(c), _p(h16), 2, None, B, T, H, 0, _p(wf), nf, _stream())
     def bwd_h():     # half mode: gate gradient as bf16 only
         _lib.call("avc_lstm_seq_bwd_h", _p(dH), H, _p(WTb), 1, _p(gates), _p(c), None, _p(dP16), B, T, H, 0, _p(wb), nb, _stream())
     for name, fn in (("fwd", fwd), ("bwd", bwd), ("fwd_h", fwd_h), ("bwd_h", bwd_h)):
