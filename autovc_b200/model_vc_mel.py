@@ -68,7 +68,8 @@ class ConvNorm(nn.Module):
         raise RuntimeError("ConvNorm is fused with its BatchNorm and activation; call the owning block")
 
 
-def _conv_bn_act(block: nn.Sequential, x, act: str, residual=None, prec=PREC_FP32, x16=None, x16b=None, need_z32=True):
+def _conv_bn_act(block: nn.Sequential, x, act: str, residual=None, prec=PREC_FP32, x16=None, x16b=None, need_z32=True,
+                 side_wgrad=False):
     """act(BN(conv(x))) (+ residual) on channels-last x; bumps num_batches_tracked like nn.BatchNorm1d.
     Returns (z, z16, z16b): the fp16 / bf16 operand copies in half mode, else None.  ``need_z32=False`` (half mode only):
     the caller promises that nothing reads the fp32 activation, which is then not written (z is the autograd carrier)."""
@@ -79,7 +80,7 @@ def _conv_bn_act(block: nn.Sequential, x, act: str, residual=None, prec=PREC_FP3
         Cout = conv.weight.shape[0]
         z, z16, z16b = ops.ConvBnActH.apply(x, x16, x16b, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
                                             bn.running_var, residual, ACT_CODES[act], training,
-                                            need_z32 or Cout % 8 != 0 or not training)
+                                            need_z32 or Cout % 8 != 0 or not training, side_wgrad)
         z16 = z16 if z16.numel() else None
         z16b = z16b if z16b.numel() else None
     else:
@@ -90,7 +91,7 @@ def _conv_bn_act(block: nn.Sequential, x, act: str, residual=None, prec=PREC_FP3
     return z, z16, z16b
 
 
-def _lstm(x, lstm: nn.LSTM, prec, x16=None, x16b=None):
+def _lstm(x, lstm: nn.LSTM, prec, x16=None, x16b=None, side_wgrad=False):
     """Run an nn.LSTM's parameters through the LstmLayer kernels, layer by layer.  Returns (h, h16, h16b)."""
     H = lstm.hidden_size
     half = prec == PREC_HALF and not lstm.bidirectional and 128 <= H <= 1024 and H % 64 == 0
@@ -99,7 +100,7 @@ def _lstm(x, lstm: nn.LSTM, prec, x16=None, x16b=None):
         for suffix in (("", "_reverse") if lstm.bidirectional else ("",)):
             ws += [getattr(lstm, f"{n}_l{l}{suffix}") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
         if half:
-            x, x16, x16b = ops.LstmLayerH.apply(x, x16, x16b, *ws)
+            x, x16, x16b = ops.LstmLayerH.apply(x, x16, x16b, *ws, side_wgrad)
             x16b = x16b if x16b.numel() else None
         else:   # encoder BiLSTM (H = dim_neck): tiny GEMMs, fp32 recurrence; tf32 operands in half mode
             x = ops.LstmLayer.apply(x, PREC_TF32 if prec == PREC_HALF else prec, *ws)
@@ -157,18 +158,20 @@ class Decoder(nn.Module):
         self.lstm2 = nn.LSTM(dim_pre, 1024, 2, batch_first=True)
         self.linear_projection = LinearNorm(1024, n_bins)
 
-    def forward(self, x):
-        h, h16, h16b = _lstm(x, self.lstm1, self.prec)
+    def forward(self, x, side_wgrad: bool = False):
+        # side_wgrad (set by Generator.forward, where decoder / postnet parameters are used once per graph): the weight
+        # gradients are computed on the side stream (ops._wgrad_side)
+        h, h16, h16b = _lstm(x, self.lstm1, self.prec, side_wgrad=side_wgrad)
         # half mode: lstm2 (persistent kernels, H = 1024) reads the 16-bit copies only -> no fp32 activation in between
         lstm2_half = self.prec == PREC_HALF and 128 <= self.lstm2.hidden_size <= 1024 and self.lstm2.hidden_size % 64 == 0
         n = len(self.convolutions)
         for i, block in enumerate(self.convolutions):
             h, h16, h16b = _conv_bn_act(block, h, "relu", prec=self.prec, x16=h16, x16b=h16b,
-                                        need_z32=(i == n - 1 and not lstm2_half))
-        h, h16, h16b = _lstm(h, self.lstm2, self.prec, x16=h16, x16b=h16b)
+                                        need_z32=(i == n - 1 and not lstm2_half), side_wgrad=side_wgrad)
+        h, h16, h16b = _lstm(h, self.lstm2, self.prec, x16=h16, x16b=h16b, side_wgrad=side_wgrad)
         lin = self.linear_projection.linear_layer
         if self.prec == PREC_HALF:
-            return ops.LinearH.apply(h, h16, h16b, lin.weight, lin.bias)
+            return ops.LinearH.apply(h, h16, h16b, lin.weight, lin.bias, side_wgrad)
         return ops.Linear.apply(h, lin.weight, lin.bias, self.prec)
 
 
@@ -190,13 +193,15 @@ class Postnet(nn.Module):
             ConvNorm(512, n_bins, kernel_size=5, stride=1, padding=2, dilation=1, w_init_gain="linear"),
             nn.BatchNorm1d(n_bins)))
 
-    def channels_last(self, x, residual=None):
+    def channels_last(self, x, residual=None, side_wgrad: bool = False):
         """x (B,T,n_bins) -> postnet(x) (+ residual), channels-last."""
         n = len(self.convolutions)
         x16 = x16b = None
         for i in range(n - 1):
-            x, x16, x16b = _conv_bn_act(self.convolutions[i], x, "tanh", prec=self.prec, x16=x16, x16b=x16b, need_z32=False)
-        return _conv_bn_act(self.convolutions[-1], x, "none", residual=residual, prec=self.prec, x16=x16, x16b=x16b)[0]
+            x, x16, x16b = _conv_bn_act(self.convolutions[i], x, "tanh", prec=self.prec, x16=x16, x16b=x16b, need_z32=False,
+                                        side_wgrad=side_wgrad)
+        return _conv_bn_act(self.convolutions[-1], x, "none", residual=residual, prec=self.prec, x16=x16, x16b=x16b,
+                            side_wgrad=side_wgrad)[0]
 
     def forward(self, x):
         # reference layout: channel-first (B, n_bins, T) in and out (model_vc_mel.py:163-169, :196)
@@ -228,10 +233,11 @@ class Generator(nn.Module):
         if x.dim() != 3:
             raise ValueError("full forward takes x of shape (B, T, n_bins)")
         ops._GLOBAL_CACHE.begin_step()
+        ops.note_full_forward()
         T = x.size(1)
         codes = self.encoder.codes(x, c_org)
         dec_in = ops.UpsampleConcat.apply(codes, c_trg, T)          # :186-192
-        x_identic = self.decoder(dec_in)                             # :194
-        x_identic_psnt = self.postnet.channels_last(x_identic, residual=x_identic)   # :196-197
+        x_identic = self.decoder(dec_in, side_wgrad=True)            # :194
+        x_identic_psnt = self.postnet.channels_last(x_identic, residual=x_identic, side_wgrad=True)   # :196-197
         code_real = codes.reshape(codes.size(0), -1)                 # :201
         return x_identic.unsqueeze(1), x_identic_psnt.unsqueeze(1), code_real

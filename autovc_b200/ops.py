@@ -7,6 +7,7 @@ are channels-last (B, T, C) float32 contiguous.  No CPU fallback: CPU tensors ra
 from __future__ import annotations
 
 import ctypes
+import os
 import weakref
 from typing import List, Optional, Sequence
 
@@ -44,6 +45,68 @@ def _ws(nbytes: int, device) -> Optional[torch.Tensor]:
     if nbytes <= 0:
         return None
     return torch.empty((nbytes + 15) // 16 * 2, dtype=torch.float64, device=device)
+
+
+# --------------------------------------------------------------------------------------
+# weight-gradient side stream
+# --------------------------------------------------------------------------------------
+# A weight gradient is a leaf of the backward graph: nothing in backward reads it, only the optimizer (and the
+# data-parallel all-reduce) after the pass.  The blocks that own single-use parameters (decoder, postnet) therefore
+# launch their weight-gradient GEMMs / bias column sums on a second stream: they then run concurrently with the next
+# layer's HBM-bound BatchNorm passes and on the SMs a persistent recurrence leaves idle, instead of in front of them.
+# The main stream re-joins the side stream in an end-of-backward engine callback (and in GradBucketReducer's hooks).
+# Parameters used more than once per graph (the encoder: two passes per step) stay on the main stream, because autograd
+# sums their contributions there.
+_WGRAD = {"on": os.environ.get("AUTOVC_B200_WGRAD_STREAM", "1") != "0", "streams": {}, "armed": set(), "fwd_since_bwd": 0}
+
+
+def wgrad_stream(device) -> Optional[torch.cuda.Stream]:
+    """The weight-gradient side stream of `device` if one was ever used, else None (GradBucketReducer joins it)."""
+    return _WGRAD["streams"].get(torch.device(device).index)
+
+
+def note_full_forward():
+    """Called by Generator.forward: two graph-building forwards before one backward mean a parameter may receive two
+    contributions, which autograd sums on the main stream -> the side stream is not used for that backward."""
+    if torch.is_grad_enabled():
+        _WGRAD["fwd_since_bwd"] += 1
+    _WGRAD["armed"].clear()
+
+
+def _side_join(index: int):
+    st = _WGRAD["streams"].get(index)
+    if st is not None:
+        torch.cuda.current_stream(st.device).wait_stream(st)
+    _WGRAD["armed"].discard(index)
+    _WGRAD["fwd_since_bwd"] = 0
+
+
+class _MainStream:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+def _wgrad_side(allowed: bool, device, reads: Sequence[Optional[torch.Tensor]]):
+    """Context manager for the weight-gradient launches of one backward node: the side stream (ordered after everything
+    queued on the main stream so far) when allowed, else a no-op.  `reads`: tensors the side launches read, which the
+    main-stream allocator must not recycle before they ran."""
+    if not (allowed and _WGRAD["on"] and _WGRAD["fwd_since_bwd"] <= 1):
+        return _MainStream()
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _WGRAD["streams"].get(idx)
+    if st is None:
+        st = _WGRAD["streams"][idx] = torch.cuda.Stream(device=device)
+    st.wait_stream(torch.cuda.current_stream(device))
+    for t in reads:
+        if t is not None:
+            t.record_stream(st)
+    if idx not in _WGRAD["armed"]:
+        _WGRAD["armed"].add(idx)
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: _side_join(idx))
+    return torch.cuda.stream(st)
 
 
 # --------------------------------------------------------------------------------------
@@ -547,7 +610,7 @@ class ConvBnActH(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, x16, x16b, weight, bias, gamma, beta, running_mean, running_var, residual, act: int, training: bool,
-                need_z32: bool = True):
+                need_z32: bool = True, side_wgrad: bool = False):
         x = x.contiguous()
         _check(x, x16, x16b, weight, bias, gamma, beta, running_mean, running_var, residual)
         if residual is not None and act != ACT_NONE:
@@ -590,6 +653,7 @@ class ConvBnActH(torch.autograd.Function):
         ctx.save_for_backward(x if xb is None else None, xb, weight, gamma, beta, y, mean, rstd, z if Cout % 4 != 0 else None)
         ctx.x_shape = tuple(x.shape)
         ctx.act, ctx.training, ctx.has_res, ctx.wd = act, training, residual is not None, wd
+        ctx.side_wgrad = side_wgrad
         ctx.mark_non_differentiable(z16, z16b)
         ctx.set_materialize_grads(False)      # no zero tensors for the 16-bit side outputs' (absent) gradients
         return z, z16, z16b
@@ -622,18 +686,19 @@ class ConvBnActH(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, T, Cin, device=dz.device, dtype=torch.float32)
             gemm_nt_taps_hw(dy, y_fmt, Cout, ctx.wd, FMT_BF16, ctx.wd.shape[-1], None, dx, Cin, B, T, Cin, Cout, k, -(k // 2))
-        dw = torch.empty_like(weight)
-        # both operands of a GEMM must share a 16-bit format: bf16 copy of the activation from its producer, else cast here
-        if y_fmt == FMT_BF16:
-            X, x_fmt = (xb, FMT_BF16) if xb is not None else _operand(x, None, Cin, FMT_BF16)
-        else:
-            if x is None:
-                raise _lib.AvcError("conv backward: fp32 input was not saved")
-            X, x_fmt = x, FMT_FP32
-        gemm_tn_taps_h(dy, y_fmt, Cout, X, x_fmt, Cin, dw, B, T, Cout, Cin, k, -(k // 2), out_mode=1)   # fp32 operands are staged to bf16
+        with _wgrad_side(ctx.side_wgrad, dz.device, (dy, x, xb)):
+            dw = torch.empty_like(weight)
+            # both operands of a GEMM must share a 16-bit format: bf16 copy of the activation from its producer, else cast here
+            if y_fmt == FMT_BF16:
+                X, x_fmt = (xb, FMT_BF16) if xb is not None else _operand(x, None, Cin, FMT_BF16)
+            else:
+                if x is None:
+                    raise _lib.AvcError("conv backward: fp32 input was not saved")
+                X, x_fmt = x, FMT_FP32
+            gemm_tn_taps_h(dy, y_fmt, Cout, X, x_fmt, Cin, dw, B, T, Cout, Cin, k, -(k // 2), out_mode=1)   # fp32 operands are staged to bf16
         db = torch.zeros(Cout, device=dz.device, dtype=torch.float32)
         dres = dz if ctx.has_res else None
-        return dx, None, None, dw, db, dgamma, dbeta, None, None, dres, None, None, None
+        return dx, None, None, dw, db, dgamma, dbeta, None, None, dres, None, None, None, None
 
 
 class LstmLayerH(torch.autograd.Function):
@@ -642,9 +707,10 @@ class LstmLayerH(torch.autograd.Function):
     fp16 operands, gradient GEMMs on bf16 (dP) x bf16 (x, h)."""
 
     @staticmethod
-    def forward(ctx, x, x16, x16b, w_ih, w_hh, b_ih, b_hh):
+    def forward(ctx, x, x16, x16b, w_ih, w_hh, b_ih, b_hh, side_wgrad: bool = False):
         x = x.contiguous()
         _check(x, x16, x16b, w_ih, w_hh, b_ih, b_hh)
+        ctx.side_wgrad = side_wgrad
         B, T, I = x.shape
         H = w_hh.shape[1]
         G = 4 * H
@@ -687,26 +753,29 @@ class LstmLayerH(torch.autograd.Function):
         ws = _ws(nbytes, dout.device)
         call("avc_lstm_seq_bwd_h", _p(dout), H, _p(wh_pT), FMT_BF16, _p(gates), _p(c_seq), _NULL, _p(dP16), B, T, H, 0, _p(ws),
              nbytes, _stream())
-        dw_ih = torch.empty_like(w_ih)
-        X, x_fmt = (xb, FMT_BF16) if xb is not None else _operand(x, None, I, FMT_BF16)
-        gemm_tn_taps_h(dP16, FMT_BF16, G, X, x_fmt, I, dw_ih, B, T, G, I, 1, 0, out_mode=2)
-        dw_hh = torch.empty_like(w_hh)
-        gemm_tn_taps_h(dP16, FMT_BF16, G, h16b, FMT_BF16, H, dw_hh, B, T, G, H, 1, -1, out_mode=2)
-        db_ih = torch.empty_like(b_ih)
-        db_hh = torch.empty_like(b_ih)
-        colsum16(dP16, FMT_BF16, G, B * T, G, db_ih, db_hh, out_mode=2)
+        # the data gradient first (the next BPTT / conv backward waits for it), the parameter gradients on the side stream
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, T, I, device=dout.device, dtype=torch.float32)
             gemm_nt_taps_hw(dP16, FMT_BF16, G, wi_pT, FMT_BF16, G, None, dx, I, B, T, I, G, 1, 0)
-        return dx, None, None, dw_ih, dw_hh, db_ih, db_hh
+        with _wgrad_side(ctx.side_wgrad, dout.device, (dP16, x, xb, h16b)):
+            dw_ih = torch.empty_like(w_ih)
+            X, x_fmt = (xb, FMT_BF16) if xb is not None else _operand(x, None, I, FMT_BF16)
+            gemm_tn_taps_h(dP16, FMT_BF16, G, X, x_fmt, I, dw_ih, B, T, G, I, 1, 0, out_mode=2)
+            dw_hh = torch.empty_like(w_hh)
+            gemm_tn_taps_h(dP16, FMT_BF16, G, h16b, FMT_BF16, H, dw_hh, B, T, G, H, 1, -1, out_mode=2)
+            db_ih = torch.empty_like(b_ih)
+            db_hh = torch.empty_like(b_ih)
+            colsum16(dP16, FMT_BF16, G, B * T, G, db_ih, db_hh, out_mode=2)
+        return dx, None, None, dw_ih, dw_hh, db_ih, db_hh, None
 
 
 class LinearH(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, x16, x16b, weight, bias):
+    def forward(ctx, x, x16, x16b, weight, bias, side_wgrad: bool = False):
         x = x.contiguous()
         _check(x, x16, x16b, weight, bias)
+        ctx.side_wgrad = side_wgrad
         B, T, K = x.shape
         N = weight.shape[0]
         A, a_fmt = _operand(x, x16, K, FMT_FP16)
@@ -729,12 +798,13 @@ class LinearH(torch.autograd.Function):
             wT = transpose2d(weight, PackCache())
             dx = torch.empty(B, T, K, device=dy.device, dtype=torch.float32)
             gemm_nt_taps_h(D, d_fmt, N, wT, None, dx, K, B, T, K, N, 1, 0, FMT_BF16)
-        dw = torch.empty_like(weight)
-        if d_fmt == FMT_BF16:
-            X, x_fmt = (xb, FMT_BF16) if xb is not None else _operand(x, None, K, FMT_BF16)
-        else:
-            X, x_fmt = (x, FMT_FP32) if x is not None else (xb, FMT_BF16)
-        gemm_tn_taps_h(D, d_fmt, N, X, x_fmt, K, dw, B, T, N, K, 1, 0, out_mode=0)
-        db = torch.empty(N, device=dy.device, dtype=torch.float32)
-        colsum(dy, N, B * T, N, db)
-        return dx, None, None, dw, db
+        with _wgrad_side(ctx.side_wgrad, dy.device, (dy, D, x, xb)):
+            dw = torch.empty_like(weight)
+            if d_fmt == FMT_BF16:
+                X, x_fmt = (xb, FMT_BF16) if xb is not None else _operand(x, None, K, FMT_BF16)
+            else:
+                X, x_fmt = (x, FMT_FP32) if x is not None else (xb, FMT_BF16)
+            gemm_tn_taps_h(D, d_fmt, N, X, x_fmt, K, dw, B, T, N, K, 1, 0, out_mode=0)
+            db = torch.empty(N, device=dy.device, dtype=torch.float32)
+            colsum(dy, N, B * T, N, db)
+        return dx, None, None, dw, db, None

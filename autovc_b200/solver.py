@@ -175,7 +175,16 @@ class GradBucketReducer:
         bi, off = self._where[p]
         b = self.buckets[bi]
         view = b["flat"][off:off + p.numel()].view_as(p)
-        view.copy_(p.grad)
+        side = ops.wgrad_stream(p.device) if p.is_cuda else None
+        if side is None:
+            view.copy_(p.grad)
+        else:
+            # the gradient may have been produced on the weight-gradient side stream (ops._wgrad_side): copy it there,
+            # after everything queued on the main stream, so that the main stream never waits for a weight-gradient GEMM
+            side.wait_stream(torch.cuda.current_stream(p.device))
+            with torch.cuda.stream(side):
+                view.copy_(p.grad)
+            p.grad.record_stream(side)
         p.grad = view
         b["ready"] += 1
         if b["ready"] == len(b["params"]):
@@ -189,6 +198,9 @@ class GradBucketReducer:
         op = dist.ReduceOp.AVG if self.backend == "nccl" else dist.ReduceOp.SUM
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
+            side = ops.wgrad_stream(b["flat"].device)
+            if side is not None:
+                self.comm_stream.wait_stream(side)
             with torch.cuda.stream(self.comm_stream):
                 work = dist.all_reduce(b["flat"], op=op, group=self.group, async_op=True)
         else:

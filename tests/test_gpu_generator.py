@@ -182,3 +182,43 @@ def test_host_batch_prefetcher_hands_over_batches_in_order():
             pf.put(xs[i + 1], es[i + 1])
         y = (xd * 2).sum() + ed.sum()          # consume on the compute stream
         assert float(y) == float(xs[i].sum() * 2 + es[i].sum())
+
+
+def _half_step_grads(side_on, two_forwards=False, seed=3):
+    """One half-mode training step from a fixed state; returns (losses, {name: grad})."""
+    from autovc_b200 import ops
+    torch.manual_seed(seed)
+    G = autovc_b200.Generator(16, 256, 512, 16, precision="half").cuda().train()
+    x, e, _ = synth_inputs(8, 64, 80, 256, 11)
+    x, e = x.cuda(), e.cuda()
+    old = ops._WGRAD["on"]
+    ops._WGRAD["on"] = side_on
+    try:
+        if two_forwards:
+            # two graph-building forwards, ONE backward: decoder / postnet parameters receive two contributions, which
+            # autograd sums on the main stream -> the side stream must stand down for that backward
+            l1, _, _ = solver.generator_losses(G, x, e)
+            l2, _, _ = solver.generator_losses(G, x.flip(0).contiguous(), e.flip(0).contiguous())
+            (l1 + l2).backward()
+            losses = [float(l1), float(l2)]
+        else:
+            loss, terms, _ = solver.generator_losses(G, x, e)
+            loss.backward()
+            losses = [float(loss)] + [float(t) for t in terms]
+        torch.cuda.synchronize()
+        return losses, {n: p.grad.detach().clone() for n, p in G.named_parameters()}
+    finally:
+        ops._WGRAD["on"] = old
+
+
+@pytest.mark.parametrize("two_forwards", [False, True])
+def test_weight_gradient_side_stream_changes_nothing(two_forwards):
+    """The weight-gradient GEMMs of decoder/postnet run on a second stream (ops._wgrad_side); same kernels, same inputs
+    -> the gradients must equal the single-stream ones (up to the order of the fp64 atomics in the BatchNorm sums)."""
+    for trial in range(3):          # a race would show up sporadically
+        l_ref, g_ref = _half_step_grads(False, two_forwards)
+        l_got, g_got = _half_step_grads(True, two_forwards)
+        np.testing.assert_allclose(l_got, l_ref, rtol=1e-6)
+        for n in g_ref:
+            a, b = g_got[n].double(), g_ref[n].double()
+            assert float((a - b).norm()) <= 1e-5 * float(b.norm()) + 1e-12, (trial, n)
