@@ -89,13 +89,20 @@ class _MainStream:
         return False
 
 
-def _wgrad_side(allowed: bool, device, reads: Sequence[Optional[torch.Tensor]]):
+def _wgrad_side(allowed: bool, device, reads: Sequence[Optional[torch.Tensor]], params: Sequence[torch.Tensor] = ()):
     """Context manager for the weight-gradient launches of one backward node: the side stream (ordered after everything
     queued on the main stream so far) when allowed, else a no-op.  `reads`: tensors the side launches read, which the
-    main-stream allocator must not recycle before they ran."""
-    if not (allowed and _WGRAD["on"] and _WGRAD["fwd_since_bwd"] <= 1):
+    main-stream allocator must not recycle before they ran.  `params`: the parameters whose gradients are produced; if
+    one already holds a gradient (accumulation over several backward passes) autograd adds to it on the main stream,
+    so the node stays there."""
+    if not (allowed and _WGRAD["on"]):
         return _MainStream()
     idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _WGRAD["armed"]:        # once per backward pass: join the side stream and reset the forward counter at its end
+        _WGRAD["armed"].add(idx)
+        torch.autograd.Variable._execution_engine.queue_callback(lambda: _side_join(idx))
+    if _WGRAD["fwd_since_bwd"] > 1 or any(p.grad is not None for p in params):
+        return _MainStream()
     st = _WGRAD["streams"].get(idx)
     if st is None:
         st = _WGRAD["streams"][idx] = torch.cuda.Stream(device=device)
@@ -103,9 +110,6 @@ def _wgrad_side(allowed: bool, device, reads: Sequence[Optional[torch.Tensor]]):
     for t in reads:
         if t is not None:
             t.record_stream(st)
-    if idx not in _WGRAD["armed"]:
-        _WGRAD["armed"].add(idx)
-        torch.autograd.Variable._execution_engine.queue_callback(lambda: _side_join(idx))
     return torch.cuda.stream(st)
 
 
@@ -686,7 +690,7 @@ class ConvBnActH(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, T, Cin, device=dz.device, dtype=torch.float32)
             gemm_nt_taps_hw(dy, y_fmt, Cout, ctx.wd, FMT_BF16, ctx.wd.shape[-1], None, dx, Cin, B, T, Cin, Cout, k, -(k // 2))
-        with _wgrad_side(ctx.side_wgrad, dz.device, (dy, x, xb)):
+        with _wgrad_side(ctx.side_wgrad, dz.device, (dy, x, xb), (weight,)):
             dw = torch.empty_like(weight)
             # both operands of a GEMM must share a 16-bit format: bf16 copy of the activation from its producer, else cast here
             if y_fmt == FMT_BF16:
@@ -758,7 +762,7 @@ class LstmLayerH(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(B, T, I, device=dout.device, dtype=torch.float32)
             gemm_nt_taps_hw(dP16, FMT_BF16, G, wi_pT, FMT_BF16, G, None, dx, I, B, T, I, G, 1, 0)
-        with _wgrad_side(ctx.side_wgrad, dout.device, (dP16, x, xb, h16b)):
+        with _wgrad_side(ctx.side_wgrad, dout.device, (dP16, x, xb, h16b), (w_ih, w_hh, b_ih)):
             dw_ih = torch.empty_like(w_ih)
             X, x_fmt = (xb, FMT_BF16) if xb is not None else _operand(x, None, I, FMT_BF16)
             gemm_tn_taps_h(dP16, FMT_BF16, G, X, x_fmt, I, dw_ih, B, T, G, I, 1, 0, out_mode=2)
@@ -798,7 +802,7 @@ class LinearH(torch.autograd.Function):
             wT = transpose2d(weight, PackCache())
             dx = torch.empty(B, T, K, device=dy.device, dtype=torch.float32)
             gemm_nt_taps_h(D, d_fmt, N, wT, None, dx, K, B, T, K, N, 1, 0, FMT_BF16)
-        with _wgrad_side(ctx.side_wgrad, dy.device, (dy, D, x, xb)):
+        with _wgrad_side(ctx.side_wgrad, dy.device, (dy, D, x, xb), (weight,)):
             dw = torch.empty_like(weight)
             if d_fmt == FMT_BF16:
                 X, x_fmt = (xb, FMT_BF16) if xb is not None else _operand(x, None, K, FMT_BF16)

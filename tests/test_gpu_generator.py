@@ -184,7 +184,7 @@ def test_host_batch_prefetcher_hands_over_batches_in_order():
         assert float(y) == float(xs[i].sum() * 2 + es[i].sum())
 
 
-def _half_step_grads(side_on, two_forwards=False, seed=3):
+def _half_step_grads(side_on, mode="step", seed=3):
     """One half-mode training step from a fixed state; returns (losses, {name: grad})."""
     from autovc_b200 import ops
     torch.manual_seed(seed)
@@ -194,7 +194,13 @@ def _half_step_grads(side_on, two_forwards=False, seed=3):
     old = ops._WGRAD["on"]
     ops._WGRAD["on"] = side_on
     try:
-        if two_forwards:
+        if mode == "accumulate":
+            # gradient accumulation over two backward passes without zero_grad: AccumulateGrad adds on the main stream
+            for xx, ee in ((x, e), (x.flip(0).contiguous(), e.flip(0).contiguous())):
+                loss, _, _ = solver.generator_losses(G, xx, ee)
+                loss.backward()
+            losses = [float(loss)]
+        elif mode == "two_forwards":
             # two graph-building forwards, ONE backward: decoder / postnet parameters receive two contributions, which
             # autograd sums on the main stream -> the side stream must stand down for that backward
             l1, _, _ = solver.generator_losses(G, x, e)
@@ -211,13 +217,13 @@ def _half_step_grads(side_on, two_forwards=False, seed=3):
         ops._WGRAD["on"] = old
 
 
-@pytest.mark.parametrize("two_forwards", [False, True])
-def test_weight_gradient_side_stream_changes_nothing(two_forwards):
+@pytest.mark.parametrize("mode", ["step", "two_forwards", "accumulate"])
+def test_weight_gradient_side_stream_changes_nothing(mode):
     """The weight-gradient GEMMs of decoder/postnet run on a second stream (ops._wgrad_side); same kernels, same inputs
     -> the gradients must equal the single-stream ones (up to the order of the fp64 atomics in the BatchNorm sums)."""
     for trial in range(3):          # a race would show up sporadically
-        l_ref, g_ref = _half_step_grads(False, two_forwards)
-        l_got, g_got = _half_step_grads(True, two_forwards)
+        l_ref, g_ref = _half_step_grads(False, mode)
+        l_got, g_got = _half_step_grads(True, mode)
         np.testing.assert_allclose(l_got, l_ref, rtol=1e-6)
         for n in g_ref:
             a, b = g_got[n].double(), g_ref[n].double()
