@@ -9,26 +9,28 @@
 //            20*log10(max(1e-5,.)) - 16, (x+100)/100 clipped to [0,1]                              :78-83
 // HBM-bound by design: every stage streams its input once; the FFT, window, mel and log work stay in
 // shared memory / registers.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace avc {
 
 constexpr int FE_NFFT = 1024, FE_HOP = 256, FE_BINS = 513, FE_MELS = 80, FE_PADLEN = 18, FE_REFLECT = 512;
-constexpr int FE_FRAMES_PER_CTA = 8;   // 4 complex FFTs per CTA
-constexpr int FE_THREADS = 256;
+constexpr int FE_FRAMES_PER_CTA = 8;   // 4 complex FFTs per CTA, one warp each
+constexpr int FE_THREADS = 32 * (FE_FRAMES_PER_CTA / 2);
 
 struct FeTables {           // lives at the head of the workspace
-  float2 tw[FE_NFFT / 2];   // exp(-2*pi*i*k/1024)
+  float2 tw2[FE_NFFT];      // tw2[c*32 + b] = exp(-2*pi*i*(b*c)/1024): the inter-pass twiddles of the 32 x 32 decomposition
   float win[FE_NFFT];       // periodic Hann
   int2 band[FE_MELS];       // [first, last+1) non-zero FFT bin of each mel filter
 };
 
 __global__ void fe_tables_kernel(const float* __restrict__ mel_basis, FeTables* __restrict__ tb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < FE_NFFT / 2) {
+  if (i < FE_NFFT) {
     double s, c;
-    sincospi(-2.0 * (double)i / (double)FE_NFFT, &s, &c);
-    tb->tw[i] = make_float2((float)c, (float)s);
+    sincospi(-2.0 * (double)(((i >> 5) * (i & 31)) & (FE_NFFT - 1)) / (double)FE_NFFT, &s, &c);
+    tb->tw2[i] = make_float2((float)c, (float)s);
   }
   if (i < FE_NFFT) tb->win[i] = (float)(0.5 - 0.5 * cospi(2.0 * (double)i / (double)FE_NFFT));
   if (i < FE_MELS) {
@@ -301,8 +303,242 @@ __global__ void fe_iir_output_kernel(const float* __restrict__ wav, const float*
   }
 }
 
+// --- stage 1+2, fused: one CTA per utterance walks the sweep tile by tile ------------------------------------------
+// The three-launch scheme above reads every input twice and lets each thread walk its own 256-sample chunk straight from
+// global memory (lanes 1 KB apart: r01c ncu 1.3-1.7 TB/s at 62-94% L1/TEX busy, 5.3 of 13.1 ms per 1024 utterances).
+// Here a CTA of 128 threads owns an utterance and processes tiles of 128 chunks x 64 samples = 8192 samples:
+//   load    the tile into shared memory as fp64 with coalesced (forward) / reversed-coalesced (backward) accesses,
+//           one pad word per chunk so that the per-thread walks below are bank-conflict free;
+//   pass 1  thread t runs its chunk from a zero state -> e[t]; thread 0 adds A^64 * (carry-in of the tile);
+//   scan    Kogge-Stone over the 128 chunk states: w_i <- P[k] w_{i-2^k} + w_i with P[k] = A^(64*2^k) (all chunks share the
+//           linear part, so a level is ONE 6x6 mat-vec per thread); w_i is then the true END state of chunk i;
+//   pass 2  thread t re-runs its chunk from w_{t-1} and overwrites the tile with the outputs;
+//   store   coalesced: forward y1 (fp64), backward 0.96*y + dither as fp32 (reversed).
+// Every input is read once and every output written once per sweep.
+constexpr int FE_TCH = 64;                      // samples per thread-chunk
+constexpr int FE_TNT = 128;                     // threads = chunks per tile
+constexpr int FE_TILE = FE_TCH * FE_TNT;        // 8192 samples
+constexpr int FE_TLEV = 7;                      // log2(FE_TNT)
+
+// PW[k] = A^(FE_TCH * 2^k), k = 0..FE_TLEV-1 (row-major 6x6 each).  Single thread.
+__global__ void fe_tile_powers_kernel(const double* __restrict__ filt, double* __restrict__ PW) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  constexpr int N = FE_NST;
+  double M[N * N], R[N * N];
+  Df2t f;
+  f.load(filt);
+  for (int k = 0; k < N; ++k) {
+    for (int i = 0; i < N; ++i) f.z[i] = (i == k) ? 1.0 : 0.0;
+    f.step(0.0);
+    for (int i = 0; i < N; ++i) M[i * N + k] = f.z[i];
+  }
+  auto square = [&]() {
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) {
+        double acc = 0.0;
+        for (int k = 0; k < N; ++k) acc = fma(M[i * N + k], M[k * N + j], acc);
+        R[i * N + j] = acc;
+      }
+    for (int i = 0; i < N * N; ++i) M[i] = R[i];
+  };
+  for (int L = FE_TCH; L > 1; L >>= 1) square();          // A^64
+  for (int k = 0; k < FE_TLEV; ++k) {
+    for (int i = 0; i < N * N; ++i) PW[k * N * N + i] = M[i];
+    square();
+  }
+}
+
+template <bool BACKWARD>
+__global__ void __launch_bounds__(FE_TNT)
+fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dither, const int* __restrict__ lengths,
+                    int max_len, const double* __restrict__ filt, const double* __restrict__ zi,
+                    const double* __restrict__ PW, double* __restrict__ y1buf, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int N = FE_NST;
+  double* tile = reinterpret_cast<double*>(smem_raw);                 // [FE_TNT][FE_TCH + 1]
+  double* wst = tile + FE_TNT * (FE_TCH + 1);                         // [2][FE_TNT][N]  ping-pong chunk states
+  double* pw = wst + 2 * FE_TNT * N;                                  // [FE_TLEV][N*N]
+  double* carry = pw + FE_TLEV * N * N;                               // [N] carry-in of the current tile
+  const int u = blockIdx.x, tid = threadIdx.x;
+  const int n = lengths[u];
+  const float* x = wav + (size_t)u * max_len;
+  const float* dz = dither + (size_t)u * max_len;
+  float* o = out + (size_t)u * max_len;
+  double* y1 = y1buf + (size_t)u * (max_len + 2 * FE_PADLEN);
+  if (n <= FE_PADLEN) {   // scipy raises for such inputs; emit dither-only silence deterministically
+    if (BACKWARD)
+      for (int i = tid; i < n; i += FE_TNT) o[i] = (float)(((double)dz[i] - 0.5) * 1e-6);
+    return;
+  }
+  const int ne = n + 2 * FE_PADLEN;
+  for (int i = tid; i < FE_TLEV * N * N; i += FE_TNT) pw[i] = PW[i];
+  if (tid < N) carry[tid] = zi[tid] * sweep_input<BACKWARD>(x, y1, n, ne, 0);   // scipy: zi * first sample of the sweep's input
+  Df2t f;
+  f.load(filt);
+  double* mine = tile + tid * (FE_TCH + 1);
+  for (int i0 = 0; i0 < ne; i0 += FE_TILE) {
+    __syncthreads();                                      // previous tile fully stored; carry / pw visible
+    // interior tiles (all but the first and the last one or two): branch-free, 16 independent loads in flight per thread --
+    // with a rolled loop the 64 dependent-latency loads per thread made a tile take ~50 us
+    const bool interior = i0 + FE_TILE <= ne && (BACKWARD || (i0 >= FE_PADLEN && i0 + FE_TILE <= FE_PADLEN + n));
+    if (interior) {
+      const float* xs = x + (i0 - FE_PADLEN);
+      const double* ys = y1 + (ne - 1 - i0);
+#pragma unroll 16
+      for (int q = 0; q < FE_TCH; ++q) {
+        const int s = q * FE_TNT + tid;
+        tile[s + q * 2 + (tid >> 6)] = BACKWARD ? ys[-s] : (double)xs[s];        // s + (s >> 6) with s = 128 q + tid
+      }
+    } else {
+#pragma unroll 8
+      for (int q = 0; q < FE_TCH; ++q) {
+        const int s = q * FE_TNT + tid;
+        const int i = i0 + s;
+        tile[s + q * 2 + (tid >> 6)] = i < ne ? sweep_input<BACKWARD>(x, y1, n, ne, i) : 0.0;   // zeros past the end: pure state decay
+      }
+    }
+    __syncthreads();
+    // pass 1: zero-state end state of my chunk
+#pragma unroll
+    for (int k = 0; k < N; ++k) f.z[k] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < FE_TCH; ++k) f.step(mine[k]);
+    double w[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) w[k] = f.z[k];
+    if (tid == 0) {                                       // chunk 0 starts from the tile's carry-in: end = A^64 carry + e_0
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        double acc = w[i];
+#pragma unroll
+        for (int k = 0; k < N; ++k) acc = fma(pw[i * N + k], carry[k], acc);
+        w[i] = acc;
+      }
+    }
+    int cur = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) wst[tid * N + k] = w[k];
+    __syncthreads();
+#pragma unroll 1
+    for (int lev = 0; lev < FE_TLEV; ++lev) {
+      const int d = 1 << lev;
+      if (tid >= d) {
+        const double* src = wst + (cur * FE_TNT + tid - d) * N;
+        const double* P = pw + lev * N * N;
+        double sv[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) sv[k] = src[k];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          double acc = w[i];
+#pragma unroll
+          for (int k = 0; k < N; ++k) acc = fma(P[i * N + k], sv[k], acc);
+          w[i] = acc;
+        }
+      }
+      cur ^= 1;
+#pragma unroll
+      for (int k = 0; k < N; ++k) wst[(cur * FE_TNT + tid) * N + k] = w[k];
+      __syncthreads();
+    }
+    // pass 2: from the true start state (= end state of the previous chunk)
+    if (tid == 0) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) f.z[k] = carry[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; ++k) f.z[k] = wst[(cur * FE_TNT + tid - 1) * N + k];
+    }
+#pragma unroll 4
+    for (int k = 0; k < FE_TCH; ++k) mine[k] = f.step(mine[k]);
+    __syncthreads();                                      // every thread has read carry / its neighbour's state
+    if (tid == FE_TNT - 1) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) carry[k] = w[k];        // end state of the tile's last chunk
+    }
+    const bool interior_out = i0 + FE_TILE <= ne && (!BACKWARD || (i0 >= FE_PADLEN && i0 + FE_TILE <= FE_PADLEN + n));
+    if (interior_out) {
+      const int jb = (ne - 1 - i0) - FE_PADLEN;            // backward: output position of tile sample s is jb - s
+#pragma unroll 16
+      for (int q = 0; q < FE_TCH; ++q) {
+        const int s = q * FE_TNT + tid;
+        const double y = tile[s + q * 2 + (tid >> 6)];
+        if (!BACKWARD) y1[i0 + s] = y;
+        else o[jb - s] = (float)(y * 0.96 + ((double)dz[jb - s] - 0.5) * 1e-6);
+      }
+    } else {
+#pragma unroll 8
+      for (int q = 0; q < FE_TCH; ++q) {
+        const int s = q * FE_TNT + tid;
+        const int i = i0 + s;
+        const double y = tile[s + q * 2 + (tid >> 6)];
+        if (!BACKWARD) {
+          if (i < ne) y1[i] = y;
+        } else {
+          const int j = (ne - 1 - i) - FE_PADLEN;
+          if (i < ne && j >= 0 && j < n) o[j] = (float)(y * 0.96 + ((double)dz[j] - 0.5) * 1e-6);
+        }
+      }
+    }
+  }
+}
+
 // --- stage 3: framing + FFT + mel + log ---------------------------------------------------------------
-__device__ __forceinline__ int bitrev10(int v) { return (int)(__brev((unsigned)v) >> 22); }
+// 1024-point complex FFT as 32 x 32 (n = 32a + b, k = c + 32d), ONE WARP per transform, 32 points per thread in registers:
+//   pass 1  lane b: Y_b[c] = DFT32_a(x[32a + b]) * W1024^(b c)      (inputs read with lanes consecutive: conflict-free)
+//   exchange through a [32][33] shared tile (row c, column b; written and read conflict-free)
+//   pass 2  lane c: X[c + 32d] = DFT32_b(Y_b[c])                    (outputs written with lanes consecutive)
+// Two shared-memory round trips per transform instead of the five of an in-place radix-4 loop, whose power-of-two strides
+// also cost 4- to 16-way bank conflicts on data and twiddles (r01c ncu: 7.4 ms per 1024 utterances at 80% L1/TEX busy).
+__constant__ float2 c_w32[16] = {
+    {1.0f, -0.0f},
+    {0.98078528040323043f, -0.19509032201612825f},
+    {0.92387953251128674f, -0.38268343236508978f},
+    {0.83146961230254524f, -0.55557023301960218f},
+    {0.70710678118654757f, -0.70710678118654757f},
+    {0.55557023301960229f, -0.83146961230254524f},
+    {0.38268343236508984f, -0.92387953251128674f},
+    {0.19509032201612833f, -0.98078528040323043f},
+    {0.0f, -1.0f},
+    {-0.19509032201612819f, -0.98078528040323043f},
+    {-0.38268343236508973f, -0.92387953251128674f},
+    {-0.55557023301960196f, -0.83146961230254546f},
+    {-0.70710678118654746f, -0.70710678118654757f},
+    {-0.83146961230254535f, -0.55557023301960218f},
+    {-0.92387953251128674f, -0.38268343236508989f},
+    {-0.98078528040323043f, -0.19509032201612861f},
+};
+
+__host__ __device__ constexpr int bitrev5(int v) {
+  return ((v & 1) << 4) | ((v & 2) << 2) | (v & 4) | ((v & 8) >> 2) | ((v & 16) >> 4);
+}
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+
+// forward 32-point DFT in registers (decimation in frequency): X[k] ends up in v[bitrev5(k)].  Fully unrolled: every index and
+// every twiddle is a compile-time constant.
+__device__ __forceinline__ void fft32(float2 (&v)[32]) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+#pragma unroll
+    for (int g = 0; g < 32; g += 2 * half) {
+#pragma unroll
+      for (int j = 0; j < half; ++j) {
+        const float2 a = v[g + j], b = v[g + j + half];
+        v[g + j] = make_float2(a.x + b.x, a.y + b.y);
+        const float2 d = make_float2(a.x - b.x, a.y - b.y);
+        const int m = j * (16 / half);
+        if (m == 0) v[g + j + half] = d;
+        else if (m == 8) v[g + j + half] = make_float2(d.y, -d.x);      // * (-i)
+        else v[g + j + half] = cmul(d, c_w32[m]);
+      }
+    }
+  }
+}
+
+constexpr int FE_EXLD = 33;                          // padded row of the exchange tile
+constexpr int FE_EX = 32 * FE_EXLD;                  // float2 per transform
+
+constexpr int FE_GROUPS_PER_CTA = 5;                 // a CTA walks 5 groups of 8 frames: the twiddle tile is loaded once per 40 frames
 
 __global__ void __launch_bounds__(FE_THREADS)
 fe_stft_mel_kernel(const float* __restrict__ sig, const int* __restrict__ lengths, int max_len,
@@ -311,92 +547,95 @@ fe_stft_mel_kernel(const float* __restrict__ sig, const int* __restrict__ length
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NPAIR = FE_FRAMES_PER_CTA / 2;
   constexpr int CHUNK = (FE_FRAMES_PER_CTA - 1) * FE_HOP + FE_NFFT;
-  float2* z = reinterpret_cast<float2*>(smem_raw);                 // [NPAIR][1024]
-  float2* tw = z + NPAIR * FE_NFFT;                                // [512]
-  float* win = reinterpret_cast<float*>(tw + FE_NFFT / 2);         // [1024]
-  float* chunk = win + FE_NFFT;                                    // [CHUNK]
-  float* mag = chunk + CHUNK;                                      // [FRAMES][513 (+pad)]
-  constexpr int MAGLD = FE_BINS + 3;
+  float2* ex = reinterpret_cast<float2*>(smem_raw);                // [NPAIR][32][33]; after the transform: X[k], then (|A_k|, |B_k|)
+  float2* tw2 = ex + NPAIR * FE_EX;                                // [32][32]
+  float* chunk = reinterpret_cast<float*>(tw2 + FE_NFFT);          // [CHUNK]
 
   const int u = blockIdx.y;
-  const int f0 = blockIdx.x * FE_FRAMES_PER_CTA;
   const int n = lengths[u];
   const int n_frames = n > FE_PADLEN ? 1 + n / FE_HOP : 0;
   const int tid = threadIdx.x;
-  float* o = out + ((size_t)u * max_frames + f0) * FE_MELS;
-  if (f0 >= n_frames) {   // zero padding frames (conversion.py:40-44 pad_seq)
-    for (int i = tid; i < FE_FRAMES_PER_CTA * FE_MELS; i += FE_THREADS)
-      if (f0 + i / FE_MELS < max_frames) o[i] = 0.f;
-    return;
-  }
-  for (int i = tid; i < FE_NFFT / 2; i += FE_THREADS) tw[i] = tb->tw[i];
-  for (int i = tid; i < FE_NFFT; i += FE_THREADS) win[i] = tb->win[i];
-  // reflect-padded samples [f0*hop, f0*hop + CHUNK) of the padded signal (np.pad mode='reflect')
   const float* x = sig + (size_t)u * max_len;
-  for (int i = tid; i < CHUNK; i += FE_THREADS) {
-    int j = f0 * FE_HOP + i - FE_REFLECT;
-    if (j < 0) j = -j;
-    if (j >= n) j = 2 * (n - 1) - j;
-    chunk[i] = (j >= 0 && j < n) ? x[j] : 0.f;
-  }
-  __syncthreads();
-  // windowed frames -> bit-reversed complex buffers (frame 2p real, frame 2p+1 imaginary)
-  for (int i = tid; i < NPAIR * FE_NFFT; i += FE_THREADS) {
-    const int p = i >> 10, k = i & 1023;
-    const float w = win[k];
-    z[p * FE_NFFT + bitrev10(k)] = make_float2(w * chunk[(2 * p) * FE_HOP + k], w * chunk[(2 * p + 1) * FE_HOP + k]);
-  }
-  __syncthreads();
-  // radix-2 DIT butterflies, two stages (s, s+1) per pass: a thread carries four points through both stages in registers,
-  // which halves the shared-memory traffic and the block barriers of the plain 10-stage loop (r01b ncu: L1/TEX 90% busy)
-#pragma unroll 1
-  for (int s = 0; s < 10; s += 2) {
-    const int h = 1 << s;
-    for (int i = tid; i < NPAIR * (FE_NFFT / 4); i += FE_THREADS) {
-      const int p = i >> 8, j = i & 255;
-      const int pos = j & (h - 1);
-      const int base = ((j >> s) << (s + 2)) + pos;
-      float2* zz = z + p * FE_NFFT;
-      const float2 w1 = tw[pos << (9 - s)];                 // W_{2h}^pos      (stage s)
-      const float2 w2 = tw[pos << (8 - s)];                 // W_{4h}^pos      (stage s+1, first pair)
-      const float2 w3 = tw[(pos + h) << (8 - s)];           // W_{4h}^(pos+h)  (stage s+1, second pair)
-      const float2 a0 = zz[base], a1 = zz[base + h], a2 = zz[base + 2 * h], a3 = zz[base + 3 * h];
-      const float2 t1 = make_float2(a1.x * w1.x - a1.y * w1.y, a1.x * w1.y + a1.y * w1.x);
-      const float2 t3 = make_float2(a3.x * w1.x - a3.y * w1.y, a3.x * w1.y + a3.y * w1.x);
-      const float2 b0 = make_float2(a0.x + t1.x, a0.y + t1.y), b1 = make_float2(a0.x - t1.x, a0.y - t1.y);
-      const float2 b2 = make_float2(a2.x + t3.x, a2.y + t3.y), b3 = make_float2(a2.x - t3.x, a2.y - t3.y);
-      const float2 u2 = make_float2(b2.x * w2.x - b2.y * w2.y, b2.x * w2.y + b2.y * w2.x);
-      const float2 u3 = make_float2(b3.x * w3.x - b3.y * w3.y, b3.x * w3.y + b3.y * w3.x);
-      zz[base] = make_float2(b0.x + u2.x, b0.y + u2.y);
-      zz[base + 2 * h] = make_float2(b0.x - u2.x, b0.y - u2.y);
-      zz[base + h] = make_float2(b1.x + u3.x, b1.y + u3.y);
-      zz[base + 3 * h] = make_float2(b1.x - u3.x, b1.y - u3.y);
+  const float* win = tb->win;
+  bool have_tw = false;
+  for (int g = 0; g < FE_GROUPS_PER_CTA; ++g) {
+    const int f0 = (blockIdx.x * FE_GROUPS_PER_CTA + g) * FE_FRAMES_PER_CTA;
+    if (f0 >= max_frames) break;
+    float* o = out + ((size_t)u * max_frames + f0) * FE_MELS;
+    if (f0 >= n_frames) {   // zero padding frames (conversion.py:40-44 pad_seq)
+      for (int i = tid; i < FE_FRAMES_PER_CTA * FE_MELS; i += FE_THREADS)
+        if (f0 + i / FE_MELS < max_frames) o[i] = 0.f;
+      continue;
+    }
+    if (!have_tw) {
+      for (int i = tid; i < FE_NFFT; i += FE_THREADS) tw2[i] = tb->tw2[i];
+      have_tw = true;
+    }
+    // reflect-padded samples [f0*hop, f0*hop + CHUNK) of the padded signal (np.pad mode='reflect')
+    const int j0 = f0 * FE_HOP - FE_REFLECT;
+    if (j0 >= 0 && j0 + CHUNK <= n) {
+#pragma unroll
+      for (int q = 0; q < CHUNK / FE_THREADS; ++q) chunk[q * FE_THREADS + tid] = x[j0 + q * FE_THREADS + tid];
+    } else {
+#pragma unroll 4
+      for (int q = 0; q < CHUNK / FE_THREADS; ++q) {
+        const int i = q * FE_THREADS + tid;
+        int j = j0 + i;
+        if (j < 0) j = -j;
+        if (j >= n) j = 2 * (n - 1) - j;
+        chunk[i] = (j >= 0 && j < n) ? x[j] : 0.f;
+      }
     }
     __syncthreads();
-  }
-  // split the two real spectra and take magnitudes
-  for (int i = tid; i < NPAIR * FE_BINS; i += FE_THREADS) {
-    const int p = i / FE_BINS, k = i - p * FE_BINS;
-    const float2 a = z[p * FE_NFFT + k];
-    const float2 b = z[p * FE_NFFT + ((FE_NFFT - k) & (FE_NFFT - 1))];
-    const float ar = 0.5f * (a.x + b.x), ai = 0.5f * (a.y - b.y);      // frame 2p
-    const float br = 0.5f * (a.y + b.y), bi = 0.5f * (b.x - a.x);      // frame 2p+1
-    mag[(2 * p) * MAGLD + k] = sqrtf(ar * ar + ai * ai);
-    mag[(2 * p + 1) * MAGLD + k] = sqrtf(br * br + bi * bi);
-  }
-  __syncthreads();
-  for (int i = tid; i < FE_FRAMES_PER_CTA * FE_MELS; i += FE_THREADS) {
-    const int fr = i / FE_MELS, m = i - fr * FE_MELS;
-    if (f0 + fr >= max_frames) continue;
-    float v = 0.f;
-    if (f0 + fr < n_frames) {
-      const int2 bd = tb->band[m];
-      float acc = 0.f;
-      for (int k = bd.x; k < bd.y; ++k) acc = fmaf(mag[fr * MAGLD + k], __ldg(mel_basis + k * FE_MELS + m), acc);
-      const float db = 20.f * log10f(fmaxf(1e-5f, acc)) - 16.f;
-      v = fminf(fmaxf((db + 100.f) / 100.f, 0.f), 1.f);
+    {
+      const int p = tid >> 5, lane = tid & 31;                       // transform p: frame 2p real, frame 2p+1 imaginary
+      float2* e = ex + p * FE_EX;
+      const float* c0 = chunk + (2 * p) * FE_HOP;
+      const float* c1 = c0 + FE_HOP;
+      float2 v[32];
+#pragma unroll
+      for (int a = 0; a < 32; ++a) {
+        const int k = 32 * a + lane;
+        const float w = __ldg(win + k);
+        v[a] = make_float2(w * c0[k], w * c1[k]);
+      }
+      fft32(v);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) e[c * FE_EXLD + lane] = cmul(v[bitrev5(c)], tw2[c * 32 + lane]);
+      __syncwarp();
+#pragma unroll
+      for (int b = 0; b < 32; ++b) v[b] = e[lane * FE_EXLD + b];
+      __syncwarp();
+      fft32(v);
+#pragma unroll
+      for (int d = 0; d < 32; ++d) e[lane + 32 * d] = v[bitrev5(d)];   // natural order X[k], k = lane + 32 d
+      __syncwarp();
+      // split the two real spectra and take magnitudes IN PLACE: slot k <- (|A_k|, |B_k|), k = 0..512.  Slot k is read and
+      // written by one lane only and the mirror slots 1024-k > 512 are never written, so the loop needs no barrier.
+      for (int k = lane; k < FE_BINS; k += 32) {
+        const float2 a = e[k];
+        const float2 b = e[(FE_NFFT - k) & (FE_NFFT - 1)];
+        const float ar = 0.5f * (a.x + b.x), ai = 0.5f * (a.y - b.y);      // frame 2p
+        const float br = 0.5f * (a.y + b.y), bi = 0.5f * (b.x - a.x);      // frame 2p+1
+        e[k] = make_float2(sqrtf(ar * ar + ai * ai), sqrtf(br * br + bi * bi));
+      }
     }
-    o[i] = v;
+    __syncthreads();
+    for (int i = tid; i < FE_FRAMES_PER_CTA * FE_MELS; i += FE_THREADS) {
+      const int fr = i / FE_MELS, m = i - fr * FE_MELS;
+      if (f0 + fr >= max_frames) continue;
+      float v = 0.f;
+      if (f0 + fr < n_frames) {
+        const int2 bd = tb->band[m];
+        const float* mg = reinterpret_cast<const float*>(ex + (fr >> 1) * FE_EX) + (fr & 1);
+        float acc = 0.f;
+        for (int k = bd.x; k < bd.y; ++k) acc = fmaf(mg[2 * k], __ldg(mel_basis + k * FE_MELS + m), acc);
+        const float db = 20.f * log10f(fmaxf(1e-5f, acc)) - 16.f;
+        v = fminf(fmaxf((db + 100.f) / 100.f, 0.f), 1.f);
+      }
+      o[i] = v;
+    }
+    __syncthreads();        // ex / chunk are rewritten by the next group
   }
 }
 
@@ -413,7 +652,7 @@ extern "C" size_t avc_logmel_workspace_bytes(int n_utt, int max_len) {
   const size_t fwd = ((size_t)n_utt * (max_len + 2 * FE_PADLEN) * sizeof(double) + 255) / 256 * 256;
   const size_t sig = ((size_t)n_utt * max_len * sizeof(float) + 255) / 256 * 256;
   const size_t zs = ((size_t)n_utt * fe_nchunk(max_len) * FE_NST * sizeof(double) + 255) / 256 * 256;
-  return fe_tables_bytes() + sig + fwd + zs + 512;
+  return fe_tables_bytes() + sig + fwd + zs + 4096;      // tail: A^L (36 doubles) or the 7 tile powers (252 doubles)
 }
 
 extern "C" int avc_logmel_frontend(const float* wav, const float* dither, const int* lengths, int n_utt, int max_len,
@@ -439,6 +678,19 @@ extern "C" int avc_logmel_frontend(const float* wav, const float* dither, const 
   double* AL = (double*)(ws + fe_tables_bytes() + sig_b + fwd_b + ((size_t)n_utt * nchunk * FE_NST * sizeof(double) + 255) / 256 * 256);
   fe_tables_kernel<<<ceil_div(FE_NFFT, 256), 256, 0, st>>>(mel_basis, tb);
   AVC_LAUNCHED();
+  static const bool tiled = getenv("AVC_FE_IIR_TILED") ? atoi(getenv("AVC_FE_IIR_TILED")) != 0 : true;
+  if (tiled) {
+    // one CTA per utterance, tiles staged through shared memory (AL's slot holds the 7 tile powers: 7*36 doubles)
+    fe_tile_powers_kernel<<<1, 32, 0, st>>>(filt, AL);
+    AVC_LAUNCHED();
+    const size_t ism = ((size_t)FE_TNT * (FE_TCH + 1) + 2 * FE_TNT * FE_NST + FE_TLEV * FE_NST * FE_NST + FE_NST) * sizeof(double);
+    AVC_CUDA(cudaFuncSetAttribute(fe_iir_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
+    AVC_CUDA(cudaFuncSetAttribute(fe_iir_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
+    fe_iir_sweep_kernel<false><<<n_utt, FE_TNT, ism, st>>>(wav, dither, lengths, max_len, filt, zi, AL, fwd, sig);
+    AVC_LAUNCHED();
+    fe_iir_sweep_kernel<true><<<n_utt, FE_TNT, ism, st>>>(wav, dither, lengths, max_len, filt, zi, AL, fwd, sig);
+    AVC_LAUNCHED();
+  } else {
   fe_state_power_kernel<<<1, 32, 0, st>>>(filt, AL);
   AVC_LAUNCHED();
   {
@@ -456,12 +708,12 @@ extern "C" int avc_logmel_frontend(const float* wav, const float* dither, const 
     fe_iir_output_kernel<true><<<cgrid, 128, 0, st>>>(wav, dither, lengths, n_utt, max_len, nchunk, filt, zs, fwd, sig);
     AVC_LAUNCHED();
   }
+  }
   constexpr int NPAIR = FE_FRAMES_PER_CTA / 2;
   constexpr int CHUNK = (FE_FRAMES_PER_CTA - 1) * FE_HOP + FE_NFFT;
-  const size_t smem = NPAIR * FE_NFFT * sizeof(float2) + (FE_NFFT / 2) * sizeof(float2) + FE_NFFT * sizeof(float) +
-                      CHUNK * sizeof(float) + FE_FRAMES_PER_CTA * (FE_BINS + 3) * sizeof(float);
+  const size_t smem = NPAIR * FE_EX * sizeof(float2) + FE_NFFT * sizeof(float2) + CHUNK * sizeof(float);
   AVC_CUDA(cudaFuncSetAttribute(fe_stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(ceil_div(max_frames, FE_FRAMES_PER_CTA), n_utt);
+  dim3 grid(ceil_div(max_frames, FE_FRAMES_PER_CTA * FE_GROUPS_PER_CTA), n_utt);
   fe_stft_mel_kernel<<<grid, FE_THREADS, smem, st>>>(sig, lengths, max_len, mel_basis, tb, out, max_frames);
   AVC_LAUNCHED();
   return AVC_OK;
