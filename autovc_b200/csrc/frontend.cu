@@ -538,104 +538,94 @@ __device__ __forceinline__ void fft32(float2 (&v)[32]) {
 constexpr int FE_EXLD = 33;                          // padded row of the exchange tile
 constexpr int FE_EX = 32 * FE_EXLD;                  // float2 per transform
 
-constexpr int FE_GROUPS_PER_CTA = 5;                 // a CTA walks 5 groups of 8 frames: the twiddle tile is loaded once per 40 frames
+constexpr int FE_PAIRS_PER_WARP = 5;                 // a warp walks 5 frame pairs: a CTA (4 warps) covers 40 consecutive frames
+constexpr int FE_FRAMES_PER_BLOCK = FE_FRAMES_PER_CTA * FE_PAIRS_PER_WARP;
 
-__global__ void __launch_bounds__(FE_THREADS)
+// reflect-padded sample j of an utterance of n samples (np.pad mode='reflect'; positions beyond one reflection read 0)
+__device__ __forceinline__ float fe_reflect(const float* __restrict__ x, int n, int j) {
+  if (j < 0) j = -j;
+  if (j >= n) j = 2 * (n - 1) - j;
+  return (j >= 0 && j < n) ? __ldg(x + j) : 0.f;
+}
+
+// Every warp is on its own: frames 2q, 2q+1 -> registers -> transform -> magnitudes -> the two frames' 160 mel outputs.
+// No block barrier anywhere, so the 24 resident warps of an SM sit in different phases and hide each other's latencies
+// (the block-synchronous version ran at 21% of the issue rate).
+__global__ void __launch_bounds__(FE_THREADS, 5)
 fe_stft_mel_kernel(const float* __restrict__ sig, const int* __restrict__ lengths, int max_len,
                    const float* __restrict__ mel_basis, const FeTables* __restrict__ tb, float* __restrict__ out,
                    int max_frames) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NPAIR = FE_FRAMES_PER_CTA / 2;
-  constexpr int CHUNK = (FE_FRAMES_PER_CTA - 1) * FE_HOP + FE_NFFT;
-  float2* ex = reinterpret_cast<float2*>(smem_raw);                // [NPAIR][32][33]; after the transform: X[k], then (|A_k|, |B_k|)
-  float2* tw2 = ex + NPAIR * FE_EX;                                // [32][32]
-  float* chunk = reinterpret_cast<float*>(tw2 + FE_NFFT);          // [CHUNK]
-
   const int u = blockIdx.y;
   const int n = lengths[u];
   const int n_frames = n > FE_PADLEN ? 1 + n / FE_HOP : 0;
-  const int tid = threadIdx.x;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2* e = reinterpret_cast<float2*>(smem_raw) + wid * FE_EX;   // this warp's [32][33] tile; then X[k]; then (|A_k|, |B_k|)
   const float* x = sig + (size_t)u * max_len;
   const float* win = tb->win;
-  bool have_tw = false;
-  for (int g = 0; g < FE_GROUPS_PER_CTA; ++g) {
-    const int f0 = (blockIdx.x * FE_GROUPS_PER_CTA + g) * FE_FRAMES_PER_CTA;
+  const float2* tw2 = tb->tw2;
+  for (int g = 0; g < FE_PAIRS_PER_WARP; ++g) {
+    const int f0 = blockIdx.x * FE_FRAMES_PER_BLOCK + (wid * FE_PAIRS_PER_WARP + g) * 2;   // frames f0 (real part), f0+1 (imaginary)
     if (f0 >= max_frames) break;
     float* o = out + ((size_t)u * max_frames + f0) * FE_MELS;
+    const int nout = min(2, max_frames - f0) * FE_MELS;
     if (f0 >= n_frames) {   // zero padding frames (conversion.py:40-44 pad_seq)
-      for (int i = tid; i < FE_FRAMES_PER_CTA * FE_MELS; i += FE_THREADS)
-        if (f0 + i / FE_MELS < max_frames) o[i] = 0.f;
+      for (int i = lane; i < nout; i += 32) o[i] = 0.f;
       continue;
     }
-    if (!have_tw) {
-      for (int i = tid; i < FE_NFFT; i += FE_THREADS) tw2[i] = tb->tw2[i];
-      have_tw = true;
-    }
-    // reflect-padded samples [f0*hop, f0*hop + CHUNK) of the padded signal (np.pad mode='reflect')
+    float2 v[32];
     const int j0 = f0 * FE_HOP - FE_REFLECT;
-    if (j0 >= 0 && j0 + CHUNK <= n) {
-#pragma unroll
-      for (int q = 0; q < CHUNK / FE_THREADS; ++q) chunk[q * FE_THREADS + tid] = x[j0 + q * FE_THREADS + tid];
-    } else {
-#pragma unroll 4
-      for (int q = 0; q < CHUNK / FE_THREADS; ++q) {
-        const int i = q * FE_THREADS + tid;
-        int j = j0 + i;
-        if (j < 0) j = -j;
-        if (j >= n) j = 2 * (n - 1) - j;
-        chunk[i] = (j >= 0 && j < n) ? x[j] : 0.f;
-      }
-    }
-    __syncthreads();
-    {
-      const int p = tid >> 5, lane = tid & 31;                       // transform p: frame 2p real, frame 2p+1 imaginary
-      float2* e = ex + p * FE_EX;
-      const float* c0 = chunk + (2 * p) * FE_HOP;
-      const float* c1 = c0 + FE_HOP;
-      float2 v[32];
+    if (j0 >= 0 && j0 + FE_HOP + FE_NFFT <= n) {
+      const float* c0 = x + j0;
 #pragma unroll
       for (int a = 0; a < 32; ++a) {
         const int k = 32 * a + lane;
         const float w = __ldg(win + k);
-        v[a] = make_float2(w * c0[k], w * c1[k]);
+        v[a] = make_float2(w * __ldg(c0 + k), w * __ldg(c0 + FE_HOP + k));
       }
-      fft32(v);
+    } else {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) e[c * FE_EXLD + lane] = cmul(v[bitrev5(c)], tw2[c * 32 + lane]);
-      __syncwarp();
-#pragma unroll
-      for (int b = 0; b < 32; ++b) v[b] = e[lane * FE_EXLD + b];
-      __syncwarp();
-      fft32(v);
-#pragma unroll
-      for (int d = 0; d < 32; ++d) e[lane + 32 * d] = v[bitrev5(d)];   // natural order X[k], k = lane + 32 d
-      __syncwarp();
-      // split the two real spectra and take magnitudes IN PLACE: slot k <- (|A_k|, |B_k|), k = 0..512.  Slot k is read and
-      // written by one lane only and the mirror slots 1024-k > 512 are never written, so the loop needs no barrier.
-      for (int k = lane; k < FE_BINS; k += 32) {
-        const float2 a = e[k];
-        const float2 b = e[(FE_NFFT - k) & (FE_NFFT - 1)];
-        const float ar = 0.5f * (a.x + b.x), ai = 0.5f * (a.y - b.y);      // frame 2p
-        const float br = 0.5f * (a.y + b.y), bi = 0.5f * (b.x - a.x);      // frame 2p+1
-        e[k] = make_float2(sqrtf(ar * ar + ai * ai), sqrtf(br * br + bi * bi));
+      for (int a = 0; a < 32; ++a) {
+        const int k = 32 * a + lane;
+        const float w = __ldg(win + k);
+        v[a] = make_float2(w * fe_reflect(x, n, j0 + k), w * fe_reflect(x, n, j0 + FE_HOP + k));
       }
     }
-    __syncthreads();
-    for (int i = tid; i < FE_FRAMES_PER_CTA * FE_MELS; i += FE_THREADS) {
-      const int fr = i / FE_MELS, m = i - fr * FE_MELS;
-      if (f0 + fr >= max_frames) continue;
-      float v = 0.f;
+    fft32(v);
+    __syncwarp();                                          // the previous pair's mel loop is done with the tile
+#pragma unroll
+    for (int c = 0; c < 32; ++c) e[c * FE_EXLD + lane] = cmul(v[bitrev5(c)], __ldg(tw2 + c * 32 + lane));
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < 32; ++b) v[b] = e[lane * FE_EXLD + b];
+    __syncwarp();
+    fft32(v);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) e[lane + 32 * d] = v[bitrev5(d)];   // natural order X[k], k = lane + 32 d
+    __syncwarp();
+    // split the two real spectra and take magnitudes IN PLACE: slot k <- (|A_k|, |B_k|), k = 0..512.  Slot k is read and
+    // written by one lane only and the mirror slots 1024-k > 512 are never written, so the loop needs no barrier.
+    for (int k = lane; k < FE_BINS; k += 32) {
+      const float2 a = e[k];
+      const float2 b = e[(FE_NFFT - k) & (FE_NFFT - 1)];
+      const float ar = 0.5f * (a.x + b.x), ai = 0.5f * (a.y - b.y);      // frame f0
+      const float br = 0.5f * (a.y + b.y), bi = 0.5f * (b.x - a.x);      // frame f0+1
+      e[k] = make_float2(sqrtf(ar * ar + ai * ai), sqrtf(br * br + bi * bi));
+    }
+    __syncwarp();
+    const float* mg = reinterpret_cast<const float*>(e);
+    for (int i = lane; i < nout; i += 32) {
+      const int fr = i >= FE_MELS ? 1 : 0, m = i - fr * FE_MELS;
+      float val = 0.f;
       if (f0 + fr < n_frames) {
         const int2 bd = tb->band[m];
-        const float* mg = reinterpret_cast<const float*>(ex + (fr >> 1) * FE_EX) + (fr & 1);
         float acc = 0.f;
-        for (int k = bd.x; k < bd.y; ++k) acc = fmaf(mg[2 * k], __ldg(mel_basis + k * FE_MELS + m), acc);
+        for (int k = bd.x; k < bd.y; ++k) acc = fmaf(mg[2 * k + fr], __ldg(mel_basis + k * FE_MELS + m), acc);
         const float db = 20.f * log10f(fmaxf(1e-5f, acc)) - 16.f;
-        v = fminf(fmaxf((db + 100.f) / 100.f, 0.f), 1.f);
+        val = fminf(fmaxf((db + 100.f) / 100.f, 0.f), 1.f);
       }
-      o[i] = v;
+      o[i] = val;
     }
-    __syncthreads();        // ex / chunk are rewritten by the next group
   }
 }
 
@@ -709,11 +699,9 @@ extern "C" int avc_logmel_frontend(const float* wav, const float* dither, const 
     AVC_LAUNCHED();
   }
   }
-  constexpr int NPAIR = FE_FRAMES_PER_CTA / 2;
-  constexpr int CHUNK = (FE_FRAMES_PER_CTA - 1) * FE_HOP + FE_NFFT;
-  const size_t smem = NPAIR * FE_EX * sizeof(float2) + FE_NFFT * sizeof(float2) + CHUNK * sizeof(float);
+  const size_t smem = (size_t)(FE_THREADS / 32) * FE_EX * sizeof(float2);
   AVC_CUDA(cudaFuncSetAttribute(fe_stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(ceil_div(max_frames, FE_FRAMES_PER_CTA * FE_GROUPS_PER_CTA), n_utt);
+  dim3 grid(ceil_div(max_frames, FE_FRAMES_PER_BLOCK), n_utt);
   fe_stft_mel_kernel<<<grid, FE_THREADS, smem, st>>>(sig, lengths, max_len, mel_basis, tb, out, max_frames);
   AVC_LAUNCHED();
   return AVC_OK;
