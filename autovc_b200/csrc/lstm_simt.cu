@@ -24,9 +24,15 @@ __global__ void lstm_small_fwd_kernel(const float* __restrict__ P, const float* 
                                       float* __restrict__ c_seq, int nB, int T, int H, int reverse) {
   extern __shared__ float sm[];
   const int G = 4 * H;
-  if (reverse == 2) {   // both directions of a BiLSTM in one launch: blockIdx.y = direction, operands stacked [2]
+  int ldp = G;
+  if (reverse >= 2) {   // both directions of a BiLSTM in one launch: blockIdx.y = direction, operands stacked [2]
     const int d = blockIdx.y;
-    P += (size_t)d * nB * T * G;
+    if (reverse == 3) {  // ... except P, which is one (nB, T, 2G) tensor [dir 0 gates | dir 1 gates] (a single N = 2G projection GEMM)
+      P += d * G;
+      ldp = 2 * G;
+    } else {
+      P += (size_t)d * nB * T * G;
+    }
     Whh_p += (size_t)d * G * H;
     gates += (size_t)d * nB * T * G;
     c_seq += (size_t)d * nB * T * H;
@@ -45,12 +51,12 @@ __global__ void lstm_small_fwd_kernel(const float* __restrict__ P, const float* 
   float c = 0.f;
   const bool live = b < nB;
   const unsigned quad_base = ((threadIdx.y * blockDim.x + threadIdx.x) & 31) & ~3u;
-  float p_next = live ? P[((size_t)b * T + (reverse ? T - 1 : 0)) * G + j] : 0.f;
+  float p_next = live ? P[((size_t)b * T + (reverse ? T - 1 : 0)) * ldp + j] : 0.f;
   for (int step = 0; step < T; ++step) {
     const int t = reverse ? (T - 1 - step) : step;
     float acc = p_next;
     if (live && step + 1 < T)       // software prefetch: the next step's pre-activation is independent of the recurrence
-      p_next = P[((size_t)b * T + (reverse ? t - 1 : t + 1)) * G + j];
+      p_next = P[((size_t)b * T + (reverse ? t - 1 : t + 1)) * ldp + j];
     if (live) {
       const float* w = Ws + (size_t)j * (H + 1);
       const float* h = hs + ul * H;
@@ -82,13 +88,19 @@ __global__ void lstm_small_bwd_kernel(const float* __restrict__ dH, int lddh, co
                                       float* __restrict__ dP, int nB, int T, int H, int reverse) {
   extern __shared__ float sm[];
   const int G = 4 * H;
-  if (reverse == 2) {
+  int ldp = G;
+  if (reverse >= 2) {
     const int d = blockIdx.y;
     dH += d * H;
     Whh_p += (size_t)d * G * H;
     gates += (size_t)d * nB * T * G;
     c_seq += (size_t)d * nB * T * H;
-    dP += (size_t)d * nB * T * G;
+    if (reverse == 3) {  // dP is one (nB, T, 2G) tensor [dir 0 | dir 1]: the operand of single N = 2G / K = 2G gradient GEMMs
+      dP += d * G;
+      ldp = 2 * G;
+    } else {
+      dP += (size_t)d * nB * T * G;
+    }
     reverse = d;
   }
   float* Ws = sm;                              // [G][H+1]   (row j = gate column, col = hidden unit)
@@ -143,7 +155,7 @@ __global__ void lstm_small_bwd_kernel(const float* __restrict__ dH, int lddh, co
     dc_rec = dc * gf;
     __syncthreads();                 // every thread has read the previous step's dgs
     dgs[ul * G + j] = d;
-    if (live) dP[((size_t)b * T + t) * G + j] = d;
+    if (live) dP[((size_t)b * T + t) * ldp + j] = d;
     __syncthreads();
   }
 }
@@ -159,9 +171,15 @@ lstm_small_fwd_kernel_t(const float* __restrict__ P, const float* __restrict__ W
                         float* __restrict__ gates, float* __restrict__ c_seq, int nB, int T, int reverse) {
   constexpr int H = HT, G = 4 * HT, UPB = 256 / G;
   __shared__ __align__(16) float hs[2][UPB][HT];
-  if (reverse == 2) {
+  int ldp = G;
+  if (reverse >= 2) {
     const int d = blockIdx.y;
-    P += (size_t)d * nB * T * G;
+    if (reverse == 3) {
+      P += d * G;
+      ldp = 2 * G;
+    } else {
+      P += (size_t)d * nB * T * G;
+    }
     Whh_p += (size_t)d * G * H;
     gates += (size_t)d * nB * T * G;
     c_seq += (size_t)d * nB * T * H;
@@ -179,12 +197,12 @@ lstm_small_fwd_kernel_t(const float* __restrict__ P, const float* __restrict__ W
   float c = 0.f;
   const bool live = b < nB;
   const unsigned quad_base = ((threadIdx.y * blockDim.x + threadIdx.x) & 31) & ~3u;
-  float p_next = live ? P[((size_t)b * T + (reverse ? T - 1 : 0)) * G + j] : 0.f;
+  float p_next = live ? P[((size_t)b * T + (reverse ? T - 1 : 0)) * ldp + j] : 0.f;
   for (int step = 0; step < T; ++step) {
     const int t = reverse ? (T - 1 - step) : step;
     const int cur = step & 1;
     float acc = p_next;
-    if (live && step + 1 < T) p_next = P[((size_t)b * T + (reverse ? t - 1 : t + 1)) * G + j];
+    if (live && step + 1 < T) p_next = P[((size_t)b * T + (reverse ? t - 1 : t + 1)) * ldp + j];
     const float4* h4 = reinterpret_cast<const float4*>(hs[cur][ul]);
 #pragma unroll
     for (int k = 0; k < HT; k += 4) {
@@ -219,13 +237,19 @@ lstm_small_bwd_kernel_t(const float* __restrict__ dH, int lddh, const float* __r
                         const float* __restrict__ c_seq, float* __restrict__ dP, int nB, int T, int reverse) {
   constexpr int H = HT, G = 4 * HT, UPB = 256 / G;
   __shared__ __align__(16) float dgs[2][UPB][G];
-  if (reverse == 2) {
+  int ldp = G;
+  if (reverse >= 2) {
     const int d = blockIdx.y;
     dH += d * H;
     Whh_p += (size_t)d * G * H;
     gates += (size_t)d * nB * T * G;
     c_seq += (size_t)d * nB * T * H;
-    dP += (size_t)d * nB * T * G;
+    if (reverse == 3) {  // dP is one (nB, T, 2G) tensor [dir 0 | dir 1]: the operand of single N = 2G / K = 2G gradient GEMMs
+      dP += d * G;
+      ldp = 2 * G;
+    } else {
+      dP += (size_t)d * nB * T * G;
+    }
     reverse = d;
   }
   const int j = threadIdx.x, ul = threadIdx.y;
@@ -280,7 +304,7 @@ lstm_small_bwd_kernel_t(const float* __restrict__ dH, int lddh, const float* __r
     else d = dh * tc * go * (1.f - go);
     dc_rec = dc * gf;
     dgs[cur ^ 1][ul][j] = d;
-    if (live) dP[((size_t)b * T + t) * G + j] = d;
+    if (live) dP[((size_t)b * T + t) * ldp + j] = d;
     __syncthreads();
   }
 }
@@ -384,7 +408,7 @@ int lstm_seq_fwd_simt(const float* P, const float* Whh_p, float* h_seq, int ldh,
   const int G = 4 * H;
   if (H == 16 || H == 32) {
     const int upb = 256 / G;
-    const dim3 grid(ceil_div(nB, upb), reverse == 2 ? 2 : 1), block(G, upb);
+    const dim3 grid(ceil_div(nB, upb), reverse >= 2 ? 2 : 1), block(G, upb);
     if (H == 16) lstm_small_fwd_kernel_t<16><<<grid, block, 0, st>>>(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, reverse);
     else lstm_small_fwd_kernel_t<32><<<grid, block, 0, st>>>(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, reverse);
     AVC_LAUNCHED();
@@ -395,12 +419,12 @@ int lstm_seq_fwd_simt(const float* P, const float* Whh_p, float* h_seq, int ldh,
     const size_t smem = ((size_t)G * (H + 1) + (size_t)upb * H) * sizeof(float);
     if (smem > 48 * 1024)
       AVC_CUDA(cudaFuncSetAttribute(lstm_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lstm_small_fwd_kernel<<<dim3(ceil_div(nB, upb), reverse == 2 ? 2 : 1), dim3(G, upb), smem, st>>>(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, H, reverse);
+    lstm_small_fwd_kernel<<<dim3(ceil_div(nB, upb), reverse >= 2 ? 2 : 1), dim3(G, upb), smem, st>>>(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, H, reverse);
     AVC_LAUNCHED();
     return AVC_OK;
   }
-  if (reverse == 2) {
-    set_error("avc_lstm_seq_fwd: reverse=2 (both directions in one launch) needs H <= 64, H %% 8 == 0");
+  if (reverse >= 2) {
+    set_error("avc_lstm_seq_fwd: reverse=2/3 (both directions in one launch) needs H <= 64, H %% 8 == 0");
     return AVC_ERR_UNSUPPORTED;
   }
   dim3 grid(ceil_div(G, SG_BN), ceil_div(nB, SG_BM));
@@ -421,7 +445,7 @@ int lstm_seq_bwd_simt(const float* dH, int lddh, const float* Whh_p, const float
   const int G = 4 * H;
   if (H == 16 || H == 32) {
     const int upb = 256 / G;
-    const dim3 grid(ceil_div(nB, upb), reverse == 2 ? 2 : 1), block(G, upb);
+    const dim3 grid(ceil_div(nB, upb), reverse >= 2 ? 2 : 1), block(G, upb);
     if (H == 16) lstm_small_bwd_kernel_t<16><<<grid, block, 0, st>>>(dH, lddh, Whh_p, gates, c_seq, dP, nB, T, reverse);
     else lstm_small_bwd_kernel_t<32><<<grid, block, 0, st>>>(dH, lddh, Whh_p, gates, c_seq, dP, nB, T, reverse);
     AVC_LAUNCHED();
@@ -432,12 +456,12 @@ int lstm_seq_bwd_simt(const float* dH, int lddh, const float* Whh_p, const float
     const size_t smem = ((size_t)G * (H + 1) + (size_t)upb * G + (size_t)upb * H) * sizeof(float);
     if (smem > 48 * 1024)
       AVC_CUDA(cudaFuncSetAttribute(lstm_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    lstm_small_bwd_kernel<<<dim3(ceil_div(nB, upb), reverse == 2 ? 2 : 1), dim3(G, upb), smem, st>>>(dH, lddh, Whh_p, gates, c_seq, dP, nB, T, H, reverse);
+    lstm_small_bwd_kernel<<<dim3(ceil_div(nB, upb), reverse >= 2 ? 2 : 1), dim3(G, upb), smem, st>>>(dH, lddh, Whh_p, gates, c_seq, dP, nB, T, H, reverse);
     AVC_LAUNCHED();
     return AVC_OK;
   }
-  if (reverse == 2) {
-    set_error("avc_lstm_seq_bwd: reverse=2 (both directions in one launch) needs H <= 64, H %% 8 == 0");
+  if (reverse >= 2) {
+    set_error("avc_lstm_seq_bwd: reverse=2/3 (both directions in one launch) needs H <= 64, H %% 8 == 0");
     return AVC_ERR_UNSUPPORTED;
   }
   if (!ws || ws_bytes < lstm_bwd_workspace_simt(nB, T, H)) {

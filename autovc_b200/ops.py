@@ -239,6 +239,23 @@ def pack_lstm_b(b_ih: torch.Tensor, b_hh: torch.Tensor, cache: PackCache = _GLOB
     return cache.get(("lstm_b", id(b_hh), b_hh.data_ptr(), b_hh._version), b_ih, build)
 
 
+def pack_bilstm(weights, cache: PackCache = _GLOBAL_CACHE):
+    """Both directions of a small-H BiLSTM layer stacked for single GEMMs: W_ih (2G, I) [dir 0 rows | dir 1 rows, gate-
+    interleaved], its transpose (I, 2G), the folded biases (2G) and W_hh (2, G, H).  Cached per step on the first weight."""
+    def build():
+        wi, wiT, bs, wh = [], [], [], []
+        for d in range(2):
+            w_ih, w_hh, b_ih, b_hh = weights[4 * d:4 * d + 4]
+            p, pT = pack_lstm_w(w_ih, cache)
+            wi.append(p)
+            wiT.append(pT)
+            wh.append(pack_lstm_w(w_hh, cache)[0])
+            bs.append(pack_lstm_b(b_ih, b_hh, cache))
+        return torch.cat(wi, 0), torch.cat(wiT, 1).contiguous(), torch.cat(bs, 0), torch.stack(wh, 0)
+    key = ("bilstm",) + tuple((id(w), w._version, w.data_ptr()) for w in weights[1:])
+    return cache.get(key, weights[0], build)
+
+
 def transpose2d(w: torch.Tensor, cache: PackCache = _GLOBAL_CACHE):
     def build():
         R, C = w.shape
@@ -334,19 +351,16 @@ class LstmLayer(torch.autograd.Function):
         packs = []
         fused = D == 2 and H <= 64 and H % 8 == 0          # both directions of the encoder BiLSTM in one launch
         if fused:
-            Pre = torch.empty(2, B, T, G, device=x.device, dtype=torch.float32)
+            # ONE input-projection GEMM for both directions (N = 2G: x is read once), one recurrence launch (reverse=3:
+            # P rows are [dir 0 gates | dir 1 gates])
+            wi2, wiT2, b2, wh2 = pack_bilstm(weights)
+            Pre = torch.empty(B, T, 2 * G, device=x.device, dtype=torch.float32)
+            gemm_nt_taps(x, I, wi2, b2, Pre, 2 * G, B, T, 2 * G, I, 1, 0, prec=prec)
             gates = torch.empty(2, B, T, G, device=x.device, dtype=torch.float32)
             c_seq = torch.empty(2, B, T, H, device=x.device, dtype=torch.float32)
-            wh2 = torch.empty(2, G, H, device=x.device, dtype=torch.float32)
-            for d in range(2):
-                w_ih, w_hh, b_ih, b_hh = weights[4 * d:4 * d + 4]
-                wi_p, wi_pT = pack_lstm_w(w_ih)
-                wh_p, wh_pT = pack_lstm_w(w_hh)
-                wh2[d].copy_(wh_p)
-                gemm_nt_taps(x, I, wi_p, pack_lstm_b(b_ih, b_hh), Pre[d], G, B, T, G, I, 1, 0, prec=prec)
-                packs += [wi_pT, wh_p, wh_pT]
-            call("avc_lstm_seq_fwd", _p(Pre), _p(wh2), _p(out), 2 * H, _p(gates), _p(c_seq), B, T, H, 2, prec, _NULL, 0, _stream())
+            call("avc_lstm_seq_fwd", _p(Pre), _p(wh2), _p(out), 2 * H, _p(gates), _p(c_seq), B, T, H, 3, prec, _NULL, 0, _stream())
             saved = [gates, c_seq, wh2]
+            packs = [wiT2]
         for d in range(0 if not fused else D, D):
             w_ih, w_hh, b_ih, b_hh = weights[4 * d:4 * d + 4]
             wi_p, wi_pT = pack_lstm_w(w_ih)
@@ -381,25 +395,40 @@ class LstmLayer(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         dx = torch.empty_like(x) if need_dx else None
         grads: List[Optional[torch.Tensor]] = []
-        dP2 = None
         if ctx.fused:
             gates2, c2, wh2 = saved
-            dP2 = torch.empty(2, B, T, G, device=x.device, dtype=torch.float32)
-            call("avc_lstm_seq_bwd", _p(dout), 2 * H, _p(wh2), _p(wh2), _p(gates2), _p(c2), _p(dP2), B, T, H, 2, prec,
+            (wiT2,) = ctx.packs
+            dP2 = torch.empty(B, T, 2 * G, device=x.device, dtype=torch.float32)          # [dir 0 | dir 1] per row
+            call("avc_lstm_seq_bwd", _p(dout), 2 * H, _p(wh2), _p(wh2), _p(gates2), _p(c2), _p(dP2), B, T, H, 3, prec,
                  _NULL, 0, _stream())
+            # dW_ih of both directions in one GEMM: the 2G gate columns are un-permuted as ONE virtual layer of 2H units
+            # (row g*2H + d*H + u), then split per direction
+            dwi = torch.empty(4, 2, H, I, device=x.device, dtype=torch.float32)
+            gemm_tn_taps(dP2, 2 * G, x, I, dwi, B, T, 2 * G, I, 1, 0, out_mode=2, prec=prec)
+            dwi = dwi.permute(1, 0, 2, 3).contiguous()
+            if need_dx:
+                gemm_nt_taps(dP2, 2 * G, wiT2, None, dx, I, B, T, I, 2 * G, 1, 0, prec=prec)
+            for d in range(2):
+                w_ih, w_hh, b_ih, b_hh = weights[4 * d:4 * d + 4]
+                dPd = dP2.view(-1)[d * G:]
+                dw_hh = torch.empty_like(w_hh)
+                gemm_tn_taps(dPd, 2 * G, out.view(-1)[d * H:], 2 * H, dw_hh, B, T, G, H, 1, (+1 if d == 1 else -1), out_mode=2,
+                             prec=prec)
+                db_ih = torch.empty_like(b_ih)
+                db_hh = torch.empty_like(b_hh)
+                colsum(dPd, 2 * G, B * T, G, db_ih, db_hh, out_mode=2)
+                grads += [dwi[d].view(G, I), dw_hh, db_ih, db_hh]
+            return (dx, None, *grads)
         for d in range(D):
             w_ih, w_hh, b_ih, b_hh = weights[4 * d:4 * d + 4]
             wi_pT, wh_p, wh_pT = ctx.packs[3 * d:3 * d + 3]
             rev = int(d == 1)
-            if ctx.fused:
-                dP = dP2[d]
-            else:
-                gates, c_seq = saved[2 * d:2 * d + 2]
-                dP = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
-                nbytes = query("avc_lstm_bwd_workspace_bytes", B, T, H, prec)
-                ws = _ws(nbytes, x.device)
-                call("avc_lstm_seq_bwd", _p(dout.view(-1)[d * H:]), D * H, _p(wh_p), _p(wh_pT), _p(gates), _p(c_seq), _p(dP),
-                     B, T, H, rev, prec, _p(ws), nbytes, _stream())
+            gates, c_seq = saved[2 * d:2 * d + 2]
+            dP = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
+            nbytes = query("avc_lstm_bwd_workspace_bytes", B, T, H, prec)
+            ws = _ws(nbytes, x.device)
+            call("avc_lstm_seq_bwd", _p(dout.view(-1)[d * H:]), D * H, _p(wh_p), _p(wh_pT), _p(gates), _p(c_seq), _p(dP),
+                 B, T, H, rev, prec, _p(ws), nbytes, _stream())
             dw_ih = torch.empty_like(w_ih)
             gemm_tn_taps(dP, G, x, I, dw_ih, B, T, G, I, 1, 0, out_mode=2, prec=prec)
             dw_hh = torch.empty_like(w_hh)

@@ -155,6 +155,8 @@ int avc_colsum16(const void* x16, int fmt, int ldx, int M, int C, float* out, fl
  * reverse = 1 walks t = T-1 .. 0 (the *_reverse direction).  h0 = c0 = 0.  reverse = 2 (H <= 64 only): both
  * directions of a BiLSTM in ONE launch; P, Whh_p, gates, c_seq, dP are stacked [2][...] (forward first) and
  * direction d reads/writes h_seq / dH at column offset d*H of a shared (nB,T,2H) buffer (ldh = lddh = 2H).
+ * reverse = 3: as 2, except that P and dP are ONE (nB, T, 8H) tensor each, [direction 0 gates | direction 1 gates] per row --
+ * the output of a single N = 8H input-projection GEMM / the operand of single dW_ih (N = 8H) and dX (K = 8H) GEMMs.
  * AVC_PREC_FP32: H <= 64 runs the whole sequence in one launch (W_hh in shared memory), larger H
  * one launch per step.  AVC_PREC_BF16 with 128 <= H <= 1024, H % 64 == 0: ONE persistent cooperative
  * launch per layer-direction -- W_hh slices resident in shared memory across the SMs, tcgen05 MMAs
