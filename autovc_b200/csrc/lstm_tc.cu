@@ -691,6 +691,9 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
   const int ut = (cluster_id % (UT / PAIRS)) * PAIRS + (int)ug, mt = cluster_id / (UT / PAIRS);
   constexpr int SLICE_ROWS = 128 / PAIRS;                   // rows of the activation tile this CTA loads (and multicasts)
   const uint16_t mc_mask = (uint16_t)((1u << r) | (PAIRS == 2 ? (1u << (4 + r)) : 0u));
+  // reduce-scatter of the partial tiles by bulk DSMEM copies (see the epilogue); not with per-k-block release counters, whose
+  // producers may refill the ring (= the send staging area) before every CTA has published
+  const bool rs_bulk = !(PAIRS == 1 && p.kflags != 0) && !(p.exp_mode & 128);
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -702,7 +705,7 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
     mbar_init(w_bar, 1);
     mbar_init(tfull, 1);
     mbar_init(tempty, 4);
-    mbar_init(red_full, 3 * 4);                             // one arrive per epilogue warp of each of the 3 peers
+    mbar_init(red_full, rs_bulk ? 1 : 3 * 4);               // bulk: my own arrive.expect_tx (+ 3 x 8 KB of complete_tx); else one arrive per epilogue warp of each of the 3 peers
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 64);
@@ -746,6 +749,7 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
         if (lane == 0) {
           while (ld_acquire(counter) < (unsigned)s * per_step) {
           }
+          LT_TRACE(0);
           if (p.exp_mode == 4) fence_proxy_async();
         }
         __syncwarp();
@@ -758,6 +762,8 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
             else
               tma_load_3d_mc(ring + stage * LT_STAGE + ug * SLICE_ROWS * 128, &mapX, full_bar(stage), (int)r * H + kb * 64,
                              row0 + (int)ug * SLICE_ROWS, 0, mc_mask);
+            if (kb == 0) LT_TRACE(1);
+            if (kb == kblocks - 1) LT_TRACE(2);
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -784,13 +790,18 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
         if (kflags) kb = slot_kb[stage];
         const uint32_t sa = ring + stage * LT_STAGE, sb = w_base + kb * w_block;
         if (elect_one()) {
+          if (kb0 == 0) LT_TRACE(3);
+          if (kb0 == kblocks - 1) LT_TRACE(4);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_f16(tmem_base, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc,
                      (kb0 > 0 || k > 0) ? 1u : 0u);
           if (PAIRS == 1) umma_commit(empty_bar(stage));
           else umma_commit_mc(empty_bar(stage), mc_mask);
-          if (kb0 == kblocks - 1) umma_commit(tfull);
+          if (kb0 == kblocks - 1) {
+            umma_commit(tfull);
+            LT_TRACE(5);
+          }
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -856,9 +867,51 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
 #pragma unroll
         for (int j = 0; j < 4 * U; ++j) g4[j] = 0.f;
       }
+      if (rs_bulk && s > 0 && threadIdx.x == 64) mbar_expect_tx(red_full, 3 * 128 * 16 * 4);   // this step's three foreign partials
       mbar_wait(tfull, s & 1);
+      if (threadIdx.x == 64) LT_TRACE(6);
       tc_fence_after();
-      if (s > 0) {
+      if (s > 0 && rs_bulk) {
+        // my partial 128 x 64 tile: keep quarter r; quarter qq goes to cluster rank qq.  As per-thread st.shared::cluster stores
+        // + release arrives this took 2.8 us of a 12.5 us step (trace): 12 remote 16-byte stores per thread, then an arrive
+        // that has to wait for all of them.  Now the three foreign quarters are staged in LOCAL shared memory (the ring is
+        // idle between the last MMA of a step and this CTA's publish, so its first 24 KB serve as staging) and one thread
+        // hands each 8 KB tile to the copy engine, which signals the receiver's mbarrier with the byte count.
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float d[32];
+          tmem_ld32(t_addr + half * 32, d);
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const uint32_t qq = half * 2 + h2;
+            if (qq == r) {
+#pragma unroll
+              for (int i = 0; i < U; ++i) dh[i] += d[h2 * 16 + i];
+            } else {
+              const uint32_t j = qq < r ? qq : qq - 1;           // staging slot of destination qq
+              const uint32_t dst = ring + (j * 128 + row) * 64;
+#pragma unroll
+              for (int i = 0; i < U; i += 4) st_shared_v4(dst + i * 4, d[h2 * 16 + i], d[h2 * 16 + i + 1], d[h2 * 16 + i + 2], d[h2 * 16 + i + 3]);
+            }
+          }
+        }
+        tc_fence_before();
+        fence_async_smem();                                       // my staged rows are visible to the copy engine
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+#pragma unroll
+          for (uint32_t qq = 0; qq < KS_CL; ++qq) {
+            if (qq == r) continue;
+            const uint32_t j = qq < r ? qq : qq - 1;
+            const uint32_t slot = r < qq ? r : r - 1;            // my index among qq's three senders
+            const uint32_t peer = (ug << 2) | qq;
+            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             mapa_shared(red_s + slot * 8192u, peer)),
+                         "r"(ring + j * 8192u), "r"(8192u), "r"(mapa_shared(red_full, peer))
+                         : "memory");
+          }
+        }
+      } else if (s > 0) {
         // my partial 128 x 64 tile: keep quarter r, ship quarter qq to cluster rank qq
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -886,7 +939,11 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
           for (uint32_t qq = 0; qq < KS_CL; ++qq)
             if (qq != r) mbar_arrive_cluster(mapa_shared(red_full, (ug << 2) | qq));
         }
+      }
+      if (s > 0) {
+        if (threadIdx.x == 64) LT_TRACE(9);
         mbar_wait_cluster(red_full, (s - 1) & 1);
+        if (threadIdx.x == 64) LT_TRACE(10);
 #pragma unroll
         for (int src = 0; src < 3; ++src) {
 #pragma unroll
@@ -918,10 +975,13 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
 #pragma unroll
         for (int j = 0; j < 4 * U; j += 16) stg_v8(xb + j, reinterpret_cast<const uint32_t*>(&gb[j]));
       }
+      if (threadIdx.x == 64) LT_TRACE(7);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 64) {
+        LT_TRACE(11);
         fence_proxy_async();
         red_release_add(kflags ? counter + (u0 >> 4) : counter, 1u);   // dG columns 4*u0 .. 4*u0+63 = k-block u0/16
+        LT_TRACE(8);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (live && !(p.exp_mode & 8)) {

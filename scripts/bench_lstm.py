@@ -60,7 +60,7 @@ dH = torch.randn(B, T, H, device=dev) * 0.1
 dP = torch.empty(B, T, G, device=dev)
 nf = _lib.query("avc_lstm_fwd_workspace_bytes", B, T, H, prec); wf = _ws(nf, dev)
 nb = _lib.query("avc_lstm_bwd_workspace_bytes", B, T, H, prec); wb = _ws(nb, dev)
-names = ["barrier", "tma0", "tmaN", "land0", "landN", "mma_issued", "epi_wake", "math_done", "published"]
+names = ["barrier", "tma0", "tmaN", "land0", "landN", "mma_issued", "epi_wake", "math_done", "published", "rs_sent", "rs_done", "bar_passed"]
 for which in ("fwd", "bwd"):
     trace = torch.zeros(16 * T + 9 * 1024, dtype=torch.int64, device=dev)
     _lib.load().avc_debug_set_trace(ctypes.c_void_p(trace.data_ptr()))
@@ -71,7 +71,7 @@ for which in ("fwd", "bwd"):
     torch.cuda.synchronize()
     _lib.load().avc_debug_set_trace(ctypes.c_void_p(0))
     full = trace.cpu()
-    tr = full[:16 * T].view(T, 16)[:, :9].double()
+    tr = full[:16 * T].view(T, 16)[:, :12].double()
     # steps 20..100: offsets of each event relative to the previous step's 'published'
     rows = []
     for s in range(20, 100):
