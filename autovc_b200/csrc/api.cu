@@ -191,7 +191,8 @@ extern "C" size_t avc_gemm_tn_h_workspace_bytes(int nB, int T, int N, int K, int
 extern "C" int avc_lstm_seq_fwd_h(const float* P, const void* Whh_p, int w_fmt, float* h_seq, int ldh, float* gates, float* c_seq,
                                   void* h16, int fmt16, void* h16b, int nB, int T, int H, int reverse, void* workspace,
                                   size_t workspace_bytes, void* stream) {
-  AVC_REQUIRE(P && Whh_p && h_seq && gates && c_seq && h16, "avc_lstm_seq_fwd_h: null pointer");
+  AVC_REQUIRE(P && Whh_p && h_seq && h16, "avc_lstm_seq_fwd_h: null pointer");
+  AVC_REQUIRE((gates == nullptr) == (c_seq == nullptr), "avc_lstm_seq_fwd_h: gates and c_seq are saved together or not at all");
   AVC_REQUIRE(nB > 0 && T > 0 && lstm_tc_supported(H) && ldh >= H && ldh % 4 == 0 && (fmt16 == 1 || fmt16 == 2), "avc_lstm_seq_fwd_h: unsupported shape");
   AVC_REQUIRE(w_fmt == 0 || w_fmt == 1, "avc_lstm_seq_fwd_h: W_hh must be fp32 (0) or bf16 (1)");
   return lstm_seq_tc(false, Whh_p, P, h_seq, ldh, gates, c_seq, nullptr, 0, nullptr, nB, T, H, reverse, workspace, workspace_bytes,

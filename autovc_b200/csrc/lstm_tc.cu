@@ -433,8 +433,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           // utterances (b >= nB) are clipped by the TMA unit.
           const uint32_t buf = out_stage + (uint32_t)(warp - 2) * 4096u;
           const int brow = mt * 128 + q * 32;
+          const bool save_bptt = p.gates != nullptr;                   // inference (no backward): only h leaves the kernel
 #pragma unroll
           for (int half = 0; half < BN / 32; ++half) {                 // gates: 32 columns (one 128-byte swizzle row) per round
+            if (!save_bptt) break;
             if (lane == 0) bulk_wait_read<0>();
             __syncwarp();
 #pragma unroll
@@ -458,7 +460,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&om.c, buf, u0, t, brow);
+            if (save_bptt) tma_store_3d(&om.c, buf, u0, t, brow);
             tma_store_3d(&om.h, buf + 2048, u0, t, brow);
             bulk_commit();
           }
@@ -495,14 +497,17 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__
             }
           }
         } else if (live && !(p.exp_mode & 8)) {
+          if (p.gates != nullptr) {
 #pragma unroll
-          for (int j = 0; j < BN; j += 4)
-            *reinterpret_cast<float4*>(p.gates + rowi * G + n0 + j) = *reinterpret_cast<const float4*>(&pre[j]);
+            for (int j = 0; j < BN; j += 4)
+              *reinterpret_cast<float4*>(p.gates + rowi * G + n0 + j) = *reinterpret_cast<const float4*>(&pre[j]);
 #pragma unroll
-          for (int i = 0; i < U; i += 4) {
-            *reinterpret_cast<float4*>(p.c_seq + rowi * H + u0 + i) = *reinterpret_cast<const float4*>(&c[i]);
-            *reinterpret_cast<float4*>(p.h_seq + rowi * p.ldh + u0 + i) = *reinterpret_cast<const float4*>(&hf[i]);
+            for (int i = 0; i < U; i += 4)
+              *reinterpret_cast<float4*>(p.c_seq + rowi * H + u0 + i) = *reinterpret_cast<const float4*>(&c[i]);
           }
+#pragma unroll
+          for (int i = 0; i < U; i += 4)
+            *reinterpret_cast<float4*>(p.h_seq + rowi * p.ldh + u0 + i) = *reinterpret_cast<const float4*>(&hf[i]);
           if (p.h16 != nullptr) {
             uint16_t* h16 = reinterpret_cast<uint16_t*>(p.h16) + rowi * H + u0;
             if (p.fmt16 == 2) {
@@ -1254,8 +1259,8 @@ int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh,
     p.P = P ? P + (size_t)b0 * T * G : nullptr;
     p.h_seq = h_seq ? h_seq + (size_t)b0 * T * ldh : nullptr;
     p.ldh = ldh;
-    p.gates = gates + (size_t)b0 * T * G;
-    p.c_seq = c_seq + (size_t)b0 * T * H;
+    p.gates = gates ? gates + (size_t)b0 * T * G : nullptr;       // forward without BPTT state (inference): both NULL
+    p.c_seq = c_seq ? c_seq + (size_t)b0 * T * H : nullptr;
     p.dH = dH ? dH + (size_t)b0 * T * lddh : nullptr;
     p.lddh = lddh;
     p.dP = dP ? dP + (size_t)b0 * T * G : nullptr;
@@ -1297,8 +1302,8 @@ int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh,
     if (!bwd && out_tma_env && pl.out_stage > 0 && (((uintptr_t)p.gates | (uintptr_t)p.c_seq | (uintptr_t)p.h_seq | (uintptr_t)p.h16 | (uintptr_t)p.h16b) & 15) == 0) {
       const int U = pl.BN / 4;
       const uint64_t Tn = (uint64_t)T;
-      rc = make_map3_store(&om.gates, p.gates, 4, G, Tn, nb, G, Tn * G, 32, 1, 32, true);
-      if (!rc) rc = make_map3_store(&om.c, p.c_seq, 4, H, Tn, nb, H, Tn * H, U, 1, 32, false);
+      if (p.gates) rc = make_map3_store(&om.gates, p.gates, 4, G, Tn, nb, G, Tn * G, 32, 1, 32, true);
+      if (!rc && p.c_seq) rc = make_map3_store(&om.c, p.c_seq, 4, H, Tn, nb, H, Tn * H, U, 1, 32, false);
       if (!rc) rc = make_map3_store(&om.h, p.h_seq, 4, H, Tn, nb, ldh, Tn * ldh, U, 1, 32, false);
       if (!rc && p.h16) rc = make_map3_store(&om.h16, p.h16, 2, H, Tn, nb, H, Tn * H, U, 1, 32, false);
       if (!rc && p.h16b) rc = make_map3_store(&om.h16b, p.h16b, 2, H, Tn, nb, H, Tn * H, U, 1, 32, false);

@@ -755,9 +755,10 @@ class LstmLayerH(torch.autograd.Function):
         gemm_nt_taps_hw(A, a_fmt, I, wi_p, FMT_FP16, wi_p.shape[-1], b_p, Pre, G, B, T, G, I, 1, 0)
         out = torch.empty(B, T, H, device=x.device, dtype=torch.float32)
         h16 = torch.empty(B, T, H, device=x.device, dtype=torch.float16)
-        h16b = torch.empty(B, T, H, device=x.device, dtype=torch.bfloat16) if any(ctx.needs_input_grad) else None
-        gates = torch.empty(B, T, G, device=x.device, dtype=torch.float32)
-        c_seq = torch.empty(B, T, H, device=x.device, dtype=torch.float32)
+        train = any(ctx.needs_input_grad)          # under no_grad (conversion) nothing is saved for BPTT
+        h16b = torch.empty(B, T, H, device=x.device, dtype=torch.bfloat16) if train else None
+        gates = torch.empty(B, T, G, device=x.device, dtype=torch.float32) if train else None
+        c_seq = torch.empty(B, T, H, device=x.device, dtype=torch.float32) if train else None
         nbytes = query("avc_lstm_fwd_workspace_bytes", B, T, H, PREC_BF16)
         ws = _ws(nbytes, x.device)
         call("avc_lstm_seq_fwd_h", _p(Pre), _p(wh_p), FMT_BF16, _p(out), H, _p(gates), _p(c_seq), _p(h16), FMT_FP16, _p(h16b),

@@ -388,7 +388,7 @@ def main():
     ap.add_argument("--cpu-sample-batch", dest="cpu_sample_batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "frontend", "convert"])
-    ap.add_argument("--utterances", type=int, default=1024, help="frontend/convert legs: number of 10 s utterances")
+    ap.add_argument("--utterances", type=int, default=4096, help="frontend/convert legs: number of 10 s utterances (BASELINE.json configs[4]: 4096)")
     args = ap.parse_args()
     if args.workload != "train":
         return run_frontend_or_convert(args)

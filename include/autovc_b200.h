@@ -206,7 +206,8 @@ int avc_bn_act_bwd_apply_h(const float* dz, const float* z, const float* y, cons
 /* persistent recurrences (128 <= H <= 1024, H % 64 == 0) with a 16-bit side output: h16 (nB,T,H) / dP16 (nB,T,4H, bf16) */
 /* w_fmt: AVC_FMT_FP32 = Whh_p / Whh_pT are the fp32 packings of avc_pack_lstm_weight (converted per call);
  *        AVC_FMT_BF16 = the bf16 packings of avc_pack_lstm_weight_h (ld = H resp. 4H), read in place. */
-/* h16b (optional, may be NULL): a bf16 copy of h next to h16 -- the operand of the dW_hh / next layer's dW_ih GEMMs. */
+/* h16b (optional, may be NULL): a bf16 copy of h next to h16 -- the operand of the dW_hh / next layer's dW_ih GEMMs.
+ * gates and c_seq may BOTH be NULL (inference, conversion.py:91-92 under no_grad): nothing is saved for BPTT. */
 int avc_lstm_seq_fwd_h(const float* P, const void* Whh_p, int w_fmt, float* h_seq, int ldh, float* gates, float* c_seq, void* h16,
                        int fmt16, void* h16b, int nB, int T, int H, int reverse, void* workspace, size_t workspace_bytes, void* stream);
 /* (dP, the fp32 gate-gradient tensor, may be NULL: only dP16 is then written) */
