@@ -724,10 +724,10 @@ class ConvBnActH(torch.autograd.Function):
             # both operands of a GEMM must share a 16-bit format: bf16 copy of the activation from its producer, else cast here
             if y_fmt == FMT_BF16:
                 X, x_fmt = (xb, FMT_BF16) if xb is not None else _operand(x, None, Cin, FMT_BF16)
-            else:
-                if x is None:
-                    raise _lib.AvcError("conv backward: fp32 input was not saved")
+            elif x is not None:
                 X, x_fmt = x, FMT_FP32
+            else:                       # fp32 dy (odd Cout, e.g. 513 bins) is staged to bf16 inside the GEMM: the bf16 copy of x matches it
+                X, x_fmt = xb, FMT_BF16
             gemm_tn_taps_h(dy, y_fmt, Cout, X, x_fmt, Cin, dw, B, T, Cout, Cin, k, -(k // 2), out_mode=1)   # fp32 operands are staged to bf16
         db = torch.zeros(Cout, device=dz.device, dtype=torch.float32)
         dres = dz if ctx.has_res else None

@@ -180,6 +180,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        solver.nccl_env_defaults()      # cap NCCL's CTAs so that its kernels co-reside with the 128-CTA recurrence kernels
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)
@@ -235,16 +236,21 @@ def run_ours(args):
             ms = float(t.item())
         return ms / steps
 
-    for _ in range(args.warmup):
-        step_resident()
+    # the sampler starts BEFORE the warm-up: nvidia-smi's NVML initialisation briefly stalls every GPU of the box, which must
+    # not fall into the timed region (it cost one of two timed loops ~35 ms on a 4-GPU box)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
+    if sampler:
+        torch.cuda.synchronize()
+        sampler.rows.clear()            # keep only the samples taken during the timed region
     n0 = autovc_b200.launch_count()
     ms = timed(step_resident, args.steps)
     launches = (autovc_b200.launch_count() - n0) // args.steps
     clocks = sampler.stop() if sampler else None
-    for _ in range(2):
+    for _ in range(3):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 

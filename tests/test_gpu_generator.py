@@ -169,6 +169,21 @@ def test_tensor_core_modes_within_rel_l2_gate(name, precision):
     assert not bad, bad
 
 
+def test_half_mode_513_bin_variant_within_gate():
+    """model_vc_stft shapes (513 / 769 channels: odd counts fall back to internally staged operands) in half mode, against
+    the reference's fp32 golden -- the path bench.py --n-bins 513 runs (BASELINE.json configs[3])."""
+    g, G, (dim_neck, freq, B, T, n_bins, iseed) = _build("train_stft_16_16_b2_t32")
+    G.set_precision("half")
+    x, e, _ = synth_inputs(B, T, n_bins, 256, iseed)
+    opt = autovc_b200.FusedAdam(G.parameters(), 1e-4)
+    out = solver.train_step(G.train(), opt, x.cuda(), e.cuda(), return_outputs=True)
+    errs = {k: _rel_l2(out[k].cpu().numpy(), g["s0_" + k]) for k in ("x_identic", "x_identic_psnt", "code_real", "code_reconst")}
+    print("half 513:", errs)
+    assert max(errs.values()) < 5e-2, errs          # B*T = 64 rows per BatchNorm channel: the noisiest statistics in the suite
+    for n, gr in out["grads"].items():
+        assert torch.isfinite(gr).all(), n
+
+
 @pytest.mark.gpu
 def test_host_batch_prefetcher_hands_over_batches_in_order():
     from autovc_b200.solver import HostBatchPrefetcher
