@@ -57,7 +57,8 @@ def _ws(nbytes: int, device) -> Optional[torch.Tensor]:
 # The main stream re-joins the side stream in an end-of-backward engine callback (and in GradBucketReducer's hooks).
 # Parameters used more than once per graph (the encoder: two passes per step) stay on the main stream, because autograd
 # sums their contributions there.
-_WGRAD = {"on": os.environ.get("AUTOVC_B200_WGRAD_STREAM", "1") != "0", "streams": {}, "armed": set(), "fwd_since_bwd": 0}
+_WGRAD = {"on": os.environ.get("AUTOVC_B200_WGRAD_STREAM", "1") != "0", "streams": {}, "armed": set(), "fwd_since_bwd": 0,
+          "keep": []}
 
 
 def wgrad_stream(device) -> Optional[torch.cuda.Stream]:
@@ -73,10 +74,19 @@ def note_full_forward():
     _WGRAD["armed"].clear()
 
 
+def keep_until_join(tensors):
+    """Main-stream tensors that side-stream work reads stay referenced until the main stream has re-joined the side stream
+    (end of backward): freed after that point, their blocks can only be reused by work ordered after the readers.
+    (`Tensor.record_stream` would do the same, but it parks every such block behind an event and made the caching
+    allocator call cudaMalloc inside steady-state steps -- 7 to 14 calls per 10 steps, with sporadic 30 ms stalls.)"""
+    _WGRAD["keep"].extend(t for t in tensors if t is not None)
+
+
 def _side_join(index: int):
     st = _WGRAD["streams"].get(index)
     if st is not None:
         torch.cuda.current_stream(st.device).wait_stream(st)
+    _WGRAD["keep"].clear()
     _WGRAD["armed"].discard(index)
     _WGRAD["fwd_since_bwd"] = 0
 
@@ -92,7 +102,7 @@ class _MainStream:
 def _wgrad_side(allowed: bool, device, reads: Sequence[Optional[torch.Tensor]], params: Sequence[torch.Tensor] = ()):
     """Context manager for the weight-gradient launches of one backward node: the side stream (ordered after everything
     queued on the main stream so far) when allowed, else a no-op.  `reads`: tensors the side launches read, which the
-    main-stream allocator must not recycle before they ran.  `params`: the parameters whose gradients are produced; if
+    main-stream allocator must not recycle before they ran (kept referenced until the join, see keep_until_join).  `params`: the parameters whose gradients are produced; if
     one already holds a gradient (accumulation over several backward passes) autograd adds to it on the main stream,
     so the node stays there."""
     if not (allowed and _WGRAD["on"]):
@@ -107,9 +117,7 @@ def _wgrad_side(allowed: bool, device, reads: Sequence[Optional[torch.Tensor]], 
     if st is None:
         st = _WGRAD["streams"][idx] = torch.cuda.Stream(device=device)
     st.wait_stream(torch.cuda.current_stream(device))
-    for t in reads:
-        if t is not None:
-            t.record_stream(st)
+    keep_until_join(reads)
     return torch.cuda.stream(st)
 
 

@@ -201,8 +201,7 @@ class GradBucketReducer:
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
                 torch._foreach_copy_(views, grads)
-            for g in grads:
-                g.record_stream(side)
+            ops.keep_until_join(grads)      # read on the side stream: released when the main stream has re-joined it
         for p, v in zip(params, views):
             p.grad = v
         if self.world == 1:
@@ -228,6 +227,9 @@ class GradBucketReducer:
                 self.buckets[bi]["flat"].div_(self.world)
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+            dev = self.params[0].device
+            if ops.wgrad_stream(dev) is not None:      # buckets were gathered on the side stream: join it, release the kept gradients
+                ops._side_join(dev.index if dev.index is not None else torch.cuda.current_device())
         self._pending.clear()
 
     def remove(self):

@@ -247,7 +247,12 @@ def run_ours(args):
         torch.cuda.synchronize()
         sampler.rows.clear()            # keep only the samples taken during the timed region
     n0 = autovc_b200.launch_count()
+    mem0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     ms = timed(step_resident, args.steps)
+    if os.environ.get("AVC_BENCH_MEMSTATS"):     # cudaMalloc calls inside the timed region stall the step: should be 0
+        st = torch.cuda.memory_stats(dev)
+        print(f"[memstats] cudaMalloc calls in the timed region: {st.get('num_device_alloc', 0) - mem0}, reserved "
+              f"{st.get('reserved_bytes.all.current', 0) / 2**30:.1f} GiB, retries {st.get('num_alloc_retries', 0)}", file=sys.stderr, flush=True)
     launches = (autovc_b200.launch_count() - n0) // args.steps
     clocks = sampler.stop() if sampler else None
     for _ in range(3):

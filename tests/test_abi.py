@@ -39,3 +39,30 @@ def test_ops_refuse_cpu_tensors():
     G = Generator(16, 256, 512, 16)
     with pytest.raises(AvcError):
         G(torch.rand(1, 16, 80), torch.rand(1, 256), torch.rand(1, 256))
+
+
+def test_fused_adam_is_a_torch_adam_and_refuses_cpu():
+    """Host logic of the optimizer drop-in without a GPU: class relationship, state_dict layout, loud failure on CPU."""
+    import torch
+    from autovc_b200 import AvcError, FusedAdam
+    p = [torch.nn.Parameter(torch.zeros(8)), torch.nn.Parameter(torch.zeros(3, 5))]
+    opt = FusedAdam(p, 1e-4)
+    assert isinstance(opt, torch.optim.Adam)
+    ref = torch.optim.Adam([torch.nn.Parameter(torch.zeros(8)), torch.nn.Parameter(torch.zeros(3, 5))], 1e-4)
+    assert opt.state_dict()["param_groups"][0].keys() == ref.state_dict()["param_groups"][0].keys()
+    for q in p:
+        q.grad = torch.ones_like(q)
+    with pytest.raises(AvcError):
+        opt.step()
+    with pytest.raises(AvcError):
+        FusedAdam(p, 1e-4, amsgrad=True)
+
+
+def test_nccl_env_defaults_do_not_override_the_user(monkeypatch):
+    from autovc_b200 import solver
+    monkeypatch.delenv("NCCL_MAX_CTAS", raising=False)
+    solver.nccl_env_defaults()
+    assert os.environ["NCCL_MAX_CTAS"] == "16"
+    monkeypatch.setenv("NCCL_MAX_CTAS", "32")
+    solver.nccl_env_defaults()
+    assert os.environ["NCCL_MAX_CTAS"] == "32"
