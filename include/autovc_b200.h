@@ -258,6 +258,17 @@ int avc_loss_bwd(const float* a, const float* b, size_t n, const float* gout, in
                  float* da, float* db, int accumulate, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Crop loader, data_loader.py:61-80 (`Utterances.__getitem__`) + default collate (:90-102), over a corpus resident in HBM:
+ *   corpus    (sum_i F_i, n_bins) fp32, utterance u = rows utt_row0[u] .. utt_row0[u] + utt_len[u] - 1
+ *   per crop b: utterance sel_utt[b]; F > T: frames sel_left[b] .. sel_left[b]+T-1 (:74-76); F < T: the utterance followed by
+ *   zero frames (:70-73); F == T: as is.  e_out[b] = emb_table[sel_spk[b]] (dim_emb floats, :65).
+ * The random draws (np.random.randint(2, len(list_uttrs)), np.random.randint(F - len_crop)) stay on the host so that the
+ * reference's numpy stream is reproduced; x_out (B, T, n_bins), e_out (B, dim_emb). */
+int avc_crop_batch(const float* corpus, const long long* utt_row0, const int* utt_len, const int* sel_utt, const int* sel_left,
+                   const float* emb_table, const int* sel_spk, float* x_out, float* e_out, int B, int T, int n_bins,
+                   int dim_emb, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Optimizer step, solver_encoder.py:130 (torch.optim.Adam(G.parameters(), lr): betas (0.9, 0.999), eps 1e-8, no weight
  * decay, no amsgrad) and :300 (.step()).  ONE launch updates every parameter tensor:
  *   g' = grad_scale * g;  m += (1-beta1)(g' - m);  v = beta2 v + (1-beta2) g'^2;
