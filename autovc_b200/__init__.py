@@ -5,6 +5,7 @@ Public surface mirrors the reference's modules for this path:
   autovc_b200.model_vc_stft.GeneratorSTFT <- model_vc_stft.GeneratorSTFT
   autovc_b200.make_spect.Spect / logmel   <- make_spect.Spect (spmel branch)
   autovc_b200.data_loader.get_loader      <- data_loader.get_loader (corpus resident in HBM, one launch per batch)
+  autovc_b200.model_bl.D_VECTOR           <- model_bl.D_VECTOR (speaker encoder, inference)
   autovc_b200.optim.FusedAdam             <- torch.optim.Adam as solver_encoder.py:130 configures it (one-launch step)
   autovc_b200.solver                      <- the step maths of solver_encoder.Solver.train + data parallelism
 """

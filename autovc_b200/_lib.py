@@ -69,6 +69,7 @@ SIGNATURES = {
     "avc_mse_loss_fwd": (c_int, [P, P, c_size_t, P, P, P]),
     "avc_l1_loss_fwd": (c_int, [P, P, c_size_t, P, P, P]),
     "avc_loss_bwd": (c_int, [P, P, c_size_t, P, c_int, P, P, c_int, P]),
+    "avc_l2_normalize_rows": (c_int, [P, P, c_int, c_int, P]),
     "avc_crop_batch": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "avc_adam_chunk_elems": (c_int, []),
     "avc_adam_step": (c_int, [P, P, c_int, c_double, c_double, c_double, c_double, c_int, c_float, P]),

@@ -132,3 +132,24 @@ extern "C" int avc_copy2d(const float* src, int ldsrc, float* dst, int lddst, in
   AVC_LAUNCHED();
   return AVC_OK;
 }
+
+// embeds.div(embeds.norm(p=2, dim=-1, keepdim=True)), model_bl.py:18-19: one warp per row
+namespace avc {
+__global__ void l2_normalize_rows_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int C) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + (size_t)row * C;
+  float ss = 0.f;
+  for (int c = lane; c < C; c += 32) ss = fmaf(xr[c], xr[c], ss);
+  ss = warp_sum(ss);
+  const float nrm = sqrtf(ss);
+  for (int c = lane; c < C; c += 32) out[(size_t)row * C + c] = xr[c] / nrm;
+}
+}  // namespace avc
+
+extern "C" int avc_l2_normalize_rows(const float* x, float* out, int M, int C, void* stream) {
+  AVC_REQUIRE(x && out && M > 0 && C > 0, "avc_l2_normalize_rows: bad arguments");
+  avc::l2_normalize_rows_kernel<<<avc::ceil_div(M, 8), 256, 0, avc::as_stream(stream)>>>(x, out, M, C);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}

@@ -257,6 +257,9 @@ int avc_l1_loss_fwd(const float* a, const float* b, size_t n, double* scratch, f
 int avc_loss_bwd(const float* a, const float* b, size_t n, const float* gout, int is_l1,
                  float* da, float* db, int accumulate, void* stream);
 
+/* out[m, :] = x[m, :] / ||x[m, :]||_2   (model_bl.py:18-19, the d-vector's final normalisation; no epsilon, like the reference) */
+int avc_l2_normalize_rows(const float* x, float* out, int M, int C, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Crop loader, data_loader.py:61-80 (`Utterances.__getitem__`) + default collate (:90-102), over a corpus resident in HBM:
  *   corpus    (sum_i F_i, n_bins) fp32, utterance u = rows utt_row0[u] .. utt_row0[u] + utt_len[u] - 1

@@ -1,0 +1,32 @@
+"""GPU parity of the D_VECTOR drop-in (autovc_b200.model_bl) against the reference module's golden outputs:
+fp32 mode <= 1e-4 max-abs, half mode (persistent tcgen05 recurrences at H = 768) <= 1e-2 relative L2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_bl_ref as bref
+from tests.helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from autovc_b200.model_bl import D_VECTOR
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("half", None)])
+def test_dvector_matches_reference_golden(precision, tol):
+    g = load_golden("dvector")
+    torch.manual_seed(0)
+    C = D_VECTOR(dim_input=80, dim_cell=768, dim_emb=256, precision=precision).eval().cuda()
+    assert list(C.state_dict().keys()) == g["names"].tolist()            # 3000000-BL.ckpt's layout (make_metadata.py:44-49)
+    B, T, seed = [int(v) for v in g["meta"][:3]]
+    with torch.no_grad():
+        y = C(bref.synth_mels(B, T, seed).cuda()).cpu().numpy()
+    assert y.shape == (B, 256)
+    np.testing.assert_allclose(np.linalg.norm(y, axis=-1), 1.0, atol=1e-5)
+    if tol is not None:
+        assert np.abs(y - g["y32"]).max() < tol
+    else:
+        rel = np.linalg.norm(y - g["y64"]) / np.linalg.norm(g["y64"])
+        print("half rel-L2", rel)
+        assert rel < 1e-2
