@@ -686,6 +686,7 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
   const uint32_t w_bar = bar0 + 8u * 16, tfull = bar0 + 8u * 17, tempty = bar0 + 8u * 18, red_full = bar0 + 8u * 19;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   volatile int* slot_kb = reinterpret_cast<volatile int*>(bars + 21);
+  const uint32_t go_bar = bar0 + 8u * 26;      // producer -> epilogue: "the barrier of the next step has been seen"
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -699,6 +700,13 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
   // reduce-scatter of the partial tiles by bulk DSMEM copies (see the epilogue); not with per-k-block release counters, whose
   // producers may refill the ring (= the send staging area) before every CTA has published
   const bool rs_bulk = !(PAIRS == 1 && p.kflags != 0) && !(p.exp_mode & 128);
+  // The epilogue's row-per-thread traffic (dP16 stores of a step, dH / c / gates loads of the next: 16 + 48 KB per CTA) queues in
+  // the SM's load/store path right where the producer's ld.acquire polls the step counter: the all-CTA trace showed CTAs noticing
+  // the completed barrier up to 3.8 us late (median 0.5-1.5).  With defer_lsu (AVC_LSTM_EXP bit 256) the epilogue holds that
+  // traffic back until the producer has seen the barrier.  Measured (r01e): detection becomes tight (0.3-0.8 us, publish spread
+  // 3.6 -> 1.8 us) but the operand loads then compete with the TMA stream (first k-block lands after 1.5 us instead of 0.3) and
+  // the step stays at 10.5-10.7 us: the memory system around the SM is the bound, not the ordering.  Off by default.
+  const bool defer_lsu = !(PAIRS == 1 && p.kflags != 0) && (p.exp_mode & 256) != 0;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
@@ -710,6 +718,7 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
     mbar_init(w_bar, 1);
     mbar_init(tfull, 1);
     mbar_init(tempty, 4);
+    mbar_init(go_bar, 1);
     mbar_init(red_full, rs_bulk ? 1 : 3 * 4);               // bulk: my own arrive.expect_tx (+ 3 x 8 KB of complete_tx); else one arrive per epilogue warp of each of the 3 peers
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -754,7 +763,14 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
         if (lane == 0) {
           while (ld_acquire(counter) < (unsigned)s * per_step) {
           }
+          if (defer_lsu) mbar_arrive(go_bar);
           LT_TRACE(0);
+          LT_TRACE_ALL(0);
+          if (p.trace != nullptr && s == 64) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            p.trace[(size_t)16 * T + (size_t)8 * gridDim.x + blockIdx.x] = smid;
+          }
           if (p.exp_mode == 4) fence_proxy_async();
         }
         __syncwarp();
@@ -987,8 +1003,10 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
         fence_proxy_async();
         red_release_add(kflags ? counter + (u0 >> 4) : counter, 1u);   // dG columns 4*u0 .. 4*u0+63 = k-block u0/16
         LT_TRACE(8);
+        LT_TRACE_ALL(1);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (defer_lsu && s + 1 < T) mbar_wait(go_bar, s & 1);
       if (live && !(p.exp_mode & 8)) {
         if (p.dP == nullptr) {
           // half mode: every consumer (dX / dW GEMMs, bias column sums) reads the bf16 copy

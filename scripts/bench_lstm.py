@@ -80,6 +80,26 @@ for which in ("fwd", "bwd"):
     import numpy as np
     med = np.median(np.array(rows), axis=0)
     print(which, "median us after previous publish:", {n: round(float(v), 2) for n, v in zip(names, med)}, flush=True)
+    if which == "bwd":
+        # all-CTA skew of the K-split BPTT kernel: cluster = 4 consecutive CTAs (K ranks), 16 clusters per batch tile
+        ncta = 128
+        allc = full[16 * T:16 * T + ncta * 8].view(ncta, 4, 2).double()
+        smid = full[16 * T + 8 * ncta:16 * T + 9 * ncta]
+        for tile in range(2):
+            sl = slice(tile * 64, tile * 64 + 64)
+            for st in range(1, 4):
+                pub_prev, bar, pub = allc[sl, st - 1, 1], allc[sl, st, 0], allc[sl, st, 1]
+                t1 = pub_prev.max()
+                print(f"bwd tile {tile} step {64 + st}: publish spread {float((t1 - pub_prev.min()) / 1e3):.2f} us | barrier pass after LAST publish "
+                      f"min/med/max {float((bar.min() - t1) / 1e3):.2f}/{float((bar.median() - t1) / 1e3):.2f}/{float((bar.max() - t1) / 1e3):.2f} | "
+                      f"publish after barrier pass min/med/max {float((pub - bar).min() / 1e3):.2f}/{float((pub - bar).median() / 1e3):.2f}/{float((pub - bar).max() / 1e3):.2f}")
+            work = torch.stack([(allc[sl, st, 1] - allc[sl, st, 0]) / 1e3 for st in range(1, 4)], 1).mean(1)   # (64,) us barrier -> publish
+            det = torch.stack([(allc[sl, st, 0] - allc[sl, st - 1, 1].max()) / 1e3 for st in range(1, 4)], 1).mean(1)
+            print("   per cluster (cluster, smids, barrier->publish us per rank, detection us per rank):")
+            for cl in range(16):
+                ids = [tile * 64 + cl * 4 + r for r in range(4)]
+                print("     ", cl, [int(smid[i]) for i in ids], [round(float(work[cl * 4 + r]), 2) for r in range(4)],
+                      [round(float(det[cl * 4 + r]), 2) for r in range(4)])
     if which == "fwd":
         ncta = 128
         allc = full[16 * T:16 * T + ncta * 8].view(ncta, 4, 2).double()
