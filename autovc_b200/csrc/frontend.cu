@@ -306,19 +306,21 @@ __global__ void fe_iir_output_kernel(const float* __restrict__ wav, const float*
 // --- stage 1+2, fused: one CTA per utterance walks the sweep tile by tile ------------------------------------------
 // The three-launch scheme above reads every input twice and lets each thread walk its own 256-sample chunk straight from
 // global memory (lanes 1 KB apart: r01c ncu 1.3-1.7 TB/s at 62-94% L1/TEX busy, 5.3 of 13.1 ms per 1024 utterances).
-// Here a CTA of 128 threads owns an utterance and processes tiles of 128 chunks x 64 samples = 8192 samples:
+// Here a CTA of 256 threads owns an utterance and processes tiles of 256 chunks x 32 samples = 8192 samples (first version:
+// 128 x 64 -- same shared memory, half the warps and twice the serial chunk length; ncu: 11% warps active, 0.88 IPC):
 //   load    the tile into shared memory as fp64 with coalesced (forward) / reversed-coalesced (backward) accesses,
 //           one pad word per chunk so that the per-thread walks below are bank-conflict free;
-//   pass 1  thread t runs its chunk from a zero state -> e[t]; thread 0 adds A^64 * (carry-in of the tile);
-//   scan    Kogge-Stone over the 128 chunk states: w_i <- P[k] w_{i-2^k} + w_i with P[k] = A^(64*2^k) (all chunks share the
+//   pass 1  thread t runs its chunk from a zero state -> e[t]; thread 0 adds A^32 * (carry-in of the tile);
+//   scan    Kogge-Stone over the 256 chunk states: w_i <- P[k] w_{i-2^k} + w_i with P[k] = A^(32*2^k) (all chunks share the
 //           linear part, so a level is ONE 6x6 mat-vec per thread); w_i is then the true END state of chunk i;
 //   pass 2  thread t re-runs its chunk from w_{t-1} and overwrites the tile with the outputs;
 //   store   coalesced: forward y1 (fp64), backward 0.96*y + dither as fp32 (reversed).
 // Every input is read once and every output written once per sweep.
-constexpr int FE_TCH = 64;                      // samples per thread-chunk
-constexpr int FE_TNT = 128;                     // threads = chunks per tile
+constexpr int FE_TCH = 32;                      // samples per thread-chunk
+constexpr int FE_TSH = 5;                       // log2(FE_TCH)
+constexpr int FE_TNT = 256;                     // threads = chunks per tile
 constexpr int FE_TILE = FE_TCH * FE_TNT;        // 8192 samples
-constexpr int FE_TLEV = 7;                      // log2(FE_TNT)
+constexpr int FE_TLEV = 8;                      // log2(FE_TNT)
 
 // PW[k] = A^(FE_TCH * 2^k), k = 0..FE_TLEV-1 (row-major 6x6 each).  Single thread.
 __global__ void fe_tile_powers_kernel(const double* __restrict__ filt, double* __restrict__ PW) {
@@ -387,14 +389,14 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
 #pragma unroll 16
       for (int q = 0; q < FE_TCH; ++q) {
         const int s = q * FE_TNT + tid;
-        tile[s + q * 2 + (tid >> 6)] = BACKWARD ? ys[-s] : (double)xs[s];        // s + (s >> 6) with s = 128 q + tid
+        tile[s + (s >> FE_TSH)] = BACKWARD ? ys[-s] : (double)xs[s];
       }
     } else {
 #pragma unroll 8
       for (int q = 0; q < FE_TCH; ++q) {
         const int s = q * FE_TNT + tid;
         const int i = i0 + s;
-        tile[s + q * 2 + (tid >> 6)] = i < ne ? sweep_input<BACKWARD>(x, y1, n, ne, i) : 0.0;   // zeros past the end: pure state decay
+        tile[s + (s >> FE_TSH)] = i < ne ? sweep_input<BACKWARD>(x, y1, n, ne, i) : 0.0;   // zeros past the end: pure state decay
       }
     }
     __syncthreads();
@@ -462,7 +464,7 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
 #pragma unroll 16
       for (int q = 0; q < FE_TCH; ++q) {
         const int s = q * FE_TNT + tid;
-        const double y = tile[s + q * 2 + (tid >> 6)];
+        const double y = tile[s + (s >> FE_TSH)];
         if (!BACKWARD) y1[i0 + s] = y;
         else o[jb - s] = (float)(y * 0.96 + ((double)dz[jb - s] - 0.5) * 1e-6);
       }
@@ -471,7 +473,7 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
       for (int q = 0; q < FE_TCH; ++q) {
         const int s = q * FE_TNT + tid;
         const int i = i0 + s;
-        const double y = tile[s + q * 2 + (tid >> 6)];
+        const double y = tile[s + (s >> FE_TSH)];
         if (!BACKWARD) {
           if (i < ne) y1[i] = y;
         } else {
@@ -642,7 +644,7 @@ extern "C" size_t avc_logmel_workspace_bytes(int n_utt, int max_len) {
   const size_t fwd = ((size_t)n_utt * (max_len + 2 * FE_PADLEN) * sizeof(double) + 255) / 256 * 256;
   const size_t sig = ((size_t)n_utt * max_len * sizeof(float) + 255) / 256 * 256;
   const size_t zs = ((size_t)n_utt * fe_nchunk(max_len) * FE_NST * sizeof(double) + 255) / 256 * 256;
-  return fe_tables_bytes() + sig + fwd + zs + 4096;      // tail: A^L (36 doubles) or the 7 tile powers (252 doubles)
+  return fe_tables_bytes() + sig + fwd + zs + 4096;      // tail: A^L (36 doubles) or the 8 tile powers (288 doubles)
 }
 
 extern "C" int avc_logmel_frontend(const float* wav, const float* dither, const int* lengths, int n_utt, int max_len,
@@ -670,7 +672,7 @@ extern "C" int avc_logmel_frontend(const float* wav, const float* dither, const 
   AVC_LAUNCHED();
   static const bool tiled = getenv("AVC_FE_IIR_TILED") ? atoi(getenv("AVC_FE_IIR_TILED")) != 0 : true;
   if (tiled) {
-    // one CTA per utterance, tiles staged through shared memory (AL's slot holds the 7 tile powers: 7*36 doubles)
+    // one CTA per utterance, tiles staged through shared memory (AL's slot holds the FE_TLEV tile powers: 8*36 doubles)
     fe_tile_powers_kernel<<<1, 32, 0, st>>>(filt, AL);
     AVC_LAUNCHED();
     const size_t ism = ((size_t)FE_TNT * (FE_TCH + 1) + 2 * FE_TNT * FE_NST + FE_TLEV * FE_NST * FE_NST + FE_NST) * sizeof(double);
