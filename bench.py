@@ -384,6 +384,75 @@ def run_frontend_or_convert(args):
     print(json.dumps(line), flush=True)
 
 
+def run_widened(args):
+    """Secondary legs for the rows SURVEY 8(f) marks "next": `--workload loader` (crop loader, HBM roofline: 2*4*T*n_bins bytes per
+    crop) and `--workload dvector` (speaker encoder forward on 128-frame crops, make_metadata.py:42 shapes)."""
+    import numpy as np
+    import autovc_b200
+    from autovc_b200 import data_loader
+    from autovc_b200.model_bl import D_VECTOR
+    from oracle import data_loader_ref as lref
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    peaks = measured_peaks()
+    B, T = args.batch, args.len_crop
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    if args.workload == "loader":
+        rs = np.random.RandomState(3)
+        corpus = [["p%03d" % s, rs.randn(256).astype(np.float32)] + [rs.rand(int(f), 80).astype(np.float32) for f in rs.randint(64, 900, size=24)]
+                  for s in range(512)]                                            # 512 speakers x 24 utterances, ~1.9 GB
+        ds = data_loader.Utterances(corpus=corpus, len_crop=T)
+        idx = rs.randint(0, len(ds), size=B).tolist()
+        sel = ds.draw(idx, rs)
+        ms_k = timed(lambda: ds.gather(sel), args.steps * 20, 10)                 # kernel + the 3 KB index upload
+        t0 = time.perf_counter()
+        for _ in range(50):
+            ds.draw(idx, rs)
+        ms_draw = (time.perf_counter() - t0) / 50 * 1e3                           # host-side numpy draws (reference order)
+        k = 16
+        t0 = time.perf_counter()
+        for _ in range(5):
+            lref.get_batch(corpus, idx[:k], T, rs)
+        cpu = k * 5 / (time.perf_counter() - t0)
+        alg = B * (2 * 4 * T * 80 + 2 * 4 * 256)
+        gbs = alg / (ms_k * 1e-3) / 1e9
+        line = {"metric": "crop-loader utterance-crops/sec", "value": B / (ms_k * 1e-3), "unit": "crops/s", "n_gpus": 1, "steps": args.steps * 20,
+                "warmup": 10, "ms_per_step": ms_k, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (copy)",
+                "data": "synthetic", "config": {"workload": f"data_loader batch: {B} crops x {T} frames x 80 bins from a 512-speaker corpus resident in HBM",
+                                                "host_draw_ms_per_batch": ms_draw},
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"], "traffic": None,
+                             "note": "a 10.5 MB batch is launch-latency sized: one launch, ~2 us of data at the HBM rate"},
+                "cpu_baseline": {"value": cpu, "unit": "crops/s", "cores": 1, "kind": "port",
+                                 "sample": f"{k}-crop batches through oracle/data_loader_ref.py (numpy restatement of Utterances.__getitem__)"}}
+        print(json.dumps(line), flush=True)
+        return
+    torch.manual_seed(0)
+    C = D_VECTOR(dim_input=80, dim_cell=768, dim_emb=256, precision=args.precision).eval().to(dev)
+    x = torch.rand(B, T, 80, device=dev)
+    with torch.no_grad():
+        ms = timed(lambda: C(x), args.steps, args.warmup)
+    mac = 80 * 3072 + 768 * 3072 + 2 * (768 * 3072 * 2) + 768 * 256 / T        # per frame: 3 layers (input proj + recurrence) + the last-frame linear
+    flops = 2.0 * mac * B * T
+    line = {"metric": "speaker-encoder utterance-crops/sec", "value": B / (ms * 1e-3), "unit": "crops/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+            "data": "synthetic", "config": {"workload": f"D_VECTOR(80, 768, 256) forward, {B} crops x {T} frames (make_metadata.py:42,:77)"},
+            "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                         "frac": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"], "traffic": None}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -398,9 +467,11 @@ def main():
     ap.add_argument("--n-bins", dest="n_bins", type=int, default=80, choices=[80, 513], help="513 = model_vc_stft variant (configs[3])")
     ap.add_argument("--cpu-sample-batch", dest="cpu_sample_batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="train", choices=["train", "frontend", "convert"])
+    ap.add_argument("--workload", default="train", choices=["train", "frontend", "convert", "loader", "dvector"])
     ap.add_argument("--utterances", type=int, default=4096, help="frontend/convert legs: number of 10 s utterances (BASELINE.json configs[4]: 4096)")
     args = ap.parse_args()
+    if args.workload in ("loader", "dvector"):
+        return run_widened(args)
     if args.workload != "train":
         return run_frontend_or_convert(args)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
