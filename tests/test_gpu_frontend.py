@@ -47,3 +47,24 @@ def test_frontend_matches_oracle_on_synthetic_and_pads_with_zeros():
         assert err < TOL, (i, err)
         assert np.all(out[i, F:] == 0.0)
     assert out.min() >= 0.0 and out.max() <= 1.0
+
+
+def test_frontend_tile_and_frame_boundaries():
+    """Lengths that sit on the internal boundaries of the kernels: the filtfilt sweeps walk tiles of 8192 samples of the
+    odd-extended signal (n + 36), the STFT kernel handles frame pairs in blocks of 40 frames; the shortest accepted
+    utterance is 513 samples (one reflection)."""
+    from autovc_b200.make_spect import Spect
+    lens = [513, 514, 767, 768, 8192 - 36 - 1, 8192 - 36, 8192 - 36 + 1, 8192, 2 * 8192 - 36, 2 * 8192 - 35, 40 * 256 - 1, 40 * 256,
+            40 * 256 + 1, 3 * 8192 + 5]
+    L = max(lens)
+    wav, dither = fref.synthetic_waveforms(len(lens), L, seed=11)
+    lengths = np.array(lens, np.int32)
+    Fmax = 1 + L // 256
+    out = Spect().logmel(torch.from_numpy(wav).cuda(), torch.from_numpy(dither.astype(np.float32)).cuda(),
+                         torch.from_numpy(lengths).cuda(), max_frames=Fmax + 3).cpu().numpy()
+    for i, n in enumerate(lens):
+        ref = fref.logmel_from_wav(wav[i, :n], dither[i, :n])
+        F = 1 + n // 256
+        err = np.abs(out[i, :F] - ref).max()
+        assert err < TOL, (n, err)
+        assert np.all(out[i, F:] == 0.0), n
