@@ -88,6 +88,31 @@ def test_forward_matches_oracle_and_handles_4d_input():
     assert isinstance(lst, list) and len(lst) == 4 and lst[0].shape == (4, 32)
 
 
+@pytest.mark.parametrize("precision,B,T,neck,freq", [("half", 130, 80, 32, 16), ("half", 5, 48, 16, 16), ("fp32", 3, 80, 32, 8)])
+def test_train_step_matches_oracle_at_ragged_sizes(precision, B, T, neck, freq):
+    """Sizes off the tile grid: a batch that spills a few utterances into a second 128-utterance tile of the persistent
+    recurrences, crop lengths that are multiples of freq but not of 32 / 64, a freq that differs from dim_neck.  One training
+    step against the CPU oracle from the same init: fp32 mode within 1e-4, half mode within the relative-L2 gate."""
+    torch.manual_seed(0)
+    G = autovc_b200.Generator(neck, 256, 512, freq, precision=precision).cuda().train()
+    sd = {k: v.detach().cpu().clone() for k, v in G.state_dict().items()}
+    x, e, _ = synth_inputs(B, T, 80, 256, 123)
+    out = solver.train_step(G, autovc_b200.FusedAdam(G.parameters(), 1e-4), x.cuda(), e.cuda(), return_outputs=True)
+    losses, outs, grads = gref.train_step(sd, x, e, neck, freq)
+    assert out["code_real"].shape == (B, 2 * neck * (T // freq))
+    for k in ("x_identic_psnt", "code_real", "code_reconst"):
+        a, b = out[k].cpu(), outs[k]
+        if precision == "fp32":
+            assert (a - b).abs().max() < FP32_TOL, k
+        else:
+            rel = float((a.double() - b.double()).norm() / b.double().norm())
+            assert rel < (1e-2 if B >= 16 else 3e-2), (k, rel)
+    for k in ("L_id", "L_id_psnt", "L_cd"):
+        assert abs(out[k] - float(losses[k])) < (FP32_TOL if precision == "fp32" else 2e-2 * abs(float(losses[k])) + 1e-4), k
+    for n, gr in out["grads"].items():
+        assert torch.isfinite(gr).all(), n
+
+
 def test_eval_conversion_matches_reference_golden():
     g = load_golden("eval_32_32_b2_t96")
     dim_neck, freq, B, T, n_bins, wseed, iseed = g["meta"].tolist()
