@@ -17,12 +17,17 @@ namespace avc {
 
 constexpr int FE_NFFT = 1024, FE_HOP = 256, FE_BINS = 513, FE_MELS = 80, FE_PADLEN = 18, FE_REFLECT = 512;
 constexpr int FE_FRAMES_PER_CTA = 8;   // 4 complex FFTs per CTA, one warp each
+constexpr int FE_SEG = 8;              // bins per work item of the mel projection
 constexpr int FE_THREADS = 32 * (FE_FRAMES_PER_CTA / 2);
 
 struct FeTables {           // lives at the head of the workspace
   float2 tw2[FE_NFFT];      // tw2[c*32 + b] = exp(-2*pi*i*(b*c)/1024): the inter-pass twiddles of the 32 x 32 decomposition
   float win[FE_NFFT];       // periodic Hann
   int2 band[FE_MELS];       // [first, last+1) non-zero FFT bin of each mel filter
+  // balanced schedule of the mel projection: every filter's bin range cut into segments of <= FE_SEG bins; filter m owns the
+  // segments [seg0[m], seg0[m+1]) (consecutive, so its partial sums are added in a fixed order)
+  int4 seg[256];            // (filter, first bin, last bin + 1, -)
+  int seg0[FE_MELS + 1];
 };
 
 __global__ void fe_tables_kernel(const float* __restrict__ mel_basis, FeTables* __restrict__ tb) {
@@ -42,6 +47,16 @@ __global__ void fe_tables_kernel(const float* __restrict__ mel_basis, FeTables* 
       }
     if (hi == 0) lo = 0;
     tb->band[i] = make_int2(lo, hi);
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int n = 0;
+    for (int m = 0; m < FE_MELS; ++m) {
+      tb->seg0[m] = n;
+      const int2 bd = tb->band[m];
+      for (int k = bd.x; k < bd.y && n < 256; k += FE_SEG) tb->seg[n++] = make_int4(m, k, min(bd.y, k + FE_SEG), 0);
+    }
+    tb->seg0[FE_MELS] = n;
   }
 }
 
@@ -615,14 +630,31 @@ fe_stft_mel_kernel(const float* __restrict__ sig, const int* __restrict__ length
       e[k] = make_float2(sqrtf(ar * ar + ai * ai), sqrtf(br * br + bi * bi));
     }
     __syncwarp();
-    const float* mg = reinterpret_cast<const float*>(e);
+    // mel projection of BOTH frames: the bin ranges of the 80 filters are cut into segments of <= 8 bins (tb->seg), a lane takes
+    // every 32nd segment and sums it for the two frames at once (one 8-byte magnitude pair + one weight per bin), the partial
+    // sums go to the dead upper half of the tile and each output adds its filter's partials in a fixed order.  The first version
+    // gave every lane whole filters: 2 to 45 bins wide, so a warp always waited for its widest one (~130 dependent iterations per
+    // frame pair, the hottest lines of the r01e profile); this is ~40.
+    float2* part = e + 640;                                  // [<= 256] partial sums (frame f0, frame f0+1)
+    const int nseg = tb->seg0[FE_MELS];
+    for (int it = lane; it < nseg; it += 32) {
+      const int4 sg = tb->seg[it];
+      float a0 = 0.f, a1 = 0.f;
+      for (int k = sg.y; k < sg.z; ++k) {
+        const float2 mg = e[k];
+        const float wt = __ldg(mel_basis + k * FE_MELS + sg.x);
+        a0 = fmaf(mg.x, wt, a0);
+        a1 = fmaf(mg.y, wt, a1);
+      }
+      part[it] = make_float2(a0, a1);
+    }
+    __syncwarp();
     for (int i = lane; i < nout; i += 32) {
       const int fr = i >= FE_MELS ? 1 : 0, m = i - fr * FE_MELS;
       float val = 0.f;
       if (f0 + fr < n_frames) {
-        const int2 bd = tb->band[m];
         float acc = 0.f;
-        for (int k = bd.x; k < bd.y; ++k) acc = fmaf(mg[2 * k + fr], __ldg(mel_basis + k * FE_MELS + m), acc);
+        for (int it = tb->seg0[m]; it < tb->seg0[m + 1]; ++it) acc += fr ? part[it].y : part[it].x;
         const float db = 20.f * log10f(fmaxf(1e-5f, acc)) - 16.f;
         val = fminf(fmaxf((db + 100.f) / 100.f, 0.f), 1.f);
       }
