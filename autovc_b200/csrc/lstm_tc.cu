@@ -888,6 +888,19 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
 #pragma unroll
         for (int j = 0; j < 4 * U; ++j) g4[j] = 0.f;
       }
+      // everything of the gate algebra that does not depend on dh is done NOW, while the MMAs of this step are still running:
+      // g4 <- (d i, d f, d g, d o) per unit of dc resp. dh, ct <- d(dc)/d(dh), cp <- f (the carry factor of dc)
+#pragma unroll
+      for (int i = 0; i < U; ++i) {
+        const float gi = g4[4 * i], gf = g4[4 * i + 1], gg = g4[4 * i + 2], go = g4[4 * i + 3];
+        const float tc = tanh_fast(ct[i]);
+        g4[4 * i] = gg * gi * (1.f - gi);
+        g4[4 * i + 1] = cp[i] * gf * (1.f - gf);
+        g4[4 * i + 2] = gi * (1.f - gg * gg);
+        g4[4 * i + 3] = tc * go * (1.f - go);
+        ct[i] = go * (1.f - tc * tc);
+        cp[i] = gf;
+      }
       if (rs_bulk && s > 0 && threadIdx.x == 64) mbar_expect_tx(red_full, 3 * 128 * 16 * 4);   // this step's three foreign partials
       mbar_wait(tfull, s & 1);
       if (threadIdx.x == 64) LT_TRACE(6);
@@ -979,14 +992,12 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
       alignas(32) __nv_bfloat16 gb[4 * U];
 #pragma unroll
       for (int i = 0; i < U; ++i) {
-        const float gi = g4[4 * i], gf = g4[4 * i + 1], gg = g4[4 * i + 2], go = g4[4 * i + 3];
-        const float tc = tanh_fast(ct[i]);
-        const float dc = fmaf(dh[i] * go, 1.f - tc * tc, dc_rec[i]);
-        const float di = dc * gg * gi * (1.f - gi);
-        const float df = dc * cp[i] * gf * (1.f - gf);
-        const float dg = dc * gi * (1.f - gg * gg);
-        const float dO = dh[i] * tc * go * (1.f - go);
-        dc_rec[i] = dc * gf;
+        const float dc = fmaf(dh[i], ct[i], dc_rec[i]);
+        const float di = dc * g4[4 * i];
+        const float df = dc * g4[4 * i + 1];
+        const float dg = dc * g4[4 * i + 2];
+        const float dO = dh[i] * g4[4 * i + 3];
+        dc_rec[i] = dc * cp[i];
         g4[4 * i] = di; g4[4 * i + 1] = df; g4[4 * i + 2] = dg; g4[4 * i + 3] = dO;
         gb[4 * i] = __float2bfloat16_rn(di); gb[4 * i + 1] = __float2bfloat16_rn(df);
         gb[4 * i + 2] = __float2bfloat16_rn(dg); gb[4 * i + 3] = __float2bfloat16_rn(dO);
