@@ -22,6 +22,39 @@ from . import _lib
 from ._lib import call
 
 
+class CorpusIndex:
+    """Host-side (numpy) index of a corpus in the reference's in-memory layout `[[speaker, emb, utt, ...], ...]`: the
+    per-speaker utterance ranges, the utterance lengths / row offsets of the ragged buffer, and the random draws of a batch in
+    the reference's order.  No device needed (the CPU tests replay it against the oracle)."""
+
+    def __init__(self, corpus, len_crop: int):
+        self.len_crop = len_crop
+        lens, first = [], []
+        for spk in corpus:
+            if len(spk) < 3:
+                raise ValueError(f"speaker {spk[0]!r} has no utterance")
+            first.append(len(lens))
+            lens += [int(np.asarray(u).shape[0]) for u in spk[2:]]
+        self.spk_first = np.asarray(first, dtype=np.int64)                  # global index of a speaker's first utterance
+        self.spk_count = np.asarray([len(s) - 2 for s in corpus], dtype=np.int64)
+        self.utt_len = np.asarray(lens, dtype=np.int64)
+        self.utt_row0 = np.concatenate([[0], np.cumsum(self.utt_len)[:-1]]).astype(np.int64)
+        self.num_tokens = len(corpus)                                       # data_loader.py:45
+
+    def draw(self, indices: Sequence[int], rs=np.random) -> np.ndarray:
+        """The host-side random choices of one batch, in the reference's order: (3, B) int32 = utterance, left, speaker."""
+        sel = np.zeros((3, len(indices)), dtype=np.int32)
+        T = self.len_crop
+        for k, i in enumerate(indices):
+            a = rs.randint(2, self.spk_count[i] + 2)                        # data_loader.py:68
+            u = self.spk_first[i] + a - 2
+            F = self.utt_len[u]
+            sel[0, k] = u
+            sel[1, k] = rs.randint(F - T) if F > T else 0                   # :75 (no draw otherwise, like the reference)
+            sel[2, k] = i
+        return sel
+
+
 class Utterances:
     """Device-resident counterpart of data_loader.Utterances (one entry per speaker, like the reference)."""
 
@@ -36,44 +69,22 @@ class Utterances:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.AvcError("autovc_b200.data_loader keeps the corpus in GPU memory (there is no CPU fallback)")
-        lens, first, embs, chunks = [], [], [], []
-        for spk in corpus:
-            if len(spk) < 3:
-                raise ValueError(f"speaker {spk[0]!r} has no utterance")
-            first.append(len(lens))
-            embs.append(np.asarray(spk[1], dtype=np.float32))
-            for u in spk[2:]:
-                u = np.ascontiguousarray(np.asarray(u, dtype=np.float32))
-                lens.append(u.shape[0])
-                chunks.append(u)
+        self.index = CorpusIndex(corpus, len_crop)
+        chunks = [np.ascontiguousarray(np.asarray(u, dtype=np.float32)) for spk in corpus for u in spk[2:]]
         self.n_bins = chunks[0].shape[1]
         if any(c.shape[1] != self.n_bins for c in chunks):
             raise ValueError("all utterances must have the same number of bins")
-        self.spk_first = np.asarray(first, dtype=np.int64)                  # global index of a speaker's first utterance
-        self.spk_count = np.asarray([len(s) - 2 for s in corpus], dtype=np.int64)
-        self.utt_len_host = np.asarray(lens, dtype=np.int64)
-        row0 = np.concatenate([[0], np.cumsum(self.utt_len_host)[:-1]])
         self.corpus = torch.from_numpy(np.concatenate(chunks, 0)).to(self.device)         # (sum F, n_bins)
-        self.utt_row0 = torch.from_numpy(row0.astype(np.int64)).to(self.device)
-        self.utt_len = torch.from_numpy(self.utt_len_host.astype(np.int32)).to(self.device)
-        self.emb_table = torch.from_numpy(np.stack(embs)).to(self.device)                 # (n_speakers, dim_emb)
-        self.num_tokens = len(corpus)                                                      # :45
+        self.utt_row0 = torch.from_numpy(self.index.utt_row0).to(self.device)
+        self.utt_len = torch.from_numpy(self.index.utt_len.astype(np.int32)).to(self.device)
+        self.emb_table = torch.from_numpy(np.stack([np.asarray(s[1], dtype=np.float32) for s in corpus])).to(self.device)
+        self.num_tokens = self.index.num_tokens
 
     def __len__(self):
         return self.num_tokens
 
     def draw(self, indices: Sequence[int], rs=np.random) -> np.ndarray:
-        """The host-side random choices of one batch, in the reference's order: (3, B) int32 = utterance, left, speaker."""
-        sel = np.zeros((3, len(indices)), dtype=np.int32)
-        T = self.len_crop
-        for k, i in enumerate(indices):
-            a = rs.randint(2, self.spk_count[i] + 2)                        # data_loader.py:68
-            u = self.spk_first[i] + a - 2
-            F = self.utt_len_host[u]
-            sel[0, k] = u
-            sel[1, k] = rs.randint(F - T) if F > T else 0                   # :75 (no draw otherwise, like the reference)
-            sel[2, k] = i
-        return sel
+        return self.index.draw(indices, rs)
 
     def batch(self, indices: Sequence[int], rs=np.random) -> Tuple[torch.Tensor, torch.Tensor]:
         """(x_real (B, len_crop, n_bins), emb_org (B, dim_emb)) on the device for the given speaker indices."""
