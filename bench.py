@@ -8,6 +8,10 @@ Workload (BASELINE.json configs[1]): Generator(dim_neck=16, dim_emb=256, dim_pre
 synthetic 80-bin mel crops, batch 256 per GPU, len_crop 128; one step = solver_encoder.py:228-300
 (two Generator calls, three losses, zero_grad, backward, Adam.step, gradient all-reduce when N>1).
 Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for the definition of every key.
+
+Secondary legs (not the driver's default): --workload frontend | convert (BASELINE.json configs[4], 4096 x 10 s utterances),
+--workload loader | dvector (the rows SURVEY 8(f) marks "next"); --n-bins 513 (configs[3]); --dim-neck 32 --freq 32 --batch 128
+--len-crop 256 (configs[2]); --precision fp32 | tf32 | half | bf16.
 """
 from __future__ import annotations
 
