@@ -2,7 +2,8 @@
 swapped speaker embedding and removal of the padded frames), batched: waveforms -> log-mel front-end
 (make_spect.py:72-83) -> zero-pad frames to a multiple of 32 -> Generator.eval() forward -> trim.
 
-Eval-mode BatchNorm has no cross-sample coupling, so batching many utterances is exact.
+Eval-mode BatchNorm has no cross-sample coupling, so batching utterances of equal padded length is exact
+(SURVEY §3.4); utterances of different padded lengths run in separate groups (see ``convert``).
 """
 from __future__ import annotations
 
@@ -26,20 +27,48 @@ def convert(G, spect: Spect, wav: torch.Tensor, dither: torch.Tensor, lengths: O
             ) -> Tuple[torch.Tensor, torch.Tensor]:
     """wav, dither: (n, L) float32 CUDA; emb_org/emb_trg: (n, dim_emb).  Returns
     (x_identic_psnt (n, 1, Tpad, 80), n_frames (n,)): frames >= n_frames[i] are padding
-    (what conversion.py:97-100 drops)."""
+    (what conversion.py:97-100 drops).
+
+    The reference pads EACH utterance to its own multiple of 32 frames (conversion.py:40-44) and the padded
+    frames still carry the speaker embedding, so the state of the encoder's reverse LSTM direction reaching the
+    real frames depends on the pad length.  Utterances are therefore grouped by their own padded length and each
+    group runs at that length; rows of a shorter group are zero beyond their own padded length in the returned
+    tensor (allocated at the batch-wide maximum)."""
     was_training = G.training
     G.eval()
     n, L = wav.shape
     Tpad = padded_frames(L, spect.hop_length, base)
     S = spect.logmel(wav, dither, lengths, max_frames=Tpad)
-    outs: List[torch.Tensor] = []
-    for i in range(0, n, chunk):
-        _, x_identic_psnt, _ = G(S[i:i + chunk], emb_org[i:i + chunk], emb_trg[i:i + chunk])
-        outs.append(x_identic_psnt)
     if lengths is None:
         n_frames = torch.full((n,), 1 + L // spect.hop_length, dtype=torch.int32, device=wav.device)
+        groups = {Tpad: None}                                   # one group: every utterance, in place
     else:
         n_frames = 1 + lengths.to(torch.int32) // spect.hop_length
+        own = ((n_frames + (base - 1)) // base * base).tolist()  # one host sync per call: the grouping is host logic
+        groups = {}
+        for i, t in enumerate(own):
+            groups.setdefault(int(t), []).append(i)
+        if len(groups) == 1 and Tpad in groups:
+            groups = {Tpad: None}
+    n_bins = S.shape[-1]
+    out = None
+    for Tg, idx in sorted(groups.items()):
+        if idx is None:
+            Sg, eo, et = S, emb_org, emb_trg
+        else:
+            sel = torch.tensor(idx, dtype=torch.long, device=wav.device)
+            Sg, eo, et = S.index_select(0, sel)[:, :Tg].contiguous(), emb_org.index_select(0, sel), emb_trg.index_select(0, sel)
+        outs: List[torch.Tensor] = []
+        for i in range(0, Sg.shape[0], chunk):
+            _, x_identic_psnt, _ = G(Sg[i:i + chunk], eo[i:i + chunk].contiguous(), et[i:i + chunk].contiguous())
+            outs.append(x_identic_psnt)
+        res = torch.cat(outs, 0) if len(outs) > 1 else outs[0]
+        if idx is None:
+            out = res
+        else:
+            if out is None:
+                out = torch.zeros(n, 1, Tpad, n_bins, dtype=res.dtype, device=res.device)
+            out[sel, :, :Tg] = res
     if was_training:
         G.train()
-    return torch.cat(outs, 0), n_frames
+    return out, n_frames

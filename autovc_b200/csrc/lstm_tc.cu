@@ -1202,6 +1202,20 @@ static int lt_launch(const CUtensorMap& mW, const CUtensorMap& mX, const CUtenso
       set_error("lstm_tc: only %d clusters of %d CTAs can be co-resident, %d needed", max_clusters, CL, p.MT * p.NT / CL);
       return AVC_ERR_UNSUPPORTED;
     }
+    // the CTAs spin on each other's global counters: the occupancy query above assumes an empty GPU, the cooperative
+    // attribute makes the runtime hold the launch until the whole grid can be resident next to whatever else runs
+    attrs[na].id = cudaLaunchAttributeCooperative;
+    attrs[na].val.cooperative = 1;
+    ++na;
+    cfg.numAttrs = na;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mW, mX, mX2, om, p);
+    if (e != cudaSuccess) {                  // refused: the caller retries with a smaller cluster, down to the plain cooperative launch
+      (void)cudaGetLastError();
+      set_error("lstm_tc: cooperative launch of %d clusters of %d CTAs refused: %s", p.MT * p.NT / CL, CL, cudaGetErrorString(e));
+      return AVC_ERR_UNSUPPORTED;
+    }
+    g_launches.fetch_add(1);
+    return AVC_OK;
   } else {
     attrs[na].id = cudaLaunchAttributeCooperative;    // the runtime enforces co-residency
     attrs[na].val.cooperative = 1;

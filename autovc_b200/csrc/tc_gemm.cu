@@ -953,14 +953,26 @@ __global__ void cvt_pad_w_f32_kernel(const float* __restrict__ src, float* __res
 
 static int cvt_blocks(size_t total) { return (int)std::min<size_t>(ceil_div(total, (size_t)256), (size_t)num_sms() * 16); }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember per device (not per process) whether the
+// kernel has been configured, so a second GPU driven from the same process configures its own copy of the function
+struct AttrOnce {
+  std::atomic<unsigned long long> done{0};        // bit d: set on device d (devices >= 64 set it on every call)
+  template <class K>
+  int ensure(K kern, int smem) {
+    int dev = 0;
+    AVC_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && (done.load(std::memory_order_acquire) >> dev) & 1ull) return AVC_OK;
+    AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+    return AVC_OK;
+  }
+};
+
 template <int MODE, int EB, int BN>
 static int tc_launch(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int grid, cudaStream_t st) {
-  static bool attr_done = false;
+  static AttrOnce attr;
   auto kern = tc_gemm_kernel<MODE, EB, BN>;
-  if (!attr_done) {
-    AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM_BYTES));
-    attr_done = true;
-  }
+  if (int rc = attr.ensure(kern, TcCfg<BN>::SMEM_BYTES)) return rc;
   kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(mA, mB, p);
   AVC_LAUNCHED();
   return AVC_OK;
@@ -970,12 +982,9 @@ void tc_gemm_set_trace(unsigned long long* p) { g_gemm_trace = p; }
 
 template <int EB>
 static int tc2_launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mC, const TcParams& p, int grid, cudaStream_t st) {
-  static bool attr_done = false;
+  static AttrOnce attr;
   auto kern = tc_gemm2_nt_kernel<EB>;
-  if (!attr_done) {
-    AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
+  if (int rc = attr.ensure(kern, Tc2Cfg::SMEM_BYTES)) return rc;
   kern<<<grid, TC_THREADS, Tc2Cfg::SMEM_BYTES, st>>>(mA, mB, mC, p);
   AVC_LAUNCHED();
   return AVC_OK;
@@ -987,13 +996,10 @@ static bool use_cta_pairs() {
 }
 template <int EB>
 static int tc2_tn_launch(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int grid, cudaStream_t st) {
-  static bool attr_done = false;
+  static AttrOnce attr;
   constexpr int SMEM = 1024 + 6 * 32768 + 256;
   auto kern = tc_gemm2_tn_kernel<EB>;
-  if (!attr_done) {
-    AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_done = true;
-  }
+  if (int rc = attr.ensure(kern, SMEM)) return rc;
   kern<<<grid, TC_THREADS, SMEM, st>>>(mA, mB, p);
   AVC_LAUNCHED();
   return AVC_OK;

@@ -30,11 +30,18 @@ def _stream():
 
 
 def _check(*tensors):
+    cur = None
     for t in tensors:
         if t is None:
             continue
         if not t.is_cuda:
             raise _lib.AvcError("autovc_b200 ops need CUDA tensors (there is no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            # the launchers use the CURRENT device and its current stream: a tensor elsewhere would be touched from the wrong GPU
+            raise _lib.AvcError(f"autovc_b200 ops launch on the current CUDA device ({cur}) but got a tensor on {t.device}; "
+                                f"use torch.cuda.set_device / `with torch.cuda.device(...)` for modules placed on another GPU")
         if t.dtype not in (torch.float32, torch.float16, torch.bfloat16):
             raise _lib.AvcError(f"autovc_b200 ops take float32 tensors (or their 16-bit operand copies), got {t.dtype}")
         if not t.is_contiguous():

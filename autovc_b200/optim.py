@@ -15,7 +15,7 @@ from typing import List
 
 import torch
 
-from . import _lib
+from . import _lib, ops
 from ._lib import call, query
 
 
@@ -105,4 +105,8 @@ class FusedAdam(torch.optim.Adam):
             call("avc_adam_step", ctypes.c_void_p(plan["table"].data_ptr()), ctypes.c_void_p(plan["chunks"].data_ptr()),
                  plan["nchunks"], float(group["lr"]), float(b1), float(b2), float(group["eps"]), steps.pop(),
                  float(self.grad_scale), ctypes.c_void_p(torch.cuda.current_stream(plist[0].device).cuda_stream))
+        # the kernel writes the parameters through raw pointers, so their autograd version counters do not move: drop the
+        # packed-weight cache explicitly (torch.optim.Adam invalidates it through the counters) -- an encoder-only call or a
+        # direct sub-module call right after this step must not read packs of the previous weights
+        ops._GLOBAL_CACHE.begin_step()
         return loss

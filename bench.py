@@ -3,6 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun)
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+    python bench.py --impl torch-gpu --steps K                       # comparison: the same nn.Module tree on stock PyTorch/cuDNN (GPU)
 
 Workload (BASELINE.json configs[1]): Generator(dim_neck=16, dim_emb=256, dim_pre=512, freq=16),
 synthetic 80-bin mel crops, batch 256 per GPU, len_crop 128; one step = solver_encoder.py:228-300
@@ -11,7 +12,7 @@ Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for the definition 
 
 Secondary legs (not the driver's default): --workload frontend | convert (BASELINE.json configs[4], 4096 x 10 s utterances),
 --workload loader | dvector (the rows SURVEY 8(f) marks "next"); --n-bins 513 (configs[3]); --dim-neck 32 --freq 32 --batch 128
---len-crop 256 (configs[2]); --precision fp32 | tf32 | half | bf16.
+--len-crop 256 (configs[2]); --precision fp32 | tf32 | half.
 """
 from __future__ import annotations
 
@@ -91,21 +92,31 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port of the reference's PyTorch CPU path
 # ----------------------------------------------------------------------------------------
-def cpu_reference_throughput(dim_neck, freq, T, sample_B, steps, warmup, threads=None):
+def cpu_reference_throughput(dim_neck, freq, T, sample_B, steps, warmup, threads=None, n_bins=80, full_B=0):
+    """Oracle port of the reference's PyTorch CPU training step on ALL host cores (torchrun exports OMP_NUM_THREADS=1 to
+    its workers: the thread count is therefore set explicitly).  `steps` timed steps on a `sample_B`-crop slice of the batch;
+    with `full_B` one additional step at the full per-GPU batch is timed on its own (its crops/s is reported next to the
+    sample's, so the two batch sizes can be compared)."""
     from oracle import generator_ref as gref
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     torch.manual_seed(0)
-    G = gref.build_reference_like_module(dim_neck, 256, 512, freq).train()
+    G = gref.build_reference_like_module(dim_neck, 256, 512, freq, n_bins=n_bins).train()
     opt = torch.optim.Adam(G.parameters(), 1e-4)
-    x, e = synth_batch(sample_B, T, 80, 256, 1234)
+    x, e = synth_batch(sample_B, T, n_bins, 256, 1234)
     for _ in range(warmup):
         gref.module_train_step(G, opt, x, e)
     t0 = time.perf_counter()
     for _ in range(steps):
         gref.module_train_step(G, opt, x, e)
     dt = (time.perf_counter() - t0) / steps
-    return sample_B / dt, dt, torch.get_num_threads()
+    full = None
+    if full_B and full_B != sample_B:
+        xf, ef = synth_batch(full_B, T, n_bins, 256, 1234)
+        t0 = time.perf_counter()
+        gref.module_train_step(G, opt, xf, ef)
+        dtf = time.perf_counter() - t0
+        full = {"batch": full_B, "crops_per_s": full_B / dtf, "s_per_step": dtf, "steps": 1}
+    return sample_B / dt, dt, torch.get_num_threads(), full
 
 
 def run_reference(args):
@@ -113,29 +124,76 @@ def run_reference(args):
     if rank != 0:
         return
     sample_B = args.cpu_sample_batch
-    val, dt, threads = cpu_reference_throughput(args.dim_neck, args.freq, args.len_crop, sample_B, args.steps, args.warmup)
+    val, dt, threads, full = cpu_reference_throughput(args.dim_neck, args.freq, args.len_crop, sample_B, args.steps, args.warmup,
+                                                      n_bins=args.n_bins, full_B=args.batch)
     line = {
         "impl": "reference", "metric": "AutoVC train utterance-crops/sec", "value": val, "unit": "crops/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": workload_config(args, note=f"CPU: each step is a {sample_B}-crop sample of the 256-crop batch"),
+        "config": workload_config(args),
         "cpu_baseline": {"value": val, "unit": "crops/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample_B} crops x {args.len_crop} frames per step, {args.warmup} warm-up + {args.steps} timed steps, "
-                                   f"torch {torch.__version__} CPU (oneDNN) through the oracle port of model_vc_mel.py + solver_encoder.py:228-300"},
+                         "sample": f"each timed step is a {sample_B}-crop x {args.len_crop}-frame slice of the {args.batch}-crop batch "
+                                   f"({args.warmup} warm-up + {args.steps} timed steps), torch {torch.__version__} CPU (oneDNN), fp32, {threads} threads, "
+                                   f"through the oracle port of model_vc_mel.py + solver_encoder.py:228-300; full_batch = one step at the whole batch",
+                         "full_batch": full},
         "e2e": {"value": val, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, note=None):
-    c = {"workload": f"AutoVC mel Generator train step (solver_encoder.py:228-300), dim_neck={args.dim_neck} dim_emb=256 dim_pre=512 "
-                     f"freq={args.freq}, synthetic {args.n_bins}-bin {'mel' if args.n_bins == 80 else 'linear spectrogram'}, batch {args.batch} per GPU, len_crop {args.len_crop}",
-         "global_batch": args.batch * args.gpus, "len_crop": args.len_crop, "precision": args.precision,
-         "parallelism": f"dp{args.gpus}",
-         "l2": "per-step working set (>5 GB of activations) far exceeds the 126 MB L2; no explicit flush"}
-    if note:
-        c["note"] = note
-    return c
+def run_torch_gpu(args):
+    """Comparison arm asked for by the round-1 review (SURVEY 2.3's bar): the SAME nn.Module tree the CPU baseline uses
+    (torch.nn Conv1d / BatchNorm1d / LSTM / Linear), moved to the GPU, i.e. cuDNN / cuBLAS kernels through stock PyTorch, in
+    three settings: fp32 (TF32 off), TF32 on, bf16 autocast.  Single GPU; not the product path."""
+    from oracle import generator_ref as gref
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    B, T = args.batch, args.len_crop
+    x, e = synth_batch(B, T, args.n_bins, 256, 1234)
+    x, e = x.to(dev), e.to(dev)
+    res = {}
+    for mode in ("fp32", "tf32", "bf16_autocast"):
+        torch.backends.cuda.matmul.allow_tf32 = mode != "fp32"
+        torch.backends.cudnn.allow_tf32 = mode != "fp32"
+        torch.manual_seed(0)
+        G = gref.build_reference_like_module(args.dim_neck, 256, 512, args.freq, n_bins=args.n_bins).to(dev).train()
+        opt = torch.optim.Adam(G.parameters(), 1e-4, fused=True)
+
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16_autocast")):
+                x_identic, x_identic_psnt, code_real = G(x, e, e)
+                code_reconst = G(x_identic_psnt, e, None)
+            l = F.mse_loss(x, x_identic.float().squeeze(1)) + F.mse_loss(x, x_identic_psnt.float().squeeze(1)) + \
+                F.l1_loss(code_real.float(), code_reconst.float())
+            opt.zero_grad(set_to_none=True)
+            l.backward()
+            opt.step()
+        for _ in range(max(3, args.warmup)):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        res[mode] = {"ms_per_step": ms, "crops_per_s": B / (ms * 1e-3)}
+    best = max(res.values(), key=lambda r: r["crops_per_s"])
+    line = {"impl": "torch-gpu", "metric": "AutoVC train utterance-crops/sec", "value": best["crops_per_s"], "unit": "crops/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": best["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32 / tf32 / bf16 autocast (best reported as value)", "data": "synthetic",
+            "config": workload_config(args), "modes": res,
+            "note": f"stock PyTorch {torch.__version__} (cuDNN conv/LSTM, cuBLAS, fused Adam) on the same module tree, inputs resident in HBM"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    """The same dict in every arm (the driver compares them): the precision of the arm is the line's `dtype`."""
+    return {"workload": f"AutoVC mel Generator train step (solver_encoder.py:228-300), dim_neck={args.dim_neck} dim_emb=256 dim_pre=512 "
+                        f"freq={args.freq}, synthetic {args.n_bins}-bin {'mel' if args.n_bins == 80 else 'linear spectrogram'}, batch {args.batch} per GPU, len_crop {args.len_crop}",
+            "global_batch": args.batch * args.gpus, "len_crop": args.len_crop, "parallelism": f"dp{args.gpus}",
+            "l2": "per-step working set (>5 GB of activations) far exceeds the 126 MB L2; no explicit flush"}
 
 
 # ----------------------------------------------------------------------------------------
@@ -296,13 +354,41 @@ def run_ours(args):
                      for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])[:(64 if os.environ.get("AVC_BENCH_ALL_FAMILIES") else 8)]},
     }
 
+    # ---- sustained leg: a seconds-long run with its own clock trace (the timed region above is K steps = a fraction of a
+    # second at boost clock; this shows whether the rate holds once the power limit has had time to act)
+    sustained = None
+    if args.sustained > 0:
+        samp2 = ClockSampler(local) if rank == 0 else None
+        if samp2:
+            samp2.start()
+            time.sleep(0.5)             # NVML initialisation of the sampler stays out of the region
+            samp2.rows.clear()
+        ms_s = timed(step_resident, args.sustained)
+        ck = samp2.stop() if samp2 else None
+        trace = [float(r[0]) for r in samp2.rows if r and r[0].replace(".", "", 1).isdigit()] if samp2 else []
+        sustained = {"steps": args.sustained, "ms_per_step": ms_s, "value": B * world / (ms_s * 1e-3), "unit": "crops/s", "clocks": ck,
+                     "sm_mhz_trace_200ms": trace[:200]}
+
+    # ---- the other precision modes of the same module, same process, same inputs (N=1 only: keeps the scaling runs short)
+    modes = {args.precision: {"ms_per_step": ms, "value": B * world / (ms * 1e-3), "steps": args.steps}}
+    if world == 1 and args.modes:
+        for mode in [m for m in ("tf32", "fp32", "half") if m != args.precision]:
+            G.set_precision(mode)
+            k = args.steps if mode != "fp32" else max(2, min(args.steps, 5))
+            for _ in range(3 if mode != "fp32" else 2):
+                step_resident()
+            ms_m = timed(step_resident, k)
+            modes[mode] = {"ms_per_step": ms_m, "value": B / (ms_m * 1e-3), "steps": k}
+        G.set_precision(args.precision)
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            val, dt, threads = cpu_reference_throughput(args.dim_neck, args.freq, T, args.cpu_sample_batch, 2, 1)
+            val, dt, threads, full = cpu_reference_throughput(args.dim_neck, args.freq, T, args.cpu_sample_batch, 2, 1, n_bins=args.n_bins, full_B=B)
             cpu = {"value": val, "unit": "crops/s", "cores": threads, "kind": "port",
                    "sample": f"{args.cpu_sample_batch} crops x {T} frames per step (a slice of the {B}-crop batch), 1 warm-up + 2 timed steps, "
-                             f"oracle port of the reference's PyTorch CPU path"}
+                             f"oracle port of the reference's PyTorch CPU path (fp32, {threads} threads); full_batch = one step at the whole batch",
+                   "full_batch": full}
         line = {
             "metric": "AutoVC train utterance-crops/sec", "value": B * world / (ms * 1e-3), "unit": "crops/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -311,7 +397,7 @@ def run_ours(args):
             "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": "crops/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": (x_pin.numel() + e_pin.numel()) * 4, "d2h_bytes_per_step": 16},
             "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "modes": modes, "sustained": sustained,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -462,8 +548,10 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("AUTOVC_B200_PRECISION", "half"), choices=["fp32", "bf16", "tf32", "half"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
+    ap.add_argument("--sustained", type=int, default=300, help="extra timed leg of this many steps with its own clock trace (0: off)")
+    ap.add_argument("--no-modes", dest="modes", action="store_false", help="skip the tf32 / fp32 legs of the `modes` key")
+    ap.add_argument("--precision", default=os.environ.get("AUTOVC_B200_PRECISION", "half"), choices=["fp32", "tf32", "half"])
     ap.add_argument("--batch", type=int, default=256, help="crops per GPU")
     ap.add_argument("--len-crop", dest="len_crop", type=int, default=128)
     ap.add_argument("--dim-neck", dest="dim_neck", type=int, default=16)
@@ -481,6 +569,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch-gpu":
+        run_torch_gpu(args)
     else:
         run_ours(args)
 

@@ -61,3 +61,31 @@ def build_stft_like_module(dim_neck, freq, seed):
     G.postnet.convolutions[0][0] = convnorm(513, 512, "tanh")
     G.postnet.convolutions[4] = nn.Sequential(convnorm(512, 513, "linear"), nn.BatchNorm1d(513))
     return G
+
+
+def loss_curve_corpus(n_utt=64, frames=400, seed=7):
+    """Synthetic 'speakers' of the loss-curve gate: smooth band-limited mel-like trajectories in [0,1] plus
+    per-speaker embeddings (shared by oracle/gen_loss_curve_ref.py, tests/test_gpu_loss_curve.py and
+    scripts/loss_curve.py so that the reference curve and the GPU curves see the same data stream)."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand(n_utt, frames // 8 + 2, 80, generator=g)
+    x = F.interpolate(base.permute(0, 2, 1), size=frames, mode="linear", align_corners=True).permute(0, 2, 1)
+    x = (0.7 * x + 0.3 * torch.rand(n_utt, frames, 80, generator=g)).clamp(0, 1)
+    e = F.normalize(torch.randn(n_utt, 256, generator=g), dim=-1) * 0.8
+    return x, e
+
+
+def loss_curve_batches(steps, B, T, n_utt=64, frames=400, seed=123):
+    """The (utterance index, crop offset) draws of every step of the loss-curve gate."""
+    rs = np.random.RandomState(seed)
+    out = []
+    for _ in range(steps):
+        idx = rs.randint(0, n_utt, size=B)
+        off = rs.randint(0, frames - T, size=B)
+        out.append((idx, off))
+    return out
+
+
+def movavg(v, w=25):
+    c = np.cumsum(np.insert(np.asarray(v, np.float64), 0, 0.0))
+    return (c[w:] - c[:-w]) / w

@@ -1,0 +1,121 @@
+"""Parity AT THE BENCHED SHAPES against the unmodified reference (compact goldens of oracle/gen_golden_big.py):
+BASELINE.json configs[1] (B=256, T=128, 16/16 -- what bench.py times), configs[2] per GPU (B=128, T=256, 32/32) and the
+config-5 eval forward at T=640.  fp32 mode: <= 1e-4 max-abs on outputs, codes and each loss; half mode (the bench
+default): <= 1e-2 relative L2 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import digest, load_golden, synth_inputs
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import autovc_b200
+    from autovc_b200 import solver
+
+FP32_TOL = 1e-4
+N_STRIDED = 2048
+
+
+def _rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def _build(g, precision):
+    dim_neck, freq, B, T, n_bins, wseed, iseed = g["meta"].tolist()[:7]
+    torch.manual_seed(wseed)
+    G = autovc_b200.Generator(dim_neck, 256, 512, freq, precision=precision)
+    if "param_digest0" in g.files:
+        got = np.stack([digest(p) for p in G.parameters()])
+        np.testing.assert_array_equal(got[:, 3:], g["param_digest0"][:, 3:])       # bit-exact reference init
+    return G.cuda(), (dim_neck, freq, B, T, n_bins, iseed)
+
+
+@pytest.mark.parametrize("name", ["train_c2_16_16_b256_t128", "train_c3_32_32_b128_t256"])
+@pytest.mark.parametrize("precision", ["fp32", "half"])
+def test_train_step_at_benched_shape(name, precision):
+    g = load_golden(name)
+    G, (dim_neck, freq, B, T, n_bins, iseed) = _build(g, precision)
+    x, e, _ = synth_inputs(B, T, n_bins, 256, iseed)
+    opt = torch.optim.Adam(G.parameters(), 1e-4) if precision == "fp32" else autovc_b200.FusedAdam(G.parameters(), 1e-4)
+    out = solver.train_step(G.train(), opt, x.cuda(), e.cuda(), return_outputs=True)
+    sel = g["sel"].tolist()
+    got_l = np.array([out["g_loss"], out["L_id"], out["L_id_psnt"], out["L_cd"]])
+    ref_l = g["s0_losses"]
+    errs = {}
+    for k in ("x_identic", "x_identic_psnt", "code_real", "code_reconst"):
+        got = out[k].cpu()
+        full = digest(got, N_STRIDED)
+        ref_d = g[f"s0_{k}_digest"]
+        if k.startswith("code"):
+            ref, mine = g["s0_" + k], got.numpy()
+        else:
+            ref, mine = g[f"s0_{k}_sel"], got[sel].numpy()
+        assert mine.shape == ref.shape, k
+        if precision == "fp32":
+            assert np.abs(mine - ref).max() < FP32_TOL, (k, np.abs(mine - ref).max())
+            assert np.abs(full[3:] - ref_d[3:]).max() < FP32_TOL, k              # samples strided over the WHOLE batch
+            assert abs(full[2] - ref_d[2]) < 1e-5 * ref_d[2], k                  # l2 norm of the whole tensor
+        else:
+            errs[k] = max(_rel_l2(mine, ref), _rel_l2(full[3:], ref_d[3:]))
+    if precision == "fp32":
+        np.testing.assert_allclose(got_l, ref_l, rtol=0, atol=FP32_TOL)
+        ref = g["s0_grad_digest"]
+        for i, (n, p) in enumerate(G.named_parameters()):
+            d = digest(out["grads"][n])
+            if ".conv.bias" in n:
+                assert np.abs(d[3:]).max() < 1e-6            # exact zero here; 1e-8 noise in the reference
+                continue
+            rms = max(ref[i][2] / np.sqrt(p.numel()), 1e-12)
+            assert abs(d[2] - ref[i][2]) <= 2e-3 * ref[i][2] + 1e-9, (n, d[2], ref[i][2])
+            assert np.abs(d[3:] - ref[i][3:]).max() <= 5e-2 * rms + 1e-7, n
+        sd = G.state_dict()
+        for k in g.files:
+            if k.startswith("s0_buf/"):
+                np.testing.assert_allclose(sd[k[7:]].cpu().numpy(), g[k], rtol=1e-4, atol=1e-5, err_msg=k)
+        got_p = np.stack([digest(p) for p in G.parameters()])
+        np.testing.assert_allclose(got_p[:, 3:], g["s0_param_digest"][:, 3:], rtol=0, atol=2e-5)   # one Adam step (lr 1e-4)
+    else:
+        lerr = {k: abs(a - r) / abs(r) for k, a, r in zip(("g_loss", "L_id", "L_id_psnt", "L_cd"), got_l, ref_l)}
+        print(name, "half rel-L2:", errs, "loss rel err:", lerr)
+        assert max(errs.values()) < 1e-2, errs
+        assert max(lerr.values()) < 1e-2, lerr
+        ref = g["s0_grad_digest"]
+        worst = {}
+        for i, (n, p) in enumerate(G.named_parameters()):
+            if ".conv.bias" in n:
+                continue
+            d = digest(out["grads"][n])
+            worst[n] = (abs(d[2] - ref[i][2]) / ref[i][2], _rel_l2(d[3:], ref[i][3:]))
+        top = sorted(worst.items(), key=lambda kv: -kv[1][1])[:4]
+        print(name, "half gradient digests, worst (norm rel err, sample rel-L2):", top)
+        assert max(v[0] for v in worst.values()) < 0.05, top      # per-tensor gradient norm
+        assert max(v[1] for v in worst.values()) < 0.15, top      # per-tensor rel-L2 over the 96 sampled entries
+
+
+@pytest.mark.parametrize("name", ["eval_32_32_b2_t640", "eval_16_16_b3_t640"])
+@pytest.mark.parametrize("precision", ["fp32", "half"])
+def test_eval_forward_at_conversion_length(name, precision):
+    """conversion.py:47,:91-92 at the config-5 length (10 s utterances -> 626 frames -> padded to 640)."""
+    g = load_golden(name)
+    G, (dim_neck, freq, B, T, n_bins, iseed) = _build(g, precision)
+    x, e, e2 = synth_inputs(B, T, n_bins, 256, iseed)
+    x, e, e2 = x.cuda(), e.cuda(), e2.cuda()
+    G.set_precision("fp32")          # the running statistics come from two fp32 train-mode forwards, as in the golden
+    G.train()
+    with torch.no_grad():
+        G(x[:, :128].contiguous(), e, e)
+        G(x[:, 128:256].flip(0).contiguous(), e2, e)
+    G.set_precision(precision)
+    G.eval()
+    with torch.no_grad():
+        xi, xp, codes = G(x, e, e2)
+    for k, got in (("x_identic", xi), ("x_identic_psnt", xp), ("codes", codes)):
+        if precision == "fp32":
+            err = np.abs(got.cpu().numpy() - g[k]).max()
+            assert err < FP32_TOL, (k, err)
+        else:
+            rel = _rel_l2(got.cpu().numpy(), g[k])
+            assert rel < 1e-2, (k, rel)

@@ -34,7 +34,8 @@ def test_conversion_matches_chained_oracles():
         S = fref.logmel_from_wav(wav[i, :lengths[i]], dither[i, :lengths[i]])
         F = S.shape[0]
         assert int(n_frames[i]) == F
-        Sp = np.zeros((Tpad, 80), np.float32)
+        Town = padded_frames(int(lengths[i]))                          # conversion.py:40-44: each utterance's OWN multiple of 32
+        Sp = np.zeros((Town, 80), np.float32)
         Sp[:F] = S                                                      # pad_seq: zero frames
         with torch.no_grad():
             _, ref, _ = gref.generator_forward(sd, torch.from_numpy(Sp)[None], e[i:i + 1], e2[i:i + 1], 32, 32, training=False)

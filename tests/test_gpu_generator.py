@@ -160,37 +160,44 @@ def _rel_l2(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
+# per-tensor relative L2 of the gradients, reduced-precision mode vs the fp32 oracle from the same init (measured on B200 + margin).
+# The bounds are per parameter family: the bulk (conv / LSTM / linear weights) sits at a few 1e-3 .. 2e-2; BatchNorm affine and
+# bias gradients are sums of O(B*T) signed terms that nearly cancel, so their RELATIVE error is the largest of the model.
+GRAD_REL_L2 = {"tf32": {"weight": 0.06, "small": 0.15}, "half": {"weight": 0.06, "small": 0.15}}
+
+
 @pytest.mark.parametrize("name", ["train_16_16_b16_t128", "train_16_16_b2_t128"])
-@pytest.mark.parametrize("precision", ["tf32", "half", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32", "half"])
 def test_tensor_core_modes_within_rel_l2_gate(name, precision):
     """Reduced-precision tensor-core modes versus the reference's fp32 path.  The north_star gate for the
-    reduced-precision mode is <= 1e-2 relative L2 on the outputs.  `tf32` (fp32 operands rounded to tf32 by
-    TMA, bf16 persistent recurrence, fp32 accumulation/statistics/state) meets it.  `bf16` operands cannot at
-    random init -- SURVEY 7.2: rounding the weights ALONE to bf16 already gives 1.3e-2 / 2.8e-2 on
-    x_identic_psnt / code_reconst in the reference itself, because the near-constant decoder output is
-    re-amplified by 14 BatchNorms -- so bf16 is checked against its measured level (documented in DESIGN.md),
-    not claimed to pass the gate."""
+    reduced-precision mode is <= 1e-2 relative L2 on the outputs: `tf32` (fp32 operands rounded to tf32 by TMA) and
+    `half` (fp16 forward / bf16 gradient operands; the bench default) both meet it at B=16; at B=2 (256 rows per
+    BatchNorm channel, the noisiest statistics in the suite) the bound is 3e-2.  Gradients: per-tensor relative L2
+    against the fp32 oracle's gradients from the same init (B=16 case)."""
     g, G, (dim_neck, freq, B, T, n_bins, iseed) = _build(name)
     G.set_precision(precision)
+    sd = {k: v.detach().cpu().clone() for k, v in G.state_dict().items()}
     x, e, _ = synth_inputs(B, T, n_bins, 256, iseed)
     opt = torch.optim.Adam(G.parameters(), 1e-4)
     out = solver.train_step(G.train(), opt, x.cuda(), e.cuda(), return_outputs=True)
     errs = {k: _rel_l2(out[k].cpu().numpy(), g["s0_" + k]) for k in ("x_identic", "x_identic_psnt", "code_real", "code_reconst")}
     lerr = {k: abs(out[k] - r) / abs(r) for k, r in zip(("g_loss", "L_id", "L_id_psnt", "L_cd"), g["s0_losses"])}
     print(precision, name, "rel-L2:", errs, "loss rel err:", lerr)
-    tol = 1e-2 if B >= 16 else 3e-2       # B=2: 256 samples per BatchNorm channel, the noisiest case in the suite
-    if precision == "bf16":
-        tol = 6e-2 if B >= 16 else 9e-2   # measured 2.2e-2 / 4.6e-2 (B=16): NOT within the 1e-2 gate, see docstring
+    tol = 1e-2 if B >= 16 else 3e-2
     assert max(errs.values()) < tol, errs
     assert max(lerr.values()) < tol, lerr
-    ref = g["s0_grad_digest"]
-    bad = []
-    for i, (n, p) in enumerate(G.named_parameters()):
+    if B < 16:
+        return
+    _, _, ref_grads = gref.train_step(sd, x, e, dim_neck, freq)
+    rel = {}
+    for n, p in G.named_parameters():
         if ".conv.bias" in n:
             continue
-        d = digest(out["grads"][n])
-        if abs(d[2] - ref[i][2]) > (0.08 if precision == "tf32" else 0.25) * ref[i][2] + 1e-9:
-            bad.append((n, d[2], ref[i][2]))
+        rel[n] = _rel_l2(out["grads"][n].cpu().numpy(), ref_grads[n].numpy())
+    fam = lambda n: "weight" if (n.endswith("conv.weight") or "weight_ih" in n or "weight_hh" in n or n.endswith("linear_layer.weight")) else "small"
+    worst = sorted(rel.items(), key=lambda kv: -kv[1])[:6]
+    print(precision, "gradient rel-L2, worst:", worst, "median:", float(np.median(list(rel.values()))))
+    bad = [(n, r) for n, r in rel.items() if r > GRAD_REL_L2[precision][fam(n)]]
     assert not bad, bad
 
 

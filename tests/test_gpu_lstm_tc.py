@@ -1,5 +1,7 @@
-"""Persistent tensor-core LSTM recurrence (AVC_PREC_BF16, lstm_tc.cu) against the fp32 kernels
-and torch.nn.LSTM in fp64.  bf16 operands + tanh.approx gate math: tolerances are relative."""
+"""Persistent tensor-core LSTM recurrences (bf16 operands, fp32 state) against (i) this library's fp32 kernels
+(which tests/test_gpu_kernels.py ties to torch.nn.LSTM) at short sequences and (ii) torch.nn.LSTM in fp64 directly, at
+the benched lengths (T=128 / 256) through the half-mode layer the Generator uses.  bf16 operands + tanh.approx gate
+math: tolerances are relative."""
 import pytest
 import torch
 
@@ -35,5 +37,30 @@ def test_persistent_lstm_matches_fp32(B, T, I, H):
     assert torch.isfinite(out16).all()
     assert _rel(out16, out32) < 1e-2, _rel(out16, out32)
     for a, b, n in zip(g16, g32, ["dx", "dw_ih", "dw_hh", "db_ih", "db_hh"]):
+        assert torch.isfinite(a).all(), n
+        assert _rel(a, b) < 2e-2, (n, _rel(a, b))
+
+
+@pytest.mark.parametrize("B,T,I,H", [(256, 128, 512, 1024), (130, 128, 288, 512), (128, 256, 512, 1024), (40, 96, 80, 768)])
+def test_half_mode_layer_matches_nn_lstm_fp64(B, T, I, H):
+    """ops.LstmLayerH (input projection on fp16 operands, persistent bf16 recurrence forward and BPTT, bf16 gradient GEMMs)
+    against torch.nn.LSTM evaluated in float64 (model_vc_mel.py:90/:104 semantics: gate order i,f,g,o, zero initial state),
+    at the sequence lengths and batch sizes of BASELINE.json configs[1]/[2] (two batch tiles, a ragged second tile, H=512/768/1024)."""
+    torch.manual_seed(5)
+    lstm = torch.nn.LSTM(I, H, 1, batch_first=True).to(DEV)
+    ws = [lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0]
+    x = (0.5 * _rand(B, T, I, seed=8)).requires_grad_(True)
+    go = _rand(B, T, H, seed=9) / (B * T) ** 0.5
+    out, h16, h16b = ops.LstmLayerH.apply(x, None, None, *ws)
+    got = torch.autograd.grad(out, [x] + ws, go)
+    ref = torch.nn.LSTM(I, H, 1, batch_first=True).to(DEV).double()
+    ref.load_state_dict({k: v.double() for k, v in lstm.state_dict().items()})
+    xd = x.detach().double().requires_grad_(True)
+    rout, _ = ref(xd)
+    rg = torch.autograd.grad(rout, [xd, ref.weight_ih_l0, ref.weight_hh_l0, ref.bias_ih_l0, ref.bias_hh_l0], go.double())
+    assert torch.isfinite(out).all()
+    assert _rel(out, rout) < 1e-2, _rel(out, rout)
+    assert _rel(h16.float(), rout) < 1e-2 and _rel(h16b.float(), rout) < 1.5e-2
+    for a, b, n in zip(got, rg, ["dx", "dw_ih", "dw_hh", "db_ih", "db_hh"]):
         assert torch.isfinite(a).all(), n
         assert _rel(a, b) < 2e-2, (n, _rel(a, b))
