@@ -1095,9 +1095,18 @@ static LtPlan lt_plan(int nB, int H, bool bwd) {
   pl.total = pl.off_cnt + align256((size_t)nchunks * 128 * sizeof(unsigned));
   return pl;
 }
+// CTA-pair recurrences (lstm_pair.cu)
+bool lstm_pair_fwd_supported(int H);
+size_t lstm_pair_fwd_workspace(int nB, int H);
+int lstm_seq_pair_fwd(const __nv_bfloat16* Wb, const float* P, float* h_seq, int ldh, float* gates, float* c_seq, int nB, int T,
+                      int H, int reverse, void* ws, size_t ws_bytes, cudaStream_t st, void* h16, int fmt16, void* h16b);
+
 size_t lstm_tc_workspace(int nB, int T, int H, bool bwd) {
   (void)T;
-  return lt_plan(nB, H, bwd).total;       // the K-split BPTT variant uses the same layout (xbuf [2][nBpad][4H], counters)
+  const LtPlan pl = lt_plan(nB, H, bwd);     // the K-split BPTT variant uses the same layout (xbuf [2][nBpad][4H], counters)
+  size_t total = pl.total;
+  if (!bwd && lstm_pair_fwd_supported(H)) total = std::max(total, pl.off_x + lstm_pair_fwd_workspace(nB, H));
+  return total;
 }
 
 static bool bwd_ksplit_enabled(int H) {
@@ -1255,8 +1264,8 @@ int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh,
                 const float* dH, int lddh, float* dP, int nB, int T, int H, int reverse, void* ws, size_t ws_bytes,
                 cudaStream_t st, void* aux16, int fmt16, int w_fmt, void* aux16b) {
   const LtPlan pl = lt_plan(nB, H, bwd);
-  if (!ws || ws_bytes < pl.total) {
-    set_error("avc_lstm_seq_%s(bf16): workspace %zu < %zu", bwd ? "bwd" : "fwd", ws_bytes, pl.total);
+  if (!ws || ws_bytes < lstm_tc_workspace(nB, T, H, bwd)) {
+    set_error("avc_lstm_seq_%s(bf16): workspace %zu < %zu", bwd ? "bwd" : "fwd", ws_bytes, lstm_tc_workspace(nB, T, H, bwd));
     return AVC_ERR_WORKSPACE;
   }
   if (pl.smem > 227 * 1024) {
@@ -1279,6 +1288,9 @@ int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh,
     }
     Wb = (const __nv_bfloat16*)Wv;
   }
+  if (!bwd && lstm_pair_fwd_supported(H))      // CTA pairs: one resident W_hh copy for both batch tiles, 64 SMs (lstm_pair.cu)
+    return lstm_seq_pair_fwd(Wb, P, h_seq, ldh, gates, c_seq, nB, T, H, reverse, w8 + pl.off_x, ws_bytes - pl.off_x, st, aux16, fmt16,
+                             aux16b);
   const int nchunks = ceil_div(nB, pl.chunk);
   AVC_CUDA(cudaMemsetAsync(counters, 0, (size_t)nchunks * 128 * sizeof(unsigned), st));
   static int kflags_mode = -1;
