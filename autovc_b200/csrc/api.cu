@@ -45,7 +45,6 @@ size_t gemm_tn_workspace_tc(int, int, int, int, int, int);
 // persistent tensor-core recurrences (lstm_tc.cu)
 bool lstm_tc_supported(int H);
 void lstm_tc_set_trace(unsigned long long* p);
-void lstm_pair_set_trace(unsigned long long* p);
 void tc_gemm_set_trace(unsigned long long* p);
 size_t lstm_tc_workspace(int nB, int T, int H, bool bwd);
 int lstm_seq_tc(bool bwd, const void* W, const float* P, float* h_seq, int ldh, float* gates, float* c_seq, const float* dH,
@@ -146,7 +145,6 @@ extern "C" size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H, int prec) {
 
 extern "C" void avc_debug_set_trace(unsigned long long* device_buffer) {
   lstm_tc_set_trace(device_buffer);
-  lstm_pair_set_trace(device_buffer);
   tc_gemm_set_trace(device_buffer);
 }
 

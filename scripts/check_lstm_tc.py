@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Quick numeric + latency check of the CTA-pair recurrences (lstm_pair.cu) against torch.nn.LSTM in fp64.
-Run under `timeout`: a protocol bug in a persistent kernel shows up as a hang."""
+"""Quick numeric + latency check of the persistent recurrences (lstm_tc.cu) against torch.nn.LSTM in fp64, and the
+per-step trace of CTA 0 (`trace` argument).  Run under `timeout`: a protocol bug in a persistent kernel shows up as a hang."""
 import json
 import os
 import sys
@@ -108,17 +108,11 @@ def trace(B, T, H, which="fwd"):
     t = tr[:16 * T].view(T, 16).double().cpu().numpy()
     rows = []
     for s in range(20, T - 20):
-        rows.append((t[s, :12] - t[s - 1, 6]) / 1e3)
+        rows.append((t[s, :12] - t[s - 1, 8]) / 1e3)
     med = np.median(np.array(rows), axis=0)
-    names = ["counter_seen", "loads_issued", "first_landed", "mma_issued", "epi_woke", "math_done", "published", "s7", "s8", "s9", "s10", "s11"]
-    clk = t[20:T - 20, 8:14]
-    d = np.median(clk[:, 1:] - clk[:, :1], axis=0)
-    print("   SM clocks after epilogue wake: tmem+arrive %d, math+stg %d, barrier %d, fence.proxy %d, red issued %d" % tuple(int(x) for x in d))
-    ex = tr[16 * T:16 * T + 128].double().cpu().numpy()
-    iss, land = ex[0:H // 64], ex[64:64 + H // 64]
-    print("   step 64 k-block issue clocks:", [int(x - iss[0]) for x in iss])
-    print("   step 64 k-block land  clocks:", [int(x - iss[0]) for x in land])
-    print(which, (B, T, H), "period us:", round(float(np.median(np.diff(t[20:T - 20, 6])) / 1e3), 2),
+    names = ["counter_seen", "tma_first", "tma_last", "land_first", "land_last", "mma_issued", "epi_woke", "math_done", "published",
+             "rs_sent", "rs_received", "bar_passed"]
+    print(which, (B, T, H), "period us:", round(float(np.median(np.diff(t[20:T - 20, 8])) / 1e3), 2),
           {n: round(float(v), 2) for n, v in zip(names, med) if v > -1e6}, flush=True)
 
 

@@ -75,8 +75,15 @@ def test_train_step_at_benched_shape(name, precision):
         for k in g.files:
             if k.startswith("s0_buf/"):
                 np.testing.assert_allclose(sd[k[7:]].cpu().numpy(), g[k], rtol=1e-4, atol=1e-5, err_msg=k)
+        # one Adam step (lr 1e-4): the FIRST step moves every element by lr * g / (|g| + eps) ~ +-1e-4 whatever |g| is, so
+        # an element whose gradient is rounding noise (conv biases under train-mode BatchNorm) may move the other
+        # way: nothing moves by more than lr, and all but a few per cent of the sampled elements agree to 2e-6
         got_p = np.stack([digest(p) for p in G.parameters()])
-        np.testing.assert_allclose(got_p[:, 3:], g["s0_param_digest"][:, 3:], rtol=0, atol=2e-5)   # one Adam step (lr 1e-4)
+        diff = np.abs(got_p[:, 3:] - g["s0_param_digest"][:, 3:])
+        assert diff.max() <= 2.05e-4, diff.max()
+        names = [n for n, _ in G.named_parameters()]
+        rows = [i for i, n in enumerate(names) if ".conv.bias" not in n]
+        assert (diff[rows] > 2e-6).mean() < 0.03, float((diff[rows] > 2e-6).mean())
     else:
         lerr = {k: abs(a - r) / abs(r) for k, a, r in zip(("g_loss", "L_id", "L_id_psnt", "L_cd"), got_l, ref_l)}
         print(name, "half rel-L2:", errs, "loss rel err:", lerr)
