@@ -73,6 +73,7 @@ SIGNATURES = {
     "avc_crop_batch": (c_int, [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, P]),
     "avc_adam_chunk_elems": (c_int, []),
     "avc_adam_step": (c_int, [P, P, c_int, c_double, c_double, c_double, c_double, c_int, c_float, P]),
+    "avc_ema_blend": (c_int, [P, P, c_int, c_double, P]),
     "avc_logmel_frontend": (c_int, [P, P, P, c_int, c_int, P, P, P, P, c_int, P, c_size_t, P]),
     "avc_logmel_workspace_bytes": (c_size_t, [c_int, c_int]),
 }

@@ -72,6 +72,36 @@ adam_multi_kernel(const AdamTensor* __restrict__ tab, const int2* __restrict__ c
   }
 }
 
+// solver_encoder.py:168-177 model_EMA: avg = ema * flat + (1 - ema) * flat, written back over the parameters.  In exact
+// arithmetic that is the identity; in fp32 it is three roundings per element (two products, one sum) that move
+// most parameters by an ulp, and a checkpoint holds the result.  Same operations, same order, no fma contraction.
+__global__ void __launch_bounds__(ADAM_THREADS)
+ema_blend_kernel(const AdamTensor* __restrict__ tab, const int2* __restrict__ chunks, int nchunks, float a, float b) {
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const int2 ch = chunks[c];
+    const AdamTensor t = tab[ch.x];
+    const size_t start = (size_t)ch.y * ADAM_CHUNK;
+    const size_t end = min(start + (size_t)ADAM_CHUNK, (size_t)t.n);
+    if ((((uintptr_t)t.p) & 15) == 0 && end - start == ADAM_CHUNK) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const size_t i = start + (size_t)(k * ADAM_THREADS + threadIdx.x) * 4;
+        float4 v = *reinterpret_cast<const float4*>(t.p + i);
+        v.x = __fadd_rn(__fmul_rn(a, v.x), __fmul_rn(b, v.x));
+        v.y = __fadd_rn(__fmul_rn(a, v.y), __fmul_rn(b, v.y));
+        v.z = __fadd_rn(__fmul_rn(a, v.z), __fmul_rn(b, v.z));
+        v.w = __fadd_rn(__fmul_rn(a, v.w), __fmul_rn(b, v.w));
+        *reinterpret_cast<float4*>(t.p + i) = v;
+      }
+    } else {
+      for (size_t i = start + threadIdx.x; i < end; i += ADAM_THREADS) {
+        const float x = t.p[i];
+        t.p[i] = __fadd_rn(__fmul_rn(a, x), __fmul_rn(b, x));
+      }
+    }
+  }
+}
+
 }  // namespace avc
 
 using namespace avc;
@@ -91,6 +121,17 @@ extern "C" int avc_adam_step(const void* table, const void* chunks, int nchunks,
   adam_multi_kernel<<<grid, ADAM_THREADS, 0, as_stream(stream)>>>(
       reinterpret_cast<const AdamTensor*>(table), reinterpret_cast<const int2*>(chunks), nchunks, (float)(1.0 - beta1), (float)beta2,
       (float)(1.0 - beta2), (float)eps, step_size, bc2_sqrt, grad_scale);
+  AVC_LAUNCHED();
+  return AVC_OK;
+}
+
+extern "C" int avc_ema_blend(const void* table, const void* chunks, int nchunks, double ema, void* stream) {
+  AVC_REQUIRE(table && chunks && nchunks > 0, "avc_ema_blend: null table / no chunks");
+  // torch multiplies an fp32 tensor by a python float in fp32 with the scalar cast to float; (1 - ema) is formed in double first
+  const int grid = std::min(nchunks, num_sms() * 8);
+  ema_blend_kernel<<<grid, ADAM_THREADS, 0, as_stream(stream)>>>(reinterpret_cast<const AdamTensor*>(table),
+                                                                 reinterpret_cast<const int2*>(chunks), nchunks, (float)ema,
+                                                                 (float)(1.0 - ema));
   AVC_LAUNCHED();
   return AVC_OK;
 }

@@ -238,6 +238,131 @@ class GradBucketReducer:
         self._hooks = []
 
 
+# --------------------------------------------------------------------------------------
+# model_EMA + checkpoint                                       solver_encoder.py:168-177, :333-346, :147-153
+# --------------------------------------------------------------------------------------
+class _ParamTable:
+    """Device pointer table + chunk map over a parameter list (the layout avc_adam_step / avc_ema_blend walk)."""
+
+    _cache: Dict[tuple, "_ParamTable"] = {}
+
+    def __init__(self, plist):
+        import ctypes
+        from ._lib import query
+        chunk = query("avc_adam_chunk_elems")
+        dev = plist[0].device
+        rows, pairs = [], []
+        for ti, p in enumerate(plist):
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("autovc_b200: parameters must be contiguous float32 CUDA tensors (there is no CPU fallback)")
+            rows.append([p.data_ptr(), 0, 0, 0, p.numel()])
+            pairs += [(ti, c) for c in range((p.numel() + chunk - 1) // chunk)]
+        self.table = torch.tensor(rows, dtype=torch.int64).to(dev)
+        self.chunks = torch.tensor(pairs, dtype=torch.int32).to(dev)
+        self.nchunks = len(pairs)
+        self.ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    @classmethod
+    def of(cls, plist):
+        key = tuple((p.data_ptr(), p.numel()) for p in plist)
+        hit = cls._cache.get(key)
+        if hit is None:
+            cls._cache.clear()
+            hit = cls._cache[key] = cls(plist)
+        return hit
+
+
+@torch.no_grad()
+def model_EMA(G, ema: float):
+    """``Solver.model_EMA`` (solver_encoder.py:168-177): overwrite every parameter with ``ema * p + (1 - ema) * p`` -- the
+    near-identity the reference applies before each checkpoint, reproduced bit for bit (two fp32 products and
+    one sum per element, in that order) in ONE launch instead of a 113 MB concatenation, three ATen passes and 74 copies."""
+    import ctypes
+    from ._lib import call
+    plist = [p for p in G.parameters()]
+    if not plist:
+        return
+    tab = _ParamTable.of(plist)
+    call("avc_ema_blend", tab.ptr(tab.table), tab.ptr(tab.chunks), tab.nchunks, float(ema),
+         ctypes.c_void_p(torch.cuda.current_stream(plist[0].device).cuda_stream))
+    ops._GLOBAL_CACHE.begin_step()          # the parameters changed behind autograd's version counters
+
+
+class AsyncCheckpoint:
+    """Handle of a checkpoint being written in the background; ``wait()`` blocks until the file is on disk."""
+
+    def __init__(self, thread, path):
+        self._thread, self.path = thread, path
+
+    def wait(self):
+        self._thread.join()
+        return self.path
+
+
+def save_checkpoint(G, optimizer, epoch: int, loss: dict, path: str, ema: Optional[float] = None, blocking: bool = False):
+    """The checkpoint of solver_encoder.py:333-346: ``model_EMA()`` first (when ``ema`` is given), then
+    ``torch.save({'epoch', 'state_dict', 'optimizer', 'loss'}, path)`` with the reference's layout, so that the reference's
+    resume code (:147-153) and ``load_checkpoint`` below read it.
+
+    The reference stalls the training loop for the device->host copy and the pickling.  Here the step only pays a
+    device-side snapshot (one multi-tensor copy, ~0.3 ms for 340 MB of parameters + Adam state); the snapshot goes to pinned
+    host memory on a copy stream and a background thread writes the file.  Returns an ``AsyncCheckpoint``."""
+    import threading
+    if ema is not None:
+        model_EMA(G, ema)
+    dev = next(G.parameters()).device
+    sd = G.state_dict()
+    osd = optimizer.state_dict()
+    src: List[torch.Tensor] = [v for v in sd.values() if isinstance(v, torch.Tensor) and v.is_cuda]
+    for st in osd["state"].values():
+        src += [v for v in st.values() if isinstance(v, torch.Tensor) and v.is_cuda]
+    snap = [torch.empty_like(t) for t in src]
+    if snap:
+        torch._foreach_copy_(snap, src)                                   # device-side snapshot on the compute stream
+    copy_stream = torch.cuda.Stream(device=dev)
+    copy_stream.wait_stream(torch.cuda.current_stream(dev))
+    host = []
+    with torch.cuda.stream(copy_stream):
+        for t in snap:
+            h = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            host.append(h)
+        done = torch.cuda.Event()
+        done.record(copy_stream)
+    it = iter(host)
+
+    def swap(v):
+        return next(it) if (isinstance(v, torch.Tensor) and v.is_cuda) else v
+    sd_h = type(sd)((k, swap(v)) for k, v in sd.items())
+    osd_h = {"state": {k: {kk: swap(vv) for kk, vv in st.items()} for k, st in osd["state"].items()},
+             "param_groups": osd["param_groups"]}
+    state = {"epoch": int(epoch), "state_dict": sd_h, "optimizer": osd_h, "loss": dict(loss)}
+
+    def write():
+        done.synchronize()
+        del snap[:]
+        tmp = path + ".tmp"
+        torch.save(state, tmp)
+        import os
+        os.replace(tmp, path)
+    th = threading.Thread(target=write, daemon=False)
+    th.start()
+    handle = AsyncCheckpoint(th, path)
+    if blocking:
+        handle.wait()
+    return handle
+
+
+def load_checkpoint(path: str, G, optimizer, map_location=None):
+    """solver_encoder.py:147-153: restore model and optimizer from a checkpoint (ours or the reference's); returns
+    (epoch, loss)."""
+    ckpt = torch.load(path, map_location=map_location or next(G.parameters()).device, weights_only=False)
+    G.load_state_dict(ckpt["state_dict"])
+    optimizer.load_state_dict(ckpt["optimizer"])
+    ops._GLOBAL_CACHE.begin_step()
+    return ckpt["epoch"], ckpt["loss"]
+
+
 def nccl_env_defaults():
     """Call BEFORE ``dist.init_process_group("nccl")``.  The persistent recurrence kernels are cooperative launches of 128
     CTAs (one per SM, ~220 KB of shared memory each) that spin on each other: they start only when 128 SMs are free at

@@ -284,6 +284,11 @@ int avc_adam_chunk_elems(void);
 int avc_adam_step(const void* table, const void* chunks, int nchunks, double lr, double beta1, double beta2, double eps,
                   int step, float grad_scale, void* stream);
 
+/* solver_encoder.py:168-177 Solver.model_EMA (called before every checkpoint, :334): every parameter p is overwritten with
+ *   fl(fl(ema * p) + fl((1 - ema) * p))      (fp32, two products and one sum, no fma -- the reference's three ATen passes)
+ * in ONE launch over all tensors.  table / chunks as for avc_adam_step (only the p and n columns are read). */
+int avc_ema_blend(const void* table, const void* chunks, int nchunks, double ema, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * make_spect front-end, make_spect.py:72-83 (spmel branch) + :30-48:
  *   y = filtfilt(butter(5, 30 Hz HP), wav) [fp64, scipy odd-extension padlen 18, lfilter_zi]
