@@ -76,6 +76,13 @@ SIGNATURES = {
     "avc_ema_blend": (c_int, [P, P, c_int, c_double, P]),
     "avc_logmel_frontend": (c_int, [P, P, P, c_int, c_int, P, P, P, P, c_int, P, c_size_t, P]),
     "avc_logmel_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "avc_prelu_fwd": (c_int, [P, P, P, P, c_int, c_int, P]),
+    "avc_prelu_bwd": (c_int, [P, P, P, P, P, c_int, P, c_size_t, P]),
+    "avc_sum_all": (c_int, [P, c_size_t, P, P, c_int, P]),
+    "avc_copy_rows3d": (c_int, [P, c_int, P, c_int, c_int, c_int, P]),
+    "avc_permute021": (c_int, [P, P, c_int, c_int, c_int, P]),
+    "avc_sisnr_fwd": (c_int, [P, P, c_int, c_int, P, P, P, P]),
+    "avc_sisnr_bwd": (c_int, [P, P, P, P, c_int, c_int, P, c_int, P]),
 }
 
 _lib = None

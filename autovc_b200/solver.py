@@ -31,6 +31,43 @@ def generator_losses(G, x_real, emb_org, lambda_cd: float = 1.0):
     return g_loss, (g_loss_id, g_loss_id_psnt, g_loss_cd), (x_identic, x_identic_psnt, code_real, code_reconst)
 
 
+def generator_losses_wav(G, x_real, emb_org, lambda_cd: float = 1.0, lambda_SISNR: float = 1.0):
+    """The 'wav' branch of the step, solver_encoder.py:264-290 (GeneratorWav): reconstruction MSE on the waveform, MSE
+    between the analysis filterbank's output and the decoder's estimate of it, L1 content-code loss on a second encoder
+    pass over the synthesised waveform, and the SI-SNR term -- each through a fused CUDA loss kernel."""
+    from . import ops_wav
+    x_convtas, x_identic, gen_outputs, code_real = G(x_real, emb_org, emb_org)  # :265
+    g_loss_id = ops.mse_loss(x_real, x_identic)                                 # :268
+    # both are transposed views of channels-last storage: compare them in that layout (the mean is layout-independent)
+    g_loss_gen = ops.mse_loss(x_convtas.transpose(1, 2), gen_outputs.transpose(1, 2))   # :271
+    code_reconst = G(x_identic, emb_org, None)                                  # :274
+    g_loss_cd = ops.l1_loss(code_real, code_reconst)                            # :275
+    g_loss_SISNR = ops_wav.sisnr_loss(x_identic, x_real)                        # :281-288
+    g_loss = g_loss_id + lambda_SISNR * g_loss_SISNR + g_loss_gen + lambda_cd * g_loss_cd   # :291
+    return g_loss, (g_loss_id, g_loss_gen, g_loss_cd, g_loss_SISNR), (x_convtas, x_identic, gen_outputs, code_real, code_reconst)
+
+
+def train_step_wav(G, optimizer, x_real, emb_org, lambda_cd: float = 1.0, lambda_SISNR: float = 1.0,
+                   reducer: "Optional[GradBucketReducer]" = None, return_outputs: bool = False):
+    """One 'wav' training iteration (solver_encoder.py:264-300).  Returns g_loss and the four terms as floats."""
+    g_loss, terms, outs = generator_losses_wav(G, x_real, emb_org, lambda_cd, lambda_SISNR)
+    optimizer.zero_grad()
+    if reducer is not None:
+        reducer.begin_backward()
+    g_loss.backward()
+    if reducer is not None:
+        reducer.finish()
+    result: Dict[str, object] = {}
+    if return_outputs:
+        result["grads"] = {n: p.grad.detach().clone() for n, p in G.named_parameters()}
+        for k, v in zip(("x_convtas", "x_identic", "gen_outputs", "code_real", "code_reconst"), outs):
+            result[k] = v.detach()
+    optimizer.step()
+    vals = torch.stack([g_loss.detach()] + [t.detach() for t in terms]).tolist()
+    result.update({"g_loss": vals[0], "L_id": vals[1], "L_gen": vals[2], "L_cd": vals[3], "L_SISNR": vals[4]})
+    return result
+
+
 def train_step(G, optimizer, x_real, emb_org, lambda_cd: float = 1.0, reducer: "Optional[GradBucketReducer]" = None,
                return_outputs: bool = False, sync_losses: bool = True):
     """One training iteration (solver_encoder.py:228-300).  Returns the three loss terms the
@@ -307,6 +344,7 @@ def save_checkpoint(G, optimizer, epoch: int, loss: dict, path: str, ema: Option
     The reference stalls the training loop for the device->host copy and the pickling.  Here the step only pays a
     device-side snapshot (one multi-tensor copy, ~0.3 ms for 340 MB of parameters + Adam state); the snapshot goes to pinned
     host memory on a copy stream and a background thread writes the file.  Returns an ``AsyncCheckpoint``."""
+    import copy
     import threading
     if ema is not None:
         model_EMA(G, ema)
@@ -332,11 +370,16 @@ def save_checkpoint(G, optimizer, epoch: int, loss: dict, path: str, ema: Option
     it = iter(host)
 
     def swap(v):
-        return next(it) if (isinstance(v, torch.Tensor) and v.is_cuda) else v
+        # everything the file will hold is detached from the live training state NOW: device tensors through the snapshot,
+        # host tensors (Adam's per-parameter ``step`` counters, which the next optimizer step increments in place while the
+        # writer thread may not have pickled them yet) and plain values by copy
+        if isinstance(v, torch.Tensor):
+            return next(it) if v.is_cuda else v.detach().clone()
+        return copy.deepcopy(v)
     sd_h = type(sd)((k, swap(v)) for k, v in sd.items())
     osd_h = {"state": {k: {kk: swap(vv) for kk, vv in st.items()} for k, st in osd["state"].items()},
-             "param_groups": osd["param_groups"]}
-    state = {"epoch": int(epoch), "state_dict": sd_h, "optimizer": osd_h, "loss": dict(loss)}
+             "param_groups": copy.deepcopy(osd["param_groups"])}
+    state = {"epoch": int(epoch), "state_dict": sd_h, "optimizer": osd_h, "loss": copy.deepcopy(dict(loss))}
 
     def write():
         done.synchronize()

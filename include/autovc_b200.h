@@ -310,6 +310,35 @@ int avc_logmel_frontend(const float* wav, const float* dither, const int* length
                         float* out, int max_frames, void* workspace, size_t workspace_bytes, void* stream);
 size_t avc_logmel_workspace_bytes(int n_utt, int max_len);
 
+/* ---------------------------------------------------------------------------------------
+ * Waveform variant, model_vc_wav.py:11-102 (GeneratorWav, ConvTasNetEncoder / ConvTasNetDecoder) and the 'wav' branch
+ * of the step, solver_encoder.py:264-290.  The convolutions themselves run on avc_gemm_{nt,tn}_taps:
+ *   Conv1d(1 -> N, k = taps*S, stride S) on (B, L)             = taps-tap convolution over the view (B, L/S, S)
+ *   ConvTranspose1d(N -> 1, k = taps*S, stride S)              = its adjoint (the data-gradient form)
+ *   Conv1d / ConvTranspose1d(N -> N, k = 3, s = 1, p = 1)      = 3-tap forms with shift0 = -1
+ * and these entry points supply what sits between them.
+ */
+/* nn.PReLU() (one slope, model_vc_wav.py:24,:46): p = y > 0 ? y : slope[0]*y over (M, C); if chan_stats != NULL
+ * (double[2*C], caller zero-fills) the batch statistics the following BatchNorm1d needs (sum, sum of squares of p). */
+int avc_prelu_fwd(const float* y, const float* slope, float* p, double* chan_stats, int M, int C, void* stream);
+/* dy = dp * (y > 0 ? 1 : slope);  dslope[0] (+)= sum_{y <= 0} dp*y.  scratch: double[1], caller zero-fills. */
+int avc_prelu_bwd(const float* dp, const float* y, const float* slope, float* dy, float* dslope, int accumulate,
+                  double* scratch, size_t n, void* stream);
+/* out[0] (+)= sum of all n elements (gradient of the synthesis layer's single bias).  scratch: double[1], zero-filled. */
+int avc_sum_all(const float* x, size_t n, double* scratch, float* out, int accumulate, void* stream);
+/* dst (nB, Tdst, C) <- src (nB, Tsrc, C): frames t < min(Tsrc, Tdst) copied, remaining frames of dst zero-filled
+ * (brings the L/S waveform blocks and the L/S - taps + 1 frames of the filterbank onto one frame axis). */
+int avc_copy_rows3d(const float* src, int Tsrc, float* dst, int Tdst, int nB, int C, void* stream);
+/* out[b][a][c] = in[a][b][c]: filterbank weight (N, 1, taps*S) <-> packed [tap][N][S]. */
+int avc_permute021(const float* in, float* out, int A, int B, int C, void* stream);
+/* SI-SNR term, solver_encoder.py:276-283, est = x_identic (nB, L), tgt = x_real (nB, L):
+ *   out[0] = -mean_b 10*log10( sum_t scaled^2 / sum_t (est - scaled)^2 ),  scaled = (sum est*tgt) * tgt / (sum tgt^2)
+ * saved: float[4*nB] (dot, energy, numerator, denominator per utterance) for the backward; scratch: double[4*nB], zero-filled.
+ * bwd: dest (+)= gout[0] * d out / d est   (tgt carries no gradient in the reference's step). */
+int avc_sisnr_fwd(const float* est, const float* tgt, int nB, int L, double* scratch, float* saved, float* out, void* stream);
+int avc_sisnr_bwd(const float* est, const float* tgt, const float* saved, const float* gout, int nB, int L,
+                  float* dest, int accumulate, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

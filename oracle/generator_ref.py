@@ -247,7 +247,8 @@ def train_step(sd: Dict[str, Tensor], x_real: Tensor, emb_org: Tensor, dim_neck:
 # reference's own module does (model_vc_mel.py:61,:90,:104), so the timing reflects the
 # reference's CPU path rather than a Python time loop.
 # ----------------------------------------------------------------------------------------
-def build_reference_like_module(dim_neck: int, dim_emb: int, dim_pre: int, freq: int, n_bins: int = 80):
+def build_reference_like_module(dim_neck: int, dim_emb: int, dim_pre: int, freq: int, n_bins: int = 80,
+                                with_postnet: bool = True):
     """An nn.Module tree with the reference's registration order, parameter names and
     initialisers (ConvNorm xavier gains model_vc_mel.py:33-34; LinearNorm :12-14), built
     from torch.nn parts.  ``torch.manual_seed(s)`` before the call reproduces the reference
@@ -300,7 +301,8 @@ def build_reference_like_module(dim_neck: int, dim_emb: int, dim_pre: int, freq:
     class _Gen(nn.Module):
         def __init__(self):
             super().__init__()
-            self.encoder, self.decoder, self.postnet = _Enc(), _Dec(), _Post()
+            self.encoder, self.decoder = _Enc(), _Dec()
+            self.postnet = _Post() if with_postnet else None      # GeneratorWav builds none (model_vc_wav.py:66-73)
             self.dim_neck, self.freq = dim_neck, freq
 
         def _enc(self, x, c):

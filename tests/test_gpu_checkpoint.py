@@ -74,10 +74,12 @@ def test_checkpoint_layout_and_resume(tmp_path):
     opt3 = autovc_b200.FusedAdam(G3.parameters(), 1e-4)
     epoch, loss = solver.load_checkpoint(path, G3, opt3)
     assert epoch == 2 and "G/loss_id" in loss
+    assert all(int(st["step"]) == 2 for st in ck["optimizer"]["state"].values())      # not the live counter of the running loop
     nxt3 = solver.train_step(G3, opt3, x, e)
-    assert abs(nxt[k] - nxt3[k]) <= 1e-6 * abs(nxt[k])
+    for k in ("g_loss", "L_id", "L_id_psnt", "L_cd"):
+        assert abs(nxt[k] - nxt3[k]) <= 1e-6 * abs(nxt[k]), (k, nxt[k], nxt3[k])
     for a, b in zip(G.parameters(), G3.parameters()):
-        assert float((a - b).abs().max()) <= 2e-6 * float(a.abs().max()) + 1e-9
+        assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-9      # a tenth of one Adam step (lr 1e-4)
 
 
 def test_fused_adam_invalidates_packed_weights():
