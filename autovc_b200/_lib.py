@@ -12,7 +12,7 @@ from ctypes import c_double, c_float, c_int, c_size_t, c_ulonglong, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libautovc_b200.so")
 
-PREC_FP32, PREC_BF16, PREC_TF32, PREC_HALF = 0, 1, 2, 3
+PREC_FP32, PREC_BF16, PREC_TF32, PREC_HALF, PREC_FP32X3 = 0, 1, 2, 3, 4
 FMT_FP32, FMT_BF16, FMT_FP16 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 ACT_CODES = {"none": ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH}

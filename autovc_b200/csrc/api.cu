@@ -36,12 +36,22 @@ int lstm_seq_fwd_simt(const float*, const float*, float*, int, float*, float*, i
 int lstm_seq_bwd_simt(const float*, int, const float*, const float*, const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
 size_t lstm_bwd_workspace_simt(int, int, int);
 // tensor-core implementations (tc_gemm.cu)
-int gemm_nt_taps_tc(const void*, int, int, const void*, int, int, const float*, float*, int, int, int, int, int, int, int, double*, int, int, int, void*, size_t, cudaStream_t);
-int gemm_tn_taps_tc(const void*, int, int, const void*, int, int, float*, int, int, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
+int gemm_nt_taps_tc(const void*, int, int, const void*, int, int, const float*, float*, int, int, int, int, int, int, int, double*, int, int, int, void*, size_t, cudaStream_t, int chunk = 0);
+int gemm_tn_taps_tc(const void*, int, int, const void*, int, int, float*, int, int, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t, int chunk = 0);
 size_t gemm_nt_workspace_tc(int, int, int, int, int, int);
 size_t gemm_nt_workspace_h(int, int, int, int, int, int);
 size_t gemm_tn_workspace_h(int, int, int, int, int, int, int);
-size_t gemm_tn_workspace_tc(int, int, int, int, int, int);
+size_t gemm_tn_workspace_tc(int, int, int, int, int, int, int chunk = 0);
+// 3xTF32 (fp32x3.cu)
+int gemm_nt_taps_x3(const float*, int, const float*, const float*, float*, int, int, int, int, int, int, int, double*, int, void*, size_t, cudaStream_t);
+int gemm_tn_taps_x3(const float*, int, const float*, int, float*, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t);
+size_t gemm_nt_workspace_x3(int, int, int, int, int);
+size_t gemm_tn_workspace_x3(int, int, int, int, int);
+int lstm_seq_fwd_x3(const float*, const float*, float*, int, float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
+int lstm_seq_bwd_x3(const float*, int, const float*, const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
+size_t lstm_fwd_workspace_x3(int, int, int);
+size_t lstm_bwd_workspace_x3(int, int, int);
+constexpr int X3_SMALL_H = 64;      // up to here the whole-sequence CUDA-core kernels (W_hh in registers / shared memory) are used
 // persistent tensor-core recurrences (lstm_tc.cu)
 bool lstm_tc_supported(int H);
 void lstm_tc_set_trace(unsigned long long* p);
@@ -70,6 +80,9 @@ extern "C" int avc_gemm_nt_taps(const float* A, int lda, const float* W, const f
   if (prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32)
     return gemm_nt_taps_tc(A, 0, lda, W, 0, K, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate,
                            prec == AVC_PREC_BF16 ? 2 : 4, 1, workspace, workspace_bytes, as_stream(stream));
+  if (prec == AVC_PREC_FP32X3)
+    return gemm_nt_taps_x3(A, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, chan_stats, accumulate, workspace, workspace_bytes,
+                           as_stream(stream));
   set_error("avc_gemm_nt_taps: precision %d not available in this build", prec);
   return AVC_ERR_UNSUPPORTED;
 }
@@ -87,16 +100,21 @@ extern "C" int avc_gemm_tn_taps(const float* dY, int ldy, const float* X, int ld
   if (prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32)
     return gemm_tn_taps_tc(dY, 0, ldy, X, 0, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, accumulate,
                            prec == AVC_PREC_BF16 ? 2 : 4, 1, workspace, workspace_bytes, as_stream(stream));
+  if (prec == AVC_PREC_FP32X3)
+    return gemm_tn_taps_x3(dY, ldy, X, ldx, dW, nB, T, N, K, ntaps, shift0, out_mode, accumulate, workspace, workspace_bytes,
+                           as_stream(stream));
   set_error("avc_gemm_tn_taps: precision %d not available in this build", prec);
   return AVC_ERR_UNSUPPORTED;
 }
 
 extern "C" size_t avc_gemm_tn_workspace_bytes(int nB, int T, int N, int K, int ntaps, int prec) {
+  if (prec == AVC_PREC_FP32X3) return gemm_tn_workspace_x3(nB, T, N, K, ntaps);
   if (prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32) return gemm_tn_workspace_tc(nB, T, N, K, ntaps, prec == AVC_PREC_BF16 ? 2 : 4);
   return gemm_tn_workspace_simt(nB, T, N, K, ntaps);
 }
 
 extern "C" size_t avc_gemm_nt_workspace_bytes(int nB, int T, int N, int K, int ntaps, int prec) {
+  if (prec == AVC_PREC_FP32X3) return gemm_nt_workspace_x3(nB, T, N, K, ntaps);
   if (prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32) return gemm_nt_workspace_tc(nB, T, N, K, ntaps, prec == AVC_PREC_BF16 ? 2 : 4);
   return 0;
 }
@@ -110,13 +128,16 @@ extern "C" int avc_lstm_seq_fwd(const float* P, const float* Whh_p, float* h_seq
     return lstm_seq_tc(false, Whh_p, P, h_seq, ldh, gates, c_seq, nullptr, 0, nullptr, nB, T, H, reverse, workspace,
                        workspace_bytes, as_stream(stream));
   }
-  if (prec == AVC_PREC_FP32 || prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32)
+  if (prec == AVC_PREC_FP32X3 && H > X3_SMALL_H)
+    return lstm_seq_fwd_x3(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, H, reverse, workspace, workspace_bytes, as_stream(stream));
+  if (prec == AVC_PREC_FP32 || prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32 || prec == AVC_PREC_FP32X3)
     return lstm_seq_fwd_simt(P, Whh_p, h_seq, ldh, gates, c_seq, nB, T, H, reverse, as_stream(stream));
   set_error("avc_lstm_seq_fwd: unknown precision %d", prec);
   return AVC_ERR_UNSUPPORTED;
 }
 
 extern "C" size_t avc_lstm_fwd_workspace_bytes(int nB, int T, int H, int prec) {
+  if (prec == AVC_PREC_FP32X3) return H > X3_SMALL_H ? lstm_fwd_workspace_x3(nB, T, H) : 0;
   if ((prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32) && lstm_tc_supported(H)) return lstm_tc_workspace(nB, T, H, false);
   return 0;
 }
@@ -131,7 +152,9 @@ extern "C" int avc_lstm_seq_bwd(const float* dH, int lddh, const float* Whh_p, c
     return lstm_seq_tc(true, Whh_pT, nullptr, nullptr, 0, const_cast<float*>(gates), const_cast<float*>(c_seq), dH, lddh, dP,
                        nB, T, H, reverse, workspace, workspace_bytes, as_stream(stream));
   }
-  if (prec == AVC_PREC_FP32 || prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32)
+  if (prec == AVC_PREC_FP32X3 && H > X3_SMALL_H)
+    return lstm_seq_bwd_x3(dH, lddh, Whh_pT, gates, c_seq, dP, nB, T, H, reverse, workspace, workspace_bytes, as_stream(stream));
+  if (prec == AVC_PREC_FP32 || prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32 || prec == AVC_PREC_FP32X3)
     return lstm_seq_bwd_simt(dH, lddh, Whh_p, Whh_pT, gates, c_seq, dP, nB, T, H, reverse, workspace, workspace_bytes,
                              as_stream(stream));
   set_error("avc_lstm_seq_bwd: unknown precision %d", prec);
@@ -139,6 +162,7 @@ extern "C" int avc_lstm_seq_bwd(const float* dH, int lddh, const float* Whh_p, c
 }
 
 extern "C" size_t avc_lstm_bwd_workspace_bytes(int nB, int T, int H, int prec) {
+  if (prec == AVC_PREC_FP32X3) return H > X3_SMALL_H ? lstm_bwd_workspace_x3(nB, T, H) : lstm_bwd_workspace_simt(nB, T, H);
   if ((prec == AVC_PREC_BF16 || prec == AVC_PREC_TF32) && lstm_tc_supported(H)) return lstm_tc_workspace(nB, T, H, true);
   return lstm_bwd_workspace_simt(nB, T, H);
 }

@@ -96,9 +96,17 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
-template <int MODE, int EB, int BN>
+// CH > 0 ("chunked accumulation", the fp32x3 mode): the reduction of a tile is cut into chunks of CH pipeline stages; every
+// chunk is accumulated in TMEM from zero (the two accumulators alternate per CHUNK instead of per tile) and the epilogue
+// warps add the finished chunks into fp32 registers with round-to-nearest while the next chunk's MMAs run.  tcgen05.mma
+// adds into its accumulator with truncation: over the ~1000 dependent MMAs of a 3xTF32 conv tile that is a systematic
+// 5e-5 relative shrink (measured: 4e-4..7e-4 max-abs on x_identic_psnt, four to seven times the 1e-4 gate); with 32-MMA
+// chains summed in registers it is below the fp32 noise of the reference itself.  Needs BN == 128 (128 accumulator registers
+// per epilogue thread).
+template <int MODE, int EB, int BN, int CH = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  static_assert(CH == 0 || BN == 128, "chunked accumulation keeps the whole tile row in registers: BN must be 128");
   using Cf = TcCfg<BN>;
   constexpr int TC_STAGES = Cf::STAGES, TC_STAGE_BYTES = Cf::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -217,10 +225,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const int rb0 = split * p.rblocks_per_split;
           iters = max(0, min(p.rblocks, rb0 + p.rblocks_per_split) - rb0);
         }
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);      // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        if (CH == 0) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1);      // epilogue has drained this accumulator
+          tc_fence_after();
+        }
+        uint32_t d_tmem = tmem_base + acc * BN;
         for (int it = 0; it < iters; ++it) {
+          const bool chunk_start = CH > 0 && (it % (CH > 0 ? CH : 1)) == 0;
+          const bool chunk_end = CH > 0 && ((it % (CH > 0 ? CH : 1)) == (CH > 0 ? CH : 1) - 1 || it == iters - 1);
+          if (chunk_start) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1);    // epilogue has added this accumulator's previous chunk into its registers
+            tc_fence_after();
+            d_tmem = tmem_base + acc * BN;
+          }
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = stage0 + stage * TC_STAGE_BYTES, sb = sa + TC_STAGE_A;
@@ -240,19 +257,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 da = make_desc(sa + k * Gm::KMMA * 128, Gm::BOX_BYTES, EB == 2 ? 1024 : 512, EB == 2 ? 2 : 1);
                 db = make_desc(sb + k * Gm::KMMA * 128, Gm::BOX_BYTES, EB == 2 ? 1024 : 512, EB == 2 ? 2 : 1);
               }
-              umma<EB>(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+              const bool first = CH > 0 ? (chunk_start && k == 0) : (it == 0 && k == 0);
+              umma<EB>(d_tmem, da, db, idesc, first ? 0u : 1u);
             }
             umma_commit(empty_bar(stage));                // frees the smem slot when these MMAs retire
-            if (it == iters - 1) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+            if (CH > 0 ? chunk_end : (it == iters - 1)) umma_commit(tfull_bar(acc));   // accumulator (chunk) complete -> epilogue
           }
           __syncwarp();
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (chunk_end) {
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          }
         }
         if (iters == 0) {                                 // an empty split still hands its (untouched) accumulator on
+          if (CH > 0) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+            tc_fence_after();
+          }
           if (elect_one()) umma_commit(tfull_bar(acc));
           __syncwarp();
+          if (CH > 0) {
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (CH == 0) {
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
       }
     }
   } else {
@@ -266,6 +296,112 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (MODE == MODE_TN) {
         const int split = tn_decode(tile, p.k_tiles, p.n_tiles, p.ntaps).split;
         has_work = split * p.rblocks_per_split < p.rblocks;
+      }
+      if constexpr (CH > 0) {
+        // ---- chunked accumulation: add every finished chunk into this thread's row of 128 fp32 registers ----
+        int iters = kiters;
+        if (MODE == MODE_TN) {
+          const int split = tn_decode(tile, p.k_tiles, p.n_tiles, p.ntaps).split;
+          const int rb0 = split * p.rblocks_per_split;
+          iters = max(0, min(p.rblocks, rb0 + p.rblocks_per_split) - rb0);
+        }
+        float r[BN];
+#pragma unroll
+        for (int j = 0; j < BN; ++j) r[j] = 0.f;
+        const int nck = iters > 0 ? (iters + CH - 1) / CH : 1;
+#pragma unroll 1
+        for (int ck = 0; ck < nck; ++ck) {
+          mbar_wait(tfull_bar(acc), acc_phase);
+          tc_fence_after();
+          const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+          if (iters > 0) {
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+              float v[32];
+              tmem_ld32(t_addr + c * 32, v);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[c * 32 + j] += v[j];
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (MODE == MODE_NT) {
+          const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+          const int b = m_tile / p.t_tiles, t = (m_tile % p.t_tiles) * TC_BM + row;
+          const bool row_ok = t < p.T;
+          float* crow = p.C + ((size_t)b * p.T + t) * p.ldc;
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) {
+            const int n0 = n_tile * BN + c * 32;
+            if (n0 < p.N) {                      // tile-uniform
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int n = n0 + j;
+                const float x = r[c * 32 + j] + ((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f);
+                v[j] = (row_ok && n < p.N) ? x : 0.f;
+              }
+              if (row_ok) {
+                if (n0 + 32 <= p.N && (p.ldc & 3) == 0 && (((uintptr_t)p.C & 15) == 0)) {
+#pragma unroll
+                  for (int j = 0; j < 32; j += 4) {
+                    float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    float4* dst = reinterpret_cast<float4*>(crow + n0 + j);
+                    if (p.accumulate) {
+                      const float4 old = *dst;
+                      o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                    }
+                    *dst = o;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (n0 + j < p.N) crow[n0 + j] = p.accumulate ? crow[n0 + j] + v[j] : v[j];
+                }
+              }
+              if (p.stats != nullptr) {
+                float sq[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+                const float s1 = warp_colsum32(v, lane);
+                const float s2 = warp_colsum32(sq, lane);
+                stat_s[(q * 2 + 0) * BN + c * 32 + lane] = s1;
+                stat_s[(q * 2 + 1) * BN + c * 32 + lane] = s2;
+              }
+            }
+          }
+          if (p.stats != nullptr) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps
+            const int col = threadIdx.x - 64;
+            const int n = n_tile * BN + col;
+            if (n < p.N) {
+              double a = 0.0, bq = 0.0;
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                a += (double)stat_s[(w * 2 + 0) * BN + col];
+                bq += (double)stat_s[(w * 2 + 1) * BN + col];
+              }
+              atomicAdd(p.stats + n, a);
+              atomicAdd(p.stats + p.N + n, bq);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
+        } else {
+          const TnItem wi = tn_decode(tile, p.k_tiles, p.n_tiles, p.ntaps);
+          const int n = wi.n_tile * TC_BM + row;
+          float* orow = p.part + (((size_t)wi.split * p.ntaps + wi.tap) * p.N + n) * p.K;
+          if (n < p.N) {
+#pragma unroll
+            for (int j = 0; j < BN; ++j) {
+              const int k = wi.k_tile * BN + j;
+              if (k < p.K) orow[k] = r[j];
+            }
+          }
+        }
+        continue;
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -968,10 +1104,11 @@ struct AttrOnce {
   }
 };
 
-template <int MODE, int EB, int BN>
+constexpr int TC_X3_CHUNK = 8;      // pipeline stages (of 4 MMAs) per TMEM accumulation chunk of the fp32x3 mode
+template <int MODE, int EB, int BN, int CH = 0>
 static int tc_launch(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int grid, cudaStream_t st) {
   static AttrOnce attr;
-  auto kern = tc_gemm_kernel<MODE, EB, BN>;
+  auto kern = tc_gemm_kernel<MODE, EB, BN, CH>;
   if (int rc = attr.ensure(kern, TcCfg<BN>::SMEM_BYTES)) return rc;
   kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(mA, mB, p);
   AVC_LAUNCHED();
@@ -1005,7 +1142,15 @@ static int tc2_tn_launch(const CUtensorMap& mA, const CUtensorMap& mB, const TcP
   return AVC_OK;
 }
 template <int MODE>
-static int tc_dispatch(int eb, int bn, const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int grid, cudaStream_t st) {
+static int tc_dispatch(int eb, int bn, const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int grid, cudaStream_t st,
+                       int chunk = 0) {
+  if (chunk) {
+    if (eb != 4 || bn != 128) {
+      set_error("tc_gemm: chunked accumulation needs tf32 operands and 128-wide tiles");
+      return AVC_ERR_UNSUPPORTED;
+    }
+    return tc_launch<MODE, 4, 128, TC_X3_CHUNK>(mA, mB, p, grid, st);
+  }
   if (eb == 2) return bn == 256 ? tc_launch<MODE, 2, 256>(mA, mB, p, grid, st) : tc_launch<MODE, 2, 128>(mA, mB, p, grid, st);
   return bn == 256 ? tc_launch<MODE, 4, 256>(mA, mB, p, grid, st) : tc_launch<MODE, 4, 128>(mA, mB, p, grid, st);
 }
@@ -1048,10 +1193,11 @@ struct NtPlan {
   bool stageA, stageW;
   size_t offA, offW, total;
 };
-static NtPlan nt_plan(const void* A, int a_fmt, int lda, const void* W, int w_fmt, int nB, int T, int N, int K, int ntaps, int eb) {
+static NtPlan nt_plan(const void* A, int a_fmt, int lda, const void* W, int w_fmt, int nB, int T, int N, int K, int ntaps, int eb,
+                      int chunk = 0) {
   NtPlan pl;
   const int row = 128 / eb;
-  pl.bn = pick_bn(nB * ceil_div(T, TC_BM), N);
+  pl.bn = chunk ? 128 : pick_bn(nB * ceil_div(T, TC_BM), N);
   pl.Kp = round_up(K, row);
   pl.Np = round_up(N, pl.bn);
   pl.stageA = a_fmt == 0 && (eb == 2 || !direct_ok(A, lda));     // 16-bit operands are always read in place
@@ -1074,7 +1220,7 @@ size_t gemm_nt_workspace_tc(int nB, int T, int N, int K, int ntaps, int eb) {
 // a 16-bit A must then have the same format, an fp32 A is staged to it).
 int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const void* Wv, int w_fmt, int ldw, const float* bias, float* C, int ldc,
                     int nB, int T, int N, int K, int ntaps, int shift0, double* stats, int accumulate, int eb, int half_fmt, void* ws,
-                    size_t ws_bytes, cudaStream_t st) {
+                    size_t ws_bytes, cudaStream_t st, int chunk) {
   const float* A = (const float*)Av;
   const float* W = (const float*)Wv;
   if (a_fmt != 0 && (eb != 2 || !direct16_ok(Av, lda))) {
@@ -1096,7 +1242,7 @@ int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const void* Wv, int w_fm
     set_error("avc_gemm_nt_taps: chan_stats and accumulate are mutually exclusive");
     return AVC_ERR_UNSUPPORTED;
   }
-  const NtPlan pl = nt_plan(Av, a_fmt, lda, Wv, w_fmt, nB, T, N, K, ntaps, eb);
+  const NtPlan pl = nt_plan(Av, a_fmt, lda, Wv, w_fmt, nB, T, N, K, ntaps, eb, chunk);
   if (pl.total > 0 && (!ws || ws_bytes < pl.total)) {
     set_error("avc_gemm_nt_taps(tensor): workspace %zu < %zu", ws_bytes, pl.total);
     return AVC_ERR_WORKSPACE;
@@ -1123,7 +1269,7 @@ int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const void* Wv, int w_fm
     Wop = dst; w_k = pl.Kp; w_n = pl.Np; w_ld = pl.Kp;
   }
   CUtensorMap mA, mB;
-  const bool pairs = pl.bn == 256 && use_cta_pairs();
+  const bool pairs = !chunk && pl.bn == 256 && use_cta_pairs();
   rc = make_map3(&mA, Aop, a_k, T, nB, a_ld, (uint64_t)T * a_ld, row, TC_BM, eb, false, fa);
   if (rc) return rc;
   rc = make_map3(&mB, Wop, w_k, w_n, ntaps, w_ld, w_n * w_ld, row, pairs ? 128 : pl.bn, eb, false, fw);
@@ -1150,7 +1296,7 @@ int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const void* Wv, int w_fm
   p.idesc = eb == 2 ? make_idesc(TC_BM, pl.bn, 0, 0, ifmt_of(fa), ifmt_of(fw)) : make_idesc(TC_BM, pl.bn, 0, 0, 2);
   const int tiles = nB * p.t_tiles * p.n_tiles;
   const int grid = std::min(tiles, num_sms());
-  return tc_dispatch<MODE_NT>(eb, pl.bn, mA, mB, p, grid, st);
+  return tc_dispatch<MODE_NT>(eb, pl.bn, mA, mB, p, grid, st, chunk);
 }
 
 // ---- TN -------------------------------------------------------------------------------------------
@@ -1177,10 +1323,11 @@ struct TnPlan {
   int Np, Kp, rs, rblocks, tiles, splits, rps, bn;
   size_t off_y, off_x, off_part, total;
 };
-static TnPlan tn_plan(int nB, int T, int N, int K, int ntaps, int eb, bool stage_y, bool stage_x) {
+static TnPlan tn_plan(int nB, int T, int N, int K, int ntaps, int eb, bool stage_y, bool stage_x, int chunk = 0) {
   TnPlan pl;
   pl.bn = (K % 256 == 0 || K > 640) ? 256 : 128;
-  {
+  if (chunk) pl.bn = 128;
+  else {
     const char* e = getenv("AVC_GEMM_BN");
     if (e && (atoi(e) == 128 || atoi(e) == 256)) pl.bn = atoi(e);
   }
@@ -1198,8 +1345,8 @@ static TnPlan tn_plan(int nB, int T, int N, int K, int ntaps, int eb, bool stage
   pl.total = pl.off_part + align256((size_t)pl.splits * ntaps * N * K * 4);
   return pl;
 }
-size_t gemm_tn_workspace_tc(int nB, int T, int N, int K, int ntaps, int eb) {
-  return tn_plan(nB, T, N, K, ntaps, eb, true, true).total;
+size_t gemm_tn_workspace_tc(int nB, int T, int N, int K, int ntaps, int eb, int chunk) {
+  return tn_plan(nB, T, N, K, ntaps, eb, true, true, chunk).total;
 }
 size_t gemm_tn_workspace_h(int nB, int T, int N, int K, int ntaps, int y_fmt, int x_fmt) {
   return tn_plan(nB, T, N, K, ntaps, 2, y_fmt == 0, x_fmt == 0).total;
@@ -1214,7 +1361,7 @@ int launch_wgrad_reduce(const float* part, float* dW, int N, int K, int ntaps, i
 
 int gemm_tn_taps_tc(const void* dYv, int y_fmt, int ldy, const void* Xv, int x_fmt, int ldx, float* dW, int nB, int T, int N, int K,
                     int ntaps, int shift0, int out_mode, int accumulate, int eb, int half_fmt, void* ws, size_t ws_bytes,
-                    cudaStream_t st) {
+                    cudaStream_t st, int chunk) {
   const float* dY = (const float*)dYv;
   const float* X = (const float*)Xv;
   if ((y_fmt != 0 && (eb != 2 || !direct16_ok(dYv, ldy))) || (x_fmt != 0 && (eb != 2 || !direct16_ok(Xv, ldx)))) {
@@ -1228,7 +1375,7 @@ int gemm_tn_taps_tc(const void* dYv, int y_fmt, int ldy, const void* Xv, int x_f
     set_error("avc_gemm_tn_taps_h: both operands must have the same 16-bit format");
     return AVC_ERR_UNSUPPORTED;
   }
-  const TnPlan pl = tn_plan(nB, T, N, K, ntaps, eb, stage_y, stage_x);
+  const TnPlan pl = tn_plan(nB, T, N, K, ntaps, eb, stage_y, stage_x, chunk);
   if (!ws || ws_bytes < pl.total) {
     set_error("avc_gemm_tn_taps(tensor): workspace %zu < %zu", ws_bytes, pl.total);
     return AVC_ERR_WORKSPACE;
@@ -1261,7 +1408,7 @@ int gemm_tn_taps_tc(const void* dYv, int y_fmt, int ldy, const void* Xv, int x_f
   else rc = make_map3(&mA, Yop, y_c, T, nB, y_ld, (uint64_t)T * y_ld, row, pl.rs, eb, eb == 4, fy);
   if (rc) return rc;
   // CTA pairs (256 dY channels x 256 X channels per pair tile): whole grouped boxes and an even number of dY tiles
-  const bool pairs = use_cta_pairs() && pl.bn == 256 && ga && gb && ((pl.Np / TC_BM) % 2 == 0);
+  const bool pairs = !chunk && use_cta_pairs() && pl.bn == 256 && ga && gb && ((pl.Np / TC_BM) % 2 == 0);
   if (gb) rc = make_map4_grouped(&mB, Xop, x_c, T, nB, x_ld, row, pl.rs, (pairs ? 128 : pl.bn) / row, eb, eb == 4, fx);
   else rc = make_map3(&mB, Xop, x_c, T, nB, x_ld, (uint64_t)T * x_ld, row, pl.rs, eb, eb == 4, fx);
   if (rc) return rc;
@@ -1278,7 +1425,7 @@ int gemm_tn_taps_tc(const void* dYv, int y_fmt, int ldy, const void* Xv, int x_f
     rc = eb == 2 ? tc2_tn_launch<2>(mA, mB, p, grid2, st) : tc2_tn_launch<4>(mA, mB, p, grid2, st);
   } else {
     const int grid = std::min(items, num_sms());
-    rc = tc_dispatch<MODE_TN>(eb, pl.bn, mA, mB, p, grid, st);
+    rc = tc_dispatch<MODE_TN>(eb, pl.bn, mA, mB, p, grid, st, chunk);
   }
   if (rc) return rc;
   return launch_wgrad_reduce(part, dW, N, K, ntaps, pl.splits, out_mode, accumulate, st);

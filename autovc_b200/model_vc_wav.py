@@ -11,8 +11,8 @@ Return contract of ``forward(x, c_org, c_trg)`` (model_vc_wav.py:74-102): ``x`` 
 concatenated codes; otherwise ``(x_CTencoder (B,512,T), x_identic (B,L,1), x_decoder (B,512,T), code_real)``.  The two
 (B,512,T) tensors are transposed *views* of channels-last storage.
 
-Precision: the filterbank and k=3 layers run fp32 (CUDA cores) in ``fp32`` mode and tf32 on the tensor cores in ``tf32`` /
-``half`` mode; the AutoVC encoder / decoder in between follow the mode like the mel model.
+Precision: the filterbank and k=3 layers run as 3xTF32 split products in ``fp32`` mode (CUDA-core fp32 in ``fp32_simt``)
+and as plain tf32 on the tensor cores in ``tf32`` / ``half`` mode; the AutoVC encoder / decoder in between follow the mode like the mel model.
 """
 from __future__ import annotations
 
@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import ops, ops_wav
-from ._lib import PREC_FP32, PREC_TF32
+from ._lib import PREC_FP32, PREC_FP32X3, PREC_TF32
 from .model_vc_mel import _PREC, ConvNorm, Decoder, Encoder, LinearNorm, _default_precision
 
 _N, _L, _S = 512, 1024, 256          # model_vc_wav.py:14-16 / :38-40
@@ -108,7 +108,7 @@ class GeneratorWav(nn.Module):
         for m in (self.encoder, self.decoder, self.decoder.linear_projection):
             m.prec = _PREC[precision]
         for m in (self.tasEncoder, self.tasDecoder):
-            m.prec = PREC_FP32 if precision == "fp32" else PREC_TF32
+            m.prec = {"fp32": PREC_FP32X3, "fp32_simt": PREC_FP32}.get(precision, PREC_TF32)
         return self
 
     def forward(self, x, c_org, c_trg):

@@ -133,7 +133,7 @@ def _wgrad_side(allowed: bool, device, reads: Sequence[Optional[torch.Tensor]], 
 # --------------------------------------------------------------------------------------
 def gemm_nt_taps(A, lda, W, bias, C, ldc, nB, T, N, K, ntaps, shift0, stats=None, accumulate=False, prec=PREC_FP32):
     nbytes = query("avc_gemm_nt_workspace_bytes", nB, T, N, K, ntaps, prec) if prec != PREC_FP32 else 0
-    ws = _ws(nbytes, A.device)
+    ws = _ws(nbytes, C.device)
     call("avc_gemm_nt_taps", _p(A), lda, _p(W), _p(bias), _p(C), ldc, nB, T, N, K, ntaps, shift0, _p(stats),
          int(accumulate), prec, _p(ws), nbytes, _stream())
 

@@ -12,7 +12,7 @@ Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for the definition 
 
 Secondary legs (not the driver's default): --workload frontend | convert (BASELINE.json configs[4], 4096 x 10 s utterances),
 --workload loader | dvector (the rows SURVEY 8(f) marks "next"); --n-bins 513 (configs[3]); --dim-neck 32 --freq 32 --batch 128
---len-crop 256 (configs[2]); --precision fp32 | tf32 | half.
+--len-crop 256 (configs[2]); --precision fp32 (3xTF32 on the tensor cores) | fp32_simt (CUDA cores) | tf32 | half.
 """
 from __future__ import annotations
 
@@ -372,10 +372,11 @@ def run_ours(args):
     # ---- the other precision modes of the same module, same process, same inputs (N=1 only: keeps the scaling runs short)
     modes = {args.precision: {"ms_per_step": ms, "value": B * world / (ms * 1e-3), "steps": args.steps}}
     if world == 1 and args.modes:
-        for mode in [m for m in ("tf32", "fp32", "half") if m != args.precision]:
+        for mode in [m for m in ("tf32", "fp32", "fp32_simt", "half") if m != args.precision]:
             G.set_precision(mode)
-            k = args.steps if mode != "fp32" else max(2, min(args.steps, 5))
-            for _ in range(3 if mode != "fp32" else 2):
+            slow = mode == "fp32_simt"          # CUDA-core cross-check of the parity mode: ~0.5 s per step
+            k = args.steps if not slow else max(2, min(args.steps, 3))
+            for _ in range(3 if not slow else 1):
                 step_resident()
             ms_m = timed(step_resident, k)
             modes[mode] = {"ms_per_step": ms_m, "value": B / (ms_m * 1e-3), "steps": k}
@@ -551,7 +552,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
     ap.add_argument("--sustained", type=int, default=300, help="extra timed leg of this many steps with its own clock trace (0: off)")
     ap.add_argument("--no-modes", dest="modes", action="store_false", help="skip the tf32 / fp32 legs of the `modes` key")
-    ap.add_argument("--precision", default=os.environ.get("AUTOVC_B200_PRECISION", "half"), choices=["fp32", "tf32", "half"])
+    ap.add_argument("--precision", default=os.environ.get("AUTOVC_B200_PRECISION", "half"), choices=["fp32", "fp32_simt", "tf32", "half"])
     ap.add_argument("--batch", type=int, default=256, help="crops per GPU")
     ap.add_argument("--len-crop", dest="len_crop", type=int, default=128)
     ap.add_argument("--dim-neck", dest="dim_neck", type=int, default=16)

@@ -20,7 +20,11 @@
  *   - `prec`: AVC_PREC_FP32 = CUDA-core FFMA, fp32 operands and accumulation (parity mode,
  *     <=1e-4 of the reference's fp32 path); AVC_PREC_BF16 / AVC_PREC_TF32 = tcgen05/TMEM tensor-core
  *     path with bf16 operands, or fp32 operands fetched by TMA as tf32 (no staging copies); fp32
- *     accumulation, fp32 statistics and fp32 recurrent state in both.
+ *     accumulation, fp32 statistics and fp32 recurrent state in both.  AVC_PREC_FP32X3 = fp32-accurate
+ *     products on the tensor cores: every fp32 operand is split into a tf32 head and an fp32 remainder and
+ *     a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi runs as ONE kind::tf32 GEMM over a three times longer
+ *     reduction (operands staged in `workspace`); recurrences with H > 64 become one such GEMM per time step.
+ *     Same <=1e-4 gate as AVC_PREC_FP32, measured at ~3e-5.
  */
 #ifndef AUTOVC_B200_H_
 #define AUTOVC_B200_H_
@@ -37,7 +41,7 @@ extern "C" {
 
 #define AVC_VERSION 100
 
-enum { AVC_PREC_FP32 = 0, AVC_PREC_BF16 = 1, AVC_PREC_TF32 = 2, AVC_PREC_HALF = 3 };
+enum { AVC_PREC_FP32 = 0, AVC_PREC_BF16 = 1, AVC_PREC_TF32 = 2, AVC_PREC_HALF = 3, AVC_PREC_FP32X3 = 4 };
 /* operand formats of the *_h entry points */
 enum { AVC_FMT_FP32 = 0, AVC_FMT_BF16 = 1, AVC_FMT_FP16 = 2 };
 enum { AVC_ACT_NONE = 0, AVC_ACT_RELU = 1, AVC_ACT_TANH = 2 };

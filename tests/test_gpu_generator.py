@@ -33,8 +33,12 @@ def _build(name):
 
 
 @pytest.mark.parametrize("name", ["train_16_16_b2_t128", "train_32_32_b3_t64", "train_stft_16_16_b2_t32"])
-def test_train_step_matches_reference_golden(name):
+@pytest.mark.parametrize("precision", ["fp32", "fp32_simt"])
+def test_train_step_matches_reference_golden(name, precision):
+    """Both implementations of the fp32 parity mode: 3xTF32 split products on the tensor cores ("fp32", the default) and
+    CUDA-core FFMA ("fp32_simt")."""
     g, G, (dim_neck, freq, B, T, n_bins, iseed) = _build(name)
+    G.set_precision(precision)
     x, e, _ = synth_inputs(B, T, n_bins, 256, iseed)
     x, e = x.cuda(), e.cuda()
     G.train()

@@ -8,7 +8,14 @@ pytestmark = pytest.mark.gpu
 
 if torch.cuda.is_available():
     from autovc_b200 import ops
-    from autovc_b200._lib import ACT_CODES, PREC_FP32
+    from autovc_b200._lib import ACT_CODES, PREC_FP32, PREC_FP32X3
+
+# both implementations of the fp32 parity contract: CUDA-core FFMA ("simt") and 3xTF32 split products on the tensor cores ("x3")
+FP32_IMPLS = ["simt", "x3"]
+
+
+def _prec(impl):
+    return PREC_FP32 if impl == "simt" else PREC_FP32X3
 
 DEV = "cuda"
 
@@ -20,7 +27,8 @@ def _rand(*shape, seed=0, scale=1.0):
 
 @pytest.mark.parametrize("B,T,Cin,Cout", [(3, 32, 24, 40), (2, 128, 336, 512), (2, 48, 769, 130), (1, 5, 8, 8)])
 @pytest.mark.parametrize("act", ["relu", "tanh", "none"])
-def test_conv_bn_act_fwd_bwd(B, T, Cin, Cout, act):
+@pytest.mark.parametrize("impl", FP32_IMPLS)
+def test_conv_bn_act_fwd_bwd(B, T, Cin, Cout, act, impl):
     x = _rand(B, T, Cin, seed=1).requires_grad_(True)
     conv = torch.nn.Conv1d(Cin, Cout, 5, padding=2).to(DEV)
     bn = torch.nn.BatchNorm1d(Cout).to(DEV)
@@ -31,7 +39,7 @@ def test_conv_bn_act_fwd_bwd(B, T, Cin, Cout, act):
     bn_ref.load_state_dict(bn.state_dict())
     res = _rand(B, T, Cout, seed=5).requires_grad_(True) if act == "none" else None
     z = ops.ConvBnAct.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, res,
-                            ACT_CODES[act], True, PREC_FP32)
+                            ACT_CODES[act], True, _prec(impl))
     go = _rand(B, T, Cout, seed=2)
     gx, gw, gb, gg, gbeta = torch.autograd.grad(z, [x, conv.weight, conv.bias, bn.weight, bn.bias], go,
                                                 retain_graph=res is not None)
@@ -64,8 +72,9 @@ def test_conv_bn_act_fwd_bwd(B, T, Cin, Cout, act):
 
 
 @pytest.mark.parametrize("B,T,I,H,bidir", [(5, 24, 40, 16, True), (3, 16, 32, 32, True), (4, 12, 48, 128, False),
-                                           (130, 6, 20, 72, False), (2, 9, 12, 20, True)])
-def test_lstm_layer_fwd_bwd(B, T, I, H, bidir):
+                                           (130, 6, 20, 72, False), (2, 9, 12, 20, True), (260, 7, 36, 256, False)])
+@pytest.mark.parametrize("impl", FP32_IMPLS)
+def test_lstm_layer_fwd_bwd(B, T, I, H, bidir, impl):
     torch.manual_seed(3)
     lstm = torch.nn.LSTM(I, H, 1, batch_first=True, bidirectional=bidir).to(DEV)
     x = _rand(B, T, I, seed=4).requires_grad_(True)
@@ -73,7 +82,7 @@ def test_lstm_layer_fwd_bwd(B, T, I, H, bidir):
     ws = [getattr(lstm, n) for n in names]
     if bidir:
         ws += [getattr(lstm, n + "_reverse") for n in names]
-    out = ops.LstmLayer.apply(x, PREC_FP32, *ws)
+    out = ops.LstmLayer.apply(x, _prec(impl), *ws)
     go = _rand(*out.shape, seed=6)
     grads = torch.autograd.grad(out, [x] + ws, go)
     ref = torch.nn.LSTM(I, H, 1, batch_first=True, bidirectional=bidir).to(DEV).double()
@@ -88,11 +97,12 @@ def test_lstm_layer_fwd_bwd(B, T, I, H, bidir):
         torch.testing.assert_close(a.double(), b, rtol=2e-4, atol=2e-5 * max(1.0, float(b.abs().max())))
 
 
-def test_linear_and_glue_and_losses():
+@pytest.mark.parametrize("impl", FP32_IMPLS)
+def test_linear_and_glue_and_losses(impl):
     B, T, K, N = 3, 20, 64, 80
     x = _rand(B, T, K, seed=1).requires_grad_(True)
     lin = torch.nn.Linear(K, N).to(DEV)
-    y = ops.Linear.apply(x, lin.weight, lin.bias, PREC_FP32)
+    y = ops.Linear.apply(x, lin.weight, lin.bias, _prec(impl))
     go = _rand(B, T, N, seed=2)
     g = torch.autograd.grad(y, [x, lin.weight, lin.bias], go)
     xr = x.detach().double().requires_grad_(True)
