@@ -36,7 +36,8 @@ int lstm_seq_fwd_simt(const float*, const float*, float*, int, float*, float*, i
 int lstm_seq_bwd_simt(const float*, int, const float*, const float*, const float*, const float*, float*, int, int, int, int, void*, size_t, cudaStream_t);
 size_t lstm_bwd_workspace_simt(int, int, int);
 // tensor-core implementations (tc_gemm.cu)
-int gemm_nt_taps_tc(const void*, int, int, const void*, int, int, const float*, float*, int, int, int, int, int, int, int, double*, int, int, int, void*, size_t, cudaStream_t, int chunk = 0);
+int gemm_nt_taps_tc(const void*, int, int, const void*, int, int, const float*, float*, int, int, int, int, int, int, int, double*, int, int, int, void*, size_t, cudaStream_t, int chunk = 0,
+                    int ksplit = 1, size_t c_split_stride = 0);
 int gemm_tn_taps_tc(const void*, int, int, const void*, int, int, float*, int, int, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t, int chunk = 0);
 size_t gemm_nt_workspace_tc(int, int, int, int, int, int);
 size_t gemm_nt_workspace_h(int, int, int, int, int, int);

@@ -16,7 +16,8 @@
 
 namespace avc {
 
-int gemm_nt_taps_tc(const void*, int, int, const void*, int, int, const float*, float*, int, int, int, int, int, int, int, double*, int, int, int, void*, size_t, cudaStream_t, int chunk = 0);
+int gemm_nt_taps_tc(const void*, int, int, const void*, int, int, const float*, float*, int, int, int, int, int, int, int, double*, int, int, int, void*, size_t, cudaStream_t, int chunk = 0,
+                    int ksplit = 1, size_t c_split_stride = 0);
 int gemm_tn_taps_tc(const void*, int, int, const void*, int, int, float*, int, int, int, int, int, int, int, int, int, int, void*, size_t, cudaStream_t, int chunk = 0);
 size_t gemm_tn_workspace_tc(int, int, int, int, int, int, int chunk = 0);
 
@@ -117,40 +118,63 @@ int gemm_tn_taps_x3(const float* dY, int ldy, const float* X, int ldx, float* dW
 }
 
 // ---- recurrences (H > 64) ----------------------------------------------------------------------------------------
-// gate algebra of one forward step: pre = P[b, t, :] (+ R[b, :]), rows gate-interleaved (u*4 + g)
+// Per time step: ONE chunked tensor-core GEMM (the step's B x K' operand against the pre-split W_hh; the reduction is cut into
+// `ksplit` work items so that ~all SMs take part: B = 256 rows are only two 128-row tiles) and ONE gate kernel that sums the
+// partial products, applies the cell algebra and writes the NEXT step's split operand [hi | hi | lo] in place.
+struct X3Split { int tiles, ksplit; };
+static X3Split x3_split(int rows, int N, int Kp) {
+  X3Split r;
+  r.tiles = ceil_div(rows, 128) * ceil_div(N, 128);
+  const int kiters = Kp / 32;
+  r.ksplit = std::max(1, std::min(num_sms() / std::max(1, r.tiles), kiters / 8));
+  return r;
+}
+
+// gate algebra of one forward step: pre = P[b, t, :] + sum_s R[s][b, :], rows gate-interleaved (u*4 + g);
+// A3 (nB x Kp): the split of h_t for the next step's GEMM
 __global__ void __launch_bounds__(256)
-lstm_gate_fwd_kernel(const float* __restrict__ P, const float* __restrict__ R, float* __restrict__ h_seq, int ldh,
-                     float* __restrict__ gates, float* __restrict__ c_seq, int nB, int T, int H, int t, int t_prev) {
+lstm_gate_fwd_kernel(const float* __restrict__ P, const float* __restrict__ R, int nsplit, float* __restrict__ h_seq, int ldh,
+                     float* __restrict__ gates, float* __restrict__ c_seq, float* __restrict__ A3, int Kp, int nB, int T, int H,
+                     int t, int t_prev) {
   const int G = 4 * H;
   const size_t total = (size_t)nB * H;
+  const size_t rs = (size_t)nB * G;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / H), u = (int)(i - (size_t)b * H);
     const size_t row = (size_t)b * T + t;
     float4 p = *reinterpret_cast<const float4*>(P + row * G + 4 * u);
-    if (R) {
-      const float4 r = *reinterpret_cast<const float4*>(R + (size_t)b * G + 4 * u);
+    for (int s = 0; s < nsplit; ++s) {
+      const float4 r = *reinterpret_cast<const float4*>(R + s * rs + (size_t)b * G + 4 * u);
       p.x += r.x; p.y += r.y; p.z += r.z; p.w += r.w;
     }
     const float gi = sigmoidf_acc(p.x), gf = sigmoidf_acc(p.y), gg = tanhf(p.z), go = sigmoidf_acc(p.w);
     const float cp = (t_prev >= 0) ? c_seq[((size_t)b * T + t_prev) * H + u] : 0.f;
     const float c = gf * cp + gi * gg;
+    const float h = go * tanhf(c);
     *reinterpret_cast<float4*>(gates + row * G + 4 * u) = make_float4(gi, gf, gg, go);
     c_seq[row * H + u] = c;
-    h_seq[row * ldh + u] = go * tanhf(c);
+    h_seq[row * ldh + u] = h;
+    const float hi = tf32_hi(h);
+    float* a = A3 + (size_t)b * Kp;
+    a[u] = hi;
+    a[H + u] = hi;
+    a[2 * H + u] = h - hi;
   }
 }
 
-// gate algebra of one BPTT step: dh = dH[b, t, :] (+ R[b, :] = dG_{t_next} W_hh)
+// gate algebra of one BPTT step: dh = dH[b, t, :] + sum_s R[s][b, :] (= dG_{t_next} W_hh); A3 (nB x Kp): the split of dG_t
 __global__ void __launch_bounds__(256)
-lstm_gate_bwd_kernel(const float* __restrict__ dH, int lddh, const float* __restrict__ R, const float* __restrict__ gates,
-                     const float* __restrict__ c_seq, float* __restrict__ dP, float* __restrict__ dc_rec, int nB, int T, int H,
-                     int t, int t_next, int t_prev) {
+lstm_gate_bwd_kernel(const float* __restrict__ dH, int lddh, const float* __restrict__ R, int nsplit, const float* __restrict__ gates,
+                     const float* __restrict__ c_seq, float* __restrict__ dP, float* __restrict__ dc_rec, float* __restrict__ A3,
+                     int Kp, int nB, int T, int H, int t, int t_next, int t_prev) {
   const int G = 4 * H;
   const size_t total = (size_t)nB * H;
+  const size_t rs = (size_t)nB * H;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / H), u = (int)(i - (size_t)b * H);
     const size_t row = (size_t)b * T + t;
-    const float dh = dH[row * lddh + u] + (R ? R[(size_t)b * H + u] : 0.f);
+    float dh = dH[row * lddh + u];
+    for (int s = 0; s < nsplit; ++s) dh += R[s * rs + (size_t)b * H + u];
     const float4 a = *reinterpret_cast<const float4*>(gates + row * G + 4 * u);
     const float ct = c_seq[row * H + u];
     const float cp = (t_prev >= 0) ? c_seq[((size_t)b * T + t_prev) * H + u] : 0.f;
@@ -163,15 +187,21 @@ lstm_gate_bwd_kernel(const float* __restrict__ dH, int lddh, const float* __rest
     d.w = dh * tc * a.w * (1.f - a.w);
     dc_rec[(size_t)b * H + u] = dc * a.y;
     *reinterpret_cast<float4*>(dP + row * G + 4 * u) = d;
+    const float4 hi = make_float4(tf32_hi(d.x), tf32_hi(d.y), tf32_hi(d.z), tf32_hi(d.w));
+    float* q = A3 + (size_t)b * Kp + 4 * u;
+    *reinterpret_cast<float4*>(q) = hi;
+    *reinterpret_cast<float4*>(q + G) = hi;
+    *reinterpret_cast<float4*>(q + 2 * G) = make_float4(d.x - hi.x, d.y - hi.y, d.z - hi.z, d.w - hi.w);
   }
 }
 
 static int gate_blocks(size_t total) { return (int)std::min<size_t>(ceil_div(total, (size_t)256), (size_t)num_sms() * 8); }
 
-// forward: W3 (4H x Kp, Kp = 3H rounded to 32), A3 (nB x Kp), R (nB x 4H)
+// forward: W3 (4H x Kp, Kp = 3H rounded to 32), A3 (nB x Kp), R (ksplit x nB x 4H)
 size_t lstm_fwd_workspace_x3(int nB, int T, int H) {
   const int Kp = round_up_i(3 * H, 32);
-  return align256x((size_t)4 * H * Kp * 4) + align256x((size_t)nB * Kp * 4) + align256x((size_t)nB * 4 * H * 4);
+  const int S = x3_split(nB, 4 * H, Kp).ksplit;
+  return align256x((size_t)4 * H * Kp * 4) + align256x((size_t)nB * Kp * 4) + align256x((size_t)S * nB * 4 * H * 4);
 }
 
 int lstm_seq_fwd_x3(const float* P, const float* Whh_p, float* h_seq, int ldh, float* gates, float* c_seq, int nB, int T, int H,
@@ -185,31 +215,34 @@ int lstm_seq_fwd_x3(const float* P, const float* Whh_p, float* h_seq, int ldh, f
     return AVC_ERR_WORKSPACE;
   }
   const int G = 4 * H, Kp = round_up_i(3 * H, 32);
+  const int S = x3_split(nB, G, Kp).ksplit;
   float* W3 = (float*)ws;
   float* A3 = (float*)((uint8_t*)ws + align256x((size_t)G * Kp * 4));
   float* R = (float*)((uint8_t*)A3 + align256x((size_t)nB * Kp * 4));
   split3_k_kernel<<<split_blocks(G), 256, 0, st>>>(Whh_p, (size_t)H, W3, Kp, (size_t)G, H, 1);
   AVC_LAUNCHED();
+  AVC_CUDA(cudaMemsetAsync(A3, 0, (size_t)nB * Kp * 4, st));          // the K padding columns stay zero
   for (int step = 0; step < T; ++step) {
     const int t = reverse ? T - 1 - step : step;
     const int t_prev = step == 0 ? -1 : (reverse ? t + 1 : t - 1);
     if (t_prev >= 0) {
-      split3_k_kernel<<<split_blocks(nB), 256, 0, st>>>(h_seq + (size_t)t_prev * ldh, (size_t)T * ldh, A3, Kp, (size_t)nB, H, 0);
-      AVC_LAUNCHED();
       // the utterances of one step form ONE "utterance" of nB frames for the taps-GEMM (no tap shift)
-      if (int rc = gemm_nt_taps_tc(A3, 0, Kp, W3, 0, Kp, nullptr, R, G, 1, nB, G, Kp, 1, 0, nullptr, 0, 4, 1, nullptr, 0, st, 1)) return rc;
+      if (int rc = gemm_nt_taps_tc(A3, 0, Kp, W3, 0, Kp, nullptr, R, G, 1, nB, G, Kp, 1, 0, nullptr, 0, 4, 1, nullptr, 0, st, 1, S,
+                                   (size_t)nB * G))
+        return rc;
     }
-    lstm_gate_fwd_kernel<<<gate_blocks((size_t)nB * H), 256, 0, st>>>(P, t_prev >= 0 ? R : nullptr, h_seq, ldh, gates, c_seq, nB,
-                                                                      T, H, t, t_prev);
+    lstm_gate_fwd_kernel<<<gate_blocks((size_t)nB * H), 256, 0, st>>>(P, R, t_prev >= 0 ? S : 0, h_seq, ldh, gates, c_seq, A3, Kp,
+                                                                      nB, T, H, t, t_prev);
     AVC_LAUNCHED();
   }
   return AVC_OK;
 }
 
-// BPTT: W3 (H x Kp, Kp = 12H rounded to 32) from Whh_pT (H x 4H), A3 (nB x Kp), R (nB x H), dc_rec (nB x H)
+// BPTT: W3 (H x Kp, Kp = 12H rounded to 32) from Whh_pT (H x 4H), A3 (nB x Kp), R (ksplit x nB x H), dc_rec (nB x H)
 size_t lstm_bwd_workspace_x3(int nB, int T, int H) {
   const int Kp = round_up_i(12 * H, 32);
-  return align256x((size_t)H * Kp * 4) + align256x((size_t)nB * Kp * 4) + 2 * align256x((size_t)nB * H * 4);
+  const int S = x3_split(nB, H, Kp).ksplit;
+  return align256x((size_t)H * Kp * 4) + align256x((size_t)nB * Kp * 4) + align256x((size_t)S * nB * H * 4) + align256x((size_t)nB * H * 4);
 }
 
 int lstm_seq_bwd_x3(const float* dH, int lddh, const float* Whh_pT, const float* gates, const float* c_seq, float* dP, int nB,
@@ -223,23 +256,25 @@ int lstm_seq_bwd_x3(const float* dH, int lddh, const float* Whh_pT, const float*
     return AVC_ERR_WORKSPACE;
   }
   const int G = 4 * H, Kp = round_up_i(3 * G, 32);
+  const int S = x3_split(nB, H, Kp).ksplit;
   float* W3 = (float*)ws;
   float* A3 = (float*)((uint8_t*)ws + align256x((size_t)H * Kp * 4));
   float* R = (float*)((uint8_t*)A3 + align256x((size_t)nB * Kp * 4));
-  float* dc_rec = (float*)((uint8_t*)R + align256x((size_t)nB * H * 4));
+  float* dc_rec = (float*)((uint8_t*)R + align256x((size_t)S * nB * H * 4));
   split3_k_kernel<<<split_blocks(H), 256, 0, st>>>(Whh_pT, (size_t)G, W3, Kp, (size_t)H, G, 1);
   AVC_LAUNCHED();
+  AVC_CUDA(cudaMemsetAsync(A3, 0, (size_t)nB * Kp * 4, st));
   for (int step = T - 1; step >= 0; --step) {
     const int t = reverse ? T - 1 - step : step;
     const int t_next = step == T - 1 ? -1 : (reverse ? t - 1 : t + 1);
     const int t_prev = step == 0 ? -1 : (reverse ? t + 1 : t - 1);
     if (t_next >= 0) {
-      split3_k_kernel<<<split_blocks(nB), 256, 0, st>>>(dP + (size_t)t_next * G, (size_t)T * G, A3, Kp, (size_t)nB, G, 0);
-      AVC_LAUNCHED();
-      if (int rc = gemm_nt_taps_tc(A3, 0, Kp, W3, 0, Kp, nullptr, R, H, 1, nB, H, Kp, 1, 0, nullptr, 0, 4, 1, nullptr, 0, st, 1)) return rc;
+      if (int rc = gemm_nt_taps_tc(A3, 0, Kp, W3, 0, Kp, nullptr, R, H, 1, nB, H, Kp, 1, 0, nullptr, 0, 4, 1, nullptr, 0, st, 1, S,
+                                   (size_t)nB * H))
+        return rc;
     }
-    lstm_gate_bwd_kernel<<<gate_blocks((size_t)nB * H), 256, 0, st>>>(dH, lddh, t_next >= 0 ? R : nullptr, gates, c_seq, dP,
-                                                                      dc_rec, nB, T, H, t, t_next, t_prev);
+    lstm_gate_bwd_kernel<<<gate_blocks((size_t)nB * H), 256, 0, st>>>(dH, lddh, R, t_next >= 0 ? S : 0, gates, c_seq, dP, dc_rec, A3,
+                                                                      Kp, nB, T, H, t, t_next, t_prev);
     AVC_LAUNCHED();
   }
   return AVC_OK;

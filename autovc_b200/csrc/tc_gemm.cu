@@ -51,6 +51,8 @@ struct TcParams {
   int N, K;            // logical (unpadded) sizes of the output's two dims (NT: C cols = N; TN: dW is N x K)
   // NT
   int t_tiles, n_tiles, kblocks;   // tiles along T (128 frames), along N (128 cols), one-swizzle-row k blocks per tap
+  int ksplit;                      // NT, chunked kernel only: the reduction of a tile is cut into ksplit work items; item s writes its
+  size_t c_split_stride;           // partial result to C + s * c_split_stride (the caller sums them; bias goes with item 0)
   const float* bias;
   float* C;
   int ldc, accumulate;
@@ -147,13 +149,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   int total_tiles, kiters;
   if (MODE == MODE_NT) {
-    total_tiles = p.nB * p.t_tiles * p.n_tiles;
+    total_tiles = p.nB * p.t_tiles * p.n_tiles * (p.ksplit > 1 ? p.ksplit : 1);
     kiters = p.ntaps * p.kblocks;
   } else {
     total_tiles = p.ntaps * p.n_tiles * p.k_tiles * p.splits;
     kiters = 0;  // per tile
   }
 
+  // NT with split reduction: work item -> (tile, first and one-past-last pipeline stage)
+  const int ksplit = (MODE == MODE_NT && p.ksplit > 1) ? p.ksplit : 1;
+  const int kper = (kiters + ksplit - 1) / ksplit;
   if (warp == 0) {
     // ===================== TMA producer (whole warp loops, one elected lane issues) =====================
     {
@@ -161,9 +166,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         if (MODE == MODE_NT) {
-          const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+          const int ks = tile % ksplit, tl = tile / ksplit;
+          const int n_tile = tl % p.n_tiles, m_tile = tl / p.n_tiles;
           const int b = m_tile / p.t_tiles, t0 = (m_tile % p.t_tiles) * TC_BM;
-          for (int it = 0; it < kiters; ++it) {
+          for (int it = ks * kper; it < min(kiters, (ks + 1) * kper); ++it) {
             const int tap = it / p.kblocks, kb = it - tap * p.kblocks;
             mbar_wait(empty_bar(stage), phase ^ 1);
             if (elect_one()) {
@@ -224,6 +230,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const int split = tn_decode(tile, p.k_tiles, p.n_tiles, p.ntaps).split;
           const int rb0 = split * p.rblocks_per_split;
           iters = max(0, min(p.rblocks, rb0 + p.rblocks_per_split) - rb0);
+        } else if (ksplit > 1) {
+          const int ks = tile % ksplit;
+          iters = max(0, min(kiters, (ks + 1) * kper) - ks * kper);
         }
         if (CH == 0) {
           mbar_wait(tempty_bar(acc), acc_phase ^ 1);      // epilogue has drained this accumulator
@@ -300,10 +309,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if constexpr (CH > 0) {
         // ---- chunked accumulation: add every finished chunk into this thread's row of 128 fp32 registers ----
         int iters = kiters;
+        const int ks = tile % ksplit, tl = tile / ksplit;
         if (MODE == MODE_TN) {
           const int split = tn_decode(tile, p.k_tiles, p.n_tiles, p.ntaps).split;
           const int rb0 = split * p.rblocks_per_split;
           iters = max(0, min(p.rblocks, rb0 + p.rblocks_per_split) - rb0);
+        } else if (ksplit > 1) {
+          iters = max(0, min(kiters, (ks + 1) * kper) - ks * kper);
         }
         float r[BN];
 #pragma unroll
@@ -329,10 +341,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
         if (MODE == MODE_NT) {
-          const int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+          const int n_tile = tl % p.n_tiles, m_tile = tl / p.n_tiles;
           const int b = m_tile / p.t_tiles, t = (m_tile % p.t_tiles) * TC_BM + row;
           const bool row_ok = t < p.T;
-          float* crow = p.C + ((size_t)b * p.T + t) * p.ldc;
+          float* crow = p.C + (size_t)ks * p.c_split_stride + ((size_t)b * p.T + t) * p.ldc;
+          const bool add_bias = p.bias != nullptr && ks == 0;
 #pragma unroll
           for (int c = 0; c < BN / 32; ++c) {
             const int n0 = n_tile * BN + c * 32;
@@ -341,7 +354,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const int n = n0 + j;
-                const float x = r[c * 32 + j] + ((p.bias != nullptr && n < p.N) ? __ldg(p.bias + n) : 0.f);
+                const float x = r[c * 32 + j] + ((add_bias && n < p.N) ? __ldg(p.bias + n) : 0.f);
                 v[j] = (row_ok && n < p.N) ? x : 0.f;
               }
               if (row_ok) {
@@ -1220,7 +1233,7 @@ size_t gemm_nt_workspace_tc(int nB, int T, int N, int K, int ntaps, int eb) {
 // a 16-bit A must then have the same format, an fp32 A is staged to it).
 int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const void* Wv, int w_fmt, int ldw, const float* bias, float* C, int ldc,
                     int nB, int T, int N, int K, int ntaps, int shift0, double* stats, int accumulate, int eb, int half_fmt, void* ws,
-                    size_t ws_bytes, cudaStream_t st, int chunk) {
+                    size_t ws_bytes, cudaStream_t st, int chunk, int ksplit, size_t c_split_stride) {
   const float* A = (const float*)Av;
   const float* W = (const float*)Wv;
   if (a_fmt != 0 && (eb != 2 || !direct16_ok(Av, lda))) {
@@ -1294,7 +1307,13 @@ int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const void* Wv, int w_fm
     return eb == 2 ? tc2_launch<2>(mA, mB, mC, p, grid2, st) : tc2_launch<4>(mA, mB, mC, p, grid2, st);
   }
   p.idesc = eb == 2 ? make_idesc(TC_BM, pl.bn, 0, 0, ifmt_of(fa), ifmt_of(fw)) : make_idesc(TC_BM, pl.bn, 0, 0, 2);
-  const int tiles = nB * p.t_tiles * p.n_tiles;
+  if (ksplit > 1 && (!chunk || stats || accumulate)) {
+    set_error("tc_gemm: a split reduction needs the chunked kernel and neither chan_stats nor accumulate");
+    return AVC_ERR_UNSUPPORTED;
+  }
+  p.ksplit = ksplit > 1 ? ksplit : 1;
+  p.c_split_stride = c_split_stride;
+  const int tiles = nB * p.t_tiles * p.n_tiles * p.ksplit;
   const int grid = std::min(tiles, num_sms());
   return tc_dispatch<MODE_NT>(eb, pl.bn, mA, mB, p, grid, st, chunk);
 }

@@ -11,7 +11,7 @@ synthetic 80-bin mel crops, batch 256 per GPU, len_crop 128; one step = solver_e
 Prints ONE JSON line on rank 0.  See DESIGN.md "Measurement" for the definition of every key.
 
 Secondary legs (not the driver's default): --workload frontend | convert (BASELINE.json configs[4], 4096 x 10 s utterances),
---workload loader | dvector (the rows SURVEY 8(f) marks "next"); --n-bins 513 (configs[3]); --dim-neck 32 --freq 32 --batch 128
+--workload loader | dvector | wav (the rows SURVEY 8(f) marks "next"); --n-bins 513 (configs[3]); --dim-neck 32 --freq 32 --batch 128
 --len-crop 256 (configs[2]); --precision fp32 (3xTF32 on the tensor cores) | fp32_simt (CUDA cores) | tf32 | half.
 """
 from __future__ import annotations
@@ -414,10 +414,23 @@ def run_frontend_or_convert(args):
     from autovc_b200.conversion import convert, padded_frames
     from autovc_b200.make_spect import Spect
     from oracle import make_spect_ref as fref
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
-    n, L = args.utterances, 160000
-    g = torch.Generator(device="cuda").manual_seed(1234)
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and not (world == 1 and args.gpus > 1):
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch N>1 with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bench.py --gpus N ...")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        # replicas only: the utterances are split across the ranks, no data-path collective; the process group
+        # serves the barrier and the max-over-ranks of the device-timed region
+        dist.init_process_group("nccl", device_id=dev)
+    n_total, L = args.utterances, 160000
+    n = n_total // world
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
     env = 0.55 + 0.45 * torch.sin(torch.linspace(0, 60, L, device=dev))[None, :]
     wav = (0.1 * torch.randn(n, L, generator=g, device=dev) * env).clamp(-1.0, 1.0 - 2 ** -15)
     dither = torch.rand(n, L, generator=g, device=dev)
@@ -429,18 +442,28 @@ def run_frontend_or_convert(args):
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / steps
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
 
     if args.workload == "frontend":
         ms = timed(lambda: sp.logmel(wav, dither, None, max_frames=padded_frames(L)), args.steps, args.warmup)
         alg_bytes = n * (4 * L + 4 * L + 4 * 80 * F_)
-        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        gbs = alg_bytes / (ms * 1e-3) / 1e9          # per GPU (the roofline is a per-device figure)
+        if rank != 0:
+            dist.destroy_process_group()
+            return
         # CPU baseline: oracle restatement on a bounded sample, single process like the reference
         k = min(8, n)
         wc, dc = wav[:k].cpu().numpy(), dither[:k].double().cpu().numpy()
@@ -448,31 +471,62 @@ def run_frontend_or_convert(args):
         for i in range(k):
             fref.logmel_from_wav(wc[i], dc[i])
         cpu_fps = k * F_ / (time.perf_counter() - t0)
-        line = {"metric": "log-mel front-end mel frames/sec", "value": n * F_ / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1,
+        line = {"metric": "log-mel front-end mel frames/sec", "value": n * world * F_ / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64 IIR + f32 FFT", "data": "synthetic",
-                "config": {"workload": f"make_spect front-end, {n} synthetic 10 s 16 kHz waveforms (inputs {2*n*L*4/1e9:.2f} GB > L2)"},
+                "config": {"workload": f"make_spect front-end, {n_total} synthetic 10 s 16 kHz waveforms, {n} per GPU (inputs {2*n*L*4/1e9:.2f} GB per GPU > L2)",
+                           "parallelism": f"replicas x{world}"},
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                              "traffic": None, "peak_source": peaks["source"] + " hbm_gbs",
                              "algorithmic_bytes_per_utterance": 4 * L + 4 * L + 4 * 80 * F_},
                 "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
                                  "sample": f"{k} of the {n} utterances through oracle/make_spect_ref.py (scipy filtfilt + numpy rfft)"}}
         print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
         return
     torch.manual_seed(0)
     G = autovc_b200.Generator(32, 256, 512, 32, precision=args.precision).to(dev)
     e = F.normalize(torch.randn(n, 256, generator=torch.Generator().manual_seed(5)), dim=-1).to(dev) * 0.8
     et = e.roll(1, 0).contiguous()
     ms = timed(lambda: convert(G, sp, wav, dither, None, e, et, chunk=256), args.steps, max(1, args.warmup - 2))
-    mac = MAC_PER_FRAME[(32, 80)] - 3_481_600 - 73_728 * 0   # one encoder pass in conversion (28 385 280 MAC/frame)
-    flops = 2.0 * 28_385_280 * n * padded_frames(L)
-    line = {"metric": "conversion mel frames/sec", "value": n * F_ / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+    flops = 2.0 * 28_385_280 * n * padded_frames(L)      # per GPU; one encoder pass in conversion (28 385 280 MAC/frame)
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        # the reference's CPU path on a bounded sample: make_spect restatement (scipy/numpy, single process like the reference)
+        # + the reference-like nn.Module in eval mode on all host threads (conversion.py:40-47,:91-92)
+        from oracle import generator_ref as gref
+        k = 4
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        torch.manual_seed(0)
+        Gc = gref.build_reference_like_module(32, 256, 512, 32).eval()
+        wc, dc = wav[:k].cpu().numpy(), dither[:k].double().cpu().numpy()
+        ec = e[:k].cpu()
+        t0 = time.perf_counter()
+        mels = [torch.from_numpy(np.pad(fref.logmel_from_wav(wc[i], dc[i]), ((0, padded_frames(L) - F_), (0, 0)))) for i in range(k)]
+        t1 = time.perf_counter()
+        with torch.no_grad():
+            for i in range(k):
+                Gc(mels[i][None], ec[i:i + 1], ec.roll(1, 0)[i:i + 1])
+        t2 = time.perf_counter()
+        cpu = {"value": k * F_ / (t2 - t0), "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"{k} of the {n_total} utterances: oracle make_spect restatement (1 thread, {t1 - t0:.2f} s) + reference-like module eval "
+                         f"forward at 640 frames ({threads} threads, {t2 - t1:.2f} s)"}
+    line = {"metric": "conversion mel frames/sec", "value": n * world * F_ / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"waveform -> log-mel -> pad to x32 -> Generator(32,256,512,32).eval() forward, {n} x 10 s utterances, chunks of 256"},
+            "config": {"workload": f"waveform -> log-mel -> pad to x32 -> Generator(32,256,512,32).eval() forward, {n_total} x 10 s utterances "
+                                   f"({n} per GPU), chunks of 256", "parallelism": f"replicas x{world}"},
             "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"], "traffic": None}}
+                         "frac": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"], "traffic": None, "per": "GPU"},
+            "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_widened(args):
@@ -529,6 +583,46 @@ def run_widened(args):
                                  "sample": f"{k}-crop batches through oracle/data_loader_ref.py (numpy restatement of Utterances.__getitem__)"}}
         print(json.dumps(line), flush=True)
         return
+    if args.workload == "wav":
+        # GeneratorWav training step (model_vc_wav.py / solver_encoder.py:264-300) on waveform crops of (T-1)*256 + 1024 samples
+        from autovc_b200 import solver
+        from oracle import generator_wav_ref as wref
+        L = (T - 1) * 256 + 1024
+        torch.manual_seed(0)
+        G = autovc_b200.GeneratorWav(args.dim_neck, 256, 512, args.freq, args.depth, precision=args.precision).to(dev).train()
+        opt = autovc_b200.FusedAdam(G.parameters(), 1e-4)
+        xw, ew = wref.synth_wav_inputs(B, L, 256, 1234)
+        xw, ew = xw.to(dev), ew.to(dev)
+        ms = timed(lambda: solver.train_step_wav(G, opt, xw, ew), args.steps, args.warmup)
+        # dense MACs per frame: the mel model's encoder (twice) / lstm1 / decoder convs / lstm2 with 512-channel ends, plus the
+        # filterbanks (512*1024 each way, analysis twice) and the k=3 layers (depth * 3*512*512, analysis side twice)
+        enc = (512 + 256) * 512 * 5 + 2 * 512 * 512 * 5 + 2 * (512 * 4 * args.dim_neck + args.dim_neck * 4 * args.dim_neck) \
+            + 2 * (2 * args.dim_neck * 4 * args.dim_neck + args.dim_neck * 4 * args.dim_neck)
+        dec = (2 * args.dim_neck + 256 + 512) * 2048 + 3 * 512 * 512 * 5 + (512 + 1024) * 4096 + 2 * 1024 * 4096 + 1024 * 512
+        tas = 3 * 512 * 1024 + args.depth * 3 * 3 * 512 * 512
+        flops = 3 * 2.0 * (2 * enc + dec + tas) * B * T
+        k = 2
+        sd = None
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.manual_seed(0)
+        M = wref.build_wav_module(args.dim_neck, 256, 512, args.freq, args.depth)
+        sd = {kk: v.detach().clone() for kk, v in M.state_dict().items()}
+        xc, ec = xw[:k].cpu(), ew[:k].cpu()
+        t0 = time.perf_counter()
+        wref.wav_train_step(sd, xc, ec, args.dim_neck, args.freq)
+        cpu = k / (time.perf_counter() - t0)
+        line = {"metric": "GeneratorWav train utterance-crops/sec", "value": B / (ms * 1e-3), "unit": "crops/s", "n_gpus": 1, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+                "data": "synthetic",
+                "config": {"workload": f"GeneratorWav({args.dim_neck},256,512,{args.freq},depth={args.depth}) train step (solver_encoder.py:264-300), "
+                                       f"{B} waveform crops x {L} samples ({T} frames)"},
+                "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                             "frac": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"], "traffic": None},
+                "cpu_baseline": {"value": cpu, "unit": "crops/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                 "sample": f"one forward+backward of {k} crops through oracle/generator_wav_ref.py (explicit LSTM time loop; a lower "
+                                           f"bound on the reference's oneDNN path)"}}
+        print(json.dumps(line), flush=True)
+        return
     torch.manual_seed(0)
     C = D_VECTOR(dim_input=80, dim_cell=768, dim_emb=256, precision=args.precision).eval().to(dev)
     x = torch.rand(B, T, 80, device=dev)
@@ -560,10 +654,11 @@ def main():
     ap.add_argument("--n-bins", dest="n_bins", type=int, default=80, choices=[80, 513], help="513 = model_vc_stft variant (configs[3])")
     ap.add_argument("--cpu-sample-batch", dest="cpu_sample_batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="train", choices=["train", "frontend", "convert", "loader", "dvector"])
+    ap.add_argument("--workload", default="train", choices=["train", "frontend", "convert", "loader", "dvector", "wav"])
+    ap.add_argument("--depth", type=int, default=1, help="--workload wav: Conv-TasNet encoder/decoder depth (main.py:65)")
     ap.add_argument("--utterances", type=int, default=4096, help="frontend/convert legs: number of 10 s utterances (BASELINE.json configs[4]: 4096)")
     args = ap.parse_args()
-    if args.workload in ("loader", "dvector"):
+    if args.workload in ("loader", "dvector", "wav"):
         return run_widened(args)
     if args.workload != "train":
         return run_frontend_or_convert(args)
