@@ -76,6 +76,7 @@ SIGNATURES = {
     "avc_ema_blend": (c_int, [P, P, c_int, c_double, P]),
     "avc_logmel_frontend": (c_int, [P, P, P, c_int, c_int, P, P, P, P, c_int, P, c_size_t, P]),
     "avc_logmel_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "avc_logstft_frontend": (c_int, [P, P, P, c_int, c_int, P, P, P, P, c_int, P, c_size_t, P]),
     "avc_prelu_fwd": (c_int, [P, P, P, P, c_int, c_int, P]),
     "avc_prelu_bwd": (c_int, [P, P, P, P, P, c_int, P, c_size_t, P]),
     "avc_sum_all": (c_int, [P, c_size_t, P, P, c_int, P]),

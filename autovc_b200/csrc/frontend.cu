@@ -61,15 +61,11 @@ __global__ void fe_tables_kernel(const float* __restrict__ mel_basis, FeTables* 
 }
 
 // --- stage 1+2: filtfilt as two chunk-parallel IIR sweeps (fp64) ----------------------------------------------
-// The direct-form-II-transposed recurrence is linear in its 5-element state z:  z' = A z + B x,  y = z[0] + b0 x.
-// Each utterance (odd-extended by 18 samples per side, as scipy does) is cut into chunks of FE_CHUNK samples and
-// every sweep runs in three launches:
-//   (1) zero-state pass   -- every chunk, independently, finds the state it would END in starting from z = 0;
-//   (2) carry scan        -- one thread per utterance: z_start[c+1] = A^L z_start[c] + z_zs_end[c]   (A^L precomputed);
-//   (3) output pass       -- every chunk re-runs the recurrence from its true start state and writes y.
-// Mathematically identical to the sequential filter (rounding differs at the 1e-16 level); 4096 x 626 chunks instead
-// of 4096 sequential threads.  The backward sweep is the same on the reversed forward output, then 0.96*y + dither.
-constexpr int FE_CHUNK = 256;
+// The direct-form-II-transposed recurrence is linear in its state z:  z' = A z + B x,  y = z[0] + b0 x, so a chunk's END state
+// is  A^L z_start + (end state from z = 0): chunks run independently from a zero state, a scan over the chunk states supplies
+// the true start states, and a second pass re-runs every chunk from its true start state.  Mathematically identical to the
+// sequential filter (rounding differs at the 1e-16 level).  (r01 did this in three launches per sweep with every thread walking
+// its own 256-sample chunk straight from global memory -- 5.7 ms per 1024 utterances; the fused tile kernel below replaced it.)
 
 // Cascade of 3 second-order sections, each direct-form-II-transposed (scipy.signal.sosfilt arithmetic):
 //   y = b0 u + z0;  z0' = b1 u + z1 - a1 y;  z1' = b2 u - a2 y;  next section's input u = y.
@@ -112,33 +108,6 @@ __device__ __forceinline__ double odd_ext(const float* __restrict__ x, int n, in
   return 2.0 * (double)x[n - 1] - (double)x[n - 2 - (i - FE_PADLEN - n)];
 }
 
-// A^L for the zero-input state recurrence (FE_NST x FE_NST, row-major): columns of A are one zero-input step applied
-// to the unit vectors; L = FE_CHUNK = 2^8 by repeated squaring.  Single thread.
-__global__ void fe_state_power_kernel(const double* __restrict__ filt, double* __restrict__ AL) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  constexpr int N = FE_NST;
-  double M[N * N], R[N * N];
-  Df2t f;
-  f.load(filt);
-  for (int k = 0; k < N; ++k) {
-    for (int i = 0; i < N; ++i) f.z[i] = (i == k) ? 1.0 : 0.0;
-    f.step(0.0);
-    for (int i = 0; i < N; ++i) M[i * N + k] = f.z[i];
-  }
-  int L = FE_CHUNK;
-  while (L > 1) {
-    for (int i = 0; i < N; ++i)
-      for (int j = 0; j < N; ++j) {
-        double acc = 0.0;
-        for (int k = 0; k < N; ++k) acc = fma(M[i * N + k], M[k * N + j], acc);
-        R[i * N + j] = acc;
-      }
-    for (int i = 0; i < N * N; ++i) M[i] = R[i];
-    L >>= 1;
-  }
-  for (int i = 0; i < N * N; ++i) AL[i] = M[i];
-}
-
 // input sample i of the sweep: forward sweep reads the odd-extended waveform, backward sweep reads the forward
 // output in reverse order
 template <bool BACKWARD>
@@ -146,182 +115,8 @@ __device__ __forceinline__ double sweep_input(const float* __restrict__ x, const
   return BACKWARD ? y1[ne - 1 - i] : odd_ext(x, n, i);
 }
 
-// pass (1): one thread per chunk, zero-state end state -> zs[(u*nchunk + c)*5 ..]
-template <bool BACKWARD>
-__global__ void fe_iir_zero_state_kernel(const float* __restrict__ wav, const double* __restrict__ y1buf,
-                                         const int* __restrict__ lengths, int n_utt, int max_len, int nchunk,
-                                         const double* __restrict__ filt, double* __restrict__ zs) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int u = blockIdx.y;
-  if (c >= nchunk) return;
-  const int n = lengths[u];
-  const int ne = n + 2 * FE_PADLEN;
-  double* out = zs + ((size_t)u * nchunk + c) * FE_NST;
-  const int i0 = c * FE_CHUNK;
-  if (n <= FE_PADLEN || i0 >= ne) {
-#pragma unroll
-    for (int k = 0; k < FE_NST; ++k) out[k] = 0.0;
-    return;
-  }
-  const float* x = wav + (size_t)u * max_len;
-  const double* y1 = y1buf + (size_t)u * (max_len + 2 * FE_PADLEN);
-  Df2t f;
-  f.load(filt);
-#pragma unroll
-  for (int k = 0; k < FE_NST; ++k) f.z[k] = 0.0;
-  const int i1 = min(ne, i0 + FE_CHUNK);
-  for (int i = i0; i < i1; ++i) f.step(sweep_input<BACKWARD>(x, y1, n, ne, i));
-  // a short last chunk still has to look like FE_CHUNK steps to the scan: feed zeros (pure state decay)
-  for (int i = i1; i < i0 + FE_CHUNK; ++i) f.step(0.0);
-#pragma unroll
-  for (int k = 0; k < FE_NST; ++k) out[k] = f.z[k];
-}
-
-// pass (2), warp-parallel: the carry z[c+1] = A z[c] + e[c] over the ~626 chunks of an utterance is a 6-state linear
-// recurrence.  One WARP per utterance: every lane folds a contiguous segment of chunks from a zero state (v), the 32
-// segment results are chained with M = A^segment (32 cheap steps, operands by shuffle), and every lane re-walks its
-// segment from its true start state, overwriting zs[c] with it.  Serial depth 626 -> 2*20 + 32 (the one-thread-per-
-// utterance version above took 1.2 ms per sweep for 1024 utterances, latency-bound on 1024 threads).
-template <bool BACKWARD>
-__global__ void __launch_bounds__(128)
-fe_iir_scan_warp_kernel(const float* __restrict__ wav, const double* __restrict__ y1buf, const int* __restrict__ lengths,
-                        int n_utt, int max_len, int nchunk, const double* __restrict__ zi, const double* __restrict__ AL,
-                        double* __restrict__ zs) {
-  const int u = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (u >= n_utt) return;
-  const int n = lengths[u];
-  if (n <= FE_PADLEN) return;
-  const int ne = n + 2 * FE_PADLEN;
-  const float* x = wav + (size_t)u * max_len;
-  const double* y1 = y1buf + (size_t)u * (max_len + 2 * FE_PADLEN);
-  const double x0 = sweep_input<BACKWARD>(x, y1, n, ne, 0);
-  constexpr int N = FE_NST;
-  double A[N * N];
-#pragma unroll
-  for (int i = 0; i < N * N; ++i) A[i] = AL[i];
-  const int per = (nchunk + 31) / 32;
-  const int c0 = min(nchunk, lane * per), c1 = min(nchunk, c0 + per);
-  double* p = zs + (size_t)u * nchunk * N;
-  // (a) zero-state fold of my segment
-  double v[N];
-#pragma unroll
-  for (int k = 0; k < N; ++k) v[k] = 0.0;
-  for (int c = c0; c < c1; ++c) {
-    double nz[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      double acc = p[c * N + i];
-#pragma unroll
-      for (int k = 0; k < N; ++k) acc = fma(A[i * N + k], v[k], acc);
-      nz[i] = acc;
-    }
-#pragma unroll
-    for (int k = 0; k < N; ++k) v[k] = nz[k];
-  }
-  // (b) M = A^per, then chain the segments: S[l+1] = M S[l] + v[l]
-  double M[N * N];
-#pragma unroll
-  for (int i = 0; i < N * N; ++i) M[i] = A[i];
-  for (int e = 1; e < per; ++e) {
-    double R[N * N];
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < N; ++k) acc = fma(M[i * N + k], A[k * N + j], acc);
-        R[i * N + j] = acc;
-      }
-#pragma unroll
-    for (int i = 0; i < N * N; ++i) M[i] = R[i];
-  }
-  double S[N], mine[N];
-#pragma unroll
-  for (int k = 0; k < N; ++k) S[k] = zi[k] * x0;          // scipy: zi * first sample of the (extended / reversed) input
-#pragma unroll
-  for (int k = 0; k < N; ++k) mine[k] = S[k];
-  for (int l = 0; l < 31; ++l) {
-    double vl[N], nz[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) vl[k] = __shfl_sync(0xffffffffu, v[k], l);
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      double acc = vl[i];
-#pragma unroll
-      for (int k = 0; k < N; ++k) acc = fma(M[i * N + k], S[k], acc);
-      nz[i] = acc;
-    }
-#pragma unroll
-    for (int k = 0; k < N; ++k) S[k] = nz[k];
-    if (lane == l + 1) {
-#pragma unroll
-      for (int k = 0; k < N; ++k) mine[k] = S[k];
-    }
-  }
-  // (c) re-walk my segment from its true start state
-  for (int c = c0; c < c1; ++c) {
-    double e[N], nz[N];
-#pragma unroll
-    for (int k = 0; k < N; ++k) e[k] = p[c * N + k];
-#pragma unroll
-    for (int k = 0; k < N; ++k) p[c * N + k] = mine[k];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      double acc = e[i];
-#pragma unroll
-      for (int k = 0; k < N; ++k) acc = fma(A[i * N + k], mine[k], acc);
-      nz[i] = acc;
-    }
-#pragma unroll
-    for (int k = 0; k < N; ++k) mine[k] = nz[k];
-  }
-}
-
-// pass (3): one thread per chunk from its true start state.  Forward: y1[i] (fp64).  Backward: the sweep index i maps
-// to extended position ne-1-i; positions inside the utterance get 0.96*y + (dither-0.5)*1e-6 as fp32.
-template <bool BACKWARD>
-__global__ void fe_iir_output_kernel(const float* __restrict__ wav, const float* __restrict__ dither,
-                                     const int* __restrict__ lengths, int n_utt, int max_len, int nchunk,
-                                     const double* __restrict__ filt, const double* __restrict__ zs,
-                                     double* __restrict__ y1buf, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int u = blockIdx.y;
-  if (c >= nchunk) return;
-  const int n = lengths[u];
-  const float* dz = dither + (size_t)u * max_len;
-  float* o = out + (size_t)u * max_len;
-  if (n <= FE_PADLEN) {   // scipy raises for such inputs; emit dither-only silence deterministically
-    if (BACKWARD && c == 0)
-      for (int i = 0; i < n; ++i) o[i] = (float)(((double)dz[i] - 0.5) * 1e-6);
-    return;
-  }
-  const int ne = n + 2 * FE_PADLEN;
-  const int i0 = c * FE_CHUNK;
-  if (i0 >= ne) return;
-  const float* x = wav + (size_t)u * max_len;
-  double* y1 = y1buf + (size_t)u * (max_len + 2 * FE_PADLEN);
-  Df2t f;
-  f.load(filt);
-  const double* st = zs + ((size_t)u * nchunk + c) * FE_NST;
-#pragma unroll
-  for (int k = 0; k < FE_NST; ++k) f.z[k] = st[k];
-  const int i1 = min(ne, i0 + FE_CHUNK);
-  for (int i = i0; i < i1; ++i) {
-    const double y = f.step(sweep_input<BACKWARD>(x, y1, n, ne, i));
-    if (!BACKWARD) {
-      y1[i] = y;
-    } else {
-      const int j = (ne - 1 - i) - FE_PADLEN;
-      if (j >= 0 && j < n) o[j] = (float)(y * 0.96 + ((double)dz[j] - 0.5) * 1e-6);
-    }
-  }
-}
-
 // --- stage 1+2, fused: one CTA per utterance walks the sweep tile by tile ------------------------------------------
-// The three-launch scheme above reads every input twice and lets each thread walk its own 256-sample chunk straight from
-// global memory (lanes 1 KB apart: r01c ncu 1.3-1.7 TB/s at 62-94% L1/TEX busy, 5.3 of 13.1 ms per 1024 utterances).
-// Here a CTA of 256 threads owns an utterance and processes tiles of 256 chunks x 32 samples = 8192 samples (first version:
+// A CTA of 256 threads owns an utterance and processes tiles of 256 chunks x 32 samples = 8192 samples (first version:
 // 128 x 64 -- same shared memory, half the warps and twice the serial chunk length; ncu: 11% warps active, 0.88 IPC):
 //   load    the tile into shared memory as fp64 with coalesced (forward) / reversed-coalesced (backward) accesses,
 //           one pad word per chunk so that the per-thread walks below are bank-conflict free;
@@ -568,6 +363,9 @@ __device__ __forceinline__ float fe_reflect(const float* __restrict__ x, int n, 
 // Every warp is on its own: frames 2q, 2q+1 -> registers -> transform -> magnitudes -> the two frames' 160 mel outputs.
 // No block barrier anywhere, so the 24 resident warps of an SM sit in different phases and hide each other's latencies
 // (the block-synchronous version ran at 21% of the issue rate).
+// STFT_OUT (make_spect.py:84-86, the 'stft' model type): the 513 magnitudes themselves go through the same log / clip and are
+// written frame-major (n_utt, max_frames, 513) instead of the mel projection.
+template <bool STFT_OUT>
 __global__ void __launch_bounds__(FE_THREADS, 5)
 fe_stft_mel_kernel(const float* __restrict__ sig, const int* __restrict__ lengths, int max_len,
                    const float* __restrict__ mel_basis, const FeTables* __restrict__ tb, float* __restrict__ out,
@@ -584,8 +382,9 @@ fe_stft_mel_kernel(const float* __restrict__ sig, const int* __restrict__ length
   for (int g = 0; g < FE_PAIRS_PER_WARP; ++g) {
     const int f0 = blockIdx.x * FE_FRAMES_PER_BLOCK + (wid * FE_PAIRS_PER_WARP + g) * 2;   // frames f0 (real part), f0+1 (imaginary)
     if (f0 >= max_frames) break;
-    float* o = out + ((size_t)u * max_frames + f0) * FE_MELS;
-    const int nout = min(2, max_frames - f0) * FE_MELS;
+    constexpr int NOUT = STFT_OUT ? FE_BINS : FE_MELS;
+    float* o = out + ((size_t)u * max_frames + f0) * NOUT;
+    const int nout = min(2, max_frames - f0) * NOUT;
     if (f0 >= n_frames) {   // zero padding frames (conversion.py:40-44 pad_seq)
       for (int i = lane; i < nout; i += 32) o[i] = 0.f;
       continue;
@@ -630,6 +429,19 @@ fe_stft_mel_kernel(const float* __restrict__ sig, const int* __restrict__ length
       e[k] = make_float2(sqrtf(ar * ar + ai * ai), sqrtf(br * br + bi * bi));
     }
     __syncwarp();
+    if (STFT_OUT) {
+      for (int i = lane; i < nout; i += 32) {
+        const int fr = i >= FE_BINS ? 1 : 0, k = i - fr * FE_BINS;
+        float val = 0.f;
+        if (f0 + fr < n_frames) {
+          const float2 mg = e[k];
+          const float db = 20.f * log10f(fmaxf(1e-5f, fr ? mg.y : mg.x)) - 16.f;
+          val = fminf(fmaxf((db + 100.f) / 100.f, 0.f), 1.f);
+        }
+        o[i] = val;
+      }
+      continue;
+    }
     // mel projection of BOTH frames: the bin ranges of the 80 filters are cut into segments of <= 8 bins (tb->seg), a lane takes
     // every 32nd segment and sums it for the two frames at once (one 8-byte magnitude pair + one weight per bin), the partial
     // sums go to the dead upper half of the tile and each output adds its filter's partials in a fixed order.  The first version
@@ -669,14 +481,50 @@ static size_t fe_tables_bytes() { return (sizeof(FeTables) + 255) / 256 * 256; }
 
 using namespace avc;
 
-static int fe_nchunk(int max_len) { return ceil_div(max_len + 2 * FE_PADLEN, FE_CHUNK); }
-
 extern "C" size_t avc_logmel_workspace_bytes(int n_utt, int max_len) {
   if (n_utt <= 0 || max_len <= 0) return 0;
   const size_t fwd = ((size_t)n_utt * (max_len + 2 * FE_PADLEN) * sizeof(double) + 255) / 256 * 256;
   const size_t sig = ((size_t)n_utt * max_len * sizeof(float) + 255) / 256 * 256;
-  const size_t zs = ((size_t)n_utt * fe_nchunk(max_len) * FE_NST * sizeof(double) + 255) / 256 * 256;
-  return fe_tables_bytes() + sig + fwd + zs + 4096;      // tail: A^L (36 doubles) or the 8 tile powers (288 doubles)
+  return fe_tables_bytes() + sig + fwd + 4096;      // tail: the FE_TLEV tile powers (8 x 36 doubles)
+}
+
+static int fe_front(const float* wav, const float* dither, const int* lengths, int n_utt, int max_len, const float* mel_basis,
+                    const double* filt, const double* zi, float* out, int max_frames, int out_bins, void* workspace,
+                    size_t workspace_bytes, cudaStream_t st) {
+  if (!workspace || workspace_bytes < avc_logmel_workspace_bytes(n_utt, max_len)) {
+    set_error("avc_logmel_frontend: workspace too small");
+    return AVC_ERR_WORKSPACE;
+  }
+  unsigned char* ws = (unsigned char*)workspace;
+  FeTables* tb = (FeTables*)ws;
+  float* sig = (float*)(ws + fe_tables_bytes());
+  const size_t sig_b = ((size_t)n_utt * max_len * sizeof(float) + 255) / 256 * 256;
+  const size_t fwd_b = ((size_t)n_utt * (max_len + 2 * FE_PADLEN) * sizeof(double) + 255) / 256 * 256;
+  double* fwd = (double*)(ws + fe_tables_bytes() + sig_b);
+  double* PW = (double*)(ws + fe_tables_bytes() + sig_b + fwd_b);
+  fe_tables_kernel<<<ceil_div(FE_NFFT, 256), 256, 0, st>>>(mel_basis, tb);
+  AVC_LAUNCHED();
+  // one CTA per utterance, tiles staged through shared memory
+  fe_tile_powers_kernel<<<1, 32, 0, st>>>(filt, PW);
+  AVC_LAUNCHED();
+  const size_t ism = ((size_t)FE_TNT * (FE_TCH + 1) + 2 * FE_TNT * FE_NST + FE_TLEV * FE_NST * FE_NST + FE_NST) * sizeof(double);
+  AVC_CUDA(cudaFuncSetAttribute(fe_iir_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
+  AVC_CUDA(cudaFuncSetAttribute(fe_iir_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
+  fe_iir_sweep_kernel<false><<<n_utt, FE_TNT, ism, st>>>(wav, dither, lengths, max_len, filt, zi, PW, fwd, sig);
+  AVC_LAUNCHED();
+  fe_iir_sweep_kernel<true><<<n_utt, FE_TNT, ism, st>>>(wav, dither, lengths, max_len, filt, zi, PW, fwd, sig);
+  AVC_LAUNCHED();
+  const size_t smem = (size_t)(FE_THREADS / 32) * FE_EX * sizeof(float2);
+  dim3 grid(ceil_div(max_frames, FE_FRAMES_PER_BLOCK), n_utt);
+  if (out_bins == FE_MELS) {
+    AVC_CUDA(cudaFuncSetAttribute(fe_stft_mel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fe_stft_mel_kernel<false><<<grid, FE_THREADS, smem, st>>>(sig, lengths, max_len, mel_basis, tb, out, max_frames);
+  } else {
+    AVC_CUDA(cudaFuncSetAttribute(fe_stft_mel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fe_stft_mel_kernel<true><<<grid, FE_THREADS, smem, st>>>(sig, lengths, max_len, mel_basis, tb, out, max_frames);
+  }
+  AVC_LAUNCHED();
+  return AVC_OK;
 }
 
 extern "C" int avc_logmel_frontend(const float* wav, const float* dither, const int* lengths, int n_utt, int max_len,
@@ -686,57 +534,17 @@ extern "C" int avc_logmel_frontend(const float* wav, const float* dither, const 
   AVC_REQUIRE(n_utt > 0 && max_len > 0 && max_frames > 0, "avc_logmel_frontend: bad shape");
   AVC_REQUIRE(max_frames >= 1 + max_len / FE_HOP, "avc_logmel_frontend: max_frames %d < 1 + max_len/256 = %d", max_frames,
               1 + max_len / FE_HOP);
-  if (!workspace || workspace_bytes < avc_logmel_workspace_bytes(n_utt, max_len)) {
-    set_error("avc_logmel_frontend: workspace too small");
-    return AVC_ERR_WORKSPACE;
-  }
-  cudaStream_t st = as_stream(stream);
-  unsigned char* ws = (unsigned char*)workspace;
-  FeTables* tb = (FeTables*)ws;
-  float* sig = (float*)(ws + fe_tables_bytes());
-  const size_t sig_b = ((size_t)n_utt * max_len * sizeof(float) + 255) / 256 * 256;
-  const size_t fwd_b = ((size_t)n_utt * (max_len + 2 * FE_PADLEN) * sizeof(double) + 255) / 256 * 256;
-  const int nchunk = fe_nchunk(max_len);
-  double* fwd = (double*)(ws + fe_tables_bytes() + sig_b);
-  double* zs = (double*)(ws + fe_tables_bytes() + sig_b + fwd_b);
-  double* AL = (double*)(ws + fe_tables_bytes() + sig_b + fwd_b + ((size_t)n_utt * nchunk * FE_NST * sizeof(double) + 255) / 256 * 256);
-  fe_tables_kernel<<<ceil_div(FE_NFFT, 256), 256, 0, st>>>(mel_basis, tb);
-  AVC_LAUNCHED();
-  static const bool tiled = getenv("AVC_FE_IIR_TILED") ? atoi(getenv("AVC_FE_IIR_TILED")) != 0 : true;
-  if (tiled) {
-    // one CTA per utterance, tiles staged through shared memory (AL's slot holds the FE_TLEV tile powers: 8*36 doubles)
-    fe_tile_powers_kernel<<<1, 32, 0, st>>>(filt, AL);
-    AVC_LAUNCHED();
-    const size_t ism = ((size_t)FE_TNT * (FE_TCH + 1) + 2 * FE_TNT * FE_NST + FE_TLEV * FE_NST * FE_NST + FE_NST) * sizeof(double);
-    AVC_CUDA(cudaFuncSetAttribute(fe_iir_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
-    AVC_CUDA(cudaFuncSetAttribute(fe_iir_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
-    fe_iir_sweep_kernel<false><<<n_utt, FE_TNT, ism, st>>>(wav, dither, lengths, max_len, filt, zi, AL, fwd, sig);
-    AVC_LAUNCHED();
-    fe_iir_sweep_kernel<true><<<n_utt, FE_TNT, ism, st>>>(wav, dither, lengths, max_len, filt, zi, AL, fwd, sig);
-    AVC_LAUNCHED();
-  } else {
-  fe_state_power_kernel<<<1, 32, 0, st>>>(filt, AL);
-  AVC_LAUNCHED();
-  {
-    dim3 cgrid(ceil_div(nchunk, 128), n_utt);
-    fe_iir_zero_state_kernel<false><<<cgrid, 128, 0, st>>>(wav, fwd, lengths, n_utt, max_len, nchunk, filt, zs);
-    AVC_LAUNCHED();
-    fe_iir_scan_warp_kernel<false><<<ceil_div(n_utt, 4), 128, 0, st>>>(wav, fwd, lengths, n_utt, max_len, nchunk, zi, AL, zs);
-    AVC_LAUNCHED();
-    fe_iir_output_kernel<false><<<cgrid, 128, 0, st>>>(wav, dither, lengths, n_utt, max_len, nchunk, filt, zs, fwd, sig);
-    AVC_LAUNCHED();
-    fe_iir_zero_state_kernel<true><<<cgrid, 128, 0, st>>>(wav, fwd, lengths, n_utt, max_len, nchunk, filt, zs);
-    AVC_LAUNCHED();
-    fe_iir_scan_warp_kernel<true><<<ceil_div(n_utt, 4), 128, 0, st>>>(wav, fwd, lengths, n_utt, max_len, nchunk, zi, AL, zs);
-    AVC_LAUNCHED();
-    fe_iir_output_kernel<true><<<cgrid, 128, 0, st>>>(wav, dither, lengths, n_utt, max_len, nchunk, filt, zs, fwd, sig);
-    AVC_LAUNCHED();
-  }
-  }
-  const size_t smem = (size_t)(FE_THREADS / 32) * FE_EX * sizeof(float2);
-  AVC_CUDA(cudaFuncSetAttribute(fe_stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(ceil_div(max_frames, FE_FRAMES_PER_BLOCK), n_utt);
-  fe_stft_mel_kernel<<<grid, FE_THREADS, smem, st>>>(sig, lengths, max_len, mel_basis, tb, out, max_frames);
-  AVC_LAUNCHED();
-  return AVC_OK;
+  return fe_front(wav, dither, lengths, n_utt, max_len, mel_basis, filt, zi, out, max_frames, FE_MELS, workspace, workspace_bytes,
+                  as_stream(stream));
+}
+
+extern "C" int avc_logstft_frontend(const float* wav, const float* dither, const int* lengths, int n_utt, int max_len,
+                                    const float* mel_basis, const double* filt, const double* zi, float* out,
+                                    int max_frames, void* workspace, size_t workspace_bytes, void* stream) {
+  AVC_REQUIRE(wav && dither && lengths && mel_basis && filt && zi && out, "avc_logstft_frontend: null pointer");
+  AVC_REQUIRE(n_utt > 0 && max_len > 0 && max_frames > 0, "avc_logstft_frontend: bad shape");
+  AVC_REQUIRE(max_frames >= 1 + max_len / FE_HOP, "avc_logstft_frontend: max_frames %d < 1 + max_len/256 = %d", max_frames,
+              1 + max_len / FE_HOP);
+  return fe_front(wav, dither, lengths, n_utt, max_len, mel_basis, filt, zi, out, max_frames, FE_BINS, workspace, workspace_bytes,
+                  as_stream(stream));
 }

@@ -313,6 +313,12 @@ int avc_logmel_frontend(const float* wav, const float* dither, const int* length
                         const float* mel_basis, const double* filt, const double* zi,
                         float* out, int max_frames, void* workspace, size_t workspace_bytes, void* stream);
 size_t avc_logmel_workspace_bytes(int n_utt, int max_len);
+/* make_spect.py:84-86 (model_type 'stft'): same pipeline up to D, then S = clip((20*log10(max(1e-5, D)) - 16 + 100)/100, 0, 1)
+ * on the 513 magnitudes themselves.  out: (n_utt, max_frames, 513) float32, frame-major (the reference saves the transpose);
+ * same arguments and workspace as avc_logmel_frontend (mel_basis is only used to build the shared tables). */
+int avc_logstft_frontend(const float* wav, const float* dither, const int* lengths, int n_utt, int max_len,
+                         const float* mel_basis, const double* filt, const double* zi,
+                         float* out, int max_frames, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Waveform variant, model_vc_wav.py:11-102 (GeneratorWav, ConvTasNetEncoder / ConvTasNetDecoder) and the 'wav' branch

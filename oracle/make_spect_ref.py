@@ -106,6 +106,19 @@ def logmel_from_wav(x_f32: np.ndarray, dither_u01: np.ndarray, mel_basis=None, b
     return S.astype(np.float32)                             # :94
 
 
+def logstft_from_wav(x_f32: np.ndarray, dither_u01: np.ndarray, ba=None) -> np.ndarray:
+    """make_spect.py:72-78,:84-86,:94 (model_type 'stft') for one utterance: the log / clip of the 513 STFT magnitudes themselves.
+    Returns ``S`` (513, F) float32 in [0, 1] -- the reference does not transpose D in this branch.  Shares every statement up to
+    ``D`` with ``logmel_from_wav``, which is pinned to the reference's 71 bundled goldens."""
+    b, a = ba if ba is not None else butter_highpass()      # :53
+    y = signal.filtfilt(b, a, x_f32)                        # :74
+    wav = y * 0.96 + (dither_u01 - 0.5) * 1e-06             # :76
+    D = py_stft(wav)                                        # :78
+    D_db = 20 * np.log10(np.maximum(MIN_LEVEL, D)) - 16     # :85
+    S = np.clip((D_db + 100) / 100, 0, 1)                   # :86
+    return S.astype(np.float32)                             # :94
+
+
 def speaker_dither_streams(speaker_dir: str, lengths):
     """The per-speaker MT19937 stream of make_spect.py:68,:76: one ``RandomState(int(
     spk[1:]))`` consumed over the speaker's files in sorted order."""

@@ -30,3 +30,21 @@ def test_dvector_matches_reference_golden(precision, tol):
         rel = np.linalg.norm(y - g["y64"]) / np.linalg.norm(g["y64"])
         print("half rel-L2", rel)
         assert rel < 1e-2
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("half", 2e-3)])
+def test_speaker_embedding_pipeline_matches_oracle(precision, tol):
+    """make_metadata.py:54-78: mean d-vector of 10 random crops per speaker, all crops in ONE batched forward; same numpy
+    stream -> same crops as the oracle's restatement of the reference loop."""
+    from autovc_b200.make_metadata import speaker_embeddings
+    from oracle import make_metadata_ref as mref
+    torch.manual_seed(0)
+    C = D_VECTOR(dim_input=80, dim_cell=768, dim_emb=256, precision=precision).eval().cuda()
+    sd = {k: v.detach().cpu().clone() for k, v in C.state_dict().items()}
+    speakers = mref.synth_speakers(3, seed=5)
+    got = speaker_embeddings(C, speakers, rng=np.random.RandomState(11))
+    ref = mref.speaker_embeddings_ref(sd, speakers, rng=np.random.RandomState(11))
+    assert sorted(got) == sorted(ref)
+    for k in ref:
+        assert got[k].shape == (256,)
+        assert np.abs(got[k] - ref[k]).max() < tol, (k, np.abs(got[k] - ref[k]).max())

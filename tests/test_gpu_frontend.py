@@ -68,3 +68,24 @@ def test_frontend_tile_and_frame_boundaries():
         err = np.abs(out[i, :F] - ref).max()
         assert err < TOL, (n, err)
         assert np.all(out[i, F:] == 0.0), n
+
+
+def test_stft_branch_matches_oracle():
+    """make_spect.py:84-86 (model_type 'stft'): 513 log-magnitudes per frame; the per-utterance files are (513, F)."""
+    from autovc_b200.make_spect import Spect
+    wav, dither = fref.synthetic_waveforms(4, 20000, seed=11)
+    lengths = [20000, 777, 8192 + 40, 15000]
+    sp = Spect()
+    outs = sp.spect_utterances([wav[i, :n] for i, n in enumerate(lengths)], [dither[i, :n] for i, n in enumerate(lengths)],
+                               model_type="stft")
+    for i, n in enumerate(lengths):
+        ref = fref.logstft_from_wav(wav[i, :n], dither[i, :n])
+        assert outs[i].shape == ref.shape == (513, 1 + n // 256)
+        err = np.abs(outs[i] - ref).max()
+        assert err < TOL, (i, err)
+    # frame-major device tensor, zero rows past each utterance
+    L = max(lengths)
+    full = sp.logstft(torch.from_numpy(wav[:, :L].copy()).cuda(), torch.from_numpy(dither[:, :L].astype(np.float32)).cuda(),
+                      torch.tensor(lengths, dtype=torch.int32).cuda(), max_frames=96)
+    assert full.shape == (4, 96, 513)
+    assert float(full[1, 1 + 777 // 256:].abs().max()) == 0.0

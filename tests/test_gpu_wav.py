@@ -78,7 +78,9 @@ def test_wav_train_step_matches_reference_golden_fp32(name, precision):
         # random direction) and the one-element PReLU slopes (first Adam step = -lr * sign(g): a norm test of one number)
         keep = np.array([not n.endswith(".conv.bias") and p.numel() > 1 for n, p in G.named_parameters()])
         pd = np.stack([digest(p) for p in G.parameters()])
-        np.testing.assert_allclose(pd[keep, 2], g[f"s{s}_param_digest"][keep, 2], rtol=1e-4, err_msg=f"post-Adam norms, step {s}")
+        # the first Adam steps move every element by ~lr * sign(g): elements whose gradient is at rounding level move the other way,
+        # which shifts a tensor's norm by up to ~2 lr sqrt(fraction flipped) -- hence an absolute term of one lr
+        np.testing.assert_allclose(pd[keep, 2], g[f"s{s}_param_digest"][keep, 2], rtol=2e-5, atol=1e-4, err_msg=f"post-Adam norms, step {s}")
 
 
 @pytest.mark.parametrize("precision", ["tf32", "half"])
