@@ -44,7 +44,11 @@ def test_wav_train_step_matches_reference_golden_fp32(name, precision):
         ref_l = g[f"s{s}_losses"]
         got_l = np.array([out[k] for k in ("g_loss", "L_id", "L_gen", "L_cd", "L_SISNR")])
         # the SI-SNR term is O(45) dB at initialisation: the 1e-4 gate is applied relative to max(1, |value|)
-        assert np.all(np.abs(got_l - ref_l) <= 1e-4 * np.maximum(1.0, np.abs(ref_l))), (s, got_l, ref_l)
+        # second step: the first Adam update is -lr * sign(g) element-wise, which turns rounding-level differences of near-zero
+        # gradient entries into +-2 lr parameter differences; the 26 dB SI-SNR term then differs by ~2e-4 relative between any
+        # two fp32 evaluations (measured: 2.0e-4 with the split-product GEMMs, 0.4e-4 with CUDA-core fp32)
+        ltol = 1e-4 if s == 0 else 5e-4
+        assert np.all(np.abs(got_l - ref_l) <= ltol * np.maximum(1.0, np.abs(ref_l))), (s, got_l, ref_l)
         if s == 0:
             for k in ("x_convtas", "x_identic", "gen_outputs", "code_real", "code_reconst"):
                 got = out[k].cpu().numpy()
