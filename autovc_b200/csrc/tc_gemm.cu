@@ -62,7 +62,6 @@ struct TcParams {
   int grouped_a, grouped_b;   // operand fetched with one grouped 4-D box per stage (make_map4_grouped)
   uint32_t idesc;             // tcgen05 instruction descriptor (operand formats are chosen at run time)
   unsigned long long* trace;  // avc_debug_set_trace: %globaltimer stamps of pair 0's leader, 8 slots per tile (first 64 tiles)
-  int dbg;                    // AVC_GEMM_EPI_DEBUG (measurement only): 1 = skip the TMA store issue, 2 = also skip the smem staging
   int tma_store;              // NT pair kernel: C leaves through shared memory + TMA stores (needs ldc % 4 == 0, 16-byte aligned C)
   float* part;
 };
@@ -780,17 +779,13 @@ tc_gemm2_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           const uint32_t buf = epi_w + (uint32_t)(c & (Cf::EPI_BUFS - 1)) * 4096u;
           if (lane == 0) bulk_wait_read<Cf::EPI_BUFS - 1>();   // the store that last used this tile has drained it
           __syncwarp();
-          if (p.dbg < 2) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              st_shared_v4(buf + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            fence_async_smem();
-          } else if (v[0] == 123.456f) {
-            st_shared_v4(buf, v[1], v[2], v[3], v[31]);
-          }
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(buf + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          fence_async_smem();
           __syncwarp();
           TC2_CTRACE(2);
-          if (lane == 0 && p.dbg < 1) {
+          if (lane == 0) {
             if (p.accumulate) tma_reduce_add_3d(&mapC, buf, n0, t_blk, b);
             else tma_store_3d(&mapC, buf, n0, t_blk, b);
             bulk_commit();
@@ -1170,12 +1165,6 @@ static int tc_dispatch(int eb, int bn, const CUtensorMap& mA, const CUtensorMap&
 
 // tile-width choice: fewest (rounds x tile cost); a 256-wide tile costs ~1.41x a 128-wide one (smem-bound model)
 static int pick_bn(int row_tiles, int N) {
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("AVC_GEMM_BN");
-    forced = e ? atoi(e) : 0;
-  }
-  if (forced == 128 || forced == 256) return forced;
   if (N <= 128) return 128;
   const int sms = num_sms();
   const double c128 = (double)ceil_div(row_tiles * ceil_div(N, 128), sms) * 1.0;
@@ -1296,9 +1285,7 @@ int gemm_nt_taps_tc(const void* Av, int a_fmt, int lda, const void* Wv, int w_fm
     const int pair_tiles = ceil_div(nB * p.t_tiles, 2) * p.n_tiles;
     const int grid2 = 2 * std::min(pair_tiles, num_sms() / 2);
     CUtensorMap mC = mA;                    // placeholder when the direct-store epilogue is used
-    static const bool tma_epi = getenv("AVC_GEMM_TMA_STORE") ? atoi(getenv("AVC_GEMM_TMA_STORE")) != 0 : true;
-    p.tma_store = tma_epi && (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0);
-    p.dbg = getenv("AVC_GEMM_EPI_DEBUG") ? atoi(getenv("AVC_GEMM_EPI_DEBUG")) : 0;
+    p.tma_store = (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0);
     p.trace = g_gemm_trace;
     if (p.tma_store) {
       rc = make_map3_out_f32(&mC, C, N, T, nB, ldc, (uint64_t)T * ldc, 32);
@@ -1346,10 +1333,6 @@ static TnPlan tn_plan(int nB, int T, int N, int K, int ntaps, int eb, bool stage
   TnPlan pl;
   pl.bn = (K % 256 == 0 || K > 640) ? 256 : 128;
   if (chunk) pl.bn = 128;
-  else {
-    const char* e = getenv("AVC_GEMM_BN");
-    if (e && (atoi(e) == 128 || atoi(e) == 256)) pl.bn = atoi(e);
-  }
   pl.Np = round_up(N, TC_BM);
   pl.Kp = round_up(K, pl.bn);
   pl.rs = eb == 2 ? 64 : 32;

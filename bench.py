@@ -400,6 +400,8 @@ def run_ours(args):
             "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "modes": modes, "sustained": sustained,
         }
+        if reducer is not None:
+            line["config"]["nccl_cta_cap"] = reducer.cta_cap
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

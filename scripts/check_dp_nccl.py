@@ -17,7 +17,8 @@ from autovc_b200 import solver
 rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-solver.nccl_env_defaults()
+if os.environ.get("AVC_CHECK_NO_ENV_CAP") != "1":      # "1": prove that the reducer's own communicator carries the CTA cap
+    solver.nccl_env_defaults()
 dist.init_process_group("nccl", device_id=dev)
 world = dist.get_world_size()
 
@@ -72,6 +73,23 @@ lo, hi = ps.clone(), ps.clone()
 dist.all_reduce(lo, op=dist.ReduceOp.MIN)
 dist.all_reduce(hi, op=dist.ReduceOp.MAX)
 assert torch.equal(lo, hi), "replicas diverged after FusedAdam steps"
+# (4) step time at the benched shape with the reducer's communicator (a convoy with the cooperative recurrences would show here)
+xb = torch.rand(256, 128, 80, generator=g).to(dev)
+eb = (F.normalize(torch.randn(256, 256, generator=g), dim=-1) * 0.8).to(dev)
+for _ in range(5):
+    solver.train_step(G, opt, xb, eb, reducer=red, sync_losses=False)
+torch.cuda.synchronize()
+dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    solver.train_step(G, opt, xb, eb, reducer=red, sync_losses=False)
+e1.record()
+torch.cuda.synchronize()
+ms = torch.tensor([e0.elapsed_time(e1) / 20], device=dev)
+dist.all_reduce(ms, op=dist.ReduceOp.MAX)
 if rank == 0:
+    print(f"check_dp_nccl: NCCL CTA cap: {red.cta_cap}; NCCL_MAX_CTAS env: {os.environ.get('NCCL_MAX_CTAS')}; "
+          f"{float(ms):.2f} ms per 256-crop step on {world} GPUs")
     print(f"check_dp_nccl: OK on {world} GPUs (worst relative deviation of a reduced gradient {worst:.2e}; replicas identical after 2 optimizer steps)")
 dist.destroy_process_group()

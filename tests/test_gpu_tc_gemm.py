@@ -212,3 +212,27 @@ def test_nt_taps_prepacked_weight_equals_staged(nB, T, N, K, ntaps):
     # mixed 16-bit formats are refused (tcgen05 kind::f16 would trap)
     with pytest.raises(Exception):
         ops.gemm_nt_taps_hw(A.bfloat16(), 1, K, W16, 2, ldw, bias, C3, N, nB, T, N, K, ntaps, shift0)
+
+
+@pytest.mark.parametrize("prec", [1, 2])
+def test_single_cta_fallback_switch_matches_pair_kernels(prec, monkeypatch):
+    """AVC_GEMM_2CTA=0 (the one selection switch the library keeps: it forces the single-CTA kernels where a CTA pair would
+    run) computes the same contraction: both against the fp64 product, and against each other within accumulation order."""
+    nB, T, N, K, ntaps = 40, 128, 512, 256, 5
+    A = _rand(nB * T, K, seed=11)
+    W = _rand(ntaps, N, K, seed=12) * 0.05
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("AVC_GEMM_2CTA", flag)
+        C = torch.empty(nB * T, N, device=DEV)
+        ops.gemm_nt_taps(A, K, W, None, C, N, nB, T, N, K, ntaps, -2, prec=prec)
+        dW = torch.empty(N, K, ntaps, device=DEV)
+        ops.gemm_tn_taps(C, N, A, K, dW, nB, T, N, K, ntaps, -2, out_mode=1, prec=prec)
+        torch.cuda.synchronize()
+        out[flag] = (C, dW)
+    ref = _ref_nt(A, W, None, nB, T, ntaps, -2, prec)
+    scale = float(ref.abs().max())
+    tol = (2e-5 if prec == 1 else 2e-4) * scale * (K * ntaps / 256) ** 0.5
+    for flag in out:
+        assert float((out[flag][0].double() - ref).abs().max()) < tol, flag
+    assert float((out["0"][1] - out["1"][1]).abs().max()) <= 2e-3 * float(out["1"][1].abs().max())
