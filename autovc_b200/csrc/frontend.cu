@@ -28,8 +28,6 @@ struct FeTables {           // lives at the head of the workspace
   // segments [seg0[m], seg0[m+1]) (consecutive, so its partial sums are added in a fixed order)
   int4 seg[256];            // (filter, first bin, last bin + 1, -)
   int seg0[FE_MELS + 1];
-  double2 tw2d[FE_NFFT];    // the same twiddles and window in double: the 513-bin ('stft') output runs the transform in fp64
-  double wind[FE_NFFT];
 };
 
 __global__ void fe_tables_kernel(const float* __restrict__ mel_basis, FeTables* __restrict__ tb) {
@@ -38,12 +36,8 @@ __global__ void fe_tables_kernel(const float* __restrict__ mel_basis, FeTables* 
     double s, c;
     sincospi(-2.0 * (double)(((i >> 5) * (i & 31)) & (FE_NFFT - 1)) / (double)FE_NFFT, &s, &c);
     tb->tw2[i] = make_float2((float)c, (float)s);
-    tb->tw2d[i] = make_double2(c, s);
   }
-  if (i < FE_NFFT) {
-    tb->wind[i] = 0.5 - 0.5 * cospi(2.0 * (double)i / (double)FE_NFFT);
-    tb->win[i] = (float)tb->wind[i];
-  }
+  if (i < FE_NFFT) tb->win[i] = (float)(0.5 - 0.5 * cospi(2.0 * (double)i / (double)FE_NFFT));
   if (i < FE_MELS) {
     int lo = FE_BINS, hi = 0;
     for (int k = 0; k < FE_BINS; ++k)
@@ -353,48 +347,6 @@ __device__ __forceinline__ void fft32(float2 (&v)[32]) {
   }
 }
 
-// fp64 twin of the transform for the 513-bin output (make_spect.py:84-86).  The linear bins are NOT sums over a band like the
-// mel outputs: a bin 60 dB under the frame's level carries the fp32 transform's absolute rounding error (~3e-6 of the level)
-// as a 3e-3 relative error, which the log turns into 3e-4 -- three times the 1e-4 gate (measured).  The reference computes
-// numpy.fft.rfft in fp64; so does this path (one warp per frame pair, 32 double2 per thread).
-__constant__ double2 c_w32d[16] = {
-    {1, -0},
-    {0.98078528040323043, -0.19509032201612825},
-    {0.92387953251128674, -0.38268343236508978},
-    {0.83146961230254524, -0.55557023301960218},
-    {0.70710678118654757, -0.70710678118654746},
-    {0.55557023301960229, -0.83146961230254524},
-    {0.38268343236508984, -0.92387953251128674},
-    {0.19509032201612833, -0.98078528040323043},
-    {6.123233995736766e-17, -1},
-    {-0.19509032201612819, -0.98078528040323043},
-    {-0.38268343236508973, -0.92387953251128674},
-    {-0.55557023301960196, -0.83146961230254546},
-    {-0.70710678118654746, -0.70710678118654757},
-    {-0.83146961230254535, -0.55557023301960218},
-    {-0.92387953251128674, -0.38268343236508989},
-    {-0.98078528040323043, -0.19509032201612861},
-};
-__device__ __forceinline__ double2 cmuld(double2 a, double2 w) { return make_double2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
-__device__ __forceinline__ void fft32d(double2 (&v)[32]) {
-#pragma unroll
-  for (int half = 16; half >= 1; half >>= 1) {
-#pragma unroll
-    for (int g = 0; g < 32; g += 2 * half) {
-#pragma unroll
-      for (int j = 0; j < half; ++j) {
-        const double2 a = v[g + j], b = v[g + j + half];
-        v[g + j] = make_double2(a.x + b.x, a.y + b.y);
-        const double2 d = make_double2(a.x - b.x, a.y - b.y);
-        const int m = j * (16 / half);
-        if (m == 0) v[g + j + half] = d;
-        else if (m == 8) v[g + j + half] = make_double2(d.y, -d.x);      // * (-i)
-        else v[g + j + half] = cmuld(d, c_w32d[m]);
-      }
-    }
-  }
-}
-
 constexpr int FE_EXLD = 33;                          // padded row of the exchange tile
 constexpr int FE_EX = 32 * FE_EXLD;                  // float2 per transform
 
@@ -411,6 +363,9 @@ __device__ __forceinline__ float fe_reflect(const float* __restrict__ x, int n, 
 // Every warp is on its own: frames 2q, 2q+1 -> registers -> transform -> magnitudes -> the two frames' 160 mel outputs.
 // No block barrier anywhere, so the 24 resident warps of an SM sit in different phases and hide each other's latencies
 // (the block-synchronous version ran at 21% of the issue rate).
+// STFT_OUT (make_spect.py:84-86, the 'stft' model type): the 513 magnitudes themselves go through the same log / clip and are
+// written frame-major (n_utt, max_frames, 513) instead of the mel projection.
+template <bool STFT_OUT>
 __global__ void __launch_bounds__(FE_THREADS, 5)
 fe_stft_mel_kernel(const float* __restrict__ sig, const int* __restrict__ lengths, int max_len,
                    const float* __restrict__ mel_basis, const FeTables* __restrict__ tb, float* __restrict__ out,
@@ -427,8 +382,9 @@ fe_stft_mel_kernel(const float* __restrict__ sig, const int* __restrict__ length
   for (int g = 0; g < FE_PAIRS_PER_WARP; ++g) {
     const int f0 = blockIdx.x * FE_FRAMES_PER_BLOCK + (wid * FE_PAIRS_PER_WARP + g) * 2;   // frames f0 (real part), f0+1 (imaginary)
     if (f0 >= max_frames) break;
-    float* o = out + ((size_t)u * max_frames + f0) * FE_MELS;
-    const int nout = min(2, max_frames - f0) * FE_MELS;
+    constexpr int NOUT = STFT_OUT ? FE_BINS : FE_MELS;
+    float* o = out + ((size_t)u * max_frames + f0) * NOUT;
+    const int nout = min(2, max_frames - f0) * NOUT;
     if (f0 >= n_frames) {   // zero padding frames (conversion.py:40-44 pad_seq)
       for (int i = lane; i < nout; i += 32) o[i] = 0.f;
       continue;
@@ -473,6 +429,19 @@ fe_stft_mel_kernel(const float* __restrict__ sig, const int* __restrict__ length
       e[k] = make_float2(sqrtf(ar * ar + ai * ai), sqrtf(br * br + bi * bi));
     }
     __syncwarp();
+    if (STFT_OUT) {
+      for (int i = lane; i < nout; i += 32) {
+        const int fr = i >= FE_BINS ? 1 : 0, k = i - fr * FE_BINS;
+        float val = 0.f;
+        if (f0 + fr < n_frames) {
+          const float2 mg = e[k];
+          const float db = 20.f * log10f(fmaxf(1e-5f, fr ? mg.y : mg.x)) - 16.f;
+          val = fminf(fmaxf((db + 100.f) / 100.f, 0.f), 1.f);
+        }
+        o[i] = val;
+      }
+      continue;
+    }
     // mel projection of BOTH frames: the bin ranges of the 80 filters are cut into segments of <= 8 bins (tb->seg), a lane takes
     // every 32nd segment and sums it for the two frames at once (one 8-byte magnitude pair + one weight per bin), the partial
     // sums go to the dead upper half of the tile and each output adds its filter's partials in a fixed order.  The first version
@@ -503,66 +472,6 @@ fe_stft_mel_kernel(const float* __restrict__ sig, const int* __restrict__ length
       }
       o[i] = val;
     }
-  }
-}
-
-// 513-bin output: same framing, fp64 transform, log / clip of the magnitudes themselves, frame-major (n_utt, max_frames, 513)
-__global__ void __launch_bounds__(FE_THREADS, 2)
-fe_stft_bins_kernel(const float* __restrict__ sig, const int* __restrict__ lengths, int max_len,
-                    const FeTables* __restrict__ tb, float* __restrict__ out, int max_frames) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int u = blockIdx.y;
-  const int n = lengths[u];
-  const int n_frames = n > FE_PADLEN ? 1 + n / FE_HOP : 0;
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double2* e = reinterpret_cast<double2*>(smem_raw) + wid * FE_EX;
-  const float* x = sig + (size_t)u * max_len;
-  const double* win = tb->wind;
-  const double2* tw2 = tb->tw2d;
-  for (int g = 0; g < FE_PAIRS_PER_WARP; ++g) {
-    const int f0 = blockIdx.x * FE_FRAMES_PER_BLOCK + (wid * FE_PAIRS_PER_WARP + g) * 2;
-    if (f0 >= max_frames) break;
-    float* o = out + ((size_t)u * max_frames + f0) * FE_BINS;
-    const int nout = min(2, max_frames - f0) * FE_BINS;
-    if (f0 >= n_frames) {
-      for (int i = lane; i < nout; i += 32) o[i] = 0.f;
-      continue;
-    }
-    double2 v[32];
-    const int j0 = f0 * FE_HOP - FE_REFLECT;
-#pragma unroll
-    for (int a = 0; a < 32; ++a) {
-      const int k = 32 * a + lane;
-      const double w = win[k];
-      v[a] = make_double2(w * (double)fe_reflect(x, n, j0 + k), w * (double)fe_reflect(x, n, j0 + FE_HOP + k));
-    }
-    fft32d(v);
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < 32; ++c) e[c * FE_EXLD + lane] = cmuld(v[bitrev5(c)], tw2[c * 32 + lane]);
-    __syncwarp();
-#pragma unroll
-    for (int b = 0; b < 32; ++b) v[b] = e[lane * FE_EXLD + b];
-    __syncwarp();
-    fft32d(v);
-#pragma unroll
-    for (int d = 0; d < 32; ++d) e[lane + 32 * d] = v[bitrev5(d)];
-    __syncwarp();
-    for (int i = lane; i < nout; i += 32) {
-      const int fr = i >= FE_BINS ? 1 : 0, k = i - fr * FE_BINS;
-      float val = 0.f;
-      if (f0 + fr < n_frames) {
-        const double2 a = e[k];
-        const double2 b = e[(FE_NFFT - k) & (FE_NFFT - 1)];
-        const double re = fr ? 0.5 * (a.y + b.y) : 0.5 * (a.x + b.x);
-        const double im = fr ? 0.5 * (b.x - a.x) : 0.5 * (a.y - b.y);
-        const double mag = sqrt(re * re + im * im);
-        const double db = 20.0 * log10(fmax(1e-5, mag)) - 16.0;
-        val = (float)fmin(fmax((db + 100.0) / 100.0, 0.0), 1.0);
-      }
-      o[i] = val;
-    }
-    __syncwarp();
   }
 }
 
@@ -608,11 +517,11 @@ static int fe_front(const float* wav, const float* dither, const int* lengths, i
   const size_t smem = (size_t)(FE_THREADS / 32) * FE_EX * sizeof(float2);
   dim3 grid(ceil_div(max_frames, FE_FRAMES_PER_BLOCK), n_utt);
   if (out_bins == FE_MELS) {
-    AVC_CUDA(cudaFuncSetAttribute(fe_stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fe_stft_mel_kernel<<<grid, FE_THREADS, smem, st>>>(sig, lengths, max_len, mel_basis, tb, out, max_frames);
+    AVC_CUDA(cudaFuncSetAttribute(fe_stft_mel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fe_stft_mel_kernel<false><<<grid, FE_THREADS, smem, st>>>(sig, lengths, max_len, mel_basis, tb, out, max_frames);
   } else {
-    AVC_CUDA(cudaFuncSetAttribute(fe_stft_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * smem)));
-    fe_stft_bins_kernel<<<grid, FE_THREADS, 2 * smem, st>>>(sig, lengths, max_len, tb, out, max_frames);
+    AVC_CUDA(cudaFuncSetAttribute(fe_stft_mel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fe_stft_mel_kernel<true><<<grid, FE_THREADS, smem, st>>>(sig, lengths, max_len, mel_basis, tb, out, max_frames);
   }
   AVC_LAUNCHED();
   return AVC_OK;
