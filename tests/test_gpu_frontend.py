@@ -81,14 +81,13 @@ def test_stft_branch_matches_oracle():
     for i, n in enumerate(lengths):
         ref = fref.logstft_from_wav(wav[i, :n], dither[i, :n])
         assert outs[i].shape == ref.shape == (513, 1 + n // 256)
-        # 1e-4 wherever a bin is within 60 dB of its frame's peak; bins further down (here: DC and the two bins under the 30 Hz
-        # high-pass) carry the fp32 FFT's absolute rounding error (~1e-7 of the frame's energy) against the reference's fp64
-        # numpy.fft -- a relative error that the log turns into up to ~5e-4.  The 80 mel bands never get there (sums of >= 2
-        # bins inside 90-7600 Hz), which is why the spmel branch holds 1e-4 everywhere.
+        # 1e-4 on every bin but DC.  Bin 0 lies under the 30 Hz high-pass, 50-60 dB below the frame's level, and there the
+        # reference's OWN filter arithmetic shows: scipy's transfer-function filtfilt and the same filter as a cascade of
+        # second-order sections (the realisation a chunk-parallel IIR needs) differ by 7e-7 on the waveform, which
+        # is 3e-4 on that one log-magnitude -- reproduced on the CPU with scipy.signal.sosfiltfilt alone (bins >= 1: <= 1.2e-5).
         err = np.abs(outs[i] - ref)
-        strong = ref >= ref.max(axis=0, keepdims=True) - 0.6
-        assert err[strong].max() < TOL, (i, err[strong].max())
-        assert err.max() < 1e-3, (i, err.max())
+        assert err[1:].max() < TOL, (i, err[1:].max())
+        assert err[0].max() < 1e-3, (i, err[0].max())
     # frame-major device tensor, zero rows past each utterance
     L = max(lengths)
     full = sp.logstft(torch.from_numpy(wav[:, :L].copy()).cuda(), torch.from_numpy(dither[:, :L].astype(np.float32)).cuda(),
