@@ -503,7 +503,7 @@ def run_frontend_or_convert(args):
     G = autovc_b200.Generator(32, 256, 512, 32, precision=args.precision).to(dev)
     e = F.normalize(torch.randn(n, 256, generator=torch.Generator().manual_seed(5)), dim=-1).to(dev) * 0.8
     et = e.roll(1, 0).contiguous()
-    ms = timed(lambda: convert(G, sp, wav, dither, None, e, et, chunk=256), args.steps, max(1, args.warmup - 2))
+    ms = timed(lambda: convert(G, sp, wav, dither, None, e, et, chunk=args.chunk, streams=args.streams), args.steps, max(1, args.warmup - 2))
     flops = 2.0 * 28_385_280 * n * padded_frames(L)      # per GPU; one encoder pass in conversion (28 385 280 MAC/frame)
     if rank != 0:
         dist.destroy_process_group()
@@ -534,7 +534,7 @@ def run_frontend_or_convert(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"waveform -> log-mel -> pad to x32 -> Generator(32,256,512,32).eval() forward, {n_total} x 10 s utterances "
-                                   f"({n} per GPU), chunks of 256", "parallelism": f"replicas x{world}"},
+                                   f"({n} per GPU), chunks of {args.chunk} over {args.streams} streams", "parallelism": f"replicas x{world}"},
             "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"], "traffic": None, "per": "GPU"},
             "cpu_baseline": cpu}
@@ -669,6 +669,8 @@ def main():
     ap.add_argument("--cpu-sample-batch", dest="cpu_sample_batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "frontend", "convert", "loader", "dvector", "wav"])
+    ap.add_argument("--chunk", type=int, default=128, help="--workload convert: utterances per Generator call")
+    ap.add_argument("--streams", type=int, default=4, help="--workload convert: CUDA streams the chunks alternate over")
     ap.add_argument("--depth", type=int, default=1, help="--workload wav: Conv-TasNet encoder/decoder depth (main.py:65)")
     ap.add_argument("--utterances", type=int, default=4096, help="frontend/convert legs: number of 10 s utterances (BASELINE.json configs[4]: 4096)")
     args = ap.parse_args()

@@ -41,3 +41,27 @@ def test_conversion_matches_chained_oracles():
             _, ref, _ = gref.generator_forward(sd, torch.from_numpy(Sp)[None], e[i:i + 1], e2[i:i + 1], 32, 32, training=False)
         err = float((out[i, 0, :F].cpu() - ref[0, 0, :F]).abs().max())
         assert err < 2e-4, (i, err)          # 1e-4 front-end + 1e-4 generator budgets
+
+
+@pytest.mark.parametrize("precision", ["fp32", "half"])
+def test_chunks_on_several_streams_change_nothing(precision):
+    """convert() alternates chunks over CUDA streams (recurrences of one chunk run beside the GEMMs of another): eval-mode chunks
+    are independent, so any (chunk, streams) setting must give the result of one call over the whole batch."""
+    import autovc_b200
+    from autovc_b200.conversion import convert
+    from autovc_b200.make_spect import Spect
+    torch.manual_seed(1)
+    G = autovc_b200.Generator(32, 256, 512, 32, precision=precision).cuda()
+    x, e, e2 = synth_inputs(7, 64, 80, 256, 3)
+    G.train()
+    with torch.no_grad():
+        G(x.cuda(), e.cuda(), e.cuda())
+    wav, dither = fref.synthetic_waveforms(7, 9000, seed=2)
+    w, d = torch.from_numpy(wav).cuda(), torch.from_numpy(dither.astype(np.float32)).cuda()
+    sp = Spect()
+    ref, _ = convert(G, sp, w, d, None, e.cuda(), e2.cuda(), chunk=16, streams=1)
+    for chunk, streams in ((2, 3), (3, 2), (1, 4)):
+        for _ in range(3):
+            out, _ = convert(G, sp, w, d, None, e.cuda(), e2.cuda(), chunk=chunk, streams=streams)
+            torch.cuda.synchronize()
+            assert float((out - ref).abs().max()) < (1e-5 if precision == "fp32" else 2e-3), (chunk, streams)
