@@ -104,10 +104,15 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 // 5e-5 relative shrink (measured: 4e-4..7e-4 max-abs on x_identic_psnt, four to seven times the 1e-4 gate); with 32-MMA
 // chains summed in registers it is below the fp32 noise of the reference itself.  Needs BN == 128 (128 accumulator registers
 // per epilogue thread).
+// A chunked 256-wide tile runs EIGHT epilogue warps (320 threads): two per TMEM lane quadrant, each owning 128 of the 256 columns,
+// so that a thread still keeps 128 accumulator registers.  (r02 ncu: the chunked 128 x 128 tf32 tile pulls 32 KB of operands per
+// MFLOP and sits on the L2 -> SM delivery rate, 13.8 TB/s; 128 x 256 needs 23 KB per MFLOP.)
+template <int BN, int CH>
+struct TcThreads { static constexpr int value = (CH > 0 && BN == 256) ? 320 : TC_THREADS; };
 template <int MODE, int EB, int BN, int CH = 0>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__((TcThreads<BN, CH>::value), 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
-  static_assert(CH == 0 || BN == 128, "chunked accumulation keeps the whole tile row in registers: BN must be 128");
+  constexpr int EPI_WARPS = (CH > 0 && BN == 256) ? 8 : 4;
   using Cf = TcCfg<BN>;
   constexpr int TC_STAGES = Cf::STAGES, TC_STAGE_BYTES = Cf::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -136,7 +141,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -306,7 +311,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         has_work = split * p.rblocks_per_split < p.rblocks;
       }
       if constexpr (CH > 0) {
-        // ---- chunked accumulation: add every finished chunk into this thread's row of 128 fp32 registers ----
+        // ---- chunked accumulation: add every finished chunk into this thread's 128 fp32 registers (its row, its column half) ----
+        constexpr int EC = 128;                              // columns per epilogue thread
+        const int ch0 = (BN == 256) ? ((warp - 2) >> 2) * EC : 0;      // first column of this warp's half of the tile
         int iters = kiters;
         const int ks = tile % ksplit, tl = tile / ksplit;
         if (MODE == MODE_TN) {
@@ -316,18 +323,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         } else if (ksplit > 1) {
           iters = max(0, min(kiters, (ks + 1) * kper) - ks * kper);
         }
-        float r[BN];
+        float r[EC];
 #pragma unroll
-        for (int j = 0; j < BN; ++j) r[j] = 0.f;
+        for (int j = 0; j < EC; ++j) r[j] = 0.f;
         const int nck = iters > 0 ? (iters + CH - 1) / CH : 1;
 #pragma unroll 1
         for (int ck = 0; ck < nck; ++ck) {
           mbar_wait(tfull_bar(acc), acc_phase);
           tc_fence_after();
-          const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+          const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + ch0;
           if (iters > 0) {
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < EC / 32; ++c) {
               float v[32];
               tmem_ld32(t_addr + c * 32, v);
 #pragma unroll
@@ -346,9 +353,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           float* crow = p.C + (size_t)ks * p.c_split_stride + ((size_t)b * p.T + t) * p.ldc;
           const bool add_bias = p.bias != nullptr && ks == 0;
 #pragma unroll
-          for (int c = 0; c < BN / 32; ++c) {
-            const int n0 = n_tile * BN + c * 32;
-            if (n0 < p.N) {                      // tile-uniform
+          for (int c = 0; c < EC / 32; ++c) {
+            const int n0 = n_tile * BN + ch0 + c * 32;
+            if (n0 < p.N) {                      // warp-uniform
               float v[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
@@ -380,26 +387,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
                 const float s1 = warp_colsum32(v, lane);
                 const float s2 = warp_colsum32(sq, lane);
-                stat_s[(q * 2 + 0) * BN + c * 32 + lane] = s1;
-                stat_s[(q * 2 + 1) * BN + c * 32 + lane] = s2;
+                stat_s[(q * 2 + 0) * BN + ch0 + c * 32 + lane] = s1;
+                stat_s[(q * 2 + 1) * BN + ch0 + c * 32 + lane] = s2;
               }
+            } else if (p.stats != nullptr) {
+              stat_s[(q * 2 + 0) * BN + ch0 + c * 32 + lane] = 0.f;
+              stat_s[(q * 2 + 1) * BN + ch0 + c * 32 + lane] = 0.f;
             }
           }
           if (p.stats != nullptr) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps
-            const int col = threadIdx.x - 64;
-            const int n = n_tile * BN + col;
-            if (n < p.N) {
-              double a = 0.0, bq = 0.0;
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");      // the epilogue warps
+            const int col = threadIdx.x - 64;                                     // EPI_WARPS * 32 threads sweep the BN columns once
+            if (col < BN) {
+              const int n = n_tile * BN + col;
+              if (n < p.N) {
+                double a = 0.0, bq = 0.0;
 #pragma unroll
-              for (int w = 0; w < 4; ++w) {
-                a += (double)stat_s[(w * 2 + 0) * BN + col];
-                bq += (double)stat_s[(w * 2 + 1) * BN + col];
+                for (int w = 0; w < 4; ++w) {
+                  a += (double)stat_s[(w * 2 + 0) * BN + col];
+                  bq += (double)stat_s[(w * 2 + 1) * BN + col];
+                }
+                atomicAdd(p.stats + n, a);
+                atomicAdd(p.stats + p.N + n, bq);
               }
-              atomicAdd(p.stats + n, a);
-              atomicAdd(p.stats + p.N + n, bq);
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
           }
         } else {
           const TnItem wi = tn_decode(tile, p.k_tiles, p.n_tiles, p.ntaps);
@@ -407,8 +419,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           float* orow = p.part + (((size_t)wi.split * p.ntaps + wi.tap) * p.N + n) * p.K;
           if (n < p.N) {
 #pragma unroll
-            for (int j = 0; j < BN; ++j) {
-              const int k = wi.k_tile * BN + j;
+            for (int j = 0; j < EC; ++j) {
+              const int k = wi.k_tile * BN + ch0 + j;
               if (k < p.K) orow[k] = r[j];
             }
           }
@@ -1118,7 +1130,7 @@ static int tc_launch(const CUtensorMap& mA, const CUtensorMap& mB, const TcParam
   static AttrOnce attr;
   auto kern = tc_gemm_kernel<MODE, EB, BN, CH>;
   if (int rc = attr.ensure(kern, TcCfg<BN>::SMEM_BYTES)) return rc;
-  kern<<<grid, TC_THREADS, TcCfg<BN>::SMEM_BYTES, st>>>(mA, mB, p);
+  kern<<<grid, TcThreads<BN, CH>::value, TcCfg<BN>::SMEM_BYTES, st>>>(mA, mB, p);
   AVC_LAUNCHED();
   return AVC_OK;
 }
@@ -1153,11 +1165,11 @@ template <int MODE>
 static int tc_dispatch(int eb, int bn, const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& p, int grid, cudaStream_t st,
                        int chunk = 0) {
   if (chunk) {
-    if (eb != 4 || bn != 128) {
-      set_error("tc_gemm: chunked accumulation needs tf32 operands and 128-wide tiles");
+    if (eb != 4) {
+      set_error("tc_gemm: chunked accumulation is built for tf32 operands");
       return AVC_ERR_UNSUPPORTED;
     }
-    return tc_launch<MODE, 4, 128, TC_X3_CHUNK>(mA, mB, p, grid, st);
+    return bn == 256 ? tc_launch<MODE, 4, 256, TC_X3_CHUNK>(mA, mB, p, grid, st) : tc_launch<MODE, 4, 128, TC_X3_CHUNK>(mA, mB, p, grid, st);
   }
   if (eb == 2) return bn == 256 ? tc_launch<MODE, 2, 256>(mA, mB, p, grid, st) : tc_launch<MODE, 2, 128>(mA, mB, p, grid, st);
   return bn == 256 ? tc_launch<MODE, 4, 256>(mA, mB, p, grid, st) : tc_launch<MODE, 4, 128>(mA, mB, p, grid, st);
@@ -1199,7 +1211,7 @@ static NtPlan nt_plan(const void* A, int a_fmt, int lda, const void* W, int w_fm
                       int chunk = 0) {
   NtPlan pl;
   const int row = 128 / eb;
-  pl.bn = chunk ? 128 : pick_bn(nB * ceil_div(T, TC_BM), N);
+  pl.bn = pick_bn(nB * ceil_div(T, TC_BM), N);
   pl.Kp = round_up(K, row);
   pl.Np = round_up(N, pl.bn);
   pl.stageA = a_fmt == 0 && (eb == 2 || !direct_ok(A, lda));     // 16-bit operands are always read in place
@@ -1332,7 +1344,6 @@ struct TnPlan {
 static TnPlan tn_plan(int nB, int T, int N, int K, int ntaps, int eb, bool stage_y, bool stage_x, int chunk = 0) {
   TnPlan pl;
   pl.bn = (K % 256 == 0 || K > 640) ? 256 : 128;
-  if (chunk) pl.bn = 128;
   pl.Np = round_up(N, TC_BM);
   pl.Kp = round_up(K, pl.bn);
   pl.rs = eb == 2 ? 64 : 32;
