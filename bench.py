@@ -655,8 +655,8 @@ def run_widened(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
     ap.add_argument("--sustained", type=int, default=300, help="extra timed leg of this many steps with its own clock trace (0: off)")
     ap.add_argument("--no-modes", dest="modes", action="store_false", help="skip the tf32 / fp32 legs of the `modes` key")
