@@ -76,26 +76,17 @@ def convert(G, spect: Spect, wav: torch.Tensor, dither: torch.Tensor, lengths: O
         outs: List[torch.Tensor] = []
         starts = list(range(0, Sg.shape[0], chunk))
         if streams > 1 and len(starts) > 1:
-            from . import ops
             cur = torch.cuda.current_stream(wav.device)
             side = _side_streams(wav.device, streams)
-            # the first chunk runs on the caller's stream and packs the weights there; the other chunks reuse those packs (the
-            # weights cannot change inside this call) from the side streams, which are ordered after that first forward
-            _, first, _ = G(Sg[:chunk], eo[:chunk].contiguous(), et[:chunk].contiguous())
-            outs.append(first)
-            ops._GLOBAL_CACHE.freeze(True)
-            try:
-                for st in side:
-                    st.wait_stream(cur)
-                for j, i in enumerate(starts[1:]):
-                    with torch.cuda.stream(side[j % streams]):
-                        _, x_identic_psnt, _ = G(Sg[i:i + chunk], eo[i:i + chunk].contiguous(), et[i:i + chunk].contiguous())
-                    x_identic_psnt.record_stream(cur)      # produced on a side stream, consumed (and later freed) on `cur`
-                    outs.append(x_identic_psnt)
-                for st in side:
-                    cur.wait_stream(st)
-            finally:
-                ops._GLOBAL_CACHE.freeze(False)
+            for st in side:
+                st.wait_stream(cur)
+            for j, i in enumerate(starts):
+                with torch.cuda.stream(side[j % streams]):
+                    _, x_identic_psnt, _ = G(Sg[i:i + chunk], eo[i:i + chunk].contiguous(), et[i:i + chunk].contiguous())
+                x_identic_psnt.record_stream(cur)          # produced on a side stream, consumed (and later freed) on `cur`
+                outs.append(x_identic_psnt)
+            for st in side:
+                cur.wait_stream(st)
         else:
             for i in starts:
                 _, x_identic_psnt, _ = G(Sg[i:i + chunk], eo[i:i + chunk].contiguous(), et[i:i + chunk].contiguous())

@@ -165,7 +165,6 @@ class PackCache:
 
     def __init__(self):
         self._d = {}
-        self._frozen = False
 
     def get(self, kind, param: torch.Tensor, builder):
         k = (kind, id(param))
@@ -177,13 +176,7 @@ class PackCache:
         return val
 
     def begin_step(self):
-        if not self._frozen:
-            self._d.clear()
-
-    def freeze(self, on: bool):
-        """While frozen, ``begin_step()`` keeps the packs: for callers that KNOW the weights do not change between forwards
-        (``conversion.convert`` runs many eval-mode chunks back to back) -- repacking 28 M parameters per forward is ~0.3 ms."""
-        self._frozen = bool(on)
+        self._d.clear()
 
 
 _GLOBAL_CACHE = PackCache()
