@@ -600,13 +600,13 @@ def run_widened(args):
     if args.workload == "wav":
         # GeneratorWav training step (model_vc_wav.py / solver_encoder.py:264-300) on waveform crops of (T-1)*256 + 1024 samples
         from autovc_b200 import solver
-        from oracle import generator_wav_ref as wref
         L = (T - 1) * 256 + 1024
         torch.manual_seed(0)
         G = autovc_b200.GeneratorWav(args.dim_neck, 256, 512, args.freq, args.depth, precision=args.precision).to(dev).train()
         opt = autovc_b200.FusedAdam(G.parameters(), 1e-4)
-        xw, ew = wref.synth_wav_inputs(B, L, 256, 1234)
-        xw, ew = xw.to(dev), ew.to(dev)
+        gw = torch.Generator().manual_seed(1234)
+        xw = (0.1 * torch.randn(B, L, 1, generator=gw)).clamp(-1, 1).to(dev)          # synthetic waveform crops (B, L, 1)
+        ew = (F.normalize(torch.randn(B, 256, generator=gw), dim=-1) * 0.8).to(dev)
         ms = timed(lambda: solver.train_step_wav(G, opt, xw, ew), args.steps, args.warmup)
         # dense MACs per frame: the mel model's encoder (twice) / lstm1 / decoder convs / lstm2 with 512-channel ends, plus the
         # filterbanks (512*1024 each way, analysis twice) and the k=3 layers (depth * 3*512*512, analysis side twice)
@@ -617,6 +617,7 @@ def run_widened(args):
         flops = 3 * 2.0 * (2 * enc + dec + tas) * B * T
         k = 2
         sd = None
+        from oracle import generator_wav_ref as wref          # the CPU baseline leg (the only use of oracle/ here)
         torch.set_num_threads(os.cpu_count() or 1)
         torch.manual_seed(0)
         M = wref.build_wav_module(args.dim_neck, 256, 512, args.freq, args.depth)
