@@ -74,6 +74,11 @@ __global__ void fe_tables_kernel(const float* __restrict__ mel_basis, FeTables* 
 // transition matrix stays O(50).  scipy's tf-form filtfilt and this cascade agree to ~1e-6 on the waveform and
 // to < 1e-7 on the log-mel output (checked against the reference's bundled goldens).
 constexpr int FE_NSEC = 3, FE_NST = 2 * FE_NSEC;
+// Storage type of the forward sweep's output between the two sweeps.  The ARITHMETIC of both sweeps is fp64 like scipy's; rounding
+// the stored intermediate to fp32 (6e-8 relative, ~6e-9 absolute on a 0.1-amplitude waveform) is two orders of magnitude below the
+// 7e-7 by which scipy's own transfer-function filtfilt differs from the exact filter, and takes 8 of the 32 bytes per sample that
+// the front-end moves through HBM off the bus.
+typedef float fe_y1_t;
 struct Df2t {
   double c[FE_NSEC][5];   // b0 b1 b2 a1 a2 per section
   double z[FE_NST];
@@ -111,8 +116,8 @@ __device__ __forceinline__ double odd_ext(const float* __restrict__ x, int n, in
 // input sample i of the sweep: forward sweep reads the odd-extended waveform, backward sweep reads the forward
 // output in reverse order
 template <bool BACKWARD>
-__device__ __forceinline__ double sweep_input(const float* __restrict__ x, const double* __restrict__ y1, int n, int ne, int i) {
-  return BACKWARD ? y1[ne - 1 - i] : odd_ext(x, n, i);
+__device__ __forceinline__ double sweep_input(const float* __restrict__ x, const fe_y1_t* __restrict__ y1, int n, int ne, int i) {
+  return BACKWARD ? (double)y1[ne - 1 - i] : odd_ext(x, n, i);
 }
 
 // --- stage 1+2, fused: one CTA per utterance walks the sweep tile by tile ------------------------------------------
@@ -164,7 +169,7 @@ template <bool BACKWARD>
 __global__ void __launch_bounds__(FE_TNT)
 fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dither, const int* __restrict__ lengths,
                     int max_len, const double* __restrict__ filt, const double* __restrict__ zi,
-                    const double* __restrict__ PW, double* __restrict__ y1buf, float* __restrict__ out) {
+                    const double* __restrict__ PW, fe_y1_t* __restrict__ y1buf, float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int N = FE_NST;
   double* tile = reinterpret_cast<double*>(smem_raw);                 // [FE_TNT][FE_TCH + 1]
@@ -176,7 +181,7 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
   const float* x = wav + (size_t)u * max_len;
   const float* dz = dither + (size_t)u * max_len;
   float* o = out + (size_t)u * max_len;
-  double* y1 = y1buf + (size_t)u * (max_len + 2 * FE_PADLEN);
+  fe_y1_t* y1 = y1buf + (size_t)u * (max_len + 2 * FE_PADLEN);
   if (n <= FE_PADLEN) {   // scipy raises for such inputs; emit dither-only silence deterministically
     if (BACKWARD)
       for (int i = tid; i < n; i += FE_TNT) o[i] = (float)(((double)dz[i] - 0.5) * 1e-6);
@@ -195,11 +200,11 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
     const bool interior = i0 + FE_TILE <= ne && (BACKWARD || (i0 >= FE_PADLEN && i0 + FE_TILE <= FE_PADLEN + n));
     if (interior) {
       const float* xs = x + (i0 - FE_PADLEN);
-      const double* ys = y1 + (ne - 1 - i0);
+      const fe_y1_t* ys = y1 + (ne - 1 - i0);
 #pragma unroll 16
       for (int q = 0; q < FE_TCH; ++q) {
         const int s = q * FE_TNT + tid;
-        tile[s + (s >> FE_TSH)] = BACKWARD ? ys[-s] : (double)xs[s];
+        tile[s + (s >> FE_TSH)] = BACKWARD ? (double)ys[-s] : (double)xs[s];
       }
     } else {
 #pragma unroll 8
@@ -275,7 +280,7 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
       for (int q = 0; q < FE_TCH; ++q) {
         const int s = q * FE_TNT + tid;
         const double y = tile[s + (s >> FE_TSH)];
-        if (!BACKWARD) y1[i0 + s] = y;
+        if (!BACKWARD) y1[i0 + s] = (fe_y1_t)y;
         else o[jb - s] = (float)(y * 0.96 + ((double)dz[jb - s] - 0.5) * 1e-6);
       }
     } else {
@@ -285,7 +290,7 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
         const int i = i0 + s;
         const double y = tile[s + (s >> FE_TSH)];
         if (!BACKWARD) {
-          if (i < ne) y1[i] = y;
+          if (i < ne) y1[i] = (fe_y1_t)y;
         } else {
           const int j = (ne - 1 - i) - FE_PADLEN;
           if (i < ne && j >= 0 && j < n) o[j] = (float)(y * 0.96 + ((double)dz[j] - 0.5) * 1e-6);
@@ -483,7 +488,7 @@ using namespace avc;
 
 extern "C" size_t avc_logmel_workspace_bytes(int n_utt, int max_len) {
   if (n_utt <= 0 || max_len <= 0) return 0;
-  const size_t fwd = ((size_t)n_utt * (max_len + 2 * FE_PADLEN) * sizeof(double) + 255) / 256 * 256;
+  const size_t fwd = ((size_t)n_utt * (max_len + 2 * FE_PADLEN) * sizeof(fe_y1_t) + 255) / 256 * 256;
   const size_t sig = ((size_t)n_utt * max_len * sizeof(float) + 255) / 256 * 256;
   return fe_tables_bytes() + sig + fwd + 4096;      // tail: the FE_TLEV tile powers (8 x 36 doubles)
 }
@@ -499,8 +504,8 @@ static int fe_front(const float* wav, const float* dither, const int* lengths, i
   FeTables* tb = (FeTables*)ws;
   float* sig = (float*)(ws + fe_tables_bytes());
   const size_t sig_b = ((size_t)n_utt * max_len * sizeof(float) + 255) / 256 * 256;
-  const size_t fwd_b = ((size_t)n_utt * (max_len + 2 * FE_PADLEN) * sizeof(double) + 255) / 256 * 256;
-  double* fwd = (double*)(ws + fe_tables_bytes() + sig_b);
+  const size_t fwd_b = ((size_t)n_utt * (max_len + 2 * FE_PADLEN) * sizeof(fe_y1_t) + 255) / 256 * 256;
+  fe_y1_t* fwd = (fe_y1_t*)(ws + fe_tables_bytes() + sig_b);
   double* PW = (double*)(ws + fe_tables_bytes() + sig_b + fwd_b);
   fe_tables_kernel<<<ceil_div(FE_NFFT, 256), 256, 0, st>>>(mel_basis, tb);
   AVC_LAUNCHED();

@@ -29,7 +29,7 @@ def test_workspace_queries_run_without_gpu():
     from autovc_b200 import _lib
     assert _lib.query("avc_gemm_tn_workspace_bytes", 256, 128, 512, 512, 5, 0) > 0
     assert _lib.query("avc_lstm_bwd_workspace_bytes", 256, 128, 1024, 0) == 256 * 1024 * 4
-    assert _lib.query("avc_logmel_workspace_bytes", 4, 16000) > 4 * 16000 * 12
+    assert _lib.query("avc_logmel_workspace_bytes", 4, 16000) > 4 * 16000 * 8
 
 
 def test_ops_refuse_cpu_tensors():
