@@ -659,7 +659,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-gpu"])
-    ap.add_argument("--sustained", type=int, default=300, help="extra timed leg of this many steps with its own clock trace (0: off)")
+    ap.add_argument("--sustained", type=int, default=500, help="extra timed leg of this many steps with its own clock trace (0: off)")
     ap.add_argument("--no-modes", dest="modes", action="store_false", help="skip the tf32 / fp32 legs of the `modes` key")
     ap.add_argument("--precision", default=os.environ.get("AUTOVC_B200_PRECISION", "half"), choices=["fp32", "fp32_simt", "tf32", "half"])
     ap.add_argument("--batch", type=int, default=256, help="crops per GPU")
