@@ -7,8 +7,8 @@ Run in the build container only (needs /root/reference; ~20 min on 4 cores):
 north_star: "a 1k-step loss curve from identical init within 2%".  The reference module
 (/root/reference/model_vc_mel.py) is trained with the step of solver_encoder.py:227-243,:293-300 and
 torch.optim.Adam(lr 1e-4) (:130) from torch.manual_seed(0) on the data stream of tests.helpers
-(loss_curve_corpus / loss_curve_batches: B=16 crops of 128 frames).  The per-step losses go to
-tests/golden/loss_curve_ref_b16.npz; tests/test_gpu_loss_curve.py trains the drop-in from the same init on the
+(loss_curve_corpus / loss_curve_batches: B = CURVE_B (16; a second curve at 64) crops of 128 frames).  The per-step losses go
+to tests/golden/loss_curve_ref_b<B>.npz; tests/test_gpu_loss_curve.py trains the drop-in from the same init on the
 same stream and compares 25-step moving averages.
 """
 import os
@@ -25,7 +25,7 @@ from oracle.gen_golden import OUT, ref_step  # noqa: E402
 from tests.helpers import loss_curve_batches, loss_curve_corpus  # noqa: E402
 
 if __name__ == "__main__":
-    steps, B, T = int(os.environ.get("CURVE_STEPS", "1000")), 16, 128
+    steps, B, T = int(os.environ.get("CURVE_STEPS", "1000")), int(os.environ.get("CURVE_B", "16")), 128
     torch.set_num_threads(int(os.environ.get("GOLDEN_THREADS", "4")))
     from model_vc_mel import Generator
     torch.manual_seed(0)
@@ -43,6 +43,6 @@ if __name__ == "__main__":
         losses.append([g_loss.item()] + [l.item() for l in ls])
         if i % 50 == 0:
             print(i, losses[-1], f"{time.time() - t0:.0f}s", flush=True)
-    np.savez_compressed(os.path.join(OUT, "loss_curve_ref_b16.npz"), losses=np.array(losses, np.float64),
+    np.savez_compressed(os.path.join(OUT, f"loss_curve_ref_b{B}.npz"), losses=np.array(losses, np.float64),
                         meta=np.array([steps, B, T, 0, 123], np.int64))
     print("done", losses[0], "->", np.mean([l[0] for l in losses[-100:]]))
