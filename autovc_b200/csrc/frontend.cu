@@ -172,10 +172,13 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
                     const double* __restrict__ PW, fe_y1_t* __restrict__ y1buf, float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int N = FE_NST;
-  double* tile = reinterpret_cast<double*>(smem_raw);                 // [FE_TNT][FE_TCH + 1]
-  double* wst = tile + FE_TNT * (FE_TCH + 1);                         // [2][FE_TNT][N]  ping-pong chunk states
-  double* pw = wst + 2 * FE_TNT * N;                                  // [FE_TLEV][N*N]
+  double* wst = reinterpret_cast<double*>(smem_raw);                  // [FE_TNT][N]  chunk states
+  double* pw = wst + FE_TNT * N;                                  // [FE_TLEV][N*N]
   double* carry = pw + FE_TLEV * N * N;                               // [N] carry-in of the current tile
+  // the tile holds what the sweep reads and writes in HBM -- fp32 values (the waveform / the fp32 intermediate in, the fp32
+  // intermediate / the fp32 filtered waveform out); the filter states and all arithmetic are fp64.  As an fp64 array it took
+  // 67.6 of the block's 94.5 KB and held the kernel at 2 blocks per SM (25 % occupancy, 37 % of the FP64 pipe: r02 ncu).
+  float* tile = reinterpret_cast<float*>(carry + N);                   // [FE_TNT][FE_TCH + 1]
   const int u = blockIdx.x, tid = threadIdx.x;
   const int n = lengths[u];
   const float* x = wav + (size_t)u * max_len;
@@ -192,7 +195,7 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
   if (tid < N) carry[tid] = zi[tid] * sweep_input<BACKWARD>(x, y1, n, ne, 0);   // scipy: zi * first sample of the sweep's input
   Df2t f;
   f.load(filt);
-  double* mine = tile + tid * (FE_TCH + 1);
+  float* mine = tile + tid * (FE_TCH + 1);
   for (int i0 = 0; i0 < ne; i0 += FE_TILE) {
     __syncthreads();                                      // previous tile fully stored; carry / pw visible
     // interior tiles (all but the first and the last one or two): branch-free, 16 independent loads in flight per thread --
@@ -204,14 +207,14 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
 #pragma unroll 16
       for (int q = 0; q < FE_TCH; ++q) {
         const int s = q * FE_TNT + tid;
-        tile[s + (s >> FE_TSH)] = BACKWARD ? (double)ys[-s] : (double)xs[s];
+        tile[s + (s >> FE_TSH)] = BACKWARD ? (float)ys[-s] : xs[s];
       }
     } else {
 #pragma unroll 8
       for (int q = 0; q < FE_TCH; ++q) {
         const int s = q * FE_TNT + tid;
         const int i = i0 + s;
-        tile[s + (s >> FE_TSH)] = i < ne ? sweep_input<BACKWARD>(x, y1, n, ne, i) : 0.0;   // zeros past the end: pure state decay
+        tile[s + (s >> FE_TSH)] = i < ne ? (float)sweep_input<BACKWARD>(x, y1, n, ne, i) : 0.f;   // zeros past the end: pure state decay
       }
     }
     __syncthreads();
@@ -219,7 +222,7 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
 #pragma unroll
     for (int k = 0; k < N; ++k) f.z[k] = 0.0;
 #pragma unroll 4
-    for (int k = 0; k < FE_TCH; ++k) f.step(mine[k]);
+    for (int k = 0; k < FE_TCH; ++k) f.step((double)mine[k]);
     double w[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) w[k] = f.z[k];
@@ -232,15 +235,16 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
         w[i] = acc;
       }
     }
-    int cur = 0;
 #pragma unroll
     for (int k = 0; k < N; ++k) wst[tid * N + k] = w[k];
     __syncthreads();
+    // one state buffer, two barriers per level (read the neighbour, barrier, publish, barrier): the ping-pong pair cost 12 KB more
+    // per block and with it the fourth resident block per SM
 #pragma unroll 1
     for (int lev = 0; lev < FE_TLEV; ++lev) {
       const int d = 1 << lev;
       if (tid >= d) {
-        const double* src = wst + (cur * FE_TNT + tid - d) * N;
+        const double* src = wst + (tid - d) * N;
         const double* P = pw + lev * N * N;
         double sv[N];
 #pragma unroll
@@ -253,9 +257,11 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
           w[i] = acc;
         }
       }
-      cur ^= 1;
+      __syncthreads();
+      if (tid >= d) {
 #pragma unroll
-      for (int k = 0; k < N; ++k) wst[(cur * FE_TNT + tid) * N + k] = w[k];
+        for (int k = 0; k < N; ++k) wst[tid * N + k] = w[k];
+      }
       __syncthreads();
     }
     // pass 2: from the true start state (= end state of the previous chunk)
@@ -264,10 +270,10 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
       for (int k = 0; k < N; ++k) f.z[k] = carry[k];
     } else {
 #pragma unroll
-      for (int k = 0; k < N; ++k) f.z[k] = wst[(cur * FE_TNT + tid - 1) * N + k];
+      for (int k = 0; k < N; ++k) f.z[k] = wst[(tid - 1) * N + k];
     }
 #pragma unroll 4
-    for (int k = 0; k < FE_TCH; ++k) mine[k] = f.step(mine[k]);
+    for (int k = 0; k < FE_TCH; ++k) mine[k] = (float)f.step((double)mine[k]);
     __syncthreads();                                      // every thread has read carry / its neighbour's state
     if (tid == FE_TNT - 1) {
 #pragma unroll
@@ -279,7 +285,7 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
 #pragma unroll 16
       for (int q = 0; q < FE_TCH; ++q) {
         const int s = q * FE_TNT + tid;
-        const double y = tile[s + (s >> FE_TSH)];
+        const double y = (double)tile[s + (s >> FE_TSH)];
         if (!BACKWARD) y1[i0 + s] = (fe_y1_t)y;
         else o[jb - s] = (float)(y * 0.96 + ((double)dz[jb - s] - 0.5) * 1e-6);
       }
@@ -288,7 +294,7 @@ fe_iir_sweep_kernel(const float* __restrict__ wav, const float* __restrict__ dit
       for (int q = 0; q < FE_TCH; ++q) {
         const int s = q * FE_TNT + tid;
         const int i = i0 + s;
-        const double y = tile[s + (s >> FE_TSH)];
+        const double y = (double)tile[s + (s >> FE_TSH)];
         if (!BACKWARD) {
           if (i < ne) y1[i] = (fe_y1_t)y;
         } else {
@@ -512,7 +518,8 @@ static int fe_front(const float* wav, const float* dither, const int* lengths, i
   // one CTA per utterance, tiles staged through shared memory
   fe_tile_powers_kernel<<<1, 32, 0, st>>>(filt, PW);
   AVC_LAUNCHED();
-  const size_t ism = ((size_t)FE_TNT * (FE_TCH + 1) + 2 * FE_TNT * FE_NST + FE_TLEV * FE_NST * FE_NST + FE_NST) * sizeof(double);
+  const size_t ism = ((size_t)FE_TNT * FE_NST + FE_TLEV * FE_NST * FE_NST + FE_NST) * sizeof(double) +
+                     (size_t)FE_TNT * (FE_TCH + 1) * sizeof(float);
   AVC_CUDA(cudaFuncSetAttribute(fe_iir_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
   AVC_CUDA(cudaFuncSetAttribute(fe_iir_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
   fe_iir_sweep_kernel<false><<<n_utt, FE_TNT, ism, st>>>(wav, dither, lengths, max_len, filt, zi, PW, fwd, sig);
