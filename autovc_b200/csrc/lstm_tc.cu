@@ -47,7 +47,8 @@ constexpr int LT_OUT_STAGE = 16384;      // forward: 4 epilogue warps x 4 KB sta
 struct LstmTcParams {
   int nB, T, H, K, reverse;
   int MT, NT, nBpad, stages;
-  int kbs;              // k-blocks per ring stage (BPTT: 2 where H % 128 == 0, else 1; forward: 1)
+  int kbs;              // k-blocks per ring stage (BPTT: 2 where H % 128 == 0, else 1; forward: 1); weight-stationary forward: per TMA instruction
+  int kt;               // weight-stationary forward: leading elements of every W_hh row that live in TMEM
   const float* P;       // fwd: (nB,T,4H) pre-activations
   float* h_seq;         // fwd: out (nB,T,H) ld ldh
   int ldh;
@@ -396,6 +397,326 @@ lstm_tc_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_consta
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward, weight-stationary form (r02c):  D^T[gate rows, batch] = W_hh[gate rows, K] . h_{t-1}[batch, K]^T.
+//
+// The kernel above makes every CTA take the whole 128 x K activation tile of its batch tile through shared memory every
+// step (256 KB at H = 1024), because the resident W_hh slice (64 gate columns = 128 KB) is all the shared memory can hold.
+// Here W_hh is the A operand and lives in TENSOR MEMORY: a CTA owns 128 gate rows (32 hidden units, gate-interleaved);
+// the first KT <= 896 elements of every row are written once into TMEM (lane = gate row, two bf16 per 32-bit column:
+// 448 of the 512 columns) and read from there by `tcgen05.mma` (A from TMEM), the remaining K - KT (128 at H = 1024) sit
+// in shared memory as before.  The batch is the N dimension: a CTA multiplies only NB = 32 or 64 utterances (grid =
+// 4H/128 row tiles x batch groups), so a step ingests NB x K bf16 = 128 KB at H = 1024 / NB = 64 and 32 KB at H = 512 /
+// NB = 32 -- and the whole tile fits in shared memory at once: no ring, every TMA load of a step is in flight at the same
+// time.  The accumulator is 128 lanes x NB columns: a thread of the epilogue holds ONE gate of one unit for NB utterances,
+// applies its nonlinearity (one tanh.approx per element, sigmoid = 0.5 tanh(0.5 x) + 0.5 with per-lane constants: the same
+// arithmetic as sigmoid_fast / tanh_fast above), a 4 x 4 register transpose across the lane quad turns that into (i, f, g, o)
+// of one unit for NB / 4 utterances, and the cell update follows.  Outputs are staged in swizzled shared tiles and leave
+// as 16-byte row pieces; the activated gates are float4 stores straight from registers (8 lanes = 128 contiguous bytes).
+// Only the 4H/128 CTAs of a batch group synchronise (32 at H = 1024, was 64).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
+constexpr int WS_TM_A = 64;        // first TMEM column of the resident W_hh slice (the accumulator owns columns [0, NB))
+constexpr int WS_KT_MAX = 896;     // (512 - 64) columns x 2 bf16
+constexpr int WS_MAX_PARTS = 16;
+
+template <int NB>
+__global__ void __launch_bounds__(LT_THREADS, 1)
+lstm_tc_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const LstmTcParams p,
+                      const __nv_bfloat16* __restrict__ Wg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const int K = p.K, kblocks = K / 64, KT = p.kt, ksb = (K - KT) / 64;   // ksb: k-blocks of W_hh kept in shared memory
+  constexpr uint32_t HB = NB * 128;                       // bytes of one activation k-block [NB][64] bf16
+  const uint32_t htile = base;                            // [kblocks][NB][64] bf16, 128B swizzle
+  const uint32_t wsm = htile + kblocks * HB;              // [ksb][128][64] bf16, 128B swizzle
+  const uint32_t st_xb = wsm + ksb * 16384;               // staging: h_t bf16 [NB][32]   (the exchange slice / bf16 copy)
+  const uint32_t st_hh = st_xb + NB * 64;                 //          h_t 16-bit copy in fmt16 [NB][32]
+  const uint32_t st_h = st_hh + NB * 64;                  //          h_t fp32 [NB][32]
+  const uint32_t st_c = st_h + NB * 128;                  //          c_t fp32 [NB][32]
+  const uint32_t bar_off = (st_c + NB * 128) - base;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + bar_off);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int j) { return bar0 + 8u * j; };
+  const uint32_t w_bar = bar0 + 8u * WS_MAX_PARTS, tfull = bar0 + 8u * (WS_MAX_PARTS + 1), wtm_bar = bar0 + 8u * (WS_MAX_PARTS + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + WS_MAX_PARTS + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = blockIdx.x % p.NT, grp = blockIdx.x / p.NT;      // gate-row tile, batch group
+  const int T = p.T, H = p.H, G = 4 * p.H;
+  const int kbp = p.kbs, parts = kblocks / kbp;                    // k-blocks per TMA instruction, instructions per step
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+    for (int j = 0; j < parts; ++j) mbar_init(full_bar(j), 1);
+    mbar_init(w_bar, 1);
+    mbar_init(tfull, 1);
+    mbar_init(wtm_bar, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  unsigned* counter = p.counters + grp * 64;
+  const int b0 = grp * NB;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (ksb > 0 && elect_one()) {
+      mbar_expect_tx(w_bar, ksb * 16384);
+      for (int kb = 0; kb < ksb; ++kb) tma_load_3d(wsm + kb * 16384, &mapW, w_bar, KT + kb * 64, nt * 128, 0);
+    }
+    __syncwarp();
+    for (int s = 1; s < T; ++s) {
+      const int row0 = ((s - 1) & 1) * p.nBpad + b0;
+      const unsigned target = (unsigned)s * (unsigned)p.NT;     // every row tile of this batch group has published step s-1
+      if (lane == 0) {
+        while (ld_acquire(counter) < target) {
+        }
+        LT_TRACE(0);
+      }
+      __syncwarp();
+      // The tile is free: this CTA's own publish of step s-1 (counted in `target`) followed its epilogue's read of the
+      // accumulator, which followed the completion of every MMA that read the tile.
+      fence_proxy_async_global();
+      if (elect_one()) {
+        for (int j = 0; j < parts; ++j) {
+          mbar_expect_tx(full_bar(j), kbp * HB);
+          tma_load_4d(htile + j * kbp * HB, &mapX, full_bar(j), 0, row0, j * kbp, 0);
+          if (j == 0) LT_TRACE(1);
+        }
+        LT_TRACE(2);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(128, NB, 0, 0);
+    if (ksb > 0) mbar_wait(w_bar, 0);
+    mbar_wait(wtm_bar, 0);                 // the epilogue warps have written the W_hh slice into TMEM
+    tc_fence_after();
+    const uint32_t tmem_a = tmem_base + WS_TM_A;
+    const int kt_blocks = KT / 64;
+    for (int s = 1; s < T; ++s) {
+      for (int j = 0; j < parts; ++j) {
+        mbar_wait(full_bar(j), (s - 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          if (j == 0) LT_TRACE(3);
+          if (j == parts - 1) LT_TRACE(4);
+          for (int kk = 0; kk < kbp; ++kk) {
+            const int kb = j * kbp + kk;
+            const uint32_t sb = htile + kb * HB;
+            if (kb < kt_blocks) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ts(tmem_base, tmem_a + (uint32_t)(kb * 32 + k * 8), make_desc(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            } else {
+              const uint32_t sa = wsm + (kb - kt_blocks) * 16384;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tmem_base, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          if (j == parts - 1) {
+            umma_commit(tfull);
+            LT_TRACE(5);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+    const int lrow = q * 32 + lane;                // gate row inside the tile = TMEM lane
+    const int ul = lrow >> 2, gt = lane & 3;       // hidden unit inside the tile, gate (i, f, g, o) -- and, after the transpose, utterance j % 4
+    const int et = threadIdx.x - 64;               // 0..127
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int u0 = nt * 32;
+    const bool save_bptt = p.gates != nullptr;
+    // ---- resident W_hh slice -> TMEM: lane = gate row, column c = elements (2c, 2c+1) of the row ----
+    {
+      const uint4* wrow = reinterpret_cast<const uint4*>(Wg + (size_t)(nt * 128 + lrow) * K);
+      for (int kb = 0; kb < KT / 64; ++kb) {
+        uint32_t r[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 v = __ldg(wrow + kb * 8 + i);
+          r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        }
+        tmem_st32(t_lane + WS_TM_A + kb * 32, r);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(wtm_bar);
+    }
+    const float sc = gt == 2 ? 1.f : 0.5f, of = gt == 2 ? 0.f : 0.5f;
+    constexpr int NQ = NB / 4;                     // utterances per thread after the transpose: j = 4 m + gt
+    float c[NQ];
+#pragma unroll
+    for (int m = 0; m < NQ; ++m) c[m] = 0.f;
+    const int grow = nt * 128 + lrow;              // gate row in (4H)
+    for (int s = 0; s < T; ++s) {
+      const int t = p.reverse ? T - 1 - s : s;
+      float pre[NB];
+      {
+        const float* pp = p.P + ((size_t)b0 * T + t) * G + grow;
+#pragma unroll
+        for (int j = 0; j < NB; ++j) pre[j] = (b0 + j < p.nB) ? __ldg(pp + (size_t)j * T * G) : 0.f;
+      }
+      if (s > 0) {
+        mbar_wait(tfull, (s - 1) & 1);
+        if (et == 0) LT_TRACE(6);
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < NB / 32; ++cc) {
+          float d[32];
+          tmem_ld32(t_lane + cc * 32, d);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pre[cc * 32 + j] += d[j];
+        }
+        tc_fence_before();
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) pre[j] = fmaf(sc, tanh_fast(sc * pre[j]), of);
+      // 4 x 4 transpose across the lane quad: afterwards pre[4m + g] = gate g of (unit ul, utterance 4m + gt)
+#pragma unroll
+      for (int m = 0; m < NQ; ++m) {
+#pragma unroll
+        for (int pp2 = 0; pp2 < 4; pp2 += 2) {
+          const float snd = (lane & 1) ? pre[4 * m + pp2] : pre[4 * m + pp2 + 1];
+          const float rcv = __shfl_xor_sync(0xffffffffu, snd, 1);
+          if (lane & 1) pre[4 * m + pp2] = rcv; else pre[4 * m + pp2 + 1] = rcv;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float snd = (lane & 2) ? pre[4 * m + i] : pre[4 * m + 2 + i];
+          const float rcv = __shfl_xor_sync(0xffffffffu, snd, 2);
+          if (lane & 2) pre[4 * m + i] = rcv; else pre[4 * m + 2 + i] = rcv;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // the previous step's staged tiles have been read out
+      float hf[NQ];
+#pragma unroll
+      for (int m = 0; m < NQ; ++m) {
+        const float gi = pre[4 * m], gf = pre[4 * m + 1], gg = pre[4 * m + 2], go = pre[4 * m + 3];
+        c[m] = fmaf(gf, c[m], gi * gg);
+        hf[m] = go * tanh_fast(c[m]);
+        const int j = 4 * m + gt;
+        const __nv_bfloat16 hb = __float2bfloat16_rn(hf[m]);
+        // bf16 tiles: 64-byte rows, 16-byte piece p stored at (p + 2 ((j >> 1) & 1)) & 3; fp32 tiles: 128-byte rows, word w
+        // stored at (w + 8 (j & 3)) & 31 -- both conflict-free for these writes and for the 16-byte row reads below
+        const uint32_t o16 = (uint32_t)j * 64u + ((((uint32_t)(ul >> 3) + 2u * ((j >> 1) & 1)) & 3u) << 4) + (uint32_t)(ul & 7) * 2u;
+        st_shared_u16(st_xb + o16, *reinterpret_cast<const uint16_t*>(&hb));
+        if (p.h16 != nullptr) {
+          uint16_t v16;
+          if (p.fmt16 == 2) {
+            const __half hh = __float2half_rn(hf[m]);
+            v16 = *reinterpret_cast<const uint16_t*>(&hh);
+          } else {
+            v16 = *reinterpret_cast<const uint16_t*>(&hb);
+          }
+          st_shared_u16(st_hh + o16, v16);
+        }
+        const uint32_t o32 = (uint32_t)j * 128u + ((((uint32_t)ul + 8u * (uint32_t)gt) & 31u) << 2);
+        st_shared_f32(st_h + o32, hf[m]);
+        if (save_bptt) st_shared_f32(st_c + o32, c[m]);
+      }
+      if (et == 0) LT_TRACE(7);
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // the staged tiles are complete
+      // publish h_t: NB rows x 64 bytes of the exchange buffer, one 16-byte piece per thread and round
+      {
+        __nv_bfloat16* xb = p.xbuf + ((size_t)(s & 1) * p.nBpad + b0) * K + u0;
+#pragma unroll
+        for (int i = 0; i < NB * 4 / 128; ++i) {
+          const int idx = et + 128 * i, j = idx >> 2, pc = idx & 3;
+          const uint4 v = ld_shared_u4(st_xb + j * 64 + (((pc + 2 * ((j >> 1) & 1)) & 3) << 4));
+          *reinterpret_cast<uint4*>(xb + (size_t)j * K + pc * 8) = v;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // all rows of the slice are written (CTA scope)
+      if (et == 0) {
+        red_release_add(counter, 1u);                    // cumulative gpu-scope release
+        LT_TRACE(8);
+      }
+      // ---- tensors saved for BPTT / handed to the next layer: off the critical path ----
+      if (save_bptt) {
+#pragma unroll
+        for (int m = 0; m < NQ; ++m) {
+          const int b = b0 + 4 * m + gt;
+          if (b < p.nB)
+            *reinterpret_cast<float4*>(p.gates + ((size_t)b * T + t) * G + nt * 128 + ul * 4) =
+                make_float4(pre[4 * m], pre[4 * m + 1], pre[4 * m + 2], pre[4 * m + 3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NB * 8 / 128; ++i) {             // fp32 rows: 8 pieces of 16 bytes
+        const int idx = et + 128 * i, j = idx >> 3, pc = idx & 7;
+        const int b = b0 + j;
+        if (b < p.nB) {
+          const uint32_t so = j * 128 + (((pc + 2 * (j & 3)) & 7) << 4);
+          const size_t ro = (size_t)b * T + t;
+          *reinterpret_cast<uint4*>(p.h_seq + ro * p.ldh + u0 + pc * 4) = ld_shared_u4(st_h + so);
+          if (save_bptt) *reinterpret_cast<uint4*>(p.c_seq + ro * H + u0 + pc * 4) = ld_shared_u4(st_c + so);
+        }
+      }
+      if (p.h16 != nullptr) {
+#pragma unroll
+        for (int i = 0; i < NB * 4 / 128; ++i) {
+          const int idx = et + 128 * i, j = idx >> 2, pc = idx & 3;
+          const int b = b0 + j;
+          if (b < p.nB) {
+            const uint32_t so = j * 64 + (((pc + 2 * ((j >> 1) & 1)) & 3) << 4);
+            const size_t eo = ((size_t)b * T + t) * H + u0 + pc * 8;
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.h16) + eo) = ld_shared_u4(st_hh + so);
+            if (p.h16b != nullptr) *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.h16b) + eo) = ld_shared_u4(st_xb + so);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -797,9 +1118,53 @@ static LtPlan lt_plan(int nB, int H, bool bwd) {
   pl.total = pl.off_cnt + align256((size_t)nchunks * 128 * sizeof(unsigned));
   return pl;
 }
+// weight-stationary forward (lstm_tc_fwd_ws_kernel): NB utterances per batch group, as many groups per launch as fit next to
+// the 4H/128 row tiles at one CTA per SM
+struct LtPlanWs {
+  bool ok;
+  int NB, NT, NGmax, KT, kbp, chunk;
+  size_t smem, off_x, off_cnt, total;
+};
+constexpr int WS_MAX_GROUPS = 16;
+static LtPlanWs lt_plan_ws(int nB, int H) {
+  LtPlanWs pl{};
+  pl.ok = false;
+  if (H % 64 != 0 || H < 128 || H > 1024) return pl;
+  pl.NT = 4 * H / 128;
+  const int gmax = std::min(WS_MAX_GROUPS, num_sms() / pl.NT);
+  if (gmax < 1) return pl;
+  pl.NB = ceil_div(nB, 32) <= gmax ? 32 : 64;
+  pl.NGmax = gmax;
+  pl.chunk = std::min(nB, gmax * pl.NB);
+  pl.KT = std::min(H, WS_KT_MAX) / 64 * 64;
+  const int kblocks = H / 64;
+  pl.kbp = kblocks % 4 == 0 ? 4 : (kblocks % 2 == 0 ? 2 : 1);
+  if (kblocks / pl.kbp > WS_MAX_PARTS) return pl;
+  pl.smem = 1024 + (size_t)kblocks * pl.NB * 128 + (size_t)(H - pl.KT) / 64 * 16384 + (size_t)pl.NB * (64 + 64 + 128 + 128) + 256;
+  if (pl.smem > 227 * 1024) return pl;
+  const int NG = ceil_div(pl.chunk, pl.NB);
+  pl.off_x = align256((size_t)4 * H * H * 2);
+  pl.off_cnt = pl.off_x + align256((size_t)2 * NG * pl.NB * H * 2);
+  const int nchunks = ceil_div(nB, pl.chunk);
+  pl.total = pl.off_cnt + align256((size_t)nchunks * WS_MAX_GROUPS * 64 * sizeof(unsigned));
+  pl.ok = true;
+  return pl;
+}
+// AVC_LSTM_FWD_WS=0 keeps the forward recurrence on the ring kernel (read per call so one process can compare both; the ring
+// kernel stays the path for shapes the weight-stationary kernel does not take -- tests/test_gpu_lstm_tc.py runs both settings)
+static bool fwd_ws_enabled() {
+  const char* e = getenv("AVC_LSTM_FWD_WS");
+  return !(e && e[0] == '0');
+}
+
 size_t lstm_tc_workspace(int nB, int T, int H, bool bwd) {
   (void)T;
-  return lt_plan(nB, H, bwd).total;
+  size_t n = lt_plan(nB, H, bwd).total;
+  if (!bwd) {
+    const LtPlanWs pw = lt_plan_ws(nB, H);
+    if (pw.ok) n = std::max(n, pw.total);
+  }
+  return n;
 }
 
 // K-split BPTT launch: clusters of 4 (PAIRS = 1) or 8 (PAIRS = 2) along x, cooperative (the CTAs spin on each other's counters)
@@ -892,6 +1257,62 @@ static int lt_launch_fwd(const CUtensorMap& mW, const CUtensorMap& mX, const LtO
   return AVC_OK;
 }
 
+template <int NB>
+static int lt_launch_fwd_ws(const CUtensorMap& mW, const CUtensorMap& mX, const LstmTcParams& p, size_t smem, const __nv_bfloat16* Wb,
+                            cudaStream_t st) {
+  auto kern = lstm_tc_fwd_ws_kernel<NB>;
+  AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.MT * p.NT);
+  cfg.blockDim = dim3(LT_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeCooperative;      // the CTAs of a batch group spin on each other's release counter
+  attrs[0].val.cooperative = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  AVC_CUDA(cudaLaunchKernelEx(&cfg, kern, mW, mX, p, Wb));
+  g_launches.fetch_add(1);
+  return AVC_OK;
+}
+
+// forward through the weight-stationary kernel; ws laid out by lt_plan_ws
+static int lstm_seq_fwd_ws(const LtPlanWs& pl, const __nv_bfloat16* Wb, const float* P, float* h_seq, int ldh, float* gates, float* c_seq,
+                           int nB, int T, int H, int reverse, uint8_t* w8, cudaStream_t st, void* aux16, int fmt16, void* aux16b) {
+  __nv_bfloat16* xbuf = (__nv_bfloat16*)(w8 + pl.off_x);
+  unsigned* counters = (unsigned*)(w8 + pl.off_cnt);
+  const int nchunks = ceil_div(nB, pl.chunk);
+  AVC_CUDA(cudaMemsetAsync(counters, 0, (size_t)nchunks * WS_MAX_GROUPS * 64 * sizeof(unsigned), st));
+  CUtensorMap mW, mX;
+  int rc = make_map3(&mW, Wb, H, 4 * H, 1, H, (uint64_t)4 * H * H, 64, 128);
+  if (rc) return rc;
+  const size_t G = 4 * (size_t)H;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int b0 = ch * pl.chunk;
+    const int nb = std::min(pl.chunk, nB - b0);
+    LstmTcParams p{};
+    p.nB = nb; p.T = T; p.H = H; p.K = H; p.reverse = reverse;
+    p.MT = ceil_div(nb, pl.NB); p.NT = pl.NT; p.nBpad = p.MT * pl.NB; p.kbs = pl.kbp; p.kt = pl.KT;
+    p.P = P + (size_t)b0 * T * G;
+    p.h_seq = h_seq + (size_t)b0 * T * ldh;
+    p.ldh = ldh;
+    p.gates = gates ? gates + (size_t)b0 * T * G : nullptr;
+    p.c_seq = c_seq ? c_seq + (size_t)b0 * T * H : nullptr;
+    p.xbuf = xbuf;
+    p.counters = counters + ch * WS_MAX_GROUPS * 64;
+    p.trace = (ch == 0) ? g_trace : nullptr;
+    p.fmt16 = fmt16;
+    p.h16 = aux16 ? (void*)((uint16_t*)aux16 + (size_t)b0 * T * H) : nullptr;
+    p.h16b = (aux16 && aux16b) ? (void*)((uint16_t*)aux16b + (size_t)b0 * T * H) : nullptr;
+    rc = make_map4_grouped(&mX, xbuf, H, (uint64_t)2 * p.nBpad, 1, H, 64, pl.NB, pl.kbp, 2, false);
+    if (rc) return rc;
+    rc = pl.NB == 32 ? lt_launch_fwd_ws<32>(mW, mX, p, pl.smem, Wb, st) : lt_launch_fwd_ws<64>(mW, mX, p, pl.smem, Wb, st);
+    if (rc) return rc;
+  }
+  return AVC_OK;
+}
+
 // W: fwd -> Whh_p (4H, H);  bwd -> Whh_pT (H, 4H)  (packed/interleaved)
 // w_fmt 0: W is fp32 and converted to bf16 here; 1: W is already bf16 (avc_pack_lstm_weight_h) and read in place
 int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh, float* gates, float* c_seq,
@@ -921,6 +1342,13 @@ int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh,
       return AVC_ERR_INVALID;
     }
     Wb = (const __nv_bfloat16*)Wv;
+  }
+  if (!bwd && fwd_ws_enabled()) {
+    const LtPlanWs pw = lt_plan_ws(nB, H);
+    const bool al16 = ((((uintptr_t)P | (uintptr_t)gates | (uintptr_t)c_seq | (uintptr_t)h_seq | (uintptr_t)aux16 | (uintptr_t)aux16b) & 15) == 0) &&
+                      ldh % 4 == 0;
+    if (pw.ok && al16 && ws_bytes >= pw.total)
+      return lstm_seq_fwd_ws(pw, Wb, P, h_seq, ldh, gates, c_seq, nB, T, H, reverse, w8, st, aux16, fmt16, aux16b);
   }
   const int nchunks = ceil_div(nB, pl.chunk);
   AVC_CUDA(cudaMemsetAsync(counters, 0, (size_t)nchunks * 128 * sizeof(unsigned), st));
