@@ -449,8 +449,25 @@ constexpr int WS_TM_A = 64;        // first TMEM column of the resident W_hh sli
 constexpr int WS_KT_MAX = 896;     // (512 - 64) columns x 2 bf16
 constexpr int WS_MAX_PARTS = 16;
 
-template <int NB>
-__global__ void __launch_bounds__(LT_THREADS, 1)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// NB = utterances per batch group; EW = epilogue warps (4: one per TMEM lane quadrant; 8: two per quadrant, each taking half
+// of the NB accumulator columns: 5.93 -> 5.49 us per step at H = 1024 / NB = 64).  Sharing the TMA parts of a step over a
+// cluster of 2 or 4 row tiles by multicast was measured too and is 0.1-0.3 us per step SLOWER here (the L2 -> SM bytes per SM
+// are what they are, and the cluster adds its own start-up skew): not kept.
+template <int NB, int EW>
+__global__ void __launch_bounds__(64 + EW * 32, 1)
 lstm_tc_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const LstmTcParams p,
                       const __nv_bfloat16* __restrict__ Wg) {
   extern __shared__ uint8_t smem_raw[];
@@ -459,6 +476,7 @@ lstm_tc_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
   uint8_t* gen = smem_raw + (base - raw);
   const int K = p.K, kblocks = K / 64, KT = p.kt, ksb = (K - KT) / 64;   // ksb: k-blocks of W_hh kept in shared memory
   constexpr uint32_t HB = NB * 128;                       // bytes of one activation k-block [NB][64] bf16
+  constexpr int ET = EW * 32;                             // epilogue threads
   const uint32_t htile = base;                            // [kblocks][NB][64] bf16, 128B swizzle
   const uint32_t wsm = htile + kblocks * HB;              // [ksb][128][64] bf16, 128B swizzle
   const uint32_t st_xb = wsm + ksb * 16384;               // staging: h_t bf16 [NB][32]   (the exchange slice / bf16 copy)
@@ -483,7 +501,7 @@ lstm_tc_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
     for (int j = 0; j < parts; ++j) mbar_init(full_bar(j), 1);
     mbar_init(w_bar, 1);
     mbar_init(tfull, 1);
-    mbar_init(wtm_bar, 4);
+    mbar_init(wtm_bar, EW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -498,13 +516,18 @@ lstm_tc_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
     // ===================== TMA producer =====================
     if (ksb > 0 && elect_one()) {
       mbar_expect_tx(w_bar, ksb * 16384);
-      for (int kb = 0; kb < ksb; ++kb) tma_load_3d(wsm + kb * 16384, &mapW, w_bar, KT + kb * 64, nt * 128, 0);
+      for (int kb = 0; kb < ksb; ++kb) tma_load_3d(wsm + kb * 16384, &mapW, w_bar, kb * 64, nt * 128, 0);
     }
     __syncwarp();
     for (int s = 1; s < T; ++s) {
       const int row0 = ((s - 1) & 1) * p.nBpad + b0;
       const unsigned target = (unsigned)s * (unsigned)p.NT;     // every row tile of this batch group has published step s-1
+      // arm this step's barriers while the group is still working: the previous phase of each has completed by the time
+      // this CTA's MMAs of step s-1 were issued, long before its own publish
+      if (s > 1)
+        for (int j = 0; j < parts; ++j) mbar_wait(full_bar(j), s & 1);
       if (lane == 0) {
+        for (int j = 0; j < parts; ++j) mbar_expect_tx(full_bar(j), kbp * HB);
         while (ld_acquire(counter) < target) {
         }
         LT_TRACE(0);
@@ -515,7 +538,6 @@ lstm_tc_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
       fence_proxy_async_global();
       if (elect_one()) {
         for (int j = 0; j < parts; ++j) {
-          mbar_expect_tx(full_bar(j), kbp * HB);
           tma_load_4d(htile + j * kbp * HB, &mapX, full_bar(j), 0, row0, j * kbp, 0);
           if (j == 0) LT_TRACE(1);
         }
@@ -530,7 +552,6 @@ lstm_tc_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
     mbar_wait(wtm_bar, 0);                 // the epilogue warps have written the W_hh slice into TMEM
     tc_fence_after();
     const uint32_t tmem_a = tmem_base + WS_TM_A;
-    const int kt_blocks = KT / 64;
     for (int s = 1; s < T; ++s) {
       for (int j = 0; j < parts; ++j) {
         mbar_wait(full_bar(j), (s - 1) & 1);
@@ -541,12 +562,12 @@ lstm_tc_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
           for (int kk = 0; kk < kbp; ++kk) {
             const int kb = j * kbp + kk;
             const uint32_t sb = htile + kb * HB;
-            if (kb < kt_blocks) {
+            if (kb >= ksb) {        // the step's LAST k-blocks take A from TMEM (the faster form): shortest tail after the last part lands
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_f16_ts(tmem_base, tmem_a + (uint32_t)(kb * 32 + k * 8), make_desc(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                umma_f16_ts(tmem_base, tmem_a + (uint32_t)((kb - ksb) * 32 + k * 8), make_desc(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
             } else {
-              const uint32_t sa = wsm + (kb - kt_blocks) * 16384;
+              const uint32_t sa = wsm + kb * 16384;
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_f16(tmem_base, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
@@ -563,16 +584,20 @@ lstm_tc_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;                        // TMEM lane quadrant this warp may access
+    const int ch = (warp - 2) >> 2;                // which share of the accumulator columns (EW = 8: two warps per quadrant)
+    constexpr int NC = NB / (EW / 4);              // accumulator columns (utterances) per thread before the transpose
+    constexpr int NQ = NC / 4;                     // utterances per thread after it: j = j0 + 4 m + gt
+    const int j0 = ch * NC;
     const int lrow = q * 32 + lane;                // gate row inside the tile = TMEM lane
-    const int ul = lrow >> 2, gt = lane & 3;       // hidden unit inside the tile, gate (i, f, g, o) -- and, after the transpose, utterance j % 4
-    const int et = threadIdx.x - 64;               // 0..127
+    const int ul = lrow >> 2, gt = lane & 3;       // hidden unit inside the tile, gate (i, f, g, o)
+    const int et = threadIdx.x - 64;               // 0..ET-1
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int u0 = nt * 32;
     const bool save_bptt = p.gates != nullptr;
-    // ---- resident W_hh slice -> TMEM: lane = gate row, column c = elements (2c, 2c+1) of the row ----
+    // ---- resident W_hh slice -> TMEM: lane = gate row, column c = elements (2c, 2c+1) of the row's k-range [K - KT, K) ----
     {
-      const uint4* wrow = reinterpret_cast<const uint4*>(Wg + (size_t)(nt * 128 + lrow) * K);
-      for (int kb = 0; kb < KT / 64; ++kb) {
+      const uint4* wrow = reinterpret_cast<const uint4*>(Wg + (size_t)(nt * 128 + lrow) * K + (K - KT));
+      for (int kb = ch; kb < KT / 64; kb += EW / 4) {
         uint32_t r[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -587,35 +612,41 @@ lstm_tc_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
       if (lane == 0) mbar_arrive(wtm_bar);
     }
     const float sc = gt == 2 ? 1.f : 0.5f, of = gt == 2 ? 0.f : 0.5f;
-    constexpr int NQ = NB / 4;                     // utterances per thread after the transpose: j = 4 m + gt
     float c[NQ];
 #pragma unroll
     for (int m = 0; m < NQ; ++m) c[m] = 0.f;
     const int grow = nt * 128 + lrow;              // gate row in (4H)
     for (int s = 0; s < T; ++s) {
       const int t = p.reverse ? T - 1 - s : s;
-      float pre[NB];
+      float pre[NC];
       {
-        const float* pp = p.P + ((size_t)b0 * T + t) * G + grow;
+        const float* pp = p.P + ((size_t)(b0 + j0) * T + t) * G + grow;
 #pragma unroll
-        for (int j = 0; j < NB; ++j) pre[j] = (b0 + j < p.nB) ? __ldg(pp + (size_t)j * T * G) : 0.f;
+        for (int j = 0; j < NC; ++j) pre[j] = (b0 + j0 + j < p.nB) ? __ldg(pp + (size_t)j * T * G) : 0.f;
       }
       if (s > 0) {
         mbar_wait(tfull, (s - 1) & 1);
         if (et == 0) LT_TRACE(6);
         tc_fence_after();
+        if constexpr (NC == 16) {
+          float d[16];
+          tmem_ld16(t_lane + j0, d);
 #pragma unroll
-        for (int cc = 0; cc < NB / 32; ++cc) {
-          float d[32];
-          tmem_ld32(t_lane + cc * 32, d);
+          for (int j = 0; j < 16; ++j) pre[j] += d[j];
+        } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) pre[cc * 32 + j] += d[j];
+          for (int cc = 0; cc < NC / 32; ++cc) {
+            float d[32];
+            tmem_ld32(t_lane + j0 + cc * 32, d);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pre[cc * 32 + j] += d[j];
+          }
         }
         tc_fence_before();
       }
 #pragma unroll
-      for (int j = 0; j < NB; ++j) pre[j] = fmaf(sc, tanh_fast(sc * pre[j]), of);
-      // 4 x 4 transpose across the lane quad: afterwards pre[4m + g] = gate g of (unit ul, utterance 4m + gt)
+      for (int j = 0; j < NC; ++j) pre[j] = fmaf(sc, tanh_fast(sc * pre[j]), of);
+      // 4 x 4 transpose across the lane quad: afterwards pre[4m + g] = gate g of (unit ul, utterance j0 + 4m + gt)
 #pragma unroll
       for (int m = 0; m < NQ; ++m) {
 #pragma unroll
@@ -631,14 +662,14 @@ lstm_tc_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
           if (lane & 2) pre[4 * m + i] = rcv; else pre[4 * m + 2 + i] = rcv;
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // the previous step's staged tiles have been read out
+      asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");     // the previous step's staged tiles have been read out
       float hf[NQ];
 #pragma unroll
       for (int m = 0; m < NQ; ++m) {
         const float gi = pre[4 * m], gf = pre[4 * m + 1], gg = pre[4 * m + 2], go = pre[4 * m + 3];
         c[m] = fmaf(gf, c[m], gi * gg);
         hf[m] = go * tanh_fast(c[m]);
-        const int j = 4 * m + gt;
+        const int j = j0 + 4 * m + gt;
         const __nv_bfloat16 hb = __float2bfloat16_rn(hf[m]);
         // bf16 tiles: 64-byte rows, 16-byte piece p stored at (p + 2 ((j >> 1) & 1)) & 3; fp32 tiles: 128-byte rows, word w
         // stored at (w + 8 (j & 3)) & 31 -- both conflict-free for these writes and for the 16-byte row reads below
@@ -659,18 +690,20 @@ lstm_tc_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
         if (save_bptt) st_shared_f32(st_c + o32, c[m]);
       }
       if (et == 0) LT_TRACE(7);
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // the staged tiles are complete
-      // publish h_t: NB rows x 64 bytes of the exchange buffer, one 16-byte piece per thread and round
+      asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");     // the staged tiles are complete
+      // publish h_t: NB rows x 64 bytes of the exchange buffer in 16-byte pieces
       {
         __nv_bfloat16* xb = p.xbuf + ((size_t)(s & 1) * p.nBpad + b0) * K + u0;
 #pragma unroll
-        for (int i = 0; i < NB * 4 / 128; ++i) {
-          const int idx = et + 128 * i, j = idx >> 2, pc = idx & 3;
-          const uint4 v = ld_shared_u4(st_xb + j * 64 + (((pc + 2 * ((j >> 1) & 1)) & 3) << 4));
-          *reinterpret_cast<uint4*>(xb + (size_t)j * K + pc * 8) = v;
+        for (int i = 0; i < (NB * 4 + ET - 1) / ET; ++i) {
+          const int idx = et + ET * i, j = idx >> 2, pc = idx & 3;
+          if (NB * 4 % ET == 0 || idx < NB * 4) {
+            const uint4 v = ld_shared_u4(st_xb + j * 64 + (((pc + 2 * ((j >> 1) & 1)) & 3) << 4));
+            *reinterpret_cast<uint4*>(xb + (size_t)j * K + pc * 8) = v;
+          }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // all rows of the slice are written (CTA scope)
+      asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");     // all rows of the slice are written (CTA scope)
       if (et == 0) {
         red_release_add(counter, 1u);                    // cumulative gpu-scope release
         LT_TRACE(8);
@@ -679,15 +712,15 @@ lstm_tc_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
       if (save_bptt) {
 #pragma unroll
         for (int m = 0; m < NQ; ++m) {
-          const int b = b0 + 4 * m + gt;
+          const int b = b0 + j0 + 4 * m + gt;
           if (b < p.nB)
             *reinterpret_cast<float4*>(p.gates + ((size_t)b * T + t) * G + nt * 128 + ul * 4) =
                 make_float4(pre[4 * m], pre[4 * m + 1], pre[4 * m + 2], pre[4 * m + 3]);
         }
       }
 #pragma unroll
-      for (int i = 0; i < NB * 8 / 128; ++i) {             // fp32 rows: 8 pieces of 16 bytes
-        const int idx = et + 128 * i, j = idx >> 3, pc = idx & 7;
+      for (int i = 0; i < NB * 8 / ET; ++i) {              // fp32 rows: 8 pieces of 16 bytes
+        const int idx = et + ET * i, j = idx >> 3, pc = idx & 7;
         const int b = b0 + j;
         if (b < p.nB) {
           const uint32_t so = j * 128 + (((pc + 2 * (j & 3)) & 7) << 4);
@@ -698,10 +731,10 @@ lstm_tc_fwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
       }
       if (p.h16 != nullptr) {
 #pragma unroll
-        for (int i = 0; i < NB * 4 / 128; ++i) {
-          const int idx = et + 128 * i, j = idx >> 2, pc = idx & 3;
+        for (int i = 0; i < (NB * 4 + ET - 1) / ET; ++i) {
+          const int idx = et + ET * i, j = idx >> 2, pc = idx & 3;
           const int b = b0 + j;
-          if (b < p.nB) {
+          if ((NB * 4 % ET == 0 || idx < NB * 4) && b < p.nB) {
             const uint32_t so = j * 64 + (((pc + 2 * ((j >> 1) & 1)) & 3) << 4);
             const size_t eo = ((size_t)b * T + t) * H + u0 + pc * 8;
             *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.h16) + eo) = ld_shared_u4(st_hh + so);
@@ -1257,14 +1290,14 @@ static int lt_launch_fwd(const CUtensorMap& mW, const CUtensorMap& mX, const LtO
   return AVC_OK;
 }
 
-template <int NB>
+template <int NB, int EW>
 static int lt_launch_fwd_ws(const CUtensorMap& mW, const CUtensorMap& mX, const LstmTcParams& p, size_t smem, const __nv_bfloat16* Wb,
                             cudaStream_t st) {
-  auto kern = lstm_tc_fwd_ws_kernel<NB>;
+  auto kern = lstm_tc_fwd_ws_kernel<NB, EW>;
   AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(p.MT * p.NT);
-  cfg.blockDim = dim3(LT_THREADS);
+  cfg.blockDim = dim3(64 + EW * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attrs[1];
@@ -1307,7 +1340,10 @@ static int lstm_seq_fwd_ws(const LtPlanWs& pl, const __nv_bfloat16* Wb, const fl
     p.h16b = (aux16 && aux16b) ? (void*)((uint16_t*)aux16b + (size_t)b0 * T * H) : nullptr;
     rc = make_map4_grouped(&mX, xbuf, H, (uint64_t)2 * p.nBpad, 1, H, 64, pl.NB, pl.kbp, 2, false);
     if (rc) return rc;
-    rc = pl.NB == 32 ? lt_launch_fwd_ws<32>(mW, mX, p, pl.smem, Wb, st) : lt_launch_fwd_ws<64>(mW, mX, p, pl.smem, Wb, st);
+    if (const char* e = getenv("AVC_LSTM_WS_KBP")) { p.kbs = atoi(e); }      // TEMP experiment switch
+    rc = make_map4_grouped(&mX, xbuf, H, (uint64_t)2 * p.nBpad, 1, H, 64, pl.NB, p.kbs, 2, false);
+    if (rc) return rc;
+    rc = pl.NB == 32 ? lt_launch_fwd_ws<32, 8>(mW, mX, p, pl.smem, Wb, st) : lt_launch_fwd_ws<64, 8>(mW, mX, p, pl.smem, Wb, st);
     if (rc) return rc;
   }
   return AVC_OK;

@@ -47,7 +47,9 @@ def run(B, T, H, reverse, save, fmt16, ws_on, P, Wb, reps=0):
 def main():
     shapes = [(4, 6, 128, 0, True), (130, 9, 512, 1, True), (256, 16, 1024, 0, True), (37, 12, 768, 0, False), (300, 10, 256, 1, True),
               (256, 128, 1024, 0, True), (256, 128, 512, 1, True), (128, 256, 1024, 0, True), (256, 128, 768, 0, False)]
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        shapes = [sh for sh in shapes if sh[1] >= 64]
+    elif len(sys.argv) > 1:
         shapes = shapes[:int(sys.argv[1])]
     fails = []
     for (B, T, H, reverse, save) in shapes:

@@ -23,8 +23,12 @@ def _rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
 
 
+# AVC_LSTM_FWD_WS: "1" (default) = weight-stationary forward kernel (W_hh slice resident in tensor memory), "0" = ring kernel,
+# which stays the path for shapes the first does not take.  The switch is read per call.
+@pytest.mark.parametrize("fwd_ws", ["1", "0"])
 @pytest.mark.parametrize("B,T,I,H", [(4, 12, 48, 128), (130, 9, 32, 512), (256, 16, 64, 1024), (3, 40, 40, 256)])
-def test_persistent_lstm_matches_fp32(B, T, I, H):
+def test_persistent_lstm_matches_fp32(B, T, I, H, fwd_ws, monkeypatch):
+    monkeypatch.setenv("AVC_LSTM_FWD_WS", fwd_ws)
     torch.manual_seed(3)
     lstm = torch.nn.LSTM(I, H, 1, batch_first=True).to(DEV)
     x = _rand(B, T, I, seed=4).requires_grad_(True)
@@ -41,11 +45,13 @@ def test_persistent_lstm_matches_fp32(B, T, I, H):
         assert _rel(a, b) < 2e-2, (n, _rel(a, b))
 
 
+@pytest.mark.parametrize("fwd_ws", ["1", "0"])
 @pytest.mark.parametrize("B,T,I,H", [(256, 128, 512, 1024), (130, 128, 288, 512), (128, 256, 512, 1024), (40, 96, 80, 768)])
-def test_half_mode_layer_matches_nn_lstm_fp64(B, T, I, H):
+def test_half_mode_layer_matches_nn_lstm_fp64(B, T, I, H, fwd_ws, monkeypatch):
     """ops.LstmLayerH (input projection on fp16 operands, persistent bf16 recurrence forward and BPTT, bf16 gradient GEMMs)
     against torch.nn.LSTM evaluated in float64 (model_vc_mel.py:90/:104 semantics: gate order i,f,g,o, zero initial state),
     at the sequence lengths and batch sizes of BASELINE.json configs[1]/[2] (two batch tiles, a ragged second tile, H=512/768/1024)."""
+    monkeypatch.setenv("AVC_LSTM_FWD_WS", fwd_ws)
     torch.manual_seed(5)
     lstm = torch.nn.LSTM(I, H, 1, batch_first=True).to(DEV)
     ws = [lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0]
@@ -64,3 +70,35 @@ def test_half_mode_layer_matches_nn_lstm_fp64(B, T, I, H):
     for a, b, n in zip(got, rg, ["dx", "dw_ih", "dw_hh", "db_ih", "db_hh"]):
         assert torch.isfinite(a).all(), n
         assert _rel(a, b) < 2e-2, (n, _rel(a, b))
+
+
+@pytest.mark.parametrize("B,T,H,reverse,save", [(4, 6, 128, 0, True), (130, 9, 512, 1, True), (256, 16, 1024, 0, True), (37, 12, 768, 0, False),
+                                                (300, 10, 256, 1, True), (256, 128, 1024, 0, True), (600, 5, 1024, 1, True)])
+def test_weight_stationary_forward_equals_ring_kernel(B, T, H, reverse, save, monkeypatch):
+    """lstm_tc_fwd_ws_kernel (A operand from tensor memory, batch as N) and lstm_tc_fwd_kernel (activation ring) accumulate the
+    same products in the same k order: every output -- h, the 16-bit copies, the gates and cell states saved for BPTT -- is
+    bit-identical, on ragged batches, both directions, inference mode (nothing saved), and a batch that needs several launches."""
+    from autovc_b200 import _lib
+    from autovc_b200.ops import _p, _stream, _ws
+    g = torch.Generator().manual_seed(B * 131 + H)
+    P = (0.5 * torch.randn(B, T, 4 * H, generator=g)).to(DEV)
+    Wb = (torch.randn(4 * H, H, generator=g) / H ** 0.5).to(DEV).bfloat16()
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("AVC_LSTM_FWD_WS", flag)
+        h = torch.full((B, T, H), float("nan"), device=DEV)
+        gates = torch.full((B, T, 4 * H), float("nan"), device=DEV) if save else None
+        c = torch.full((B, T, H), float("nan"), device=DEV) if save else None
+        h16 = torch.zeros(B, T, H, device=DEV, dtype=torch.float16)
+        h16b = torch.zeros(B, T, H, device=DEV, dtype=torch.bfloat16)
+        nf = _lib.query("avc_lstm_fwd_workspace_bytes", B, T, H, PREC_BF16)
+        wf = _ws(nf, DEV)
+        _lib.call("avc_lstm_seq_fwd_h", _p(P), _p(Wb), 1, _p(h), H, _p(gates) if save else None, _p(c) if save else None, _p(h16), 2,
+                  _p(h16b), B, T, H, reverse, _p(wf), nf, _stream())
+        torch.cuda.synchronize()
+        outs[flag] = [h, gates, c, h16, h16b]
+    for a, b, n in zip(outs["0"], outs["1"], ["h", "gates", "c", "h16", "h16b"]):
+        if a is None:
+            continue
+        assert torch.isfinite(b.float()).all(), n
+        assert torch.equal(a, b), (n, float((a.float() - b.float()).abs().max()))
