@@ -1098,6 +1098,322 @@ lstm_tc_bwd_ks_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// BPTT, weight-stationary form (r02c):  dh^T[unit, utterance] = W_hh^T[unit, k] . dG_{t+1}[utterance, k]^T  with the
+// K = 4H reduction split over a cluster of 4 CTAs as above -- but the W_hh^T slice of a CTA (128 units x its K quarter) is the
+// A operand and lives in TENSOR MEMORY (plus the first 128 of 1024 k in shared memory at H = 1024), the batch is N: a CTA
+// streams only NB utterances x H of dG per step (128 KB at H = 1024 / NB = 64 instead of 256 KB), all of it in flight at once.
+// Grid = batch groups x (H/128 unit tiles) x 4 K ranks.  The accumulator (128 unit lanes x NB columns) is drained into four
+// [NB][32] fp32 tiles, one per unit quarter; quarter qq goes to cluster rank qq with one cp.async.bulk over DSMEM (as above),
+// rank r finalises units [32 r, 32 r + 32) of the tile: a thread owns 4 consecutive units of an utterance (float4 / 32-byte
+// accesses of gates, dH, c and of the bf16 gate-gradient slice it publishes).  The four partial sums are added in the order
+// the K-split kernel above uses for the same unit, so both kernels produce the same bits.
+// ---------------------------------------------------------------------------------------------------
+template <int NB, int EW>
+__global__ void __launch_bounds__(64 + EW * 32, 1)
+lstm_tc_bwd_ws_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapX, const LstmTcParams p,
+                      const __nv_bfloat16* __restrict__ WTg) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  const int T = p.T, H = p.H, G = 4 * p.H;
+  const int kblocks = H / 64, KT = p.kt, ksb = (H - KT) / 64;      // this CTA's quarter of K = 4H; ksb k-blocks of W in shared memory
+  constexpr uint32_t HB = NB * 128;                         // bytes of one dG k-block [NB][64] bf16
+  constexpr uint32_t TILE = NB * 128;                       // bytes of one [NB][32] fp32 partial-sum tile
+  constexpr int ET = EW * 32;
+  const uint32_t dtile = base;                              // [kblocks][NB][64] bf16, 128B swizzle
+  const uint32_t wsm = dtile + kblocks * HB;                // [ksb][128][64] bf16, 128B swizzle
+  const uint32_t stg = wsm + ksb * 16384;                   // my partial sums by unit quarter: [4][NB][32] fp32
+  const uint32_t red = stg + 4 * TILE;                      // the three foreign partial sums of MY unit quarter: [3][NB][32] fp32
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gen + (red + 3 * TILE - base));
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int j) { return bar0 + 8u * j; };
+  const uint32_t w_bar = bar0 + 8u * WS_MAX_PARTS, tfull = bar0 + 8u * (WS_MAX_PARTS + 1), wtm_bar = bar0 + 8u * (WS_MAX_PARTS + 2),
+                 red_full = bar0 + 8u * (WS_MAX_PARTS + 3);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + WS_MAX_PARTS + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t r = cluster_ctarank();                     // K quarter and unit quarter owned by this CTA
+  const int cluster_id = blockIdx.x / KS_CL;
+  const int UT = H / 128;
+  const int ut = cluster_id % UT, grp = cluster_id / UT;
+  const int kbp = p.kbs, parts = kblocks / kbp;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapX) : "memory");
+    for (int j = 0; j < parts; ++j) mbar_init(full_bar(j), 1);
+    mbar_init(w_bar, 1);
+    mbar_init(tfull, 1);
+    mbar_init(wtm_bar, EW);
+    mbar_init(red_full, 1);               // my own arrive.expect_tx (+ 3 tiles of complete_tx from the peers' bulk copies)
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  unsigned* counter = p.counters + grp * 64;
+  const unsigned per_step = (unsigned)(UT * KS_CL);
+  const int b0 = grp * NB;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (ksb > 0 && elect_one()) {
+      mbar_expect_tx(w_bar, ksb * 16384);
+      for (int kb = 0; kb < ksb; ++kb) tma_load_3d(wsm + kb * 16384, &mapW, w_bar, (int)r * H + kb * 64, ut * 128, 0);
+    }
+    __syncwarp();
+    for (int s = 1; s < T; ++s) {
+      const int row0 = ((s - 1) & 1) * p.nBpad + b0;
+      if (s > 1)
+        for (int j = 0; j < parts; ++j) mbar_wait(full_bar(j), s & 1);
+      if (lane == 0) {
+        for (int j = 0; j < parts; ++j) mbar_expect_tx(full_bar(j), kbp * HB);
+        while (ld_acquire(counter) < (unsigned)s * per_step) {
+        }
+        LT_TRACE(0);
+      }
+      __syncwarp();
+      fence_proxy_async_global();        // generic-proxy publishes -> my async-proxy reads
+      if (elect_one()) {
+        for (int j = 0; j < parts; ++j) {
+          tma_load_4d(dtile + j * kbp * HB, &mapX, full_bar(j), 0, row0, (int)r * kblocks + j * kbp, 0);
+          if (j == 0) LT_TRACE(1);
+        }
+        LT_TRACE(2);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(128, NB, 0, 0);
+    if (ksb > 0) mbar_wait(w_bar, 0);
+    mbar_wait(wtm_bar, 0);
+    tc_fence_after();
+    const uint32_t tmem_a = tmem_base + WS_TM_A;
+    for (int s = 1; s < T; ++s) {
+      for (int j = 0; j < parts; ++j) {
+        mbar_wait(full_bar(j), (s - 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          if (j == 0) LT_TRACE(3);
+          if (j == parts - 1) LT_TRACE(4);
+          for (int kk = 0; kk < kbp; ++kk) {
+            const int kb = j * kbp + kk;
+            const uint32_t sb = dtile + kb * HB;
+            if (kb >= ksb) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_ts(tmem_base, tmem_a + (uint32_t)((kb - ksb) * 32 + k * 8), make_desc(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            } else {
+              const uint32_t sa = wsm + kb * 16384;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(tmem_base, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          if (j == parts - 1) {
+            umma_commit(tfull);
+            LT_TRACE(5);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                        // TMEM lane quadrant = unit quarter this warp drains
+    const int ch = (warp - 2) >> 2;
+    constexpr int NC = NB / (EW / 4);              // accumulator columns drained per thread
+    const int j0 = ch * NC;
+    const int et = threadIdx.x - 64;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    // ---- resident W_hh^T slice -> TMEM: lane = unit row, k-range [r H + (H - KT), r H + H) of the row ----
+    {
+      const uint4* wrow = reinterpret_cast<const uint4*>(WTg + (size_t)(ut * 128 + q * 32 + lane) * G + (size_t)r * H + (H - KT));
+      for (int kb = ch; kb < KT / 64; kb += EW / 4) {
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 v = __ldg(wrow + kb * 8 + i);
+          w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+        tmem_st32(t_lane + WS_TM_A + kb * 32, w);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(wtm_bar);
+    }
+    // ---- gate algebra: a thread owns units [4 i4, 4 i4 + 4) of this rank's quarter for EPT utterances ----
+    constexpr int EPT = NB * 8 / ET;
+    const int i4 = et & 7;
+    const int u0 = ut * 128 + (int)r * 32 + 4 * i4;          // first of my 4 hidden units
+    // order of the partial sums: the K-split kernel adds the partial of K quarter (u % 64) / 16 first, then the others ascending
+    const uint32_t first = 2u * (r & 1u) + (uint32_t)(i4 >> 2);
+    // where the partial sum of K quarter X for my unit quarter lives: my own drain tile, or the slot its sender copied into
+    auto tile_of = [&](uint32_t X) { return (X == r) ? (stg + r * TILE) : (red + (X < r ? X : X - 1) * TILE); };
+    float dc_rec[EPT][4], c_carry[EPT][4];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dc_rec[e][i] = c_carry[e][i] = 0.f;
+    for (int s = 0; s < T; ++s) {
+      const int t = p.reverse ? s : T - 1 - s;               // BPTT walks against the forward direction
+      const bool has_prev = s < T - 1;
+      const int t_prev = p.reverse ? t + 1 : t - 1;
+      float dh[EPT][4], ct[EPT][4], cp[EPT][4], g4[EPT][16];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int bl = (et >> 3) + e * (ET / 8);
+        const int b = b0 + bl;
+        if (b < p.nB) {
+          const size_t rowi = (size_t)b * T + t;
+          if (s == 0) {
+            *reinterpret_cast<float4*>(ct[e]) = __ldg(reinterpret_cast<const float4*>(p.c_seq + rowi * H + u0));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ct[e][i] = c_carry[e][i];
+          }
+          *reinterpret_cast<float4*>(dh[e]) = __ldg(reinterpret_cast<const float4*>(p.dH + rowi * p.lddh + u0));
+          if (has_prev) {
+            *reinterpret_cast<float4*>(cp[e]) = __ldg(reinterpret_cast<const float4*>(p.c_seq + ((size_t)b * T + t_prev) * H + u0));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cp[e][i] = 0.f;
+          }
+          ldg_nc_v8(p.gates + rowi * G + 4 * u0, &g4[e][0]);
+          ldg_nc_v8(p.gates + rowi * G + 4 * u0 + 8, &g4[e][8]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) c_carry[e][i] = cp[e][i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dh[e][i] = ct[e][i] = cp[e][i] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) g4[e][j] = 0.f;
+        }
+        // everything of the gate algebra that does not depend on dh, while the MMAs of this step are still running:
+        // g4 <- (d i, d f, d g, d o) per unit of dc resp. dh, ct <- d(dc)/d(dh), cp <- f (the carry factor of dc)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float gi = g4[e][4 * i], gf = g4[e][4 * i + 1], gg = g4[e][4 * i + 2], go = g4[e][4 * i + 3];
+          const float tc = tanh_fast(ct[e][i]);
+          g4[e][4 * i] = gg * gi * (1.f - gi);
+          g4[e][4 * i + 1] = cp[e][i] * gf * (1.f - gf);
+          g4[e][4 * i + 2] = gi * (1.f - gg * gg);
+          g4[e][4 * i + 3] = tc * go * (1.f - go);
+          ct[e][i] = go * (1.f - tc * tc);
+          cp[e][i] = gf;
+        }
+      }
+      if (s > 0) {
+        if (et == 0) mbar_expect_tx(red_full, 3 * TILE);       // this step's three foreign partial tiles
+        mbar_wait(tfull, (s - 1) & 1);
+        if (et == 0) LT_TRACE(6);
+        tc_fence_after();
+        // drain my quadrant: unit quarter q of the CTA's partial sums -> tile q, [utterance][unit] (lanes = consecutive words)
+        {
+          const uint32_t dst = stg + (uint32_t)q * TILE + (uint32_t)lane * 4u;
+          if constexpr (NC == 16) {
+            float d[16];
+            tmem_ld16(t_lane + j0, d);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) st_shared_f32(dst + (uint32_t)(j0 + j) * 128u, d[j]);
+          } else {
+#pragma unroll
+            for (int cc = 0; cc < NC / 32; ++cc) {
+              float d[32];
+              tmem_ld32(t_lane + j0 + cc * 32, d);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) st_shared_f32(dst + (uint32_t)(j0 + cc * 32 + j) * 128u, d[j]);
+            }
+          }
+        }
+        tc_fence_before();
+        fence_async_smem();                                       // my staged rows are visible to the copy engine
+        asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+        if (et == 0) {
+#pragma unroll
+          for (uint32_t qq = 0; qq < KS_CL; ++qq) {
+            if (qq == r) continue;
+            const uint32_t slot = r < qq ? r : r - 1;            // my index among qq's three senders
+            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             mapa_shared(red + slot * TILE, qq)),
+                         "r"(stg + qq * TILE), "r"(TILE), "r"(mapa_shared(red_full, qq))
+                         : "memory");
+          }
+          LT_TRACE(9);
+        }
+        mbar_wait_cluster(red_full, (s - 1) & 1);
+        if (et == 0) LT_TRACE(10);
+#pragma unroll
+        for (int e = 0; e < EPT; ++e) {
+          const uint32_t ro = (uint32_t)((et >> 3) + e * (ET / 8)) * 128u + (uint32_t)i4 * 16u;
+          {
+            const float4 v = ld_shared_v4(tile_of(first) + ro);
+            dh[e][0] += v.x; dh[e][1] += v.y; dh[e][2] += v.z; dh[e][3] += v.w;
+          }
+#pragma unroll
+          for (uint32_t X = 0; X < 4; ++X) {
+            if (X == first) continue;
+            const float4 v = ld_shared_v4(tile_of(X) + ro);
+            dh[e][0] += v.x; dh[e][1] += v.y; dh[e][2] += v.z; dh[e][3] += v.w;
+          }
+        }
+      }
+      alignas(32) __nv_bfloat16 gb[EPT][16];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float dc = fmaf(dh[e][i], ct[e][i], dc_rec[e][i]);
+          const float di = dc * g4[e][4 * i];
+          const float df = dc * g4[e][4 * i + 1];
+          const float dg = dc * g4[e][4 * i + 2];
+          const float dO = dh[e][i] * g4[e][4 * i + 3];
+          dc_rec[e][i] = dc * cp[e][i];
+          g4[e][4 * i] = di; g4[e][4 * i + 1] = df; g4[e][4 * i + 2] = dg; g4[e][4 * i + 3] = dO;
+          gb[e][4 * i] = __float2bfloat16_rn(di); gb[e][4 * i + 1] = __float2bfloat16_rn(df);
+          gb[e][4 * i + 2] = __float2bfloat16_rn(dg); gb[e][4 * i + 3] = __float2bfloat16_rn(dO);
+        }
+        const int bl = (et >> 3) + e * (ET / 8);
+        stg_v8(p.xbuf + ((size_t)(s & 1) * p.nBpad + b0 + bl) * (size_t)G + 4 * u0, reinterpret_cast<const uint32_t*>(gb[e]));
+      }
+      if (et == 0) LT_TRACE(7);
+      asm volatile("bar.sync 1, %0;" ::"n"(ET) : "memory");
+      if (et == 0) {
+        LT_TRACE(11);
+        red_release_add(counter, 1u);      // cumulative gpu-scope release of the CTA's slices (the consumers run the proxy fence)
+        LT_TRACE(8);
+      }
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const int b = b0 + (et >> 3) + e * (ET / 8);
+        if (b < p.nB) {
+          const size_t rowi = (size_t)b * T + t;
+          if (p.dP != nullptr) {
+            stg_v8f(p.dP + rowi * G + 4 * u0, &g4[e][0]);
+            stg_v8f(p.dP + rowi * G + 4 * u0 + 8, &g4[e][8]);
+          }
+          if (p.dP16 != nullptr) stg_v8(reinterpret_cast<__nv_bfloat16*>(p.dP16) + rowi * G + 4 * u0, reinterpret_cast<const uint32_t*>(gb[e]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // no CTA leaves while peers may still copy into its tiles
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // fp32 -> bf16 copy of a weight matrix
 __global__ void cvt_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -1171,8 +1487,10 @@ static LtPlanWs lt_plan_ws(int nB, int H) {
   pl.chunk = std::min(nB, gmax * pl.NB);
   pl.KT = std::min(H, WS_KT_MAX) / 64 * 64;
   const int kblocks = H / 64;
-  pl.kbp = kblocks % 4 == 0 ? 4 : (kblocks % 2 == 0 ? 2 : 1);
-  if (kblocks / pl.kbp > WS_MAX_PARTS) return pl;
+  // Issuing a TMA instruction costs the producer 120-330 clocks whatever its box (scripts/micro/tma_issue.cu): the step's tile
+  // arrives in ONE box, or in two halves where it is long enough for the first half's MMAs to hide under the second's flight
+  // (H = 1024 / NB = 64, per step: 4 boxes 5.52 us, 2 boxes 5.25, 1 box 5.29; 16 boxes 7.3)
+  pl.kbp = (kblocks >= 12 && kblocks % 2 == 0) ? kblocks / 2 : kblocks;
   pl.smem = 1024 + (size_t)kblocks * pl.NB * 128 + (size_t)(H - pl.KT) / 64 * 16384 + (size_t)pl.NB * (64 + 64 + 128 + 128) + 256;
   if (pl.smem > 227 * 1024) return pl;
   const int NG = ceil_div(pl.chunk, pl.NB);
@@ -1182,6 +1500,38 @@ static LtPlanWs lt_plan_ws(int nB, int H) {
   pl.total = pl.off_cnt + align256((size_t)nchunks * WS_MAX_GROUPS * 64 * sizeof(unsigned));
   pl.ok = true;
   return pl;
+}
+// weight-stationary BPTT (lstm_tc_bwd_ws_kernel): clusters of 4 K ranks x H/128 unit tiles per batch group
+static LtPlanWs lt_plan_ws_bwd(int nB, int H) {
+  LtPlanWs pl{};
+  pl.ok = false;
+  if (H % 128 != 0 || H < 128 || H > 1024) return pl;
+  pl.NT = (H / 128) * KS_CL;                              // CTAs per batch group
+  const int gmax = std::min(WS_MAX_GROUPS, num_sms() / pl.NT);
+  if (gmax < 1) return pl;
+  pl.NB = ceil_div(nB, 32) <= gmax ? 32 : 64;
+  pl.NGmax = gmax;
+  pl.chunk = std::min(nB, gmax * pl.NB);
+  pl.KT = std::min(H, WS_KT_MAX) / 64 * 64;
+  const int kblocks = H / 64;
+  // Issuing a TMA instruction costs the producer 120-330 clocks whatever its box (scripts/micro/tma_issue.cu): the step's tile
+  // arrives in ONE box, or in two halves where it is long enough for the first half's MMAs to hide under the second's flight
+  // (H = 1024 / NB = 64, per step: 4 boxes 5.52 us, 2 boxes 5.25, 1 box 5.29; 16 boxes 7.3)
+  pl.kbp = (kblocks >= 12 && kblocks % 2 == 0) ? kblocks / 2 : kblocks;
+  pl.smem = 1024 + (size_t)kblocks * pl.NB * 128 + (size_t)(H - pl.KT) / 64 * 16384 + (size_t)7 * pl.NB * 128 + 256;
+  if (pl.smem > 227 * 1024) return pl;
+  const int NG = ceil_div(pl.chunk, pl.NB);
+  pl.off_x = align256((size_t)4 * H * H * 2);
+  pl.off_cnt = pl.off_x + align256((size_t)2 * NG * pl.NB * 4 * H * 2);
+  const int nchunks = ceil_div(nB, pl.chunk);
+  pl.total = pl.off_cnt + align256((size_t)nchunks * WS_MAX_GROUPS * 64 * sizeof(unsigned));
+  pl.ok = true;
+  return pl;
+}
+// AVC_LSTM_BWD_WS=0 keeps BPTT on the K-split kernel with the W slice in shared memory (same rules as AVC_LSTM_FWD_WS)
+static bool bwd_ws_enabled() {
+  const char* e = getenv("AVC_LSTM_BWD_WS");
+  return !(e && e[0] == '0');
 }
 // AVC_LSTM_FWD_WS=0 keeps the forward recurrence on the ring kernel (read per call so one process can compare both; the ring
 // kernel stays the path for shapes the weight-stationary kernel does not take -- tests/test_gpu_lstm_tc.py runs both settings)
@@ -1193,10 +1543,8 @@ static bool fwd_ws_enabled() {
 size_t lstm_tc_workspace(int nB, int T, int H, bool bwd) {
   (void)T;
   size_t n = lt_plan(nB, H, bwd).total;
-  if (!bwd) {
-    const LtPlanWs pw = lt_plan_ws(nB, H);
-    if (pw.ok) n = std::max(n, pw.total);
-  }
+  const LtPlanWs pw = bwd ? lt_plan_ws_bwd(nB, H) : lt_plan_ws(nB, H);
+  if (pw.ok) n = std::max(n, pw.total);
   return n;
 }
 
@@ -1340,10 +1688,66 @@ static int lstm_seq_fwd_ws(const LtPlanWs& pl, const __nv_bfloat16* Wb, const fl
     p.h16b = (aux16 && aux16b) ? (void*)((uint16_t*)aux16b + (size_t)b0 * T * H) : nullptr;
     rc = make_map4_grouped(&mX, xbuf, H, (uint64_t)2 * p.nBpad, 1, H, 64, pl.NB, pl.kbp, 2, false);
     if (rc) return rc;
-    if (const char* e = getenv("AVC_LSTM_WS_KBP")) { p.kbs = atoi(e); }      // TEMP experiment switch
-    rc = make_map4_grouped(&mX, xbuf, H, (uint64_t)2 * p.nBpad, 1, H, 64, pl.NB, p.kbs, 2, false);
-    if (rc) return rc;
     rc = pl.NB == 32 ? lt_launch_fwd_ws<32, 8>(mW, mX, p, pl.smem, Wb, st) : lt_launch_fwd_ws<64, 8>(mW, mX, p, pl.smem, Wb, st);
+    if (rc) return rc;
+  }
+  return AVC_OK;
+}
+
+template <int NB, int EW>
+static int lt_launch_bwd_ws(const CUtensorMap& mW, const CUtensorMap& mX, const LstmTcParams& p, size_t smem, const __nv_bfloat16* Wb,
+                            cudaStream_t st) {
+  auto kern = lstm_tc_bwd_ws_kernel<NB, EW>;
+  AVC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(p.MT * p.NT);
+  cfg.blockDim = dim3(64 + EW * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = KS_CL;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeCooperative;
+  attrs[1].val.cooperative = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  AVC_CUDA(cudaLaunchKernelEx(&cfg, kern, mW, mX, p, Wb));
+  g_launches.fetch_add(1);
+  return AVC_OK;
+}
+
+// BPTT through the weight-stationary kernel; ws laid out by lt_plan_ws_bwd.  Wb = Whh_pT (H, 4H) bf16
+static int lstm_seq_bwd_ws(const LtPlanWs& pl, const __nv_bfloat16* Wb, float* gates, float* c_seq, const float* dH, int lddh, float* dP,
+                           int nB, int T, int H, int reverse, uint8_t* w8, cudaStream_t st, void* aux16) {
+  __nv_bfloat16* xbuf = (__nv_bfloat16*)(w8 + pl.off_x);
+  unsigned* counters = (unsigned*)(w8 + pl.off_cnt);
+  const int nchunks = ceil_div(nB, pl.chunk);
+  AVC_CUDA(cudaMemsetAsync(counters, 0, (size_t)nchunks * WS_MAX_GROUPS * 64 * sizeof(unsigned), st));
+  const size_t G = 4 * (size_t)H;
+  CUtensorMap mW, mX;
+  int rc = make_map3(&mW, Wb, G, H, 1, G, (uint64_t)H * G, 64, 128);
+  if (rc) return rc;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int b0 = ch * pl.chunk;
+    const int nb = std::min(pl.chunk, nB - b0);
+    LstmTcParams p{};
+    p.nB = nb; p.T = T; p.H = H; p.K = 4 * H; p.reverse = reverse;
+    p.MT = ceil_div(nb, pl.NB); p.NT = pl.NT; p.nBpad = p.MT * pl.NB; p.kbs = pl.kbp; p.kt = pl.KT;
+    p.gates = gates + (size_t)b0 * T * G;
+    p.c_seq = c_seq + (size_t)b0 * T * H;
+    p.dH = dH + (size_t)b0 * T * lddh;
+    p.lddh = lddh;
+    p.dP = dP ? dP + (size_t)b0 * T * G : nullptr;
+    p.dP16 = aux16 ? (void*)((uint16_t*)aux16 + (size_t)b0 * T * G) : nullptr;
+    p.xbuf = xbuf;
+    p.counters = counters + ch * WS_MAX_GROUPS * 64;
+    p.trace = (ch == 0) ? g_trace : nullptr;
+    p.wide = 1;
+    rc = make_map4_grouped(&mX, xbuf, G, (uint64_t)2 * p.nBpad, 1, G, 64, pl.NB, pl.kbp, 2, false);
+    if (rc) return rc;
+    rc = pl.NB == 32 ? lt_launch_bwd_ws<32, 8>(mW, mX, p, pl.smem, Wb, st) : lt_launch_bwd_ws<64, 8>(mW, mX, p, pl.smem, Wb, st);
     if (rc) return rc;
   }
   return AVC_OK;
@@ -1385,6 +1789,13 @@ int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh,
                       ldh % 4 == 0;
     if (pw.ok && al16 && ws_bytes >= pw.total)
       return lstm_seq_fwd_ws(pw, Wb, P, h_seq, ldh, gates, c_seq, nB, T, H, reverse, w8, st, aux16, fmt16, aux16b);
+  }
+  if (bwd && bwd_ws_enabled()) {
+    const LtPlanWs pw = lt_plan_ws_bwd(nB, H);
+    auto al32 = [](const void* q) { return ((uintptr_t)q & 31) == 0; };
+    const bool wide = al32(gates) && al32(c_seq) && al32(dH) && al32(dP) && al32(aux16) && lddh % 8 == 0;
+    if (pw.ok && wide && ws_bytes >= pw.total)
+      return lstm_seq_bwd_ws(pw, Wb, gates, c_seq, dH, lddh, dP, nB, T, H, reverse, w8, st, aux16);
   }
   const int nchunks = ceil_div(nB, pl.chunk);
   AVC_CUDA(cudaMemsetAsync(counters, 0, (size_t)nchunks * 128 * sizeof(unsigned), st));

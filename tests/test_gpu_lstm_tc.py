@@ -23,12 +23,14 @@ def _rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
 
 
-# AVC_LSTM_FWD_WS: "1" (default) = weight-stationary forward kernel (W_hh slice resident in tensor memory), "0" = ring kernel,
-# which stays the path for shapes the first does not take.  The switch is read per call.
+# AVC_LSTM_FWD_WS / AVC_LSTM_BWD_WS: "1" (default) = weight-stationary kernels (W_hh slice resident in tensor memory, batch as the
+# N dimension), "0" = the ring (forward) / shared-memory K-split (BPTT) kernels, which stay the path for shapes the first do
+# not take.  The switches are read per call.
 @pytest.mark.parametrize("fwd_ws", ["1", "0"])
 @pytest.mark.parametrize("B,T,I,H", [(4, 12, 48, 128), (130, 9, 32, 512), (256, 16, 64, 1024), (3, 40, 40, 256)])
 def test_persistent_lstm_matches_fp32(B, T, I, H, fwd_ws, monkeypatch):
     monkeypatch.setenv("AVC_LSTM_FWD_WS", fwd_ws)
+    monkeypatch.setenv("AVC_LSTM_BWD_WS", fwd_ws)
     torch.manual_seed(3)
     lstm = torch.nn.LSTM(I, H, 1, batch_first=True).to(DEV)
     x = _rand(B, T, I, seed=4).requires_grad_(True)
@@ -52,6 +54,7 @@ def test_half_mode_layer_matches_nn_lstm_fp64(B, T, I, H, fwd_ws, monkeypatch):
     against torch.nn.LSTM evaluated in float64 (model_vc_mel.py:90/:104 semantics: gate order i,f,g,o, zero initial state),
     at the sequence lengths and batch sizes of BASELINE.json configs[1]/[2] (two batch tiles, a ragged second tile, H=512/768/1024)."""
     monkeypatch.setenv("AVC_LSTM_FWD_WS", fwd_ws)
+    monkeypatch.setenv("AVC_LSTM_BWD_WS", fwd_ws)
     torch.manual_seed(5)
     lstm = torch.nn.LSTM(I, H, 1, batch_first=True).to(DEV)
     ws = [lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0]
@@ -101,4 +104,42 @@ def test_weight_stationary_forward_equals_ring_kernel(B, T, H, reverse, save, mo
         if a is None:
             continue
         assert torch.isfinite(b.float()).all(), n
+        assert torch.equal(a, b), (n, float((a.float() - b.float()).abs().max()))
+
+
+@pytest.mark.parametrize("B,T,H,reverse,fp32_out", [(4, 6, 128, 0, True), (130, 9, 512, 1, True), (256, 16, 1024, 0, False), (37, 12, 768, 0, True),
+                                                    (300, 10, 256, 1, True), (256, 128, 1024, 0, False), (600, 5, 1024, 1, True)])
+def test_weight_stationary_bptt_equals_ksplit_kernel(B, T, H, reverse, fp32_out, monkeypatch):
+    """lstm_tc_bwd_ws_kernel (W_hh^T slice in tensor memory, 128 units x NB utterances per CTA, K split over a cluster of 4) adds the
+    four partial sums of a unit in the order lstm_tc_bwd_ks_kernel uses: the gate gradients (fp32 and bf16) are bit-identical."""
+    from autovc_b200 import _lib
+    from autovc_b200.ops import _p, _stream, _ws
+    g = torch.Generator().manual_seed(B * 131 + H)
+    P = (0.5 * torch.randn(B, T, 4 * H, generator=g)).to(DEV)
+    Wb = (torch.randn(4 * H, H, generator=g) / H ** 0.5).to(DEV).bfloat16()
+    WTb = Wb.t().contiguous()
+    dH = (0.1 * torch.randn(B, T, H, generator=g)).to(DEV)
+    h = torch.empty(B, T, H, device=DEV)
+    gates = torch.empty(B, T, 4 * H, device=DEV)
+    c = torch.empty(B, T, H, device=DEV)
+    h16 = torch.empty(B, T, H, device=DEV, dtype=torch.float16)
+    nf = _lib.query("avc_lstm_fwd_workspace_bytes", B, T, H, PREC_BF16)
+    wf = _ws(nf, DEV)
+    _lib.call("avc_lstm_seq_fwd_h", _p(P), _p(Wb), 1, _p(h), H, _p(gates), _p(c), _p(h16), 2, None, B, T, H, reverse, _p(wf), nf, _stream())
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("AVC_LSTM_BWD_WS", flag)
+        dP = torch.full((B, T, 4 * H), float("nan"), device=DEV) if fp32_out else None
+        dP16 = torch.zeros(B, T, 4 * H, device=DEV, dtype=torch.bfloat16)
+        nb = _lib.query("avc_lstm_bwd_workspace_bytes", B, T, H, PREC_BF16)
+        wb = _ws(nb, DEV)
+        _lib.call("avc_lstm_seq_bwd_h", _p(dH), H, _p(WTb), 1, _p(gates), _p(c), _p(dP) if fp32_out else None, _p(dP16), B, T, H, reverse,
+                  _p(wb), nb, _stream())
+        torch.cuda.synchronize()
+        outs[flag] = [dP, dP16]
+    for a, b, n in zip(outs["0"], outs["1"], ["dP", "dP16"]):
+        if a is None:
+            continue
+        assert torch.isfinite(b.float()).all(), n
+        assert float(b.float().abs().max()) > 0, n
         assert torch.equal(a, b), (n, float((a.float() - b.float()).abs().max()))
