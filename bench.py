@@ -228,16 +228,25 @@ def kernel_flops(name, a):
     return 0.0
 
 
-def recurrence_traffic(family, args):
-    """dram__bytes_read + dram__bytes_write per launch of the persistent recurrence families, from the committed app-range
-    replay counters (profiles/r02_traffic.json; one launch each at B=256, T=128, H=512 and H=1024).  A step launches the family
-    three times (lstm1 at H=512, the two lstm2 layers at H=1024): the average over those.  None for other families / shapes."""
-    which = {"avc_lstm_seq_fwd_h": "fwd", "avc_lstm_seq_bwd_h": "bwd"}.get(family)
-    path = os.path.join(ROOT, "profiles", "r02_traffic.json")
-    if which is None or (args.batch, args.len_crop, args.n_bins) != (256, 128, 80) or not os.path.exists(path):
+def family_traffic(family, args):
+    """dram__bytes_read + dram__bytes_write per launch (per C-ABI call) of the dominant family at config 2, from committed ncu
+    counters: the persistent recurrences from app-range replay (profiles/r02c_traffic.json: one launch each at B=256, T=128, H=512
+    and H=1024; a step launches the family three times -- lstm1 at H=512, the two lstm2 layers at H=1024 -- the average over
+    those), the GEMM / BatchNorm families from the ncu launch list of one bench step taken with the dram__bytes metrics
+    (profiles/r02c_family_traffic.json).  None for other families / shapes."""
+    if (args.batch, args.len_crop, args.n_bins) != (256, 128, 80):
         return None
-    t = json.load(open(path))["per_launch"]
-    return (t[f"{which}_h512"]["dram_bytes"] + 2 * t[f"{which}_h1024"]["dram_bytes"]) / 3.0
+    which = {"avc_lstm_seq_fwd_h": "fwd", "avc_lstm_seq_bwd_h": "bwd"}.get(family)
+    if which is not None:
+        path = os.path.join(ROOT, "profiles", "r02c_traffic.json")
+        if not os.path.exists(path):
+            return None
+        t = json.load(open(path))["per_launch"]
+        return (t[f"{which}_h512"]["dram_bytes"] + 2 * t[f"{which}_h1024"]["dram_bytes"]) / 3.0
+    path = os.path.join(ROOT, "profiles", "r02c_family_traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path))["per_call"].get(family)
 
 
 def run_ours(args):
@@ -355,7 +364,7 @@ def run_ours(args):
     achieved = top_f["flops"] / (top_f["ms"] * 1e-3) / 1e12 if top_f["ms"] > 0 else 0.0
     roofline = {
         "bound": "tensor", "kernel": top_name, "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["bf16_sustained"], "traffic": recurrence_traffic(top_name, args),
+        "frac": achieved / peaks["bf16_sustained"], "traffic": family_traffic(top_name, args),
         "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
         "launches_per_step": top_f["n"] / prof_steps, "avg_launch_ms": top_f["ms"] / max(1, top_f["n"]),
         "share_of_step_kernel_time": top_f["ms"] / tot_ms,

@@ -62,7 +62,7 @@ nf = _lib.query("avc_lstm_fwd_workspace_bytes", B, T, H, prec); wf = _ws(nf, dev
 nb = _lib.query("avc_lstm_bwd_workspace_bytes", B, T, H, prec); wb = _ws(nb, dev)
 names = ["barrier", "tma0", "tmaN", "land0", "landN", "mma_issued", "epi_wake", "math_done", "published", "rs_sent", "rs_done", "bar_passed"]
 for which in ("fwd", "bwd"):
-    trace = torch.zeros(16 * T + 9 * 1024, dtype=torch.int64, device=dev)
+    trace = torch.zeros(16 * T, dtype=torch.int64, device=dev)
     _lib.load().avc_debug_set_trace(ctypes.c_void_p(trace.data_ptr()))
     if which == "fwd":
         _lib.call("avc_lstm_seq_fwd", _p(P), _p(W), _p(h), H, _p(gates), _p(c), B, T, H, 0, prec, _p(wf), nf, _stream())
@@ -79,43 +79,4 @@ for which in ("fwd", "bwd"):
         rows.append(((tr[s] - base) / 1e3).tolist())
     import numpy as np
     med = np.median(np.array(rows), axis=0)
-    print(which, "median us after previous publish:", {n: round(float(v), 2) for n, v in zip(names, med)}, flush=True)
-    if which == "bwd":
-        # all-CTA skew of the K-split BPTT kernel: cluster = 4 consecutive CTAs (K ranks), 16 clusters per batch tile
-        ncta = 128
-        allc = full[16 * T:16 * T + ncta * 8].view(ncta, 4, 2).double()
-        smid = full[16 * T + 8 * ncta:16 * T + 9 * ncta]
-        for tile in range(2):
-            sl = slice(tile * 64, tile * 64 + 64)
-            for st in range(1, 4):
-                pub_prev, bar, pub = allc[sl, st - 1, 1], allc[sl, st, 0], allc[sl, st, 1]
-                t1 = pub_prev.max()
-                print(f"bwd tile {tile} step {64 + st}: publish spread {float((t1 - pub_prev.min()) / 1e3):.2f} us | barrier pass after LAST publish "
-                      f"min/med/max {float((bar.min() - t1) / 1e3):.2f}/{float((bar.median() - t1) / 1e3):.2f}/{float((bar.max() - t1) / 1e3):.2f} | "
-                      f"publish after barrier pass min/med/max {float((pub - bar).min() / 1e3):.2f}/{float((pub - bar).median() / 1e3):.2f}/{float((pub - bar).max() / 1e3):.2f}")
-            work = torch.stack([(allc[sl, st, 1] - allc[sl, st, 0]) / 1e3 for st in range(1, 4)], 1).mean(1)   # (64,) us barrier -> publish
-            det = torch.stack([(allc[sl, st, 0] - allc[sl, st - 1, 1].max()) / 1e3 for st in range(1, 4)], 1).mean(1)
-            print("   per cluster (cluster, smids, barrier->publish us per rank, detection us per rank):")
-            for cl in range(16):
-                ids = [tile * 64 + cl * 4 + r for r in range(4)]
-                print("     ", cl, [int(smid[i]) for i in ids], [round(float(work[cl * 4 + r]), 2) for r in range(4)],
-                      [round(float(det[cl * 4 + r]), 2) for r in range(4)])
-    if which == "fwd":
-        ncta = 128
-        allc = full[16 * T:16 * T + ncta * 8].view(ncta, 4, 2).double()
-        smid = full[16 * T + 8 * ncta:16 * T + 9 * ncta]
-        for tile in range(2):
-            sl = slice(tile * 64, tile * 64 + 64)
-            for st in range(1, 4):
-                pub_prev, bar, pub = allc[sl, st - 1, 1], allc[sl, st, 0], allc[sl, st, 1]
-                t0, t1 = pub_prev.min(), pub_prev.max()
-                print(f"tile {tile} step {64 + st}: publish spread {float((t1 - t0) / 1e3):.2f} us (median {float((pub_prev.median() - t0) / 1e3):.2f}) | "
-                      f"barrier pass after LAST publish min/med/max {float((bar.min() - t1) / 1e3):.2f}/{float((bar.median() - t1) / 1e3):.2f}/"
-                      f"{float((bar.max() - t1) / 1e3):.2f} | next publish after barrier pass min/med/max "
-                      f"{float((pub - bar).min() / 1e3):.2f}/{float((pub - bar).median() / 1e3):.2f}/{float((pub - bar).max() / 1e3):.2f}")
-            lat = torch.stack([(allc[sl, st, 0] - allc[sl, st - 1, 1].max()) / 1e3 for st in range(1, 4)], 1)   # (64, 3)
-            o2 = torch.argsort(lat.mean(1))
-            print("   detection latency by cta (cta, smid, us x3):", [(int(i) + tile * 64, int(smid[int(i) + tile * 64]), [round(float(v), 1) for v in lat[i]]) for i in o2[::5]])
-            order = torch.argsort(allc[sl, 1, 1])
-            pp = allc[sl, 1, 1]
-            print("   publish order (cta, smid, us):", [(int(i) + tile * 64, int(smid[int(i) + tile * 64]), round(float((pp[i] - pp.min()) / 1e3), 2)) for i in order[::6]])
+    print(which, "median us after previous publish:", {n: round(float(v), 2) for n, v in zip(names, med) if v > -1e6}, flush=True)

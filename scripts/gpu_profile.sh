@@ -15,5 +15,5 @@ SKIP=$((LPS * 3 + 200))
 # launch; ncu's kernel replay records nan for them and aborts, so they are excluded by name.  Their device time comes from
 # the CUDA-event family timing in the bench JSON (roofline.families) instead.  The window is several steps long (the -k
 # filter also counts torch's own kernels); summarize_profiles.py cuts exactly one step out of it between two L1-loss kernels.
-ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:^(?!.*lstm_tc).*$' -s $SKIP -c $((LPS * 4)) --csv --log-file $OUT/launches_${TAG}.csv $CMD > $OUT/ncu_${TAG}_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k 'regex:^(?!.*lstm_tc).*$' -s $SKIP -c $((LPS * 4)) --csv --log-file $OUT/launches_${TAG}.csv $CMD > $OUT/ncu_${TAG}_launches.log 2>&1
 echo "ncu launch list rc=$?"
