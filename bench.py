@@ -679,8 +679,8 @@ def main():
     ap.add_argument("--cpu-sample-batch", dest="cpu_sample_batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "frontend", "convert", "loader", "dvector", "wav"])
-    ap.add_argument("--chunk", type=int, default=128, help="--workload convert: utterances per Generator call")
-    ap.add_argument("--streams", type=int, default=4, help="--workload convert: CUDA streams the chunks alternate over")
+    ap.add_argument("--chunk", type=int, default=256, help="--workload convert: utterances per Generator call")
+    ap.add_argument("--streams", type=int, default=2, help="--workload convert: CUDA streams the chunks alternate over")
     ap.add_argument("--depth", type=int, default=1, help="--workload wav: Conv-TasNet encoder/decoder depth (main.py:65)")
     ap.add_argument("--utterances", type=int, default=4096, help="frontend/convert legs: number of 10 s utterances (BASELINE.json configs[4]: 4096)")
     args = ap.parse_args()
