@@ -197,37 +197,47 @@ lstm_small_fwd_kernel_t(const float* __restrict__ P, const float* __restrict__ W
   float c = 0.f;
   const bool live = b < nB;
   const unsigned quad_base = ((threadIdx.y * blockDim.x + threadIdx.x) & 31) & ~3u;
-  float p_next = live ? P[((size_t)b * T + (reverse ? T - 1 : 0)) * ldp + j] : 0.f;
-  for (int step = 0; step < T; ++step) {
-    const int t = reverse ? (T - 1 - step) : step;
-    const int cur = step & 1;
-    float acc = p_next;
-    if (live && step + 1 < T) p_next = P[((size_t)b * T + (reverse ? t - 1 : t + 1)) * ldp + j];
-    const float4* h4 = reinterpret_cast<const float4*>(hs[cur][ul]);
+  // The step is a short dependent chain (16-32 FMAs, two transcendental calls, one barrier): with one pre-activation fetched one
+  // step ahead it waited on the L2 / HBM latency of that load (0.56 us per step measured, r02).  PF steps are kept in flight.
+  constexpr int PF = 4;
+  float p_ring[PF];
 #pragma unroll
-    for (int k = 0; k < HT; k += 4) {
-      const float4 hv = h4[k >> 2];
-      acc = fmaf(w[k], hv.x, acc);
-      acc = fmaf(w[k + 1], hv.y, acc);
-      acc = fmaf(w[k + 2], hv.z, acc);
-      acc = fmaf(w[k + 3], hv.w, acc);
-    }
-    const float a = (g == 2) ? tanhf(acc) : sigmoidf_acc(acc);
-    const float gi = __shfl_sync(0xffffffffu, a, quad_base + 0);
-    const float gf = __shfl_sync(0xffffffffu, a, quad_base + 1);
-    const float gg = __shfl_sync(0xffffffffu, a, quad_base + 2);
-    const float go = __shfl_sync(0xffffffffu, a, quad_base + 3);
-    c = gf * c + gi * gg;
-    const float h_new = go * tanhf(c);
-    if (g == 0) hs[cur ^ 1][ul][u] = h_new;
-    if (live) {
-      gates[((size_t)b * T + t) * G + j] = a;
-      if (g == 0) {
-        h_seq[((size_t)b * T + t) * ldh + u] = h_new;
-        c_seq[((size_t)b * T + t) * H + u] = c;
+  for (int i = 0; i < PF; ++i) p_ring[i] = (live && i < T) ? P[((size_t)b * T + (reverse ? T - 1 - i : i)) * ldp + j] : 0.f;
+  for (int step0 = 0; step0 < T; step0 += PF) {
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int step = step0 + i;
+      if (step >= T) break;                     // uniform over the block
+      const int t = reverse ? (T - 1 - step) : step;
+      const int cur = step & 1;
+      float acc = p_ring[i];
+      if (live && step + PF < T) p_ring[i] = P[((size_t)b * T + (reverse ? t - PF : t + PF)) * ldp + j];
+      const float4* h4 = reinterpret_cast<const float4*>(hs[cur][ul]);
+#pragma unroll
+      for (int k = 0; k < HT; k += 4) {
+        const float4 hv = h4[k >> 2];
+        acc = fmaf(w[k], hv.x, acc);
+        acc = fmaf(w[k + 1], hv.y, acc);
+        acc = fmaf(w[k + 2], hv.z, acc);
+        acc = fmaf(w[k + 3], hv.w, acc);
       }
+      const float a = (g == 2) ? tanhf(acc) : sigmoidf_acc(acc);
+      const float gi = __shfl_sync(0xffffffffu, a, quad_base + 0);
+      const float gf = __shfl_sync(0xffffffffu, a, quad_base + 1);
+      const float gg = __shfl_sync(0xffffffffu, a, quad_base + 2);
+      const float go = __shfl_sync(0xffffffffu, a, quad_base + 3);
+      c = gf * c + gi * gg;
+      const float h_new = go * tanhf(c);
+      if (g == 0) hs[cur ^ 1][ul][u] = h_new;
+      if (live) {
+        gates[((size_t)b * T + t) * G + j] = a;
+        if (g == 0) {
+          h_seq[((size_t)b * T + t) * ldh + u] = h_new;
+          c_seq[((size_t)b * T + t) * H + u] = c;
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -263,49 +273,61 @@ lstm_small_bwd_kernel_t(const float* __restrict__ dH, int lddh, const float* __r
   const bool live = b < nB;
   float dc_rec = 0.f;
   const unsigned quad_base = ((threadIdx.y * blockDim.x + threadIdx.x) & 31) & ~3u;
-  float a_n = 0.f, ct_n = 0.f, cp_n = 0.f, dH_n = 0.f;
-  auto fetch = [&](int step) {
+  // PF steps of operands in flight (see lstm_small_fwd_kernel_t)
+  constexpr int PF = 4;
+  float a_r[PF], ct_r[PF], cp_r[PF], dH_r[PF];
+  auto fetch = [&](int step, int i) {
     const int t = reverse ? (T - 1 - step) : step;
     const int t_prev = reverse ? t + 1 : t - 1;
-    a_n = gates[((size_t)b * T + t) * G + j];
-    ct_n = c_seq[((size_t)b * T + t) * H + u];
-    cp_n = (step > 0) ? c_seq[((size_t)b * T + t_prev) * H + u] : 0.f;
-    dH_n = dH[((size_t)b * T + t) * lddh + u];
+    a_r[i] = gates[((size_t)b * T + t) * G + j];
+    ct_r[i] = c_seq[((size_t)b * T + t) * H + u];
+    cp_r[i] = (step > 0) ? c_seq[((size_t)b * T + t_prev) * H + u] : 0.f;
+    dH_r[i] = dH[((size_t)b * T + t) * lddh + u];
   };
-  if (live) fetch(T - 1);
-  int cur = 0;
-  for (int step = T - 1; step >= 0; --step, cur ^= 1) {
-    const int t = reverse ? (T - 1 - step) : step;
-    const float a = a_n, ct = ct_n, cp = cp_n, dHt = dH_n;
-    if (live && step > 0) fetch(step - 1);
-    float part = 0.f;
-    const float4* dg4 = reinterpret_cast<const float4*>(&dgs[cur][ul][g * H]);
 #pragma unroll
-    for (int jj = 0; jj < HT; jj += 4) {
-      const float4 dv = dg4[jj >> 2];
-      part = fmaf(dv.x, w[jj], part);
-      part = fmaf(dv.y, w[jj + 1], part);
-      part = fmaf(dv.z, w[jj + 2], part);
-      part = fmaf(dv.w, w[jj + 3], part);
+  for (int i = 0; i < PF; ++i) {
+    a_r[i] = ct_r[i] = cp_r[i] = dH_r[i] = 0.f;
+    if (live && T - 1 - i >= 0) fetch(T - 1 - i, i);
+  }
+  int cur = 0;
+  for (int step0 = T - 1; step0 >= 0; step0 -= PF) {
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int step = step0 - i;
+      if (step < 0) break;                      // uniform over the block
+      const int t = reverse ? (T - 1 - step) : step;
+      const float a = a_r[i], ct = ct_r[i], cp = cp_r[i], dHt = dH_r[i];
+      if (live && step - PF >= 0) fetch(step - PF, i);
+      float part = 0.f;
+      const float4* dg4 = reinterpret_cast<const float4*>(&dgs[cur][ul][g * H]);
+#pragma unroll
+      for (int jj = 0; jj < HT; jj += 4) {
+        const float4 dv = dg4[jj >> 2];
+        part = fmaf(dv.x, w[jj], part);
+        part = fmaf(dv.y, w[jj + 1], part);
+        part = fmaf(dv.z, w[jj + 2], part);
+        part = fmaf(dv.w, w[jj + 3], part);
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      const float dh = part + dHt;
+      const float gi = __shfl_sync(0xffffffffu, a, quad_base + 0);
+      const float gf = __shfl_sync(0xffffffffu, a, quad_base + 1);
+      const float gg = __shfl_sync(0xffffffffu, a, quad_base + 2);
+      const float go = __shfl_sync(0xffffffffu, a, quad_base + 3);
+      const float tc = tanhf(ct);
+      const float dc = dh * go * (1.f - tc * tc) + dc_rec;
+      float d;
+      if (g == 0) d = dc * gg * gi * (1.f - gi);
+      else if (g == 1) d = dc * cp * gf * (1.f - gf);
+      else if (g == 2) d = dc * gi * (1.f - gg * gg);
+      else d = dh * tc * go * (1.f - go);
+      dc_rec = dc * gf;
+      dgs[cur ^ 1][ul][j] = d;
+      if (live) dP[((size_t)b * T + t) * ldp + j] = d;
+      __syncthreads();
+      cur ^= 1;
     }
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    const float dh = part + dHt;
-    const float gi = __shfl_sync(0xffffffffu, a, quad_base + 0);
-    const float gf = __shfl_sync(0xffffffffu, a, quad_base + 1);
-    const float gg = __shfl_sync(0xffffffffu, a, quad_base + 2);
-    const float go = __shfl_sync(0xffffffffu, a, quad_base + 3);
-    const float tc = tanhf(ct);
-    const float dc = dh * go * (1.f - tc * tc) + dc_rec;
-    float d;
-    if (g == 0) d = dc * gg * gi * (1.f - gi);
-    else if (g == 1) d = dc * cp * gf * (1.f - gf);
-    else if (g == 2) d = dc * gi * (1.f - gg * gg);
-    else d = dh * tc * go * (1.f - go);
-    dc_rec = dc * gf;
-    dgs[cur ^ 1][ul][j] = d;
-    if (live) dP[((size_t)b * T + t) * ldp + j] = d;
-    __syncthreads();
   }
 }
 

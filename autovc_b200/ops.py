@@ -182,6 +182,33 @@ class PackCache:
 _GLOBAL_CACHE = PackCache()
 
 
+class _ZeroArena:
+    """float64 zeros handed out in slices: the BatchNorm statistics buffers (2 C doubles per layer, forward and backward) are
+    accumulated into by their kernels and must start at zero; one 512 KB fill per ~two training steps replaces 28 tiny fill
+    launches per step.  A slice is handed out once and never re-used; an exhausted arena is replaced (the old one lives on
+    until its slices are freed).  Everything happens on the calling stream."""
+    SIZE = 65536
+
+    def __init__(self):
+        self._buf = {}
+
+    def take(self, n: int, device) -> torch.Tensor:
+        n2 = (n + 1) // 2 * 2                       # 16-byte granularity
+        if n2 > self.SIZE // 4:
+            return torch.zeros(n, device=device, dtype=torch.float64)
+        key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+        ent = self._buf.get(key)
+        if ent is None or ent[1] + n2 > self.SIZE:
+            ent = [torch.zeros(self.SIZE, device=device, dtype=torch.float64), 0]
+            self._buf[key] = ent
+        out = ent[0][ent[1]:ent[1] + n]
+        ent[1] += n2
+        return out
+
+
+_ZEROS = _ZeroArena()
+
+
 def pack_conv(weight: torch.Tensor, cache: PackCache = _GLOBAL_CACHE):
     """(Cout, Cin, 5) -> fwd [5][Cout][Cin], dgrad [5][Cin][Cout] (taps flipped)."""
     def build():
@@ -301,7 +328,7 @@ class ConvBnAct(torch.autograd.Function):
         mean = torch.empty(Cout, device=x.device, dtype=torch.float32)
         rstd = torch.empty_like(mean)
         if training:
-            stats = torch.zeros(2 * Cout, device=x.device, dtype=torch.float64)
+            stats = _ZEROS.take(2 * Cout, x.device)
             gemm_nt_taps(x, Cin, wf, bias, y, Cout, B, T, Cout, Cin, k, -(k // 2), stats=stats, prec=prec)
             call("avc_bn_finalize", _p(stats), M, Cout, BN_EPS, BN_MOMENTUM, _p(mean), _p(rstd), _p(running_mean),
                  _p(running_var), _stream())
@@ -325,7 +352,7 @@ class ConvBnAct(torch.autograd.Function):
         Cout, _, k = weight.shape
         M = B * T
         prec = ctx.prec
-        sums = torch.zeros(2 * Cout, device=x.device, dtype=torch.float64)
+        sums = _ZEROS.take(2 * Cout, x.device)
         # act'(z) is recomputed from y where the float4 kernels apply (z is then not read)
         call("avc_bn_act_bwd_reduce_y", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(sums), M, Cout,
              ctx.act, _stream())
@@ -673,7 +700,7 @@ class ConvBnActH(torch.autograd.Function):
         y = torch.empty(B, T, Cout, device=x.device, dtype=torch.float32)
         mean = torch.empty(Cout, device=x.device, dtype=torch.float32)
         rstd = torch.empty_like(mean)
-        stats = torch.zeros(2 * Cout, device=x.device, dtype=torch.float64) if training else None
+        stats = _ZEROS.take(2 * Cout, x.device) if training else None
         gemm_nt_taps_hw(A, a_fmt, Cin, wf, FMT_FP16, wf.shape[-1], bias, y, Cout, B, T, Cout, Cin, k, -(k // 2), stats=stats)
         if training:
             call("avc_bn_finalize", _p(stats), M, Cout, BN_EPS, BN_MOMENTUM, _p(mean), _p(rstd), _p(running_mean),
@@ -715,7 +742,7 @@ class ConvBnActH(torch.autograd.Function):
         B, T, Cin = ctx.x_shape
         Cout, _, k = weight.shape
         M = B * T
-        sums = torch.zeros(2 * Cout, device=dz.device, dtype=torch.float64)
+        sums = _ZEROS.take(2 * Cout, dz.device)
         call("avc_bn_act_bwd_reduce_y", _p(dz), _p(z), _p(y), _p(mean), _p(rstd), _p(gamma), _p(beta), _p(sums), M, Cout,
              ctx.act, _stream())
         dgamma = torch.empty_like(gamma)
