@@ -275,7 +275,7 @@ def run_ours(args):
     reducer = None
     if world > 1:
         solver.broadcast_parameters(G)
-        reducer = solver.GradBucketReducer(G.parameters(), bucket_mb=25.0)
+        reducer = solver.GradBucketReducer(G.parameters(), bucket_mb=args.bucket_mb, nccl_max_ctas=args.nccl_max_ctas)
     B, T = args.batch, args.len_crop
     x_host, e_host = synth_batch(B, T, args.n_bins, 256, 1234 + rank)
     x_pin, e_pin = x_host.pin_memory(), e_host.pin_memory()
@@ -679,6 +679,8 @@ def main():
     ap.add_argument("--cpu-sample-batch", dest="cpu_sample_batch", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="train", choices=["train", "frontend", "convert", "loader", "dvector", "wav"])
+    ap.add_argument("--bucket-mb", type=float, default=25.0, help="N > 1: gradient bucket size of the all-reduce")
+    ap.add_argument("--nccl-max-ctas", type=int, default=16, help="N > 1: CTA cap of the reducer's NCCL communicator")
     ap.add_argument("--chunk", type=int, default=256, help="--workload convert: utterances per Generator call")
     ap.add_argument("--streams", type=int, default=2, help="--workload convert: CUDA streams the chunks alternate over")
     ap.add_argument("--depth", type=int, default=1, help="--workload wav: Conv-TasNet encoder/decoder depth (main.py:65)")
