@@ -2,33 +2,35 @@
 // sequence of a layer-direction, forward or BPTT.
 //
 // nn.LSTM (model_vc_mel.py:90/:111 lstm1, :104/:118 lstm2): per step  gates = P_t + h_{t-1} W_hh^T.
-// Grid = (batch tiles of 128 utterances) x (column tiles); every CTA keeps ITS slice of W_hh
-// resident in shared memory for the whole sequence (bf16, K-major, 128B swizzle -- loaded once by
-// TMA), streams the step's activation tile (h_{t-1}, or dG_{t+1} for BPTT) through a TMA ring,
-// multiplies with tcgen05.mma into a TMEM accumulator, and finishes the step in the epilogue warps:
-// gate nonlinearities + cell update (cell state lives in registers for the whole sequence), or the
-// BPTT gate-gradient algebra.  The new h_t / dG_t slice is published in a bf16 exchange buffer and a
-// per-batch-tile release counter; consumers acquire it before their next TMA loads.  Only CTAs that
-// share a batch tile synchronise with each other.
 //
-//   forward : CTA owns BN gate columns (BN/4 hidden units, gate-interleaved), K = H; clusters of 4 column tiles
-//   backward: a cluster of 4 CTAs owns 64 hidden units of dh = dG_{t+1} W_hh and splits K = 4H four ways
+// Two generations of kernels live here.
 //
-// What bounds a step, measured (profiles/r02_*): (1) ISSUING a TMA tensor load costs the producer thread 120-330 SM
-// clocks whatever the box size (scripts/micro/tma_issue.cu), so the ring is fed with few large boxes: forward, every CTA of
-// a cluster fetches whole 16 KB k-blocks kb = rank (mod 4) and multicasts them to the other three (4 instead of 16
-// instructions per CTA and step, a quarter of the L2 requests); BPTT fetches two k-blocks per instruction.  (2) The
-// publishers write with generic-proxy stores and release a counter; the CONSUMER executes the generic->async proxy
-// fence between its acquire and its TMA reads.  On the writer side (r01) that fence drained the CTA's outstanding stores
-// a second time (fence.proxy.async 0.5-0.9 us + red.release.gpu 0.5-1.0 us per publish, SM-clock trace).  (3) What is left
-// is SHARED-MEMORY BANDWIDTH: per step and SM the TMA unit writes the 256 KB activation tile and tcgen05.mma reads it back
-// (64 MMAs x 4 KB of A) plus the resident slice (64 x 2 KB of B) = 640 KB at 128 B/clk = 2.5 us; the load + MMA phase of the
-// trace is 3.6 us and does not move with the number of SMs that pull (64 or 128), with multicast, with the box size, or
-// with the source lines being freshly written or not.  Two cta_group::2 variants that keep ONE copy of W_hh for both batch
-// tiles (M = 128 per pair alternating the tiles; M = 256 per pair) were built, are bit-compatible, and were measured
-// SLOWER (7.5 / 9.0 us per step: same operand bytes per SM, the B halves additionally cross the pair):
-// profiles/experiments/r02_lstm_pair_*.cu.txt, profiles/r02_lstm_pair_*_trace.log.  Lifting this bound needs the
-// transposed product (W_hh slice as the A operand in TMEM, batch as N), which DESIGN.md describes as the next step.
+// (1) WEIGHT-STATIONARY kernels (lstm_tc_fwd_ws_kernel, lstm_tc_bwd_ws_kernel; r02c) -- the path every benched shape takes.
+//     The W_hh slice of a CTA (128 gate rows forward; 128 units x one K quarter for BPTT) is the A operand of tcgen05.mma
+//     and lives in TENSOR MEMORY for the whole sequence (896 of a row's k; the rest, 128 of 1024, in shared memory); the
+//     batch is the N dimension, NB = 32 or 64 utterances per CTA.  A step ingests only NB x K bf16 per SM (128 KB at
+//     H = 1024 instead of 256 KB), the whole tile is in flight at once (one or two TMA boxes, no ring), the epilogue
+//     transposes gate quads across lanes with shuffles (forward) or drains unit quarters for the DSMEM reduce-scatter
+//     (BPTT).  Per step at B = 256: forward 5.3 us (H = 1024) / 3.4 (H = 512), BPTT 6.2 / 3.8.
+//
+// (2) The ring kernel (lstm_tc_fwd_kernel) and the K-split kernel with the W slice in shared memory
+//     (lstm_tc_bwd_ks_kernel): grid = (batch tiles of 128 utterances) x (column tiles); every CTA keeps ITS slice of W_hh
+//     resident in shared memory (bf16, K-major, 128B swizzle -- loaded once by TMA) and streams the step's 128 x K
+//     activation tile (h_{t-1}, or dG_{t+1} for BPTT) through a TMA ring into tcgen05.mma.  7.5 / 10.2 us per step at
+//     H = 1024.  They remain the path for shapes (1) does not take and are what (1) is tested against: both generations
+//     produce the same bits (tests/test_gpu_lstm_tc.py).  AVC_LSTM_FWD_WS=0 / AVC_LSTM_BWD_WS=0 select them.
+//
+// Common to both: the new h_t / dG_t slice is published in a bf16 exchange buffer and a release counter per batch tile /
+// batch group; consumers acquire it before their next TMA loads.  Only CTAs that share a batch tile / group synchronise.
+//
+// What bounded (2), measured (profiles/r02_*): (a) ISSUING a TMA tensor load costs the producer thread 120-330 SM clocks
+// whatever the box size (scripts/micro/tma_issue.cu), so tiles are fetched with few large boxes; (b) the publishers write
+// with generic-proxy stores and release a counter, the CONSUMER executes the generic->async proxy fence between its acquire
+// and its TMA reads; (c) SHARED-MEMORY BANDWIDTH and L2 -> SM delivery: per step and SM the TMA unit writes the 256 KB
+// activation tile and tcgen05.mma reads it back plus the resident slice = 640 KB at 128 B/clk = 2.5 us, and the resident
+// slice leaves room for only 5 ring stages.  Two cta_group::2 variants that keep ONE copy of W_hh for both batch tiles and
+// a K-split over a CTA pair were built and measured slower (profiles/experiments/).  (1) is the decomposition with less
+// ingest per SM that those measurements asked for.
 #include <stdio.h>
 #include <stdlib.h>
 

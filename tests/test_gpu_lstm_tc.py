@@ -76,7 +76,8 @@ def test_half_mode_layer_matches_nn_lstm_fp64(B, T, I, H, fwd_ws, monkeypatch):
 
 
 @pytest.mark.parametrize("B,T,H,reverse,save", [(4, 6, 128, 0, True), (130, 9, 512, 1, True), (256, 16, 1024, 0, True), (37, 12, 768, 0, False),
-                                                (300, 10, 256, 1, True), (256, 128, 1024, 0, True), (600, 5, 1024, 1, True)])
+                                                (300, 10, 256, 1, True), (256, 128, 1024, 0, True), (600, 5, 1024, 1, True),
+                                                (20, 7, 192, 0, True), (70, 5, 960, 1, True), (9, 1, 512, 0, True), (33, 2, 1024, 1, False)])
 def test_weight_stationary_forward_equals_ring_kernel(B, T, H, reverse, save, monkeypatch):
     """lstm_tc_fwd_ws_kernel (A operand from tensor memory, batch as N) and lstm_tc_fwd_kernel (activation ring) accumulate the
     same products in the same k order: every output -- h, the 16-bit copies, the gates and cell states saved for BPTT -- is
@@ -108,7 +109,8 @@ def test_weight_stationary_forward_equals_ring_kernel(B, T, H, reverse, save, mo
 
 
 @pytest.mark.parametrize("B,T,H,reverse,fp32_out", [(4, 6, 128, 0, True), (130, 9, 512, 1, True), (256, 16, 1024, 0, False), (37, 12, 768, 0, True),
-                                                    (300, 10, 256, 1, True), (256, 128, 1024, 0, False), (600, 5, 1024, 1, True)])
+                                                    (300, 10, 256, 1, True), (256, 128, 1024, 0, False), (600, 5, 1024, 1, True),
+                                                    (70, 5, 896, 1, True), (20, 7, 320, 0, True), (9, 1, 512, 0, True), (33, 2, 1024, 1, False)])
 def test_weight_stationary_bptt_equals_ksplit_kernel(B, T, H, reverse, fp32_out, monkeypatch):
     """lstm_tc_bwd_ws_kernel (W_hh^T slice in tensor memory, 128 units x NB utterances per CTA, K split over a cluster of 4) adds the
     four partial sums of a unit in the order lstm_tc_bwd_ks_kernel uses: the gate gradients (fp32 and bf16) are bit-identical."""
