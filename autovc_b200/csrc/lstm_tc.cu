@@ -1477,6 +1477,10 @@ struct LtPlanWs {
   size_t smem, off_x, off_cnt, total;
 };
 constexpr int WS_MAX_GROUPS = 16;
+// A CTA of the weight-stationary kernels allocates all 512 TMEM columns and waits for its whole grid: two of them on one SM would
+// deadlock in tcgen05.alloc.  Their register footprint (320 threads x ~150) already keeps a second CTA off the SM; requesting more
+// than half of the SM's shared memory makes that a guarantee instead of a property of the compiler's register allocation.
+constexpr size_t WS_MIN_SMEM = 120 * 1024;
 static LtPlanWs lt_plan_ws(int nB, int H) {
   LtPlanWs pl{};
   pl.ok = false;
@@ -1494,6 +1498,7 @@ static LtPlanWs lt_plan_ws(int nB, int H) {
   // (H = 1024 / NB = 64, per step: 4 boxes 5.52 us, 2 boxes 5.25, 1 box 5.29; 16 boxes 7.3)
   pl.kbp = (kblocks >= 12 && kblocks % 2 == 0) ? kblocks / 2 : kblocks;
   pl.smem = 1024 + (size_t)kblocks * pl.NB * 128 + (size_t)(H - pl.KT) / 64 * 16384 + (size_t)pl.NB * (64 + 64 + 128 + 128) + 256;
+  pl.smem = std::max(pl.smem, WS_MIN_SMEM);
   if (pl.smem > 227 * 1024) return pl;
   const int NG = ceil_div(pl.chunk, pl.NB);
   pl.off_x = align256((size_t)4 * H * H * 2);
@@ -1521,6 +1526,7 @@ static LtPlanWs lt_plan_ws_bwd(int nB, int H) {
   // (H = 1024 / NB = 64, per step: 4 boxes 5.52 us, 2 boxes 5.25, 1 box 5.29; 16 boxes 7.3)
   pl.kbp = (kblocks >= 12 && kblocks % 2 == 0) ? kblocks / 2 : kblocks;
   pl.smem = 1024 + (size_t)kblocks * pl.NB * 128 + (size_t)(H - pl.KT) / 64 * 16384 + (size_t)7 * pl.NB * 128 + 256;
+  pl.smem = std::max(pl.smem, WS_MIN_SMEM);
   if (pl.smem > 227 * 1024) return pl;
   const int NG = ceil_div(pl.chunk, pl.NB);
   pl.off_x = align256((size_t)4 * H * H * 2);
