@@ -1661,7 +1661,10 @@ static int lt_launch_fwd_ws(const CUtensorMap& mW, const CUtensorMap& mX, const 
   attrs[0].val.cooperative = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
-  AVC_CUDA(cudaLaunchKernelEx(&cfg, kern, mW, mX, p, Wb));
+  if (cudaLaunchKernelEx(&cfg, kern, mW, mX, p, Wb) != cudaSuccess) {      // refused (co-residency): the caller falls back to the ring kernel
+    (void)cudaGetLastError();
+    return AVC_ERR_UNSUPPORTED;
+  }
   g_launches.fetch_add(1);
   return AVC_OK;
 }
@@ -1721,7 +1724,10 @@ static int lt_launch_bwd_ws(const CUtensorMap& mW, const CUtensorMap& mX, const 
   attrs[1].val.cooperative = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 2;
-  AVC_CUDA(cudaLaunchKernelEx(&cfg, kern, mW, mX, p, Wb));
+  if (cudaLaunchKernelEx(&cfg, kern, mW, mX, p, Wb) != cudaSuccess) {      // refused (cluster placement / co-residency): the caller falls back to the K-split kernel
+    (void)cudaGetLastError();
+    return AVC_ERR_UNSUPPORTED;
+  }
   g_launches.fetch_add(1);
   return AVC_OK;
 }
@@ -1795,15 +1801,19 @@ int lstm_seq_tc(bool bwd, const void* Wv, const float* P, float* h_seq, int ldh,
     const LtPlanWs pw = lt_plan_ws(nB, H);
     const bool al16 = ((((uintptr_t)P | (uintptr_t)gates | (uintptr_t)c_seq | (uintptr_t)h_seq | (uintptr_t)aux16 | (uintptr_t)aux16b) & 15) == 0) &&
                       ldh % 4 == 0;
-    if (pw.ok && al16 && ws_bytes >= pw.total)
-      return lstm_seq_fwd_ws(pw, Wb, P, h_seq, ldh, gates, c_seq, nB, T, H, reverse, w8, st, aux16, fmt16, aux16b);
+    if (pw.ok && al16 && ws_bytes >= pw.total) {
+      const int rc = lstm_seq_fwd_ws(pw, Wb, P, h_seq, ldh, gates, c_seq, nB, T, H, reverse, w8, st, aux16, fmt16, aux16b);
+      if (rc != AVC_ERR_UNSUPPORTED) return rc;      // a refused launch: the ring kernel below recomputes the whole call
+    }
   }
   if (bwd && bwd_ws_enabled()) {
     const LtPlanWs pw = lt_plan_ws_bwd(nB, H);
     auto al32 = [](const void* q) { return ((uintptr_t)q & 31) == 0; };
     const bool wide = al32(gates) && al32(c_seq) && al32(dH) && al32(dP) && al32(aux16) && lddh % 8 == 0;
-    if (pw.ok && wide && ws_bytes >= pw.total)
-      return lstm_seq_bwd_ws(pw, Wb, gates, c_seq, dH, lddh, dP, nB, T, H, reverse, w8, st, aux16);
+    if (pw.ok && wide && ws_bytes >= pw.total) {
+      const int rc = lstm_seq_bwd_ws(pw, Wb, gates, c_seq, dH, lddh, dP, nB, T, H, reverse, w8, st, aux16);
+      if (rc != AVC_ERR_UNSUPPORTED) return rc;      // a refused launch: the K-split kernel below recomputes the whole call
+    }
   }
   const int nchunks = ceil_div(nB, pl.chunk);
   AVC_CUDA(cudaMemsetAsync(counters, 0, (size_t)nchunks * 128 * sizeof(unsigned), st));
